@@ -1,0 +1,238 @@
+/*
+ * pyflyt_b200.h — C-ABI of the B200-native batched UAV stepper.
+ *
+ * This is the drop-in boundary for the ONE hot path of jjshoots/PyFlyt that this project replaces:
+ *   Aviary.step()                      PyFlyt/core/aviary.py:480-531
+ *   QuadX/Fixedwing/Rocket.update_*    PyFlyt/core/drones/{quadx,fixedwing,rocket}.py
+ *   Motors/BoringBodies/LiftingSurfaces/Boosters/Gimbals/PID   PyFlyt/core/abstractions/*.py
+ *   PyBullet stepSimulation()          (third party; restated)
+ *   env epilogues (obs / reward / term) PyFlyt/gym_envs/**, PyFlyt/pz_envs/**
+ *
+ * The reference has no FFI on this path (it is Python on top of PyBullet's CPython module), so the
+ * entry points below are what a maintainer would bind with ctypes from a new `Aviary` backend;
+ * INTEGRATION.md shows that stub.  Rules of the boundary:
+ *   - plain C types only; every buffer is a raw pointer + the sizes implied by the handle;
+ *   - device buffers are OWNED BY THE CALLER (torch tensors on the Python side); the library owns
+ *     only its constant model table and a few bytes of bookkeeping;
+ *   - every call is asynchronous on the given CUDA stream and never synchronises the device;
+ *   - every function returns 0 on success, <0 on error; pfb_last_error() gives the message
+ *     (thread-local).  There is NO CPU fallback: without a CUDA device every compute entry fails.
+ *
+ * Layout convention: SoA, field-major.  A buffer documented as [F][N] holds field f of env i at
+ * index f*N + i.  Row-major "API" buffers ([N][K]) are the shapes an RL trainer consumes.
+ */
+#ifndef PYFLYT_B200_H
+#define PYFLYT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFB_ABI_VERSION 1
+
+/* ---- vehicle kinds (reference: Aviary.drone_type_mappings, aviary.py:167-170) ------------------- */
+#define PFB_KIND_QUADX 0
+#define PFB_KIND_FIXEDWING 1
+#define PFB_KIND_ROCKET 2
+
+/* ---- env epilogues -------------------------------------------------------------------------------- */
+#define PFB_ENV_NONE 0            /* Aviary-level stepping only                                        */
+#define PFB_ENV_QUADX_HOVER 1     /* gym_envs/quadx_envs/quadx_hover_env.py                            */
+#define PFB_ENV_QUADX_WAYPOINTS 2 /* gym_envs/quadx_envs/quadx_waypoints_env.py                        */
+#define PFB_ENV_FIXEDWING_WAYPOINTS 3
+#define PFB_ENV_ROCKET_LANDING 4
+#define PFB_ENV_DOGFIGHT 5
+
+#define PFB_MAX_MOTORS 4
+#define PFB_MAX_SURFACES 5
+#define PFB_MAX_SHAPES 16
+
+#define PFB_SHAPE_BOX 0
+#define PFB_SHAPE_CYLINDER 1
+#define PFB_SHAPE_SPHERE 2
+
+/* One collision primitive used for the ground / pad contact FLAG (no contact response). */
+typedef struct PfbShape {
+  int32_t kind;
+  int32_t _pad;
+  double dims[3]; /* box: half extents; cylinder: radius, half length, -; sphere: radius            */
+  double at[3];   /* centre, base inertial frame                                                     */
+  double rot[9];  /* row-major rotation of the primitive in the base frame                           */
+} PfbShape;
+
+/* One lifting surface (abstractions/lifting_surfaces.py:180-264 precomputed on the host). */
+typedef struct PfbSurface {
+  double pos[3];        /* link COM in the base frame (point of application)                         */
+  double lift_unit[3];
+  double drag_unit[3];
+  double torque_unit[3];
+  double Cl_alpha_3D, aspect, flap_to_chord, aero_tau, eta;
+  double alpha_0_base, alpha_stall_P_base, alpha_stall_N_base; /* radians                            */
+  double Cd_0, deflection_limit_deg, dt_over_tau, area, chord, half_rho;
+} PfbSurface;
+
+/* Host-side, double-precision vehicle table; the library narrows it to fp32 once at pfb_create.     */
+typedef struct PfbModel {
+  int32_t abi_version;
+  int32_t kind;
+  double physics_hz;        /* 240 (aviary.py:79)                                                    */
+  double control_hz;        /* 120 (quadx.py:27, fixedwing.py:23, rocket.py:35)                      */
+  double gravity;           /* -9.81 (aviary.py:226)                                                 */
+  double max_coord_velocity;/* 100, btMultiBody::m_maxCoordinateVelocity                             */
+
+  /* composite rigid body about the base origin, base axes (all joints are fixed) */
+  double mass;
+  double com[3];
+  double inertia[9];        /* row-major, about the base origin                                      */
+
+  /* contact flag */
+  int32_t n_shapes;
+  int32_t _pad0;
+  PfbShape shapes[PFB_MAX_SHAPES];
+  double contact_factor;    /* 0.02: relative breaking threshold × primitive bounding radius         */
+
+  /* propeller motors (abstractions/motors.py) */
+  int32_t n_motors;
+  int32_t _pad1;
+  double motor_pos[PFB_MAX_MOTORS][3];
+  double motor_axis[PFB_MAX_MOTORS][3];
+  double thrust_coef[PFB_MAX_MOTORS];
+  double torque_coef[PFB_MAX_MOTORS];
+  double max_rpm[PFB_MAX_MOTORS];
+  double motor_dt_over_tau[PFB_MAX_MOTORS];
+  double motor_noise_ratio[PFB_MAX_MOTORS];
+
+  /* body drag (abstractions/boring_bodies.py) + quad rotational drag (quadx.py:502-510) */
+  int32_t n_bodies;
+  int32_t _pad2;
+  double body_pos[3];
+  double drag_const[3];     /* 0.5 * 1.225 * Cd * A, per link axis                                   */
+  double drag_coef_pqr;
+
+  /* QuadX PID gains (quadx.py:153-197).  index: 0 ang_vel, 1 ang_pos, 2 lin_vel, 3 lin_pos,
+   * 4 z_vel, 5 z_pos;  second index: kp, ki, kd, lim;  third: axis.                                 */
+  double pid[6][4][3];
+  double motor_map[4][4];   /* quadx.py:130-137                                                      */
+
+  /* lifting surfaces (fixedwing: 5, rocket finlets: 4) */
+  int32_t n_surfaces;
+  int32_t _pad3;
+  PfbSurface surfaces[PFB_MAX_SURFACES];
+
+  /* booster + gimbal + fuel tank (rocket; abstractions/boosters.py, gimbals.py) */
+  int32_t has_booster;
+  int32_t reignitable;
+  double booster_pos[3];
+  double booster_axis[3];
+  double booster_dt_over_tau, booster_noise_ratio;
+  double booster_min_thrust, booster_max_thrust;
+  double fuel_total_mass, fuel_max_rate;
+  double fuel_max_inertia[3];
+  double fuel_pos[3];
+  double dry_mass;           /* composite without the fuel tank link                                 */
+  double dry_first_moment[3];/* sum m_i r_i without the tank                                         */
+  double dry_inertia[9];     /* about the base origin, without the tank                              */
+  double gimbal_unit1[3], gimbal_unit2[3];
+  double gimbal_dt_over_tau;
+  double gimbal_range_rad[2];
+  double starting_fuel_ratio;
+  double starting_velocity[3]; /* fixedwing.py:35,201                                                */
+} PfbModel;
+
+/* Env-epilogue constants (gym_envs/quadx_envs/quadx_hover_env.py:29-38 and friends). */
+typedef struct PfbEnvConfig {
+  int32_t env_kind;          /* PFB_ENV_*                                                            */
+  int32_t flight_mode;       /* quadx.py:233-245                                                     */
+  int32_t env_step_ratio;    /* 120 / agent_hz                                                       */
+  int32_t max_steps;         /* agent_hz * max_duration_seconds                                      */
+  int32_t angle_representation; /* 0 euler, 1 quaternion                                             */
+  int32_t sparse_reward;
+  int32_t autoreset;         /* 1: SAME_STEP autoreset inside pfb_env_step                           */
+  int32_t warmup_steps;      /* 10 Aviary steps after reset (quadx_base_env.py:209-210)              */
+  double flight_dome_size;
+  double goal_reach_distance, goal_reach_angle;  /* waypoint envs                                    */
+  int32_t num_targets, use_yaw_targets;
+} PfbEnvConfig;
+
+/* Caller-owned DEVICE buffers.  Any pointer may be NULL if the env kind does not use it. */
+typedef struct PfbBuffers {
+  /* persistent state, fp32 SoA [F][N]; row map is fixed per vehicle kind: see pfb_state_rows()      */
+  float* state;
+  int32_t* istate;           /* [I][N] int32: step_count, flags, episode counter, ...                */
+  /* inputs */
+  const float* setpoint;     /* [N][S] row-major (S = pfb_setpoint_dim)                              */
+  const float* start_pos;    /* [N][3]                                                               */
+  const float* start_orn;    /* [N][3] euler                                                         */
+  /* outputs of pfb_env_step */
+  float* obs;                /* [N][O] row-major                                                     */
+  float* reward;             /* [N]                                                                  */
+  uint8_t* term;             /* [N]                                                                  */
+  uint8_t* trunc;            /* [N]                                                                  */
+  uint8_t* info;             /* [N] bit0 out_of_bounds, bit1 collision, bit2 env_complete            */
+  float* final_obs;          /* [N][O] terminal observation of envs that autoreset (nullable)        */
+  /* outputs of pfb_observe_state (Aviary.state / aux_state) */
+  float* drone_state;        /* [N][12] = state(i) (4,3) flattened: ang_vel_b, euler, lin_vel_b, pos */
+  float* aux_state;          /* [N][A]                                                               */
+  uint8_t* contact;          /* [N] any ground contact during the last Aviary.step()                 */
+} PfbBuffers;
+
+typedef struct PfbContext* PfbHandle;
+
+/* ---- lifecycle ---------------------------------------------------------------------------------- */
+const char* pfb_last_error(void);
+int pfb_abi_version(void);
+int pfb_sizeof_model(void);
+int pfb_sizeof_env_config(void);
+int pfb_sizeof_buffers(void);
+
+/* Replaces Aviary.__init__ (aviary.py:69-216) for n_envs independent single-drone worlds. */
+int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, int device, uint64_t seed,
+               PfbHandle* out);
+int pfb_destroy(PfbHandle h);
+
+/* Shapes the caller must allocate. */
+int pfb_state_rows(PfbHandle h);     /* F of PfbBuffers.state                                         */
+int pfb_istate_rows(PfbHandle h);    /* I of PfbBuffers.istate                                        */
+int pfb_setpoint_dim(PfbHandle h);   /* S                                                             */
+int pfb_obs_dim(PfbHandle h);        /* O                                                             */
+int pfb_aux_dim(PfbHandle h);        /* A                                                             */
+int pfb_bind(PfbHandle h, const PfbBuffers* buffers);
+
+/* ---- Aviary surface ------------------------------------------------------------------------------ */
+/* Aviary.reset + drone.reset + update_state (aviary.py:218-312, quadx.py:222-231).  mask: device
+ * [N] uint8, NULL = all envs.  Poses come from the bound start_pos/start_orn.                        */
+int pfb_reset(PfbHandle h, const uint8_t* mask, void* stream);
+/* Aviary.set_mode (aviary.py:440-458, quadx.py:233-373): same mode for every env; resets the PIDs
+ * and presets the setpoint buffer rows exactly like the reference.                                   */
+int pfb_set_mode(PfbHandle h, int mode, float* setpoint_rw, void* stream);
+/* n_steps × Aviary.step() (aviary.py:480-531).  noise: device [n_steps*updates_per_step][N] raw
+ * draws of np_random.normal(*throttle.shape) (motors.py:134-138), or NULL → on-device Philox.        */
+int pfb_aviary_step(PfbHandle h, int n_steps, const float* noise, void* stream);
+/* Fills drone_state / aux_state / contact (Aviary.state(i), aux_state(i), contact_array).            */
+int pfb_observe_state(PfbHandle h, void* stream);
+
+/* ---- gymnasium-env surface ----------------------------------------------------------------------- */
+/* env.reset(): begin_reset + end_reset (quadx_base_env.py:149-212): pose reset, set_mode, warm-up
+ * Aviary steps, first observation.  mask NULL = all.                                                 */
+int pfb_env_reset(PfbHandle h, const uint8_t* mask, const float* noise, void* stream);
+/* env.step(action) for all envs (quadx_base_env.py:269-301): actions are read from the bound
+ * setpoint buffer [N][S]; writes obs / reward / term / trunc / info.                                 */
+int pfb_env_step(PfbHandle h, const float* noise, void* stream);
+/* Benchmark rollout: n_steps env.step() calls in one launch with actions drawn on device
+ * (uniform in the env's action box) — "synthetic random-action rollouts" of BASELINE.json.           */
+int pfb_env_rollout(PfbHandle h, int n_steps, void* stream);
+
+/* Host-buffer convenience used for the end-to-end measurement: H2D(actions) → pfb_env_step →
+ * D2H(obs, reward, term, trunc).  Host pointers should be pinned.                                    */
+int pfb_env_step_host(PfbHandle h, const float* host_actions, float* host_obs, float* host_reward,
+                      uint8_t* host_term, uint8_t* host_trunc, void* stream);
+
+/* Number of kernel launches issued by this handle so far (bench.py's gpu_launches).                  */
+int64_t pfb_launch_count(PfbHandle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYFLYT_B200_H */
