@@ -4,9 +4,9 @@
  * This is the drop-in boundary for the ONE hot path of jjshoots/PyFlyt that this project replaces:
  *   Aviary.step()                      PyFlyt/core/aviary.py:480-531
  *   QuadX/Fixedwing/Rocket.update_*    PyFlyt/core/drones/{quadx,fixedwing,rocket}.py
- *   Motors/BoringBodies/LiftingSurfaces/Boosters/Gimbals/PID   PyFlyt/core/abstractions/*.py
+ *   Motors/BoringBodies/LiftingSurfaces/Boosters/Gimbals/PID   PyFlyt/core/abstractions/
  *   PyBullet stepSimulation()          (third party; restated)
- *   env epilogues (obs / reward / term) PyFlyt/gym_envs/**, PyFlyt/pz_envs/**
+ *   env epilogues (obs / reward / term) PyFlyt/gym_envs, PyFlyt/pz_envs
  *
  * The reference has no FFI on this path (it is Python on top of PyBullet's CPython module), so the
  * entry points below are what a maintainer would bind with ctypes from a new `Aviary` backend;

@@ -1,0 +1,167 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz by flying the UNMODIFIED reference (/root/reference/PyFlyt) on the
+restated Bullet engine (oracle/fakebullet).  Run in the build container only; the fixtures travel.
+
+Each fixture stores the scenario inputs (setpoints / actions, start pose), the raw
+``np_random.normal`` draws the reference consumed (one per component per physics step)
+and the reference's outputs per Aviary step / env step.  The C oracle (oracle/pfb_oracle.c) and the
+CUDA path are both replayed against these with the same injected draws.
+
+Scenarios mirror the reference's own tests: tests/test_core.py:13-31 (mode-7 hold),
+:65-93 (two set-points), tests/test_gym_envs.py:92-112 (env determinism contract).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.join(os.path.dirname(os.path.realpath(__file__)), "..")
+sys.path.insert(0, ROOT)
+from oracle import ref_in_loop as ril  # noqa: E402
+
+ril.install()
+from PyFlyt.core import Aviary  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def fly_quadx(name, mode, drone_model, start_pos, start_orn, setpoint_schedule, n_steps, seed):
+    """Aviary-level QuadX flight; setpoint_schedule: {step_index: setpoint(4)} applied before step."""
+    rng = ril.ScriptedNoise(seed)
+    env = Aviary(
+        start_pos=np.array([start_pos], dtype=np.float64),
+        start_orn=np.array([start_orn], dtype=np.float64),
+        drone_type="quadx",
+        drone_options=dict(drone_model=drone_model),
+        np_random=rng,
+    )
+    env.set_mode(mode)
+    sp_after_mode = np.array(env.drones[0].setpoint, dtype=np.float64)
+    states, auxs, pwms, contacts, raws, sps = [], [], [], [], [], []
+    for i in range(n_steps):
+        if i in setpoint_schedule:
+            env.set_setpoint(0, np.array(setpoint_schedule[i], dtype=np.float64))
+        sps.append(np.array(env.drones[0].setpoint, dtype=np.float64))
+        env.step()
+        d = env.drones[0]
+        states.append(np.array(d.state))
+        auxs.append(np.array(d.aux_state))
+        pwms.append(np.array(d.pwm))
+        contacts.append(bool(np.any(env.contact_array[env.planeId])))
+        pos, quat = env.getBasePositionAndOrientation(d.Id)
+        v, w = env.getBaseVelocity(d.Id)
+        raws.append(np.concatenate([pos, quat, v, w]))
+    np.savez_compressed(
+        os.path.join(OUT, f"{name}.npz"),
+        kind="quadx_aviary",
+        mode=mode,
+        drone_model=drone_model,
+        start_pos=np.array(start_pos, dtype=np.float64),
+        start_orn=np.array(start_orn, dtype=np.float64),
+        setpoint_after_set_mode=sp_after_mode,
+        setpoints=np.array(sps),
+        noise=np.array(rng.normal_log),
+        state=np.array(states),
+        aux=np.array(auxs),
+        pwm=np.array(pwms),
+        contact=np.array(contacts),
+        raw=np.array(raws),
+    )
+    print(name, "final pos", states[-1][3], "draws", len(rng.normal_log))
+
+
+def fly_hover(name, seed, n_steps, action_seed, angle_representation, flight_mode=0, sparse=False, dome=3.0, action_scale=1.0):
+    from PyFlyt.gym_envs.quadx_envs.quadx_hover_env import QuadXHoverEnv
+
+    env = QuadXHoverEnv(
+        sparse_reward=sparse, flight_mode=flight_mode, flight_dome_size=dome, angle_representation=angle_representation
+    )
+    rng = ril.ScriptedNoise(seed)
+    env._np_random = rng  # the env hands its generator to the Aviary (quadx_base_env.py:192)
+    obs0, _ = env.reset()
+    arng = np.random.default_rng(action_seed)
+    lo, hi = env.action_space.low, env.action_space.high
+    obs, rew, term, trunc, info, acts, episode_start = [], [], [], [], [], [], []
+    noise_splits = [len(rng.normal_log)]
+    resets_obs = []
+    for i in range(n_steps):
+        a = arng.uniform(lo, hi) * action_scale
+        o, r, te, tr, inf = env.step(a)
+        acts.append(a)
+        obs.append(o)
+        rew.append(r)
+        term.append(te)
+        trunc.append(tr)
+        info.append(int(inf["out_of_bounds"]) | (int(inf["collision"]) << 1) | (int(inf["env_complete"]) << 2))
+        noise_splits.append(len(rng.normal_log))
+        if te or tr:
+            # next-episode reset exactly as a user loop would do it
+            o2, _ = env.reset()
+            resets_obs.append(o2)
+            episode_start.append(i + 1)
+            noise_splits.append(len(rng.normal_log))
+    np.savez_compressed(
+        os.path.join(OUT, f"{name}.npz"),
+        kind="quadx_hover",
+        flight_mode=flight_mode,
+        sparse=sparse,
+        dome=dome,
+        angle_representation=angle_representation,
+        reset_obs=obs0,
+        actions=np.array(acts),
+        obs=np.array(obs),
+        reward=np.array(rew),
+        term=np.array(term),
+        trunc=np.array(trunc),
+        info=np.array(info),
+        noise=np.array(rng.normal_log),
+        noise_splits=np.array(noise_splits),
+        episode_start=np.array(episode_start, dtype=np.int64),
+        after_reset_obs=np.array(resets_obs) if resets_obs else np.zeros((0, len(obs0))),
+    )
+    print(name, "steps", n_steps, "episodes", len(episode_start) + 1, "draws", len(rng.normal_log))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    # A: tests/test_core.py:13-31
+    fly_quadx("quadx_mode7_hold", 7, "cf2x", [0, 0, 1], [0, 0, 0], {}, 1000, seed=1)
+    # B: tests/test_core.py:65-93 / examples/core/03_control.py
+    fly_quadx(
+        "quadx_mode7_setpoints", 7, "cf2x", [0, 0, 1], [0, 0, 0],
+        {0: [1.0, 0.0, 0.0, 1.0], 500: [0.0, 0.0, np.pi / 4, 2.0]}, 1000, seed=2,
+    )
+    # every flight mode, both quad models, a tilted start and setpoint changes
+    sched = {
+        -1: {0: [0.3, 0.31, 0.32, 0.3], 120: [0.5, 0.5, 0.45, 0.5]},
+        0: {0: [0.3, -0.2, 0.1, 0.45], 150: [-0.5, 0.4, -0.3, 0.3]},
+        1: {0: [0.2, -0.1, 0.5, 0.3], 150: [-0.2, 0.2, -0.5, -0.2]},
+        2: {0: [0.2, -0.2, 0.3, 6.0], 150: [-0.3, 0.1, 0.0, 4.0]},
+        3: {0: [0.15, -0.1, 0.6, 6.0], 150: [0.0, 0.0, -0.6, 4.5]},
+        4: {0: [0.8, -0.5, 0.3, 6.0], 150: [-0.6, 0.4, -0.2, 4.5]},
+        5: {0: [0.8, -0.5, 0.3, 0.4], 150: [-0.6, 0.4, -0.2, -0.3]},
+        6: {0: [0.9, 0.4, 0.5, 0.3], 150: [-0.5, -0.7, -0.4, -0.2]},
+        7: {0: [1.0, -1.0, 0.8, 6.0], 150: [-0.5, 0.5, -0.8, 4.0]},
+    }
+    for model in ["cf2x", "primitive_drone"]:
+        for mode in range(-1, 8):
+            fly_quadx(f"quadx_{model}_mode{mode}", mode, model, [0.3, -0.2, 5.0], [0.1, -0.15, 0.7], sched[mode], 300, seed=10 + mode)
+    # floor strike: contact flag + "no rotational drag while in contact" (quadx.py:509-510)
+    fly_quadx("quadx_floor_contact", 0, "cf2x", [0, 0, 0.3], [0.4, 0.2, 0], {0: [1.0, 2.0, 0.5, 0.05]}, 80, seed=3)
+    # long open-sky parity scenario: 3000 Aviary steps = 1000 Hover env-steps
+    prng = np.random.default_rng(1)
+    sched0 = {}
+    for k in range(0, 3000, 30):
+        a = prng.uniform([-np.pi, -np.pi, -np.pi, 0.0], [np.pi, np.pi, np.pi, 0.8])
+        a[:3] *= 0.3
+        sched0[k] = a
+    fly_quadx("quadx_mode0_long", 0, "cf2x", [0, 0, 50.0], [0, 0, 0], sched0, 3000, seed=4)
+    # Hover env: tests/test_gym_envs.py:92-112 shape (seeded env + scripted actions)
+    fly_hover("hover_quat_dense", seed=0, n_steps=400, action_seed=1, angle_representation="quaternion")
+    fly_hover("hover_euler_sparse", seed=5, n_steps=200, action_seed=2, angle_representation="euler", sparse=True)
+    fly_hover("hover_quat_gentle", seed=6, n_steps=450, action_seed=3, angle_representation="quaternion", action_scale=0.05, dome=50.0)
+    fly_hover("hover_mode6", seed=7, n_steps=300, action_seed=4, angle_representation="quaternion", flight_mode=6, action_scale=0.3)
+
+
+if __name__ == "__main__":
+    main()
