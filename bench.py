@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/s of the batched QuadX-Hover stepper (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            (ours; torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  (CPU arm: the oracle port, all host threads)
+
+One "step" = one env.step() of every env of this rank's shard = one k_hover_step launch (6 physics
+substeps, 3 control ticks, reward/termination/observation fused) + one k_hover_autoreset launch.
+Workload (config.workload): QuadX-Hover-v4, mode 0, 65 536 envs per GPU, uniform random actions in the
+env's action box, same-step autoreset — BASELINE.json configs[1].  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.realpath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_ENV_STEP = 330  # 2*4*28 state + 16 action + 84 obs + 6 reward/flags
+ENVS_PER_GPU = 65536
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_rate(envs: int, target_seconds: float, threads: int | None = None):
+    """env-steps/s of the CPU oracle port on the host cores; bounded sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+
+    from engines import build_model, hover_config
+    from oracle import oracle as orc_mod
+
+    L = orc_mod.lib()
+    if threads:
+        L.orc_set_num_threads(int(threads))
+    cores = int(L.orc_num_threads())
+    model = build_model("quadx", "cf2x")
+    env = hover_config(0, "quaternion", False, 3.0, autoreset=True)
+    o = orc_mod.Oracle(model, env, n=envs, seed=1, start_pos=np.array([0.0, 0.0, 1.0]), start_orn=np.zeros(3))
+    o.env_reset()
+    o.env_rollout(2)  # warm-up
+    t0 = time.perf_counter()
+    o.env_rollout(3)
+    per_step = (time.perf_counter() - t0) / 3
+    steps = max(3, int(target_seconds / max(per_step, 1e-6)))
+    t0 = time.perf_counter()
+    done = o.env_rollout(steps)
+    dt = time.perf_counter() - t0
+    return done / dt, cores, steps, dt
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the reference's algorithm (oracle port; PyBullet itself is not installable here) timed
+    on the box's host cores, same metric and config; rank 0 only."""
+    if rank != 0:
+        return
+    envs = ENVS_PER_GPU
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+
+    from engines import build_model, hover_config
+    from oracle import oracle as orc_mod
+
+    L = orc_mod.lib()
+    cores = int(L.orc_num_threads())
+    model = build_model("quadx", "cf2x")
+    env = hover_config(0, "quaternion", False, 3.0, autoreset=True)
+    o = orc_mod.Oracle(model, env, n=envs, seed=1, start_pos=np.array([0.0, 0.0, 1.0]), start_orn=np.zeros(3))
+    o.env_reset()
+    for _ in range(args.warmup):
+        o.env_rollout(1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.env_rollout(1)
+    dt = time.perf_counter() - t0
+    value = envs * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "QuadX-Hover-v4 mode 0, 65536 envs, uniform random actions, same-step autoreset", "envs": envs},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps x {envs} envs of the full workload (oracle/pfb_oracle.c, OpenMP)"},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from pyflyt_b200.gym_envs.quadx_hover_env import QuadXHoverVecEnv
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.envs
+    env = QuadXHoverVecEnv(num_envs=n, seed=args.seed, device=dev, env_offset=rank * n)
+    av = env.aviary
+    env.reset()
+    K, W = args.steps, args.warmup
+    # action pool resident in HBM before the timed region (uniform in the action box, quadx_base_env.py:79-102)
+    pool = 32
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    lo = torch.tensor([-3.14159265, -3.14159265, -3.14159265, 0.0], device=dev)
+    hi = torch.tensor([3.14159265, 3.14159265, 3.14159265, 0.8], device=dev)
+    actions = lo + (hi - lo) * torch.rand((pool, n, 4), device=dev, generator=g)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for k in range(W):
+        av.env_step(actions=actions[k % pool])
+    barrier()
+
+    # ---- timed region A: device-resident inputs, L2 flushed between steps, per-step CUDA-event pairs
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = av.launch_count
+    av.profile_begin(K)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    for k in range(K):
+        flush.fill_(float(k))
+        ev[k][0].record()
+        av.env_step(actions=actions[(W + k) % pool])
+        ev[k][1].record()
+    barrier()
+    launches = av.launch_count - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    kern_ms = av.profile_read(K)
+    av.profile_begin(0)
+
+    # ---- timed region A2 (context): back-to-back, L2-warm
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(K):
+        av.env_step(actions=actions[k % pool])
+    e1.record()
+    barrier()
+    warm_ms = e0.elapsed_time(e1)
+
+    # ---- timed region B: end to end through the host-buffer entry of the C-ABI (pinned host memory)
+    act_h = [actions[k].cpu().pin_memory() for k in range(4)]
+    obs_h = torch.empty((n, env.obs_dim), dtype=torch.float32).pin_memory()
+    rew_h = torch.empty(n, dtype=torch.float32).pin_memory()
+    te_h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    tr_h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    for k in range(3):
+        av.env_step_host(act_h[k % 4], obs_h, rew_h, te_h, tr_h)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        av.env_step_host(act_h[k % 4], obs_h, rew_h, te_h, tr_h)
+        torch.cuda.synchronize(dev)  # the caller reads obs/reward here
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop()
+
+    # ---- reduce: max over ranks
+    t = torch.tensor([total_ms, warm_ms, e2e_s * 1e3, float(sum(kern_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, warm_ms, e2e_ms, kern_total_ms = (float(x) for x in t.tolist())
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        value = world * n * K / (total_ms * 1e-3)
+        kern_avg_s = kern_total_ms * 1e-3 / max(len(kern_ms), 1)
+        achieved = ALGO_BYTES_PER_ENV_STEP * n / kern_avg_s / 1e9
+        line = {
+            "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {
+                "workload": "QuadX-Hover-v4 (BASELINE configs[1]): flight mode 0, 65536 envs per GPU, uniform random actions, same-step autoreset, 6 physics substeps + 3 control ticks per env-step",
+                "envs_per_gpu": n, "global_envs": world * n, "parallelism": f"env-shard x{world} (no data-path collective)",
+                "l2": "flushed between timed steps (256 MiB write outside the event pairs); per-step CUDA-event pairs summed",
+                "precision": "fp32 forces/control/obs; quaternion, position, velocity carried as fp64 (hi+lo fp32 words in HBM)",
+                "value_l2_warm": world * n * K / (warm_ms * 1e-3), "ms_per_step_l2_warm": warm_ms / K,
+            },
+            "e2e": {
+                "value": world * n * K / (e2e_ms * 1e-3), "unit": "env-steps/s",
+                "h2d_bytes_per_step": n * 4 * 4, "d2h_bytes_per_step": n * (env.obs_dim * 4 + 4 + 1 + 1),
+            },
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "k_hover_step<0,false,false>", "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
+                "kernel_avg_us": kern_avg_s * 1e6, "peak_source": peak_src,
+                "note": "issue/FMA-bound kernel: the HBM fraction is reported because BASELINE.json asks for it; see DESIGN.md",
+            },
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rate, cores, steps, dt = cpu_oracle_rate(4096, args.cpu_seconds)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                "sample": f"{steps} env-steps x 4096 envs ({dt:.1f} s) of the same workload on oracle/pfb_oracle.c (fp64, OpenMP)",
+            }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -162,7 +162,8 @@ typedef struct PfbBuffers {
   float* state;
   int32_t* istate;           /* [I][N] int32: step_count, flags, episode counter, ...                */
   /* inputs */
-  const float* setpoint;     /* [N][S] row-major (S = pfb_setpoint_dim)                              */
+  float* setpoint;           /* [N][S] row-major (S = pfb_setpoint_dim); the caller writes actions /
+                              * setpoints here, pfb_reset / pfb_set_mode preset it like the reference  */
   const float* start_pos;    /* [N][3]                                                               */
   const float* start_orn;    /* [N][3] euler                                                         */
   /* outputs of pfb_env_step */
@@ -191,6 +192,9 @@ int pfb_sizeof_buffers(void);
 int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, int device, uint64_t seed,
                PfbHandle* out);
 int pfb_destroy(PfbHandle h);
+/* Global index of this handle's env 0 (rank * n_envs when the batch is sharded over GPUs): keeps
+ * the Philox streams, and therefore every trajectory, independent of the number of ranks.          */
+int pfb_set_env_offset(PfbHandle h, uint64_t first_global_env);
 
 /* Shapes the caller must allocate. */
 int pfb_state_rows(PfbHandle h);     /* F of PfbBuffers.state                                         */
@@ -205,8 +209,8 @@ int pfb_bind(PfbHandle h, const PfbBuffers* buffers);
  * [N] uint8, NULL = all envs.  Poses come from the bound start_pos/start_orn.                        */
 int pfb_reset(PfbHandle h, const uint8_t* mask, void* stream);
 /* Aviary.set_mode (aviary.py:440-458, quadx.py:233-373): same mode for every env; resets the PIDs
- * and presets the setpoint buffer rows exactly like the reference.                                   */
-int pfb_set_mode(PfbHandle h, int mode, float* setpoint_rw, void* stream);
+ * and presets the bound setpoint buffer rows exactly like the reference.                             */
+int pfb_set_mode(PfbHandle h, int mode, void* stream);
 /* n_steps × Aviary.step() (aviary.py:480-531).  noise: device [n_steps*updates_per_step][N] raw
  * draws of np_random.normal(*throttle.shape) (motors.py:134-138), or NULL → on-device Philox.        */
 int pfb_aviary_step(PfbHandle h, int n_steps, const float* noise, void* stream);
@@ -217,9 +221,9 @@ int pfb_observe_state(PfbHandle h, void* stream);
 /* env.reset(): begin_reset + end_reset (quadx_base_env.py:149-212): pose reset, set_mode, warm-up
  * Aviary steps, first observation.  mask NULL = all.                                                 */
 int pfb_env_reset(PfbHandle h, const uint8_t* mask, const float* noise, void* stream);
-/* env.step(action) for all envs (quadx_base_env.py:269-301): actions are read from the bound
- * setpoint buffer [N][S]; writes obs / reward / term / trunc / info.                                 */
-int pfb_env_step(PfbHandle h, const float* noise, void* stream);
+/* env.step(action) for all envs (quadx_base_env.py:269-301): actions device [N][S] (NULL = the bound
+ * setpoint buffer); writes obs / reward / term / trunc / info.                                       */
+int pfb_env_step(PfbHandle h, const float* actions, const float* noise, void* stream);
 /* Benchmark rollout: n_steps env.step() calls in one launch with actions drawn on device
  * (uniform in the env's action box) — "synthetic random-action rollouts" of BASELINE.json.           */
 int pfb_env_rollout(PfbHandle h, int n_steps, void* stream);
@@ -231,6 +235,11 @@ int pfb_env_step_host(PfbHandle h, const float* host_actions, float* host_obs, f
 
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches).                  */
 int64_t pfb_launch_count(PfbHandle h);
+/* Measurement aid: record a CUDA-event pair around the dominant kernel of each of the next
+ * `capacity` pfb_env_step calls (0 = off); pfb_profile_read returns how many pairs were filled and
+ * their durations in ms (call after synchronising the stream).                                       */
+int pfb_profile_begin(PfbHandle h, int capacity);
+int pfb_profile_read(PfbHandle h, float* ms_out, int capacity);
 
 #ifdef __cplusplus
 }

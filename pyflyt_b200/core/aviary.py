@@ -1,0 +1,249 @@
+"""``BatchedAviary`` — N independent single-drone worlds stepped in lock-step on one B200.
+
+Mirrors the surface of the reference's ``Aviary`` that its environments use
+(/root/reference/PyFlyt/core/aviary.py): ctor kwargs ``start_pos``/``start_orn``/``drone_type``/
+``drone_options``/``seed``/``physics_hz`` (:69-83), ``reset`` (:218), ``step`` (:480), ``state(i)`` (:335),
+``aux_state(i)`` (:353), ``all_states`` (:372), ``set_mode`` (:440), ``set_setpoint`` (:460),
+``set_all_setpoints`` (:470), ``contact_array`` (:322), counters (:227-229, :528-531) — with one
+difference in meaning: drone ``i`` lives in its OWN world (the reference puts them in one Bullet world),
+so ``contact_array[i]`` is "drone i touched the floor during the last step".
+
+All state is held in caller-visible ``torch`` tensors; the CUDA library (libpyflyt_b200.so) only sees
+raw device pointers.  There is no CPU path.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Sequence
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..models import PfbEnvConfig, build_model
+
+
+class AviaryInitException(Exception):
+    """Same role as PyFlyt.core.aviary.AviaryInitException (aviary.py:21-44)."""
+
+    def __init__(self, message: str = "AviaryInitException"):
+        self.message = message
+        super().__init__(self.message)
+
+    def __str__(self) -> str:
+        return f"Aviary Error: {self.message}"
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class BatchedAviary:
+    def __init__(
+        self,
+        start_pos,
+        start_orn,
+        drone_type: str = "quadx",
+        drone_options: dict[str, Any] | None = None,
+        physics_hz: int = 240,
+        seed: None | int = None,
+        device: str | torch.device = "cuda:0",
+        env_config: PfbEnvConfig | None = None,
+        env_offset: int = 0,
+    ):
+        start_pos = np.asarray(start_pos, dtype=np.float32)
+        start_orn = np.asarray(start_orn, dtype=np.float32)
+        # shape checks with the reference's messages (aviary.py:120-131)
+        if start_pos.ndim != 2 or start_pos.shape[-1] != 3:
+            raise AviaryInitException(f"start_pos must be shape (n, 3), currently {start_pos.shape}.")
+        if start_orn.shape != start_pos.shape:
+            raise AviaryInitException(f"start_orn must be same shape as start_pos, currently {start_orn.shape}.")
+        if isinstance(drone_type, (tuple, list)):
+            if len(set(drone_type)) != 1:
+                raise AviaryInitException("the batched stepper runs one vehicle kind per batch; build one BatchedAviary per kind.")
+            drone_type = drone_type[0]
+        if drone_type not in ("quadx", "fixedwing", "rocket"):
+            raise AviaryInitException(f"Can't find `drone_type` {drone_type} amongst known types ['quadx', 'fixedwing', 'rocket'].")
+        if not torch.cuda.is_available():
+            raise _lib.PfbError("pyflyt_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+        opts = dict(drone_options or {})
+        control_hz = int(opts.pop("control_hz", 120))
+        self.device = torch.device(device)
+        self.num_drones = int(start_pos.shape[0])
+        self.drone_type = drone_type
+        self.physics_hz = int(physics_hz)
+        self.physics_period = 1.0 / physics_hz
+        self.model = build_model(drone_type, opts.pop("drone_model", None), opts.pop("model_dir", None), physics_hz, control_hz, **opts)
+        self.env_config = env_config
+        self.updates_per_step = int(physics_hz / control_hz)  # aviary.py:288-289 (single control rate)
+        self.step_period = 1.0 / control_hz
+        self.seed = 0 if seed is None else int(seed)
+
+        L = _lib.lib()
+        self._h = C.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _lib.check(L.pfb_create(C.byref(self.model), C.byref(env_config) if env_config is not None else None, self.num_drones, dev_index, self.seed, C.byref(self._h)))
+        _lib.check(L.pfb_set_env_offset(self._h, int(env_offset)))
+        n, dev = self.num_drones, self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.obs_dim = L.pfb_obs_dim(self._h)
+        self.setpoint_dim = L.pfb_setpoint_dim(self._h)
+        self.aux_dim = L.pfb_aux_dim(self._h)
+        # persistent state, SoA [F][N]
+        self.state_tensor = torch.zeros((L.pfb_state_rows(self._h), n), **f32)
+        self.istate_tensor = torch.zeros((L.pfb_istate_rows(self._h), n), dtype=torch.int32, device=dev)
+        self.setpoints = torch.zeros((n, self.setpoint_dim), **f32)
+        self.start_pos = torch.from_numpy(start_pos).to(dev).contiguous()
+        self.start_orn = torch.from_numpy(start_orn).to(dev).contiguous()
+        self.obs = torch.zeros((n, self.obs_dim), **f32)
+        self.reward = torch.zeros((n,), **f32)
+        self.term = torch.zeros((n,), dtype=torch.uint8, device=dev)
+        self.trunc = torch.zeros((n,), dtype=torch.uint8, device=dev)
+        self.info_bits = torch.zeros((n,), dtype=torch.uint8, device=dev)
+        self.final_obs = torch.zeros((n, self.obs_dim), **f32)
+        self._drone_state = torch.zeros((n, 12), **f32)
+        self._aux_state = torch.zeros((n, self.aux_dim), **f32)
+        self._contact = torch.zeros((n,), dtype=torch.uint8, device=dev)
+        b = _lib.PfbBuffers()
+        b.state, b.istate = self.state_tensor.data_ptr(), self.istate_tensor.data_ptr()
+        b.setpoint, b.start_pos, b.start_orn = self.setpoints.data_ptr(), self.start_pos.data_ptr(), self.start_orn.data_ptr()
+        b.obs, b.reward, b.term, b.trunc = self.obs.data_ptr(), self.reward.data_ptr(), self.term.data_ptr(), self.trunc.data_ptr()
+        b.info, b.final_obs = self.info_bits.data_ptr(), self.final_obs.data_ptr()
+        b.drone_state, b.aux_state, b.contact = self._drone_state.data_ptr(), self._aux_state.data_ptr(), self._contact.data_ptr()
+        self._buffers = b
+        _lib.check(L.pfb_bind(self._h, C.byref(b)))
+        self._state_fresh = False
+        self.reset()
+
+    # ------------------------------------------------------------------ lifecycle
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().pfb_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def disconnect(self) -> None:
+        self.__del__()
+
+    def _s(self):
+        return C.c_void_p(_stream_ptr(self.device))
+
+    # ------------------------------------------------------------------ Aviary surface
+    def reset(self) -> None:
+        """aviary.py:218-312: every drone back to its start pose, mode 0, zero setpoint."""
+        _lib.check(_lib.lib().pfb_reset(self._h, None, self._s()))
+        self.physics_steps = 0
+        self.aviary_steps = 0
+        self.elapsed_time = 0.0
+        self._state_fresh = False
+
+    def set_mode(self, flight_modes: int | Sequence[int]) -> None:
+        """aviary.py:440-458; one mode per batch (the kernel is specialised on it at compile time)."""
+        if isinstance(flight_modes, (list, tuple)):
+            if len(flight_modes) != self.num_drones:
+                raise AssertionError(f"Expected {self.num_drones} flight_modes, got {len(flight_modes)}.")
+            if len(set(flight_modes)) != 1:
+                raise ValueError("the batched stepper needs one flight mode per batch")
+            flight_modes = flight_modes[0]
+        mode = int(flight_modes)
+        if mode < -1 or mode > 7:
+            # quadx.py:259-262
+            raise ValueError(f"`mode` must be between -1 and 7 or be registered in self.registered_controllers.keys()=dict_keys([]), got {mode}.")
+        _lib.check(_lib.lib().pfb_set_mode(self._h, mode, self._s()))
+        self._state_fresh = False
+
+    def set_setpoint(self, index: int, setpoint) -> None:
+        self.setpoints[index] = torch.as_tensor(setpoint, dtype=torch.float32, device=self.device)
+
+    def set_all_setpoints(self, setpoints) -> None:
+        self.setpoints.copy_(torch.as_tensor(setpoints, dtype=torch.float32, device=self.device))
+
+    def step(self, n_steps: int = 1, noise: torch.Tensor | None = None) -> None:
+        """``n_steps`` x Aviary.step() (aviary.py:480-531).  ``noise``: optional device tensor
+        [n_steps*updates_per_step, N] of raw ``np_random.normal`` draws (parity tests)."""
+        ptr = None
+        if noise is not None:
+            assert noise.dtype == torch.float32 and noise.is_cuda and noise.is_contiguous()
+            assert tuple(noise.shape) == (n_steps * self.updates_per_step, self.num_drones), tuple(noise.shape)
+            ptr = C.c_void_p(noise.data_ptr())
+        _lib.check(_lib.lib().pfb_aviary_step(self._h, int(n_steps), ptr, self._s()))
+        self.physics_steps += n_steps * self.updates_per_step
+        self.aviary_steps += n_steps
+        self.elapsed_time = self.physics_steps / self.physics_hz
+        self._state_fresh = False
+
+    def _refresh(self):
+        if not self._state_fresh:
+            _lib.check(_lib.lib().pfb_observe_state(self._h, self._s()))
+            self._state_fresh = True
+
+    @property
+    def all_states(self) -> torch.Tensor:
+        """(N, 4, 3): ang_vel (body), euler, lin_vel (body), position — aviary.py:372-393."""
+        self._refresh()
+        return self._drone_state.view(self.num_drones, 4, 3)
+
+    @property
+    def all_aux_states(self) -> torch.Tensor:
+        self._refresh()
+        return self._aux_state
+
+    def state(self, index: int) -> torch.Tensor:
+        return self.all_states[index]
+
+    def aux_state(self, index: int) -> torch.Tensor:
+        return self.all_aux_states[index]
+
+    @property
+    def contact_array(self) -> torch.Tensor:
+        """(N,) bool: ground contact during the last step (aviary.py:322, 523-525, per world)."""
+        self._refresh()
+        return self._contact.bool()
+
+    @property
+    def launch_count(self) -> int:
+        return int(_lib.lib().pfb_launch_count(self._h))
+
+    # ------------------------------------------------------------------ fused env surface
+    def env_reset(self, mask: torch.Tensor | None = None, noise: torch.Tensor | None = None) -> torch.Tensor:
+        m = None if mask is None else C.c_void_p(mask.to(torch.uint8).contiguous().data_ptr())
+        nz = None if noise is None else C.c_void_p(noise.data_ptr())
+        _lib.check(_lib.lib().pfb_env_reset(self._h, m, nz, self._s()))
+        self._state_fresh = False
+        return self.obs
+
+    def env_step(self, actions: torch.Tensor | None = None, noise: torch.Tensor | None = None) -> None:
+        """One fused env.step() for every env; ``actions`` [N, S] fp32 on this device (None = ``self.setpoints``)."""
+        act = None
+        if actions is not None:
+            assert actions.is_cuda and actions.dtype == torch.float32 and actions.is_contiguous()
+            assert tuple(actions.shape) == (self.num_drones, self.setpoint_dim), tuple(actions.shape)
+            act = C.c_void_p(actions.data_ptr())
+        nz = None if noise is None else C.c_void_p(noise.data_ptr())
+        _lib.check(_lib.lib().pfb_env_step(self._h, act, nz, self._s()))
+        self._state_fresh = False
+
+    def profile_begin(self, capacity: int) -> None:
+        _lib.check(_lib.lib().pfb_profile_begin(self._h, int(capacity)))
+
+    def profile_read(self, capacity: int) -> list[float]:
+        buf = (C.c_float * capacity)()
+        n = _lib.lib().pfb_profile_read(self._h, buf, capacity)
+        if n < 0:
+            _lib.check(n)
+        return [float(buf[i]) for i in range(n)]
+
+    def env_rollout(self, n_steps: int) -> None:
+        _lib.check(_lib.lib().pfb_env_rollout(self._h, int(n_steps), self._s()))
+        self._state_fresh = False
+
+    def env_step_host(self, actions: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor, term: torch.Tensor, trunc: torch.Tensor) -> None:
+        """Pinned-host in, pinned-host out (the end-to-end path bench.py times)."""
+        for t in (actions, obs, reward, term, trunc):
+            assert not t.is_cuda and t.is_contiguous()
+        _lib.check(_lib.lib().pfb_env_step_host(self._h, C.c_void_p(actions.data_ptr()), C.c_void_p(obs.data_ptr()), C.c_void_p(reward.data_ptr()), C.c_void_p(term.data_ptr()), C.c_void_p(trunc.data_ptr()), self._s()))
+        self._state_fresh = False

@@ -1,0 +1,145 @@
+// pfb_common.cuh — shared device helpers for the batched UAV stepper (sm_100a).
+//
+// Everything here is `PFB_HD` so that tests/hostsim can compile the SAME per-env body with g++ for
+// precision studies on a machine without a GPU.  The host build is a test harness only; the product
+// library (libpyflyt_b200.so) contains the CUDA kernels and nothing else.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PFB_HD __host__ __device__ __forceinline__
+#define PFB_D __device__ __forceinline__
+#else
+#define PFB_HD inline
+#define PFB_D inline
+#endif
+
+namespace pfb {
+
+// -------------------------------------------------------------------------------------------------
+// Precision policy.  The reference integrates in fp64 end to end; plain
+// fp32 misses the 1e-3 m / 1000-step trajectory tolerance by ~10x because attitude
+// rounding tilts the thrust vector and is integrated twice.  The attitude quaternion, the position
+// and (optionally) the world velocity are therefore carried as fp64 in registers and stored as two
+// fp32 words (hi, lo) so the HBM layout stays fp32 SoA.  Everything else — forces, control, aero,
+// observations, rewards — is fp32.  B200 issues non-tensor fp64 at half the fp32 rate.
+// -------------------------------------------------------------------------------------------------
+#ifndef PFB_Q_DOUBLE
+#define PFB_Q_DOUBLE 1
+#endif
+#ifndef PFB_X_DOUBLE
+#define PFB_X_DOUBLE 1
+#endif
+#ifndef PFB_V_DOUBLE
+#define PFB_V_DOUBLE 1
+#endif
+#ifndef PFB_R_DOUBLE
+#define PFB_R_DOUBLE 0  // rotation matrix entries in fp32: no measurable loss (tools/precision_study.py)
+#endif
+
+#if PFB_Q_DOUBLE
+typedef double qreal;
+#else
+typedef float qreal;
+#endif
+#if PFB_X_DOUBLE
+typedef double xreal;
+#else
+typedef float xreal;
+#endif
+#if PFB_V_DOUBLE
+typedef double vreal;
+#else
+typedef float vreal;
+#endif
+
+struct Vec3 {
+  float x, y, z;
+};
+
+PFB_HD Vec3 v3(float x, float y, float z) { return Vec3{x, y, z}; }
+PFB_HD Vec3 operator+(Vec3 a, Vec3 b) { return Vec3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+PFB_HD Vec3 operator-(Vec3 a, Vec3 b) { return Vec3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+PFB_HD Vec3 operator*(float s, Vec3 a) { return Vec3{s * a.x, s * a.y, s * a.z}; }
+PFB_HD Vec3 cross(Vec3 a, Vec3 b) {
+  return Vec3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+PFB_HD float dot(Vec3 a, Vec3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+
+// Row-major body→world rotation.
+struct Mat3 {
+  float m00, m01, m02, m10, m11, m12, m20, m21, m22;
+};
+PFB_HD Vec3 mul(const Mat3& R, Vec3 v) {
+  return Vec3{fmaf(R.m00, v.x, fmaf(R.m01, v.y, R.m02 * v.z)), fmaf(R.m10, v.x, fmaf(R.m11, v.y, R.m12 * v.z)),
+              fmaf(R.m20, v.x, fmaf(R.m21, v.y, R.m22 * v.z))};
+}
+PFB_HD Vec3 mulT(const Mat3& R, Vec3 v) {
+  return Vec3{fmaf(R.m00, v.x, fmaf(R.m10, v.y, R.m20 * v.z)), fmaf(R.m01, v.x, fmaf(R.m11, v.y, R.m21 * v.z)),
+              fmaf(R.m02, v.x, fmaf(R.m12, v.y, R.m22 * v.z))};
+}
+
+PFB_HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+// -sign(v) * k * v^2  ==  -k * v * |v|   (boring_bodies.py:115-119, quadx.py:502-506)
+PFB_HD float signed_square(float v) { return v * fabsf(v); }
+
+// hi/lo split of an fp64 value into two fp32 words and back
+PFB_HD void split_hi_lo(double d, float& hi, float& lo) {
+  hi = (float)d;
+  lo = (float)(d - (double)hi);
+}
+PFB_HD double join_hi_lo(float hi, float lo) { return (double)hi + (double)lo; }
+
+// -------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter RNG: stateless, keyed by (seed), counter = (env, draw index) — results do
+// not depend on how envs are split over GPUs.
+// -------------------------------------------------------------------------------------------------
+struct U4 {
+  uint32_t x, y, z, w;
+};
+
+PFB_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+PFB_HD U4 philox4x32_10(U4 ctr, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = mulhi32(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = mulhi32(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = U4{hi1 ^ ctr.y ^ k0, lo1, hi0 ^ ctr.w ^ k1, lo0};
+    k0 += W0;
+    k1 += W1;
+  }
+  return ctr;
+}
+
+PFB_HD float u32_to_unit_open(uint32_t u) {
+  // (0, 1]: never returns 0 so log() is safe
+  return ((float)(u >> 8) + 1.0f) * (1.0f / 16777216.0f);
+}
+
+// two standard normals from two uniforms (Box–Muller); noise only, so fast intrinsics are fine
+PFB_HD void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+  float u1 = u32_to_unit_open(a);
+  float u2 = u32_to_unit_open(b);
+#if defined(__CUDA_ARCH__)
+  float r = sqrtf(-2.0f * __logf(u1));
+  float s, c;
+  __sincosf(6.28318530717958647692f * u2, &s, &c);
+#else
+  float r = sqrtf(-2.0f * logf(u1));
+  float s = sinf(6.28318530717958647692f * u2), c = cosf(6.28318530717958647692f * u2);
+#endif
+  n0 = r * c;
+  n1 = r * s;
+}
+
+}  // namespace pfb

@@ -1,0 +1,655 @@
+// pfb_lib.cu — CUDA kernels (sm_100a) and the C-ABI of libpyflyt_b200.so (include/pyflyt_b200.h).
+//
+// One thread integrates one env; the whole env step (control ticks, physics substeps, reward,
+// termination, observation) happens in registers between one coalesced SoA load and one store.
+// Row-major API buffers (actions [N][4], observations [N][O]) are moved with 16-byte vector loads
+// and a shared-memory transpose so that global traffic stays fully coalesced.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/pyflyt_b200.h"
+#include "pfb_quadx.cuh"
+
+using namespace pfb;
+
+// ---------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return -1;
+}
+#include "pfb_quadx_host.h"
+
+#define CUDA_OK(expr)                                                                    \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------
+struct RngParams {
+  uint32_t k0, k1;        // Philox key (seed)
+  uint32_t env_offset_lo; // global id of local env 0 (multi-GPU sharding keeps streams rank-independent)
+  uint32_t env_offset_hi;
+};
+
+struct PfbContext {
+  PfbModel model;
+  PfbEnvConfig env;
+  int64_t n;
+  int device;
+  QuadXParams qx;
+  HoverParams hover;
+  RngParams rng;
+  PfbBuffers buf;
+  bool bound;
+  int mode;               // Aviary-level flight mode
+  int32_t* d_counters;    // [4] ping-pong done-list counters
+  int32_t* d_done_list;   // [N]
+  uint64_t step_seq;      // env.step() calls so far (selects the ping-pong counter, seeds random actions)
+  int64_t launches;
+  int sm_count;
+  // optional per-step CUDA-event pairs around the dominant kernel (bench.py's roofline leg)
+  cudaEvent_t* prof_ev;   // [2 * prof_cap]
+  int prof_cap;
+  int prof_n;
+};
+
+constexpr int kBlock = 64;  // 65536 envs -> 1024 CTAs over 148 SMs: <1.2% wave imbalance
+
+static inline int grid_for(int64_t n) { return (int)((n + kBlock - 1) / kBlock); }
+
+// ---------------------------------------------------------------------------------------------------
+// noise sources: raw draws of np_random.normal(*throttle.shape)  (motors.py:134-138)
+// ---------------------------------------------------------------------------------------------------
+struct InjectedNoise {  // parity tests: the CPU-drawn sequence, [substep][N]
+  const float* ptr;
+  int64_t N;
+  __device__ __forceinline__ float operator()() {
+    float v = __ldg(ptr);
+    ptr += N;
+    return v;
+  }
+};
+
+struct PhiloxNoise {  // throughput: N(noise_loc, 1) from a counter RNG keyed by (seed, env, draw index)
+  uint32_t k0, k1, env_lo, env_hi;
+  uint32_t draw;  // physics-step index of the next draw
+  float loc;
+  float cache[4];
+  __device__ __forceinline__ void refill() {
+    U4 r = philox4x32_10(U4{env_lo, env_hi, draw >> 2, 0u}, k0, k1);
+    box_muller(r.x, r.y, cache[0], cache[1]);
+    box_muller(r.z, r.w, cache[2], cache[3]);
+  }
+  __device__ __forceinline__ void init(const RngParams& r, int64_t i, uint32_t draw0, float loc_) {
+    k0 = r.k0; k1 = r.k1;
+    uint64_t g = ((uint64_t)r.env_offset_hi << 32 | r.env_offset_lo) + (uint64_t)i;
+    env_lo = (uint32_t)g; env_hi = (uint32_t)(g >> 32);
+    draw = draw0; loc = loc_;
+    refill();
+  }
+  __device__ __forceinline__ float operator()() {
+    int k = draw & 3u;
+    float z = k == 0 ? cache[0] : (k == 1 ? cache[1] : (k == 2 ? cache[2] : cache[3]));
+    ++draw;
+    if ((draw & 3u) == 0u) refill();
+    return loc + z;
+  }
+};
+
+template <bool INJECT>
+struct NoiseSel;
+template <>
+struct NoiseSel<true> {
+  typedef InjectedNoise type;
+};
+template <>
+struct NoiseSel<false> {
+  typedef PhiloxNoise type;
+};
+
+template <bool INJECT>
+__device__ __forceinline__ typename NoiseSel<INJECT>::type make_noise(const float* noise, int64_t N, int64_t i,
+                                                                      const RngParams& r, uint32_t draw0, float loc);
+template <>
+__device__ __forceinline__ InjectedNoise make_noise<true>(const float* noise, int64_t N, int64_t i, const RngParams&,
+                                                          uint32_t, float) {
+  return InjectedNoise{noise + i, N};
+}
+template <>
+__device__ __forceinline__ PhiloxNoise make_noise<false>(const float*, int64_t, int64_t i, const RngParams& r,
+                                                         uint32_t draw0, float loc) {
+  PhiloxNoise n;
+  n.init(r, i, draw0, loc);
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// kernels — Aviary surface
+// ---------------------------------------------------------------------------------------------------
+// Aviary.reset + QuadX.reset + update_state (aviary.py:218-312, quadx.py:222-231)
+__global__ void __launch_bounds__(kBlock) k_quadx_reset(float* __restrict__ st, int32_t* __restrict__ ist,
+                                                        float* __restrict__ setpoint, const float* __restrict__ start_pos,
+                                                        const float* __restrict__ start_orn,
+                                                        const uint8_t* __restrict__ mask, int64_t N) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  if (mask && !mask[i]) return;
+  QuadXRegs s;
+  quadx_reset(s, start_pos[3 * i + 0], start_pos[3 * i + 1], start_pos[3 * i + 2], start_orn[3 * i + 0],
+              start_orn[3 * i + 1], start_orn[3 * i + 2]);
+  quadx_store<7>(st, ist, N, i, s);  // mode 7 touches every PID row
+  ist[(int64_t)QI_STEP * N + i] = 0;
+  // QI_PHYS (the Philox draw index) is monotonic over the life of the handle: never reset
+  if (setpoint) reinterpret_cast<float4*>(setpoint)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// Aviary.set_mode -> QuadX.set_mode (quadx.py:233-373): preset the setpoint, fresh attitude/position PIDs
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) k_quadx_set_mode(float* __restrict__ st, int32_t* __restrict__ ist,
+                                                           float* __restrict__ setpoint, int64_t N) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  QuadXRegs s;
+  quadx_load<7>(st, ist, N, i, s);
+  float4 sp = reinterpret_cast<const float4*>(setpoint)[i];
+  s.sp[0] = sp.x; s.sp[1] = sp.y; s.sp[2] = sp.z; s.sp[3] = sp.w;
+  quadx_set_mode<MODE>(s);
+  quadx_store<7>(st, ist, N, i, s);
+  reinterpret_cast<float4*>(setpoint)[i] = make_float4(s.sp[0], s.sp[1], s.sp[2], s.sp[3]);
+}
+
+// n_steps x Aviary.step() (aviary.py:480-531)
+template <int MODE, bool INJECT>
+__global__ void __launch_bounds__(kBlock)
+    k_quadx_aviary_step(const __grid_constant__ QuadXParams p, const __grid_constant__ RngParams rng,
+                        float* __restrict__ st, int32_t* __restrict__ ist, const float* __restrict__ setpoint,
+                        const float* __restrict__ noise, int n_steps, int64_t N) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  QuadXRegs s;
+  quadx_load<MODE>(st, ist, N, i, s);
+  float4 sp = __ldg(reinterpret_cast<const float4*>(setpoint) + i);
+  s.sp[0] = sp.x; s.sp[1] = sp.y; s.sp[2] = sp.z; s.sp[3] = sp.w;
+  uint32_t phys = (uint32_t)ist[(int64_t)QI_PHYS * N + i];
+  auto nz = make_noise<INJECT>(noise, N, i, rng, phys, p.noise_loc);
+  for (int k = 0; k < n_steps; ++k) quadx_aviary_step<MODE>(p, s, nz);
+  quadx_store<MODE>(st, ist, N, i, s);
+  ist[(int64_t)QI_PHYS * N + i] = (int32_t)(phys + (uint32_t)(n_steps * p.ratio));
+}
+
+// Aviary.state(i) / aux_state(i) / contact_array  -> row-major API buffers
+__global__ void __launch_bounds__(kBlock) k_quadx_observe(const float* __restrict__ st, const int32_t* __restrict__ ist,
+                                                          float* __restrict__ drone_state, float* __restrict__ aux,
+                                                          uint8_t* __restrict__ contact, int64_t N) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  QuadXRegs s;
+  quadx_load<-1>(st, ist, N, i, s);
+  float o[12], a[4];
+  quadx_drone_state(s, o, a);
+  if (drone_state) {
+    float4* d = reinterpret_cast<float4*>(drone_state + 12 * i);
+    d[0] = make_float4(o[0], o[1], o[2], o[3]);
+    d[1] = make_float4(o[4], o[5], o[6], o[7]);
+    d[2] = make_float4(o[8], o[9], o[10], o[11]);
+  }
+  if (aux) reinterpret_cast<float4*>(aux)[i] = make_float4(a[0], a[1], a[2], a[3]);
+  if (contact) contact[i] = (s.flags & FLAG_CONTACT_ARRAY) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// kernels — QuadX-Hover env
+// ---------------------------------------------------------------------------------------------------
+constexpr int kObsMax = 21;
+constexpr int kObsStride = 21;  // odd stride: conflict-free shared-memory transpose for O = 20 or 21
+
+// block-cooperative, fully coalesced write of this block's observations into obs[N][O]
+__device__ __forceinline__ void write_obs_block(float* smem, const float* my_obs, bool active, int O,
+                                                float* __restrict__ obs, int64_t block_first, int64_t N) {
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < kObsMax; ++k)
+      if (k < O) smem[threadIdx.x * kObsStride + k] = my_obs[k];
+  }
+  __syncthreads();
+  int64_t rows = N - block_first;
+  if (rows > kBlock) rows = kBlock;
+  int total = (int)rows * O;
+  float* dst = obs + block_first * O;
+  for (int j = threadIdx.x; j < total; j += kBlock) {
+    int r = j / O, c = j - r * O;
+    dst[j] = smem[r * kObsStride + c];
+  }
+}
+
+// env.step(action) for every env (quadx_base_env.py:269-301 + quadx_hover_env.py).
+// RANDACT: actions are drawn on device, uniform in the env's action box (quadx_base_env.py:79-102).
+template <int MODE, bool INJECT, bool RANDACT>
+__global__ void __launch_bounds__(kBlock)
+    k_hover_step(const __grid_constant__ QuadXParams p, const __grid_constant__ HoverParams h,
+                 const __grid_constant__ RngParams rng, float* __restrict__ st, int32_t* __restrict__ ist,
+                 float* __restrict__ actions, const float* __restrict__ noise, float* __restrict__ obs,
+                 float* __restrict__ reward, uint8_t* __restrict__ term, uint8_t* __restrict__ trunc,
+                 uint8_t* __restrict__ info, int32_t* __restrict__ done_count, int32_t* __restrict__ done_list,
+                 uint32_t step_seq, int64_t N) {
+  __shared__ float smem[kBlock * kObsStride];
+  const int64_t block_first = (int64_t)blockIdx.x * kBlock;
+  const int64_t i = block_first + threadIdx.x;
+  const bool active = i < N;
+  const int O = h.angle_representation == 0 ? 20 : 21;
+  float my_obs[kObsMax];
+  if (active) {
+    QuadXRegs s;
+    quadx_load<MODE>(st, ist, N, i, s);
+    float act[4];
+    if (RANDACT) {
+      uint64_t g = ((uint64_t)rng.env_offset_hi << 32 | rng.env_offset_lo) + (uint64_t)i;
+      U4 r = philox4x32_10(U4{(uint32_t)g, (uint32_t)(g >> 32), step_seq, 0x41435431u}, rng.k0, rng.k1);
+      const float pi = 3.14159265358979323846f;
+      if (MODE == -1) {
+        act[0] = 0.8f * u32_to_unit_open(r.x); act[1] = 0.8f * u32_to_unit_open(r.y);
+        act[2] = 0.8f * u32_to_unit_open(r.z); act[3] = 0.8f * u32_to_unit_open(r.w);
+      } else {
+        act[0] = pi * (2.0f * u32_to_unit_open(r.x) - 1.0f); act[1] = pi * (2.0f * u32_to_unit_open(r.y) - 1.0f);
+        act[2] = pi * (2.0f * u32_to_unit_open(r.z) - 1.0f); act[3] = 0.8f * u32_to_unit_open(r.w);
+      }
+      reinterpret_cast<float4*>(actions)[i] = make_float4(act[0], act[1], act[2], act[3]);
+    } else {
+      float4 a4 = __ldg(reinterpret_cast<const float4*>(actions) + i);
+      act[0] = a4.x; act[1] = a4.y; act[2] = a4.z; act[3] = a4.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s.sp[k] = act[k];
+    int step_count = ist[(int64_t)QI_STEP * N + i];
+    uint32_t phys = (uint32_t)ist[(int64_t)QI_PHYS * N + i];
+    auto nz = make_noise<INJECT>(noise, N, i, rng, phys, p.noise_loc);
+    float rew = -0.1f;
+    int done_steps = 0;
+    for (int k = 0; k < h.env_step_ratio; ++k) {
+      if (s.flags & (FLAG_TERM | FLAG_TRUNC)) break;  // quadx_base_env.py:289-290
+      quadx_aviary_step<MODE>(p, s, nz);
+      hover_term_trunc_reward(h, s, step_count, rew);
+      ++done_steps;
+    }
+    step_count += 1;
+    hover_observation(h, s, act, my_obs);
+    quadx_store<MODE>(st, ist, N, i, s);
+    ist[(int64_t)QI_STEP * N + i] = step_count;
+    ist[(int64_t)QI_PHYS * N + i] = (int32_t)(phys + (uint32_t)(done_steps * p.ratio));
+    reward[i] = rew;
+    term[i] = (s.flags & FLAG_TERM) ? 1 : 0;
+    trunc[i] = (s.flags & FLAG_TRUNC) ? 1 : 0;
+    if (info) info[i] = (uint8_t)(((s.flags & FLAG_OOB) ? 1 : 0) | ((s.flags & FLAG_COLLISION) ? 2 : 0));
+    // queue finished episodes for the dense autoreset pass (warp-aggregated append)
+    if (done_list) {
+      bool done = (s.flags & (FLAG_TERM | FLAG_TRUNC)) != 0;
+      unsigned m = __ballot_sync(__activemask(), done);
+      if (done) {
+        int lane = threadIdx.x & 31;
+        int leader = __ffs(m) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(done_count, __popc(m));
+        base = __shfl_sync(m, base, leader);
+        done_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+      }
+    }
+  }
+  write_obs_block(smem, my_obs, active, O, obs, block_first, N);
+}
+
+// env.reset() body for one env: begin_reset + end_reset (quadx_base_env.py:149-212)
+template <int MODE, bool INJECT>
+__device__ __forceinline__ void hover_reset_env(const QuadXParams& p, const HoverParams& h, const RngParams& rng,
+                                                float* __restrict__ st, int32_t* __restrict__ ist,
+                                                const float* __restrict__ start_pos, const float* __restrict__ start_orn,
+                                                const float* __restrict__ noise, int64_t N, int64_t i, float* my_obs) {
+  QuadXRegs s;
+  quadx_reset(s, start_pos[3 * i + 0], start_pos[3 * i + 1], start_pos[3 * i + 2], start_orn[3 * i + 0],
+              start_orn[3 * i + 1], start_orn[3 * i + 2]);
+  quadx_set_mode<MODE>(s);
+  uint32_t phys = (uint32_t)ist[(int64_t)QI_PHYS * N + i];
+  auto nz = make_noise<INJECT>(noise, N, i, rng, phys, p.noise_loc);
+  for (int k = 0; k < h.warmup_steps; ++k) quadx_aviary_step<MODE>(p, s, nz);
+  const float zero[4] = {0.f, 0.f, 0.f, 0.f};  // self.action = zeros (quadx_base_env.py:165)
+  hover_observation(h, s, zero, my_obs);
+  quadx_store<7>(st, ist, N, i, s);
+  ist[(int64_t)QI_STEP * N + i] = 0;
+  ist[(int64_t)QI_PHYS * N + i] = (int32_t)(phys + (uint32_t)(h.warmup_steps * p.ratio));
+}
+
+// env.reset() for all / masked envs; observations written coalesced
+template <int MODE, bool INJECT>
+__global__ void __launch_bounds__(kBlock)
+    k_hover_reset(const __grid_constant__ QuadXParams p, const __grid_constant__ HoverParams h,
+                  const __grid_constant__ RngParams rng, float* __restrict__ st, int32_t* __restrict__ ist,
+                  const float* __restrict__ start_pos, const float* __restrict__ start_orn,
+                  const uint8_t* __restrict__ mask, const float* __restrict__ noise, float* __restrict__ obs, int64_t N) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= N) return;
+  if (mask && !mask[i]) return;
+  const int O = h.angle_representation == 0 ? 20 : 21;
+  float my_obs[kObsMax];
+  hover_reset_env<MODE, INJECT>(p, h, rng, st, ist, start_pos, start_orn, noise, N, i, my_obs);
+  if (obs) {
+    for (int k = 0; k < O; ++k) obs[i * O + k] = my_obs[k];
+  }
+}
+
+// SAME_STEP autoreset: a dense pass over the envs the step kernel queued.  Threads are assigned to
+// list slots, so the 20 warm-up substeps run in full warps instead of diverging inside k_hover_step.
+template <int MODE>
+__global__ void __launch_bounds__(kBlock)
+    k_hover_autoreset(const __grid_constant__ QuadXParams p, const __grid_constant__ HoverParams h,
+                      const __grid_constant__ RngParams rng, float* __restrict__ st, int32_t* __restrict__ ist,
+                      const float* __restrict__ start_pos, const float* __restrict__ start_orn, float* __restrict__ obs,
+                      float* __restrict__ final_obs, const int32_t* __restrict__ done_count,
+                      const int32_t* __restrict__ done_list, int32_t* __restrict__ next_count, int64_t N) {
+  const int count = *done_count;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *next_count = 0;  // arm the other ping-pong counter
+  const int O = h.angle_representation == 0 ? 20 : 21;
+  for (int t = blockIdx.x * kBlock + threadIdx.x; t < count; t += gridDim.x * kBlock) {
+    const int64_t i = done_list[t];
+    if (final_obs) {
+      for (int k = 0; k < O; ++k) final_obs[i * O + k] = obs[i * O + k];
+    }
+    float my_obs[kObsMax];
+    hover_reset_env<MODE, false>(p, h, rng, st, ist, start_pos, start_orn, nullptr, N, i, my_obs);
+    for (int k = 0; k < O; ++k) obs[i * O + k] = my_obs[k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+#define PFB_MODE_SWITCH(mode, BODY)                         \
+  switch (mode) {                                           \
+    case -1: { constexpr int MODE = -1; BODY; } break;      \
+    case 0: { constexpr int MODE = 0; BODY; } break;        \
+    case 1: { constexpr int MODE = 1; BODY; } break;        \
+    case 2: { constexpr int MODE = 2; BODY; } break;        \
+    case 3: { constexpr int MODE = 3; BODY; } break;        \
+    case 4: { constexpr int MODE = 4; BODY; } break;        \
+    case 5: { constexpr int MODE = 5; BODY; } break;        \
+    case 6: { constexpr int MODE = 6; BODY; } break;        \
+    case 7: { constexpr int MODE = 7; BODY; } break;        \
+    default: return fail("`mode` must be between -1 and 7, got %d", mode); \
+  }
+
+extern "C" {
+
+const char* pfb_last_error(void) { return g_err; }
+int pfb_abi_version(void) { return PFB_ABI_VERSION; }
+int pfb_sizeof_model(void) { return (int)sizeof(PfbModel); }
+int pfb_sizeof_env_config(void) { return (int)sizeof(PfbEnvConfig); }
+int pfb_sizeof_buffers(void) { return (int)sizeof(PfbBuffers); }
+
+int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, int device, uint64_t seed, PfbHandle* out) {
+  if (!model || !out) return fail("pfb_create: null argument");
+  if (model->abi_version != PFB_ABI_VERSION) return fail("PfbModel ABI %d != library ABI %d", model->abi_version, PFB_ABI_VERSION);
+  if (n_envs <= 0) return fail("n_envs must be positive");
+  if (model->kind != PFB_KIND_QUADX) return fail("vehicle kind %d is not built into this library yet", model->kind);
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail("no CUDA device: libpyflyt_b200 has no CPU fallback (%s)", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+  if (device < 0 || device >= count) return fail("device %d out of range (have %d)", device, count);
+  CUDA_OK(cudaSetDevice(device));
+  PfbContext* c = new (std::nothrow) PfbContext();
+  if (!c) return fail("out of host memory");
+  memset(c, 0, sizeof(*c));
+  c->model = *model;
+  if (env) c->env = *env;
+  c->n = n_envs;
+  c->device = device;
+  if (build_quadx_params(*model, c->qx) != 0) { delete c; return -1; }
+  c->hover.env_step_ratio = env ? env->env_step_ratio : 1;
+  c->hover.max_steps = env ? env->max_steps : 0;
+  c->hover.angle_representation = env ? env->angle_representation : 1;
+  c->hover.sparse_reward = env ? env->sparse_reward : 0;
+  c->hover.warmup_steps = env ? env->warmup_steps : 0;
+  c->hover.flight_mode = env ? env->flight_mode : 0;
+  c->hover.dome = env ? (float)env->flight_dome_size : 1e30f;
+  if (env && env->env_kind != PFB_ENV_NONE && env->env_kind != PFB_ENV_QUADX_HOVER) {
+    delete c;
+    return fail("env kind %d is not built into this library yet", env->env_kind);
+  }
+  c->rng.k0 = (uint32_t)seed;
+  c->rng.k1 = (uint32_t)(seed >> 32);
+  c->mode = 0;
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  CUDA_OK(cudaMalloc(&c->d_counters, 4 * sizeof(int32_t)));
+  CUDA_OK(cudaMemset(c->d_counters, 0, 4 * sizeof(int32_t)));
+  CUDA_OK(cudaMalloc(&c->d_done_list, (size_t)n_envs * sizeof(int32_t)));
+  *out = c;
+  return 0;
+}
+
+int pfb_destroy(PfbHandle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_counters);
+  cudaFree(h->d_done_list);
+  if (h->prof_ev) {
+    for (int i = 0; i < 2 * h->prof_cap; ++i) cudaEventDestroy(h->prof_ev[i]);
+    delete[] h->prof_ev;
+  }
+  delete h;
+  return 0;
+}
+
+int pfb_set_env_offset(PfbHandle h, uint64_t first_global_env) {
+  if (!h) return fail("null handle");
+  h->rng.env_offset_lo = (uint32_t)first_global_env;
+  h->rng.env_offset_hi = (uint32_t)(first_global_env >> 32);
+  return 0;
+}
+
+int pfb_state_rows(PfbHandle h) { (void)h; return QX_ROWS; }
+int pfb_istate_rows(PfbHandle h) { (void)h; return QI_ROWS; }
+int pfb_setpoint_dim(PfbHandle h) { (void)h; return 4; }
+int pfb_obs_dim(PfbHandle h) { return h->hover.angle_representation == 0 ? 20 : 21; }
+int pfb_aux_dim(PfbHandle h) { (void)h; return 4; }
+
+int pfb_bind(PfbHandle h, const PfbBuffers* b) {
+  if (!h || !b) return fail("pfb_bind: null argument");
+  if (!b->state || !b->istate || !b->setpoint || !b->start_pos || !b->start_orn)
+    return fail("pfb_bind: state, istate, setpoint, start_pos and start_orn are mandatory");
+  if (((uintptr_t)b->setpoint & 15) || ((uintptr_t)b->state & 15)) return fail("pfb_bind: buffers must be 16-byte aligned");
+  h->buf = *b;
+  h->bound = true;
+  return 0;
+}
+
+#define REQUIRE_BOUND(h)                                   \
+  if (!(h)) return fail("null handle");                    \
+  if (!(h)->bound) return fail("buffers not bound: call pfb_bind first"); \
+  CUDA_OK(cudaSetDevice((h)->device));
+
+#define LAUNCH_CHECK(h)                                                     \
+  do {                                                                      \
+    cudaError_t _e = cudaGetLastError();                                    \
+    if (_e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(_e)); \
+    (h)->launches += 1;                                                     \
+  } while (0)
+
+int pfb_reset(PfbHandle h, const uint8_t* mask, void* stream) {
+  REQUIRE_BOUND(h);
+  cudaStream_t s = (cudaStream_t)stream;
+  k_quadx_reset<<<grid_for(h->n), kBlock, 0, s>>>(h->buf.state, h->buf.istate, h->buf.setpoint, h->buf.start_pos,
+                                                  h->buf.start_orn, mask, h->n);
+  LAUNCH_CHECK(h);
+  if (!mask) h->mode = 0;  // QuadX.reset() calls set_mode(0) (quadx.py:224)
+  return 0;
+}
+
+int pfb_set_mode(PfbHandle h, int mode, void* stream) {
+  REQUIRE_BOUND(h);
+  cudaStream_t s = (cudaStream_t)stream;
+  PFB_MODE_SWITCH(mode, (k_quadx_set_mode<MODE><<<grid_for(h->n), kBlock, 0, s>>>(h->buf.state, h->buf.istate,
+                                                                                  h->buf.setpoint, h->n)));
+  LAUNCH_CHECK(h);
+  h->mode = mode;
+  return 0;
+}
+
+int pfb_aviary_step(PfbHandle h, int n_steps, const float* noise, void* stream) {
+  REQUIRE_BOUND(h);
+  if (n_steps <= 0) return fail("n_steps must be positive");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int mode = h->mode;
+  if (noise) {
+    PFB_MODE_SWITCH(mode, (k_quadx_aviary_step<MODE, true><<<grid_for(h->n), kBlock, 0, s>>>(
+                              h->qx, h->rng, h->buf.state, h->buf.istate, h->buf.setpoint, noise, n_steps, h->n)));
+  } else {
+    PFB_MODE_SWITCH(mode, (k_quadx_aviary_step<MODE, false><<<grid_for(h->n), kBlock, 0, s>>>(
+                              h->qx, h->rng, h->buf.state, h->buf.istate, h->buf.setpoint, nullptr, n_steps, h->n)));
+  }
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int pfb_observe_state(PfbHandle h, void* stream) {
+  REQUIRE_BOUND(h);
+  k_quadx_observe<<<grid_for(h->n), kBlock, 0, (cudaStream_t)stream>>>(h->buf.state, h->buf.istate, h->buf.drone_state,
+                                                                      h->buf.aux_state, h->buf.contact, h->n);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+static int require_env(PfbHandle h) {
+  if (h->env.env_kind != PFB_ENV_QUADX_HOVER) return fail("handle was created without an env epilogue");
+  if (!h->buf.obs || !h->buf.reward || !h->buf.term || !h->buf.trunc) return fail("obs/reward/term/trunc buffers are not bound");
+  return 0;
+}
+
+int pfb_env_reset(PfbHandle h, const uint8_t* mask, const float* noise, void* stream) {
+  REQUIRE_BOUND(h);
+  if (require_env(h)) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int mode = h->hover.flight_mode;
+  if (noise) {
+    PFB_MODE_SWITCH(mode, (k_hover_reset<MODE, true><<<grid_for(h->n), kBlock, 0, s>>>(
+                              h->qx, h->hover, h->rng, h->buf.state, h->buf.istate, h->buf.start_pos, h->buf.start_orn, mask,
+                              noise, h->buf.obs, h->n)));
+  } else {
+    PFB_MODE_SWITCH(mode, (k_hover_reset<MODE, false><<<grid_for(h->n), kBlock, 0, s>>>(
+                              h->qx, h->hover, h->rng, h->buf.state, h->buf.istate, h->buf.start_pos, h->buf.start_orn, mask,
+                              nullptr, h->buf.obs, h->n)));
+  }
+  LAUNCH_CHECK(h);
+  h->mode = mode;
+  return 0;
+}
+
+static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool randact, cudaStream_t s) {
+  const int mode = h->hover.flight_mode;
+  const bool autoreset = h->env.autoreset != 0;
+  int32_t* cnt = h->d_counters + (h->step_seq & 1);
+  int32_t* cnt_next = h->d_counters + ((h->step_seq + 1) & 1);
+  int32_t* list = autoreset ? h->d_done_list : nullptr;
+  const uint32_t seq = (uint32_t)h->step_seq;
+#define STEP_ARGS h->qx, h->hover, h->rng, h->buf.state, h->buf.istate, actions, noise, h->buf.obs, h->buf.reward, \
+                  h->buf.term, h->buf.trunc, h->buf.info, cnt, list, seq, h->n
+  const bool prof = h->prof_ev && h->prof_n < h->prof_cap;
+  if (prof) CUDA_OK(cudaEventRecord(h->prof_ev[2 * h->prof_n], s));
+  if (noise) {
+    PFB_MODE_SWITCH(mode, (k_hover_step<MODE, true, false><<<grid_for(h->n), kBlock, 0, s>>>(STEP_ARGS)));
+  } else if (randact) {
+    PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, true><<<grid_for(h->n), kBlock, 0, s>>>(STEP_ARGS)));
+  } else {
+    PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, false><<<grid_for(h->n), kBlock, 0, s>>>(STEP_ARGS)));
+  }
+#undef STEP_ARGS
+  LAUNCH_CHECK(h);
+  if (prof) {
+    CUDA_OK(cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], s));
+    h->prof_n += 1;
+  }
+  if (autoreset) {
+    // a few CTAs per SM are plenty for the ~1-3% of envs that finish per step; grid-strided
+    int blocks = h->sm_count * 2;
+    int need = grid_for(h->n);
+    if (blocks > need) blocks = need;
+    PFB_MODE_SWITCH(mode, (k_hover_autoreset<MODE><<<blocks, kBlock, 0, s>>>(
+                              h->qx, h->hover, h->rng, h->buf.state, h->buf.istate, h->buf.start_pos, h->buf.start_orn,
+                              h->buf.obs, h->buf.final_obs, cnt, h->d_done_list, cnt_next, h->n)));
+    LAUNCH_CHECK(h);
+  }
+  h->step_seq += 1;
+  return 0;
+}
+
+int pfb_env_step(PfbHandle h, const float* actions, const float* noise, void* stream) {
+  REQUIRE_BOUND(h);
+  if (require_env(h)) return -1;
+  if (actions && ((uintptr_t)actions & 15)) return fail("pfb_env_step: actions must be 16-byte aligned");
+  return env_step_impl(h, actions ? const_cast<float*>(actions) : h->buf.setpoint, noise, false, (cudaStream_t)stream);
+}
+
+int pfb_env_rollout(PfbHandle h, int n_steps, void* stream) {
+  REQUIRE_BOUND(h);
+  if (require_env(h)) return -1;
+  for (int k = 0; k < n_steps; ++k)
+    if (env_step_impl(h, h->buf.setpoint, nullptr, true, (cudaStream_t)stream)) return -1;
+  return 0;
+}
+
+int pfb_env_step_host(PfbHandle h, const float* host_actions, float* host_obs, float* host_reward, uint8_t* host_term,
+                      uint8_t* host_trunc, void* stream) {
+  REQUIRE_BOUND(h);
+  if (require_env(h)) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int O = pfb_obs_dim(h);
+  CUDA_OK(cudaMemcpyAsync(h->buf.setpoint, host_actions, (size_t)h->n * 4 * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (env_step_impl(h, h->buf.setpoint, nullptr, false, s)) return -1;
+  CUDA_OK(cudaMemcpyAsync(host_obs, h->buf.obs, (size_t)h->n * O * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaMemcpyAsync(host_reward, h->buf.reward, (size_t)h->n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaMemcpyAsync(host_term, h->buf.term, (size_t)h->n, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaMemcpyAsync(host_trunc, h->buf.trunc, (size_t)h->n, cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
+int64_t pfb_launch_count(PfbHandle h) { return h ? h->launches : 0; }
+
+int pfb_profile_begin(PfbHandle h, int capacity) {
+  if (!h) return fail("null handle");
+  CUDA_OK(cudaSetDevice(h->device));
+  if (h->prof_ev) {
+    for (int i = 0; i < 2 * h->prof_cap; ++i) cudaEventDestroy(h->prof_ev[i]);
+    delete[] h->prof_ev;
+    h->prof_ev = nullptr;
+  }
+  h->prof_cap = 0;
+  h->prof_n = 0;
+  if (capacity <= 0) return 0;
+  h->prof_ev = new (std::nothrow) cudaEvent_t[2 * (size_t)capacity];
+  if (!h->prof_ev) return fail("out of host memory");
+  for (int i = 0; i < 2 * capacity; ++i) CUDA_OK(cudaEventCreate(&h->prof_ev[i]));
+  h->prof_cap = capacity;
+  return 0;
+}
+
+int pfb_profile_read(PfbHandle h, float* ms_out, int capacity) {
+  if (!h) return fail("null handle");
+  CUDA_OK(cudaSetDevice(h->device));
+  int n = h->prof_n < capacity ? h->prof_n : capacity;
+  for (int i = 0; i < n; ++i) CUDA_OK(cudaEventElapsedTime(&ms_out[i], h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
+  return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,541 @@
+// pfb_quadx.cuh — per-env body of the QuadX stepper (one thread = one drone = one env).
+//
+// Replaces, for N independent single-drone worlds (paths under /root/reference/PyFlyt/):
+//   core/aviary.py:506-531                 Aviary.step() substep loop
+//   core/drones/quadx.py:401-535           update_control / update_physics / update_state
+//   core/abstractions/motors.py:110-195    throttle lag + noise + rpm^2 thrust/torque
+//   core/abstractions/boring_bodies.py:78-127   quadratic body drag
+//   core/abstractions/pid.py:70-94         PID
+//   PyBullet stepSimulation  free rigid body, semi-implicit Euler, exp-map quaternion
+//   gym_envs/quadx_envs/quadx_hover_env.py:85-138 + quadx_base_env.py:251-301  Hover epilogue
+//
+// Formulation notes:
+//  * Angular velocity is carried in the BODY frame.  Bullet integrates w_world += R wdot_b dt and
+//    then q <- dq(w_world dt) * q; because a rotation about w leaves w invariant, the new body-frame
+//    rate is exactly w_b + wdot_b dt and dq(w_world dt) * q == q * dq(w_b dt).  The world-frame
+//    +-100 rad/s coordinate clamp is applied on a rarely-taken slow path.
+//  * Forces are evaluated from the state of the previous update_state (explicit), positions use the
+//    NEW velocities (semi-implicit), exactly like the reference.
+#pragma once
+
+#include "pfb_common.cuh"
+
+namespace pfb {
+
+// fp32 coefficient table, passed BY VALUE as a __grid_constant__ kernel parameter: it lives in the
+// constant bank and its fields are used directly as FFMA operands (no shared-memory staging needed
+// for uniformly-accessed scalars).
+struct QuadXParams {
+  float dt;            // 1 / physics_hz
+  float ctrl_dt;       // 1 / control_hz
+  float inv_ctrl_dt;
+  float inv_mass;
+  float gravity;       // -9.81
+  float vmax;          // 100: btMultiBody max coordinate velocity
+  float Ixx, Iyy, Izz;
+  float inv_Ixx, inv_Iyy, inv_Izz;
+  float motor_x[4], motor_y[4];
+  float thrust_k[4];   // thrust_coef * max_rpm^2
+  float torque_k[4];   // torque_coef * max_rpm^2 (signed)
+  float motor_lag;     // physics_period / tau
+  float noise_ratio;
+  float noise_loc;     // n_motors: the reference's normal(*shape) quirk, SURVEY §A.4
+  float drag_k[3];
+  float drag_pqr;
+  // PID: [which][kp, ki*T, kd/T, lim][axis]; which = 0 ang_vel 1 ang_pos 2 lin_vel 3 lin_pos 4 z_vel 5 z_pos
+  float pid[6][4][3];
+  // ground-contact primitives (identity orientation in the body frame)
+  int n_shapes;
+  int shape_kind[5];
+  float shape_dims[5][3];
+  float shape_at[5][3];
+  float shape_thr[5];
+  int ratio;           // physics substeps per control tick (physics_hz / control_hz)
+};
+
+struct HoverParams {
+  int env_step_ratio;
+  int max_steps;
+  int angle_representation;  // 0 euler (obs 20), 1 quaternion (obs 21)
+  int sparse_reward;
+  int warmup_steps;
+  int flight_mode;
+  float dome;
+};
+
+// PID memory rows inside the state tensor (24 words)
+enum { PID_P0 = 0, PID_P1 = 6, PID_P2 = 12, PID_P3 = 16, PID_ZV = 20, PID_ZP = 22, PID_WORDS = 24 };
+
+// state tensor rows [F][N] for QuadX
+enum {
+  QX_POS = 0,       // 3  position (hi)
+  QX_QUAT = 3,      // 4  quaternion x,y,z,w (hi)
+  QX_VEL = 7,       // 3  world linear velocity (hi)
+  QX_ANGVEL = 10,   // 3  BODY angular velocity
+  QX_THR = 13,      // 4  motor throttle (aux_state)
+  QX_PWM = 17,      // 4  last motor command
+  QX_POS_LO = 21,   // 3
+  QX_QUAT_LO = 24,  // 4
+  QX_VEL_LO = 28,   // 3
+  QX_PID = 31,      // 24 PID integrals / previous errors
+  QX_ROWS = 55
+};
+// istate rows [I][N]
+enum { QI_STEP = 0, QI_FLAGS = 1, QI_PHYS = 2, QI_ROWS = 3 };
+enum { FLAG_TERM = 1, FLAG_TRUNC = 2, FLAG_OOB = 4, FLAG_COLLISION = 8, FLAG_CONTACT_PREV = 16, FLAG_CONTACT_ARRAY = 32 };
+
+template <typename T>
+struct Rot {
+  T m00, m01, m02, m10, m11, m12, m20, m21, m22;
+};
+
+#if PFB_R_DOUBLE
+typedef double rreal;
+#else
+typedef float rreal;
+#endif
+
+struct QuadXRegs {
+  xreal px, py, pz;
+  qreal qx, qy, qz, qw;
+  vreal vx, vy, vz;   // world
+  float wx, wy, wz;   // body
+  float thr[4];
+  float pwm[4];
+  float pid[PID_WORDS];
+  float sp[4];        // setpoint
+  // derived by update_state
+  Rot<rreal> R;
+  Vec3 vb;            // body-frame linear velocity
+  uint32_t flags;
+};
+
+// p.getMatrixFromQuaternion for a unit quaternion (|q|^2 - 1 ~ 1e-16 after normalisation)
+template <typename T, typename Q>
+PFB_HD void rot_from_quat(Q x, Q y, Q z, Q w, Rot<T>& R) {
+  T X = (T)x, Y = (T)y, Z = (T)z, W = (T)w;
+  T xs = X + X, ys = Y + Y, zs = Z + Z;
+  T wx = W * xs, wy = W * ys, wz = W * zs;
+  T xx = X * xs, xy = X * ys, xz = X * zs;
+  T yy = Y * ys, yz = Y * zs, zz = Z * zs;
+  R.m00 = (T)1 - (yy + zz); R.m01 = xy - wz; R.m02 = xz + wy;
+  R.m10 = xy + wz; R.m11 = (T)1 - (xx + zz); R.m12 = yz - wx;
+  R.m20 = xz - wy; R.m21 = yz + wx; R.m22 = (T)1 - (xx + yy);
+}
+
+// quadx.py:512-535: body-frame velocities from the world state
+PFB_HD void quadx_update_state(QuadXRegs& s) {
+  rot_from_quat<rreal>(s.qx, s.qy, s.qz, s.qw, s.R);
+  const Rot<rreal>& R = s.R;
+  rreal vx = (rreal)s.vx, vy = (rreal)s.vy, vz = (rreal)s.vz;
+  s.vb.x = (float)(R.m00 * vx + R.m10 * vy + R.m20 * vz);
+  s.vb.y = (float)(R.m01 * vx + R.m11 * vy + R.m21 * vz);
+  s.vb.z = (float)(R.m02 * vx + R.m12 * vy + R.m22 * vz);
+}
+
+// p.getEulerFromQuaternion (btQuaternion::getEulerZYX with the +-0.99999 gimbal-lock branch)
+PFB_HD void euler_from_quat(float x, float y, float z, float w, float& roll, float& pitch, float& yaw) {
+  float sarg = -2.0f * (x * z - w * y);
+  if (sarg <= -0.99999f) {
+    pitch = -1.57079632679489661923f; roll = 0.0f; yaw = 2.0f * atan2f(x, -y);
+  } else if (sarg >= 0.99999f) {
+    pitch = 1.57079632679489661923f; roll = 0.0f; yaw = 2.0f * atan2f(-x, y);
+  } else {
+    float sqx = x * x, sqy = y * y, sqz = z * z, sqw = w * w;
+    pitch = asinf(sarg);
+    roll = atan2f(2.0f * (y * z + w * x), sqw - sqx - sqy + sqz);
+    yaw = atan2f(2.0f * (x * y + w * z), sqw + sqx - sqy - sqz);
+  }
+}
+
+// p.getQuaternionFromEuler (btQuaternion::setEulerZYX)
+PFB_HD void quat_from_euler(float roll, float pitch, float yaw, float& x, float& y, float& z, float& w) {
+  float hr = 0.5f * roll, hp = 0.5f * pitch, hy = 0.5f * yaw;
+  float sr = sinf(hr), cr = cosf(hr), sp = sinf(hp), cp = cosf(hp), sy = sinf(hy), cy = cosf(hy);
+  x = sr * cp * cy - cr * sp * sy;
+  y = cr * sp * cy + sr * cp * sy;
+  z = cr * cp * sy - sr * sp * cy;
+  w = cr * cp * cy + sr * sp * sy;
+}
+
+// abstractions/pid.py:70-94 for K axes; mem = [I(K), e_prev(K)]
+template <int K>
+PFB_HD void pid_step(const float (&g)[4][3], float* mem, const float* state, const float* setpoint, float* out) {
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    float error = setpoint[i] - state[i];
+    float integral = clampf(fmaf(g[1][i], error, mem[i]), -g[3][i], g[3][i]);
+    float derivative = g[2][i] * (error - mem[K + i]);
+    mem[i] = integral;
+    mem[K + i] = error;
+    out[i] = clampf(fmaf(g[0][i], error, integral) + derivative, -g[3][i], g[3][i]);
+  }
+}
+
+// quadx.py:401-493, specialised on the flight mode at compile time
+template <int MODE>
+PFB_HD void quadx_update_control(const QuadXParams& p, QuadXRegs& s) {
+  if (MODE == -1) {  // direct pwm: no mixing, no saturation handling (quadx.py:432-434)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s.pwm[i] = s.sp[i];
+    return;
+  }
+  float a[3] = {s.sp[0], s.sp[1], s.sp[2]};
+  float z = s.sp[3];
+  const float angvel[3] = {s.wx, s.wy, s.wz};
+  float roll = 0.f, pitch = 0.f, yaw = 0.f;
+  if (MODE == 1 || MODE >= 3) euler_from_quat((float)s.qx, (float)s.qy, (float)s.qz, (float)s.qw, roll, pitch, yaw);
+  const float euler[3] = {roll, pitch, yaw};
+  const float linvel[3] = {s.vb.x, s.vb.y, s.vb.z};
+  const float pos[3] = {(float)s.px, (float)s.py, (float)s.pz};
+
+  if (MODE == 7) pid_step<2>(p.pid[3], s.pid + PID_P3, pos, a, a);
+  if (MODE == 6 || MODE == 7) {  // world -> heading frame (quadx.py:448-451, 460-463)
+    float sn = sinf(yaw), c = cosf(yaw);
+    float x = c * a[0] + sn * a[1], y = -sn * a[0] + c * a[1];
+    a[0] = x; a[1] = y;
+  }
+  if (MODE >= 4) {
+    pid_step<2>(p.pid[2], s.pid + PID_P2, linvel, a, a);
+    float t0 = -a[1], t1 = a[0];
+    a[0] = t0; a[1] = t1;
+  }
+  if (MODE == 1 || MODE == 3 || MODE == 7) pid_step<3>(p.pid[1], s.pid + PID_P1, euler, a, a);
+  if (MODE == 4 || MODE == 5 || MODE == 6) pid_step<2>(p.pid[1], s.pid + PID_P1, euler, a, a);
+  pid_step<3>(p.pid[0], s.pid + PID_P0, angvel, a, a);
+
+  // height chain (quadx.py:470-479)
+  if (MODE == 2 || MODE == 3 || MODE == 4 || MODE == 7) pid_step<1>(p.pid[5], s.pid + PID_ZP, &pos[2], &z, &z);
+  if (MODE != 0) pid_step<1>(p.pid[4], s.pid + PID_ZV, &linvel[2], &z, &z);
+  z = clampf(z, 0.0f, 1.0f);
+
+  // motor mix (quadx.py:130-137, 482-483)
+  float m0 = -a[0] - a[1] - a[2] + z;
+  float m1 = +a[0] + a[1] - a[2] + z;
+  float m2 = +a[0] - a[1] + a[2] + z;
+  float m3 = -a[0] + a[1] + a[2] + z;
+  // saturation re-scale (quadx.py:485-493)
+  float high = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  float low = fminf(fminf(m0, m1), fminf(m2, m3));
+  if (high != low) {
+    float pwm_max = fminf(high, 1.0f), pwm_min = fmaxf(low, 0.05f);
+    float ka = (pwm_min - low) / (pwm_max - low);
+    float ks = (high - pwm_max) / (high - pwm_min);
+    m0 += ka * (pwm_max - m0) - ks * (m0 - pwm_min);
+    m1 += ka * (pwm_max - m1) - ks * (m1 - pwm_min);
+    m2 += ka * (pwm_max - m2) - ks * (m2 - pwm_min);
+    m3 += ka * (pwm_max - m3) - ks * (m3 - pwm_min);
+  }
+  s.pwm[0] = clampf(m0, 0.05f, 1.0f);
+  s.pwm[1] = clampf(m1, 0.05f, 1.0f);
+  s.pwm[2] = clampf(m2, 0.05f, 1.0f);
+  s.pwm[3] = clampf(m3, 0.05f, 1.0f);
+}
+
+// lowest point of the collision primitives against the plane z = 0, with the relative
+// contact-breaking threshold; evaluated on the pose at the START of the substep.
+PFB_HD bool quadx_ground_contact(const QuadXParams& p, const QuadXRegs& s) {
+  const float r20 = (float)s.R.m20, r21 = (float)s.R.m21, r22 = (float)s.R.m22;
+  const float pz = (float)s.pz;
+  bool hit = false;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    if (k < p.n_shapes) {
+      float cz = pz + r20 * p.shape_at[k][0] + r21 * p.shape_at[k][1] + r22 * p.shape_at[k][2];
+      float extent;
+      if (p.shape_kind[k] == 0) {
+        extent = fabsf(r20) * p.shape_dims[k][0] + fabsf(r21) * p.shape_dims[k][1] + fabsf(r22) * p.shape_dims[k][2];
+      } else if (p.shape_kind[k] == 1) {
+        extent = p.shape_dims[k][1] * fabsf(r22) + p.shape_dims[k][0] * sqrtf(fmaxf(0.0f, 1.0f - r22 * r22));
+      } else {
+        extent = p.shape_dims[k][0];
+      }
+      hit = hit || (cz - extent < p.shape_thr[k]);
+    }
+  }
+  return hit;
+}
+
+// One physics substep: update_physics (quadx.py:495-510) + stepSimulation + update_state.
+// xi = raw draw of np_random.normal(*throttle.shape)  (one scalar ~ N(4, 1) shared by the motors).
+PFB_HD void quadx_substep(const QuadXParams& p, QuadXRegs& s, float xi) {
+  // ---- motors (motors.py:130-155): lag, multiplicative noise, rpm^2 thrust + reaction torque
+  float Fz = 0.0f, tx = 0.0f, ty = 0.0f, tz = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float t = s.thr[i];
+    t = fmaf(p.motor_lag, s.pwm[i] - t, t);
+    t = fmaf(xi * t, p.noise_ratio, t);
+    s.thr[i] = t;
+    float a = t * fabsf(t);
+    float Ti = p.thrust_k[i] * a;
+    Fz += Ti;
+    tx = fmaf(p.motor_y[i], Ti, tx);
+    ty = fmaf(-p.motor_x[i], Ti, ty);
+    tz = fmaf(p.torque_k[i], a, tz);
+  }
+  // ---- body drag (boring_bodies.py:113-127), body link at the base origin
+  float Fx = -p.drag_k[0] * signed_square(s.vb.x);
+  float Fy = -p.drag_k[1] * signed_square(s.vb.y);
+  Fz = fmaf(-p.drag_k[2], signed_square(s.vb.z), Fz);
+  // ---- rotational drag unless something touched the floor last step (quadx.py:502-510)
+  if (!(s.flags & FLAG_CONTACT_PREV)) {
+    tx = fmaf(-p.drag_pqr, signed_square(s.wx), tx);
+    ty = fmaf(-p.drag_pqr, signed_square(s.wy), ty);
+    tz = fmaf(-p.drag_pqr, signed_square(s.wz), tz);
+  }
+  // ---- contact flag from the pose at the start of the step (collision detection precedes
+  //      integration inside stepSimulation); aviary.py:523-525
+  bool c = quadx_ground_contact(p, s);
+  s.flags = (s.flags & ~(uint32_t)FLAG_CONTACT_PREV) | (c ? (FLAG_CONTACT_PREV | FLAG_CONTACT_ARRAY) : 0u);
+
+  // ---- Newton–Euler about the COM (composite COM offset is zero for the quads; inertia diagonal)
+  float wdx = (tx - (p.Izz - p.Iyy) * s.wy * s.wz) * p.inv_Ixx;
+  float wdy = (ty - (p.Ixx - p.Izz) * s.wz * s.wx) * p.inv_Iyy;
+  float wdz = (tz - (p.Iyy - p.Ixx) * s.wx * s.wy) * p.inv_Izz;
+  // world acceleration a = R F_b / M + g, velocities first (clamped per coordinate), then positions
+  const Rot<rreal>& R = s.R;
+  rreal fx = (rreal)(Fx * p.inv_mass), fy = (rreal)(Fy * p.inv_mass), fz = (rreal)(Fz * p.inv_mass);
+  rreal ax = R.m00 * fx + R.m01 * fy + R.m02 * fz;
+  rreal ay = R.m10 * fx + R.m11 * fy + R.m12 * fz;
+  rreal az = R.m20 * fx + R.m21 * fy + R.m22 * fz + (rreal)p.gravity;
+  const vreal dt = (vreal)p.dt, vmax = (vreal)p.vmax;
+  s.vx = fmin(fmax(s.vx + (vreal)ax * dt, -vmax), vmax);
+  s.vy = fmin(fmax(s.vy + (vreal)ay * dt, -vmax), vmax);
+  s.vz = fmin(fmax(s.vz + (vreal)az * dt, -vmax), vmax);
+  s.px += (xreal)(s.vx * dt);
+  s.py += (xreal)(s.vy * dt);
+  s.pz += (xreal)(s.vz * dt);
+  s.wx = fmaf(wdx, p.dt, s.wx);
+  s.wy = fmaf(wdy, p.dt, s.wy);
+  s.wz = fmaf(wdz, p.dt, s.wz);
+  // Bullet clamps the WORLD angular velocity coordinates to +-vmax; only reachable when the body
+  // rate exceeds vmax/sqrt(3) in some axis, so the rotation to the world frame is a cold path.
+  if (fmaxf(fmaxf(fabsf(s.wx), fabsf(s.wy)), fabsf(s.wz)) > p.vmax * 0.57735f) {
+    float ox = (float)R.m00 * s.wx + (float)R.m01 * s.wy + (float)R.m02 * s.wz;
+    float oy = (float)R.m10 * s.wx + (float)R.m11 * s.wy + (float)R.m12 * s.wz;
+    float oz = (float)R.m20 * s.wx + (float)R.m21 * s.wy + (float)R.m22 * s.wz;
+    ox = clampf(ox, -p.vmax, p.vmax); oy = clampf(oy, -p.vmax, p.vmax); oz = clampf(oz, -p.vmax, p.vmax);
+    s.wx = (float)R.m00 * ox + (float)R.m10 * oy + (float)R.m20 * oz;
+    s.wy = (float)R.m01 * ox + (float)R.m11 * oy + (float)R.m21 * oz;
+    s.wz = (float)R.m02 * ox + (float)R.m12 * oy + (float)R.m22 * oz;
+  }
+  // ---- attitude: q <- q * dq(w_b dt), exp-map increment in fp32, product + renormalisation in qreal
+  float ang = sqrtf(s.wx * s.wx + s.wy * s.wy + s.wz * s.wz);
+  float scale, cw;
+  if (ang < 0.001f) {
+    scale = 0.5f * p.dt - (p.dt * p.dt * p.dt) * 0.020833333333f * ang * ang;
+    cw = 1.0f - 0.125f * (ang * p.dt) * (ang * p.dt);
+  } else {
+    float half = 0.5f * ang * p.dt;
+    scale = sinf(half) / ang;
+    cw = cosf(half);
+  }
+  qreal dx = (qreal)(s.wx * scale), dy = (qreal)(s.wy * scale), dz = (qreal)(s.wz * scale), dw = (qreal)cw;
+  qreal nx = s.qw * dx + s.qx * dw + s.qy * dz - s.qz * dy;
+  qreal ny = s.qw * dy + s.qy * dw + s.qz * dx - s.qx * dz;
+  qreal nz = s.qw * dz + s.qz * dw + s.qx * dy - s.qy * dx;
+  qreal nw = s.qw * dw - s.qx * dx - s.qy * dy - s.qz * dz;
+  qreal n2 = nx * nx + ny * ny + nz * nz + nw * nw;
+#if PFB_Q_DOUBLE
+  // |q|^2 = 1 + e with |e| ~ 1e-7 (fp32 increment): 1/sqrt(1+e) = 1 - e/2 + 3e^2/8 (error < 1e-21)
+  qreal e = n2 - 1.0;
+  qreal inv = 1.0 - 0.5 * e + 0.375 * e * e;
+#else
+  qreal inv = 1.0f / sqrtf(n2);
+#endif
+  s.qx = nx * inv; s.qy = ny * inv; s.qz = nz * inv; s.qw = nw * inv;
+  // ---- update_state (quadx.py:512-535)
+  quadx_update_state(s);
+}
+
+// Aviary.step(): one control tick + `ratio` physics substeps (aviary.py:506-531 with one drone)
+template <int MODE, typename NoiseFn>
+PFB_HD void quadx_aviary_step(const QuadXParams& p, QuadXRegs& s, NoiseFn& noise) {
+  s.flags &= ~(uint32_t)FLAG_CONTACT_ARRAY;  // contact_array &= False
+  quadx_update_control<MODE>(p, s);
+  for (int u = 0; u < p.ratio; ++u) quadx_substep(p, s, noise());
+}
+
+// quadx.py:233-373: setpoint preset + PID reset on a mode change
+template <int MODE>
+PFB_HD void quadx_set_mode(QuadXRegs& s) {
+  if (MODE == -1) return;
+  if (MODE == 0) {
+    s.sp[0] = 0.f; s.sp[1] = 0.f; s.sp[2] = 0.f; s.sp[3] = -1.0f;
+  } else if (MODE == 1 || MODE == 5 || MODE == 6) {
+    s.sp[0] = s.sp[1] = s.sp[2] = s.sp[3] = 0.0f;
+  } else if (MODE == 7) {
+    float roll, pitch, yaw;
+    euler_from_quat((float)s.qx, (float)s.qy, (float)s.qz, (float)s.qw, roll, pitch, yaw);
+    s.sp[0] = (float)s.px; s.sp[1] = (float)s.py; s.sp[2] = yaw; s.sp[3] = (float)s.pz;
+  } else {
+    s.sp[0] = s.sp[1] = s.sp[2] = 0.0f; s.sp[3] = (float)s.pz;
+  }
+#pragma unroll
+  for (int k = 0; k < PID_ZV; ++k) s.pid[k] = 0.0f;  // z_PIDs are not reset by set_mode (quadx.py:196,372)
+}
+
+// quadx.py:222-231 + aviary.py:310-311: a freshly constructed drone at its start pose
+PFB_HD void quadx_reset(QuadXRegs& s, float sx, float sy, float sz, float roll, float pitch, float yaw) {
+  s.px = (xreal)sx; s.py = (xreal)sy; s.pz = (xreal)sz;
+  {  // getQuaternionFromEuler in the attitude precision
+    qreal hr = (qreal)roll * (qreal)0.5, hp = (qreal)pitch * (qreal)0.5, hy = (qreal)yaw * (qreal)0.5;
+    qreal sr = sin(hr), cr = cos(hr), sp = sin(hp), cp = cos(hp), sy_ = sin(hy), cy = cos(hy);
+    s.qx = sr * cp * cy - cr * sp * sy_;
+    s.qy = cr * sp * cy + sr * cp * sy_;
+    s.qz = cr * cp * sy_ - sr * sp * cy;
+    s.qw = cr * cp * cy + sr * sp * sy_;
+  }
+  s.vx = s.vy = s.vz = (vreal)0;
+  s.wx = s.wy = s.wz = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { s.thr[i] = 0.0f; s.pwm[i] = 0.0f; s.sp[i] = 0.0f; }
+#pragma unroll
+  for (int k = 0; k < PID_WORDS; ++k) s.pid[k] = 0.0f;
+  s.flags = 0u;
+  quadx_update_state(s);
+}
+
+// ---- state tensor <-> registers ----------------------------------------------------------------
+// MODE-dependent PID rows: only the controllers a mode instantiates are moved.
+template <int MODE>
+PFB_HD bool pid_row_used(int k) {
+  if (MODE == -1) return false;
+  if (k < PID_P1) return true;                                                   // ang_vel
+  if (k < PID_P2) {                                                              // ang_pos
+    if (MODE == 1 || MODE == 3 || MODE == 7) return true;
+    if (MODE >= 4 && MODE <= 6) return (k - PID_P1) < 4;  // two-axis controller: [I0 I1 e0 e1]
+    return false;
+  }
+  if (k < PID_P3) return MODE >= 4;                                              // lin_vel
+  if (k < PID_ZV) return MODE == 7;                                              // lin_pos
+  if (k < PID_ZP) return MODE != 0;                                              // z_vel
+  return MODE == 2 || MODE == 3 || MODE == 4 || MODE == 7;                       // z_pos
+}
+
+template <int MODE>
+PFB_HD void quadx_load(const float* __restrict__ st, const int32_t* __restrict__ ist, int64_t N, int64_t i, QuadXRegs& s) {
+  auto F = [&](int row) { return st[(int64_t)row * N + i]; };
+#if PFB_X_DOUBLE
+  s.px = join_hi_lo(F(QX_POS + 0), F(QX_POS_LO + 0));
+  s.py = join_hi_lo(F(QX_POS + 1), F(QX_POS_LO + 1));
+  s.pz = join_hi_lo(F(QX_POS + 2), F(QX_POS_LO + 2));
+#else
+  s.px = F(QX_POS + 0); s.py = F(QX_POS + 1); s.pz = F(QX_POS + 2);
+#endif
+#if PFB_Q_DOUBLE
+  s.qx = join_hi_lo(F(QX_QUAT + 0), F(QX_QUAT_LO + 0));
+  s.qy = join_hi_lo(F(QX_QUAT + 1), F(QX_QUAT_LO + 1));
+  s.qz = join_hi_lo(F(QX_QUAT + 2), F(QX_QUAT_LO + 2));
+  s.qw = join_hi_lo(F(QX_QUAT + 3), F(QX_QUAT_LO + 3));
+#else
+  s.qx = F(QX_QUAT + 0); s.qy = F(QX_QUAT + 1); s.qz = F(QX_QUAT + 2); s.qw = F(QX_QUAT + 3);
+#endif
+#if PFB_V_DOUBLE
+  s.vx = join_hi_lo(F(QX_VEL + 0), F(QX_VEL_LO + 0));
+  s.vy = join_hi_lo(F(QX_VEL + 1), F(QX_VEL_LO + 1));
+  s.vz = join_hi_lo(F(QX_VEL + 2), F(QX_VEL_LO + 2));
+#else
+  s.vx = F(QX_VEL + 0); s.vy = F(QX_VEL + 1); s.vz = F(QX_VEL + 2);
+#endif
+  s.wx = F(QX_ANGVEL + 0); s.wy = F(QX_ANGVEL + 1); s.wz = F(QX_ANGVEL + 2);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { s.thr[k] = F(QX_THR + k); s.pwm[k] = F(QX_PWM + k); }
+#pragma unroll
+  for (int k = 0; k < PID_WORDS; ++k) s.pid[k] = pid_row_used<MODE>(k) ? F(QX_PID + k) : 0.0f;
+  s.flags = (uint32_t)ist[(int64_t)QI_FLAGS * N + i];
+  quadx_update_state(s);
+}
+
+template <int MODE>
+PFB_HD void quadx_store(float* __restrict__ st, int32_t* __restrict__ ist, int64_t N, int64_t i, const QuadXRegs& s) {
+  auto S = [&](int row, float v) { st[(int64_t)row * N + i] = v; };
+  float hi, lo;
+#if PFB_X_DOUBLE
+  split_hi_lo(s.px, hi, lo); S(QX_POS + 0, hi); S(QX_POS_LO + 0, lo);
+  split_hi_lo(s.py, hi, lo); S(QX_POS + 1, hi); S(QX_POS_LO + 1, lo);
+  split_hi_lo(s.pz, hi, lo); S(QX_POS + 2, hi); S(QX_POS_LO + 2, lo);
+#else
+  S(QX_POS + 0, s.px); S(QX_POS + 1, s.py); S(QX_POS + 2, s.pz);
+#endif
+#if PFB_Q_DOUBLE
+  split_hi_lo(s.qx, hi, lo); S(QX_QUAT + 0, hi); S(QX_QUAT_LO + 0, lo);
+  split_hi_lo(s.qy, hi, lo); S(QX_QUAT + 1, hi); S(QX_QUAT_LO + 1, lo);
+  split_hi_lo(s.qz, hi, lo); S(QX_QUAT + 2, hi); S(QX_QUAT_LO + 2, lo);
+  split_hi_lo(s.qw, hi, lo); S(QX_QUAT + 3, hi); S(QX_QUAT_LO + 3, lo);
+#else
+  S(QX_QUAT + 0, s.qx); S(QX_QUAT + 1, s.qy); S(QX_QUAT + 2, s.qz); S(QX_QUAT + 3, s.qw);
+#endif
+#if PFB_V_DOUBLE
+  split_hi_lo(s.vx, hi, lo); S(QX_VEL + 0, hi); S(QX_VEL_LO + 0, lo);
+  split_hi_lo(s.vy, hi, lo); S(QX_VEL + 1, hi); S(QX_VEL_LO + 1, lo);
+  split_hi_lo(s.vz, hi, lo); S(QX_VEL + 2, hi); S(QX_VEL_LO + 2, lo);
+#else
+  S(QX_VEL + 0, s.vx); S(QX_VEL + 1, s.vy); S(QX_VEL + 2, s.vz);
+#endif
+  (void)hi; (void)lo;
+  S(QX_ANGVEL + 0, s.wx); S(QX_ANGVEL + 1, s.wy); S(QX_ANGVEL + 2, s.wz);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { S(QX_THR + k, s.thr[k]); S(QX_PWM + k, s.pwm[k]); }
+#pragma unroll
+  for (int k = 0; k < PID_WORDS; ++k)
+    if (pid_row_used<MODE>(k)) S(QX_PID + k, s.pid[k]);
+  ist[(int64_t)QI_FLAGS * N + i] = (int32_t)s.flags;
+}
+
+// ---- Aviary.state(i) (4,3) + aux_state -----------------------------------------------------------
+PFB_HD void quadx_drone_state(const QuadXRegs& s, float* out12, float* aux4) {
+  float roll, pitch, yaw;
+  euler_from_quat((float)s.qx, (float)s.qy, (float)s.qz, (float)s.qw, roll, pitch, yaw);
+  out12[0] = s.wx; out12[1] = s.wy; out12[2] = s.wz;
+  out12[3] = roll; out12[4] = pitch; out12[5] = yaw;
+  out12[6] = s.vb.x; out12[7] = s.vb.y; out12[8] = s.vb.z;
+  out12[9] = (float)s.px; out12[10] = (float)s.py; out12[11] = (float)s.pz;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) aux4[k] = s.thr[k];
+}
+
+// ---- QuadX-Hover epilogue ------------------------------------------------------------------------
+// quadx_base_env.py:251-266 + quadx_hover_env.py:117-138, evaluated after every Aviary step
+PFB_HD void hover_term_trunc_reward(const HoverParams& h, QuadXRegs& s, int step_count, float& reward) {
+  if (step_count > h.max_steps) s.flags |= FLAG_TRUNC;
+  if (s.flags & FLAG_CONTACT_ARRAY) { reward = -100.0f; s.flags |= FLAG_COLLISION | FLAG_TERM; }
+  float px = (float)s.px, py = (float)s.py, pz = (float)s.pz;
+  float r2 = px * px + py * py;
+  if (sqrtf(r2 + pz * pz) > h.dome) { reward = -100.0f; s.flags |= FLAG_OOB | FLAG_TERM; }
+  if (!h.sparse_reward) {
+    float dz = pz - 1.0f;
+    float linear_distance = sqrtf(r2 + dz * dz);
+    float roll, pitch, yaw;
+    euler_from_quat((float)s.qx, (float)s.qy, (float)s.qz, (float)s.qw, roll, pitch, yaw);
+    float angular_distance = sqrtf(roll * roll + pitch * pitch);
+    reward -= 0.01f * s.wz * s.wz;
+    reward -= linear_distance + angular_distance;
+    reward += 1.0f;
+  }
+}
+
+// quadx_hover_env.py:85-115: [ang_vel, (euler | quat(euler)), lin_vel, lin_pos, action, aux]
+PFB_HD int hover_observation(const HoverParams& h, const QuadXRegs& s, const float* action, float* obs) {
+  float roll, pitch, yaw;
+  euler_from_quat((float)s.qx, (float)s.qy, (float)s.qz, (float)s.qw, roll, pitch, yaw);
+  int o = 0;
+  obs[o++] = s.wx; obs[o++] = s.wy; obs[o++] = s.wz;
+  if (h.angle_representation == 0) {
+    obs[o++] = roll; obs[o++] = pitch; obs[o++] = yaw;
+  } else {
+    float x, y, z, w;
+    quat_from_euler(roll, pitch, yaw, x, y, z, w);
+    obs[o++] = x; obs[o++] = y; obs[o++] = z; obs[o++] = w;
+  }
+  obs[o++] = s.vb.x; obs[o++] = s.vb.y; obs[o++] = s.vb.z;
+  obs[o++] = (float)s.px; obs[o++] = (float)s.py; obs[o++] = (float)s.pz;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) obs[o++] = action[k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) obs[o++] = s.thr[k];
+  return o;
+}
+
+}  // namespace pfb

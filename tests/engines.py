@@ -1,0 +1,311 @@
+"""Test-side adapters giving the CPU oracle, the host-compiled kernel body and the CUDA product one
+common surface, so that every golden fixture is replayed through identical code.
+
+* ``OracleEngine``  — oracle/pfb_oracle.c, fp64 (the checker).
+* ``HostSimEngine`` — tests/hostsim: the kernel body of pyflyt_b200/csrc compiled with g++ (precision
+  studies / logic checks without a GPU; NOT a product path).
+* ``CudaEngine``    — the product: pyflyt_b200.BatchedAviary → libpyflyt_b200.so on cuda:0.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.join(os.path.dirname(os.path.realpath(__file__)), "..")
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from pyflyt_b200.models import PfbEnvConfig, build_model  # noqa: E402
+
+
+def hover_config(flight_mode=0, angle_representation="quaternion", sparse=False, dome=3.0, agent_hz=40, max_duration=10.0, autoreset=False):
+    e = PfbEnvConfig()
+    e.env_kind = 1
+    e.flight_mode = int(flight_mode)
+    e.env_step_ratio = int(120 / agent_hz)
+    e.max_steps = int(agent_hz * max_duration)
+    e.angle_representation = 1 if angle_representation == "quaternion" else 0
+    e.sparse_reward = int(bool(sparse))
+    e.autoreset = int(bool(autoreset))
+    e.warmup_steps = 10
+    e.flight_dome_size = float(dome)
+    return e
+
+
+class OracleEngine:
+    name = "oracle"
+
+    def __init__(self, model, env=None, n=1, start_pos=None, start_orn=None):
+        from oracle.oracle import Oracle
+
+        self.o = Oracle(model, env, n=n, start_pos=start_pos, start_orn=start_orn)
+        self.n = n
+        self.ups = self.o.updates_per_step
+
+    def reset(self):
+        self.o.reset()
+
+    def set_mode(self, mode):
+        self.o.set_mode(mode)
+
+    def set_setpoints(self, sp):
+        self.o.set_setpoints(sp)
+
+    def get_setpoints(self):
+        return self.o.get_setpoints()
+
+    def aviary_step(self, noise, n_steps=1):
+        self.o.aviary_step(n_steps, noise)
+
+    def state(self):
+        return self.o.state()
+
+    def aux(self):
+        return self.o.aux_state()
+
+    def contact(self):
+        return self.o.contact()
+
+    def env_reset(self, noise):
+        return self.o.env_reset(noise=noise)
+
+    def env_step(self, actions, noise):
+        return self.o.env_step(actions, noise)
+
+
+_HS = None
+
+
+def hostsim_lib(flags: str = ""):
+    """Builds (if stale) and loads tests/_build/libpfb_hostsim<tag>.so; ``flags`` e.g. "-DPFB_V_DOUBLE=0"."""
+    global _HS
+    tag = "".join(ch for ch in flags if ch.isalnum())
+    out = os.path.join(ROOT, "tests", "_build", f"libpfb_hostsim{tag}.so")
+    src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
+    deps = [src] + [os.path.join(ROOT, "pyflyt_b200", "csrc", f) for f in ("pfb_common.cuh", "pfb_quadx.cuh", "pfb_quadx_host.h")]
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-mfma", "-ffp-contract=fast"] + flags.split() + ["-o", out, src]
+        subprocess.run(cmd, check=True, capture_output=True)
+    L = C.CDLL(out)
+    L.hs_last_error.restype = C.c_char_p
+    return L
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+class HostSimEngine:
+    name = "hostsim"
+
+    def __init__(self, model, env=None, n=1, start_pos=None, start_orn=None, flags: str = ""):
+        self.L = hostsim_lib(flags)
+        self.model, self.env, self.n = model, env, n
+        self.ups = int(model.physics_hz / model.control_hz)
+        self.st = np.zeros((self.L.hs_state_rows(), n), dtype=np.float32)
+        self.ist = np.zeros((self.L.hs_istate_rows(), n), dtype=np.int32)
+        self.sp = np.zeros((n, 4), dtype=np.float32)
+        self.start_pos = np.ascontiguousarray(np.broadcast_to(np.zeros(3) if start_pos is None else start_pos, (n, 3)), dtype=np.float32)
+        self.start_orn = np.ascontiguousarray(np.broadcast_to(np.zeros(3) if start_orn is None else start_orn, (n, 3)), dtype=np.float32)
+        self.mode = 0
+        self.obs_dim = 21 if (env is not None and env.angle_representation == 1) else 20
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.L.hs_last_error().decode())
+
+    def reset(self):
+        f, i32 = C.c_float, C.c_int32
+        self._chk(self.L.hs_reset(C.byref(self.model), _p(self.st, f), _p(self.ist, i32), _p(self.sp, f), _p(self.start_pos, f), _p(self.start_orn, f), None, C.c_int64(self.n)))
+        self.mode = 0
+
+    def set_mode(self, mode):
+        self._chk(self.L.hs_set_mode(int(mode), _p(self.st, C.c_float), _p(self.ist, C.c_int32), _p(self.sp, C.c_float), C.c_int64(self.n)))
+        self.mode = int(mode)
+
+    def set_setpoints(self, sp):
+        self.sp[...] = np.asarray(sp, dtype=np.float32)
+
+    def get_setpoints(self):
+        return self.sp.astype(np.float64)
+
+    def aviary_step(self, noise, n_steps=1):
+        nz = np.ascontiguousarray(noise, dtype=np.float32)
+        assert nz.shape == (n_steps * self.ups, self.n)
+        self._chk(self.L.hs_aviary_step(C.byref(self.model), self.mode, _p(self.st, C.c_float), _p(self.ist, C.c_int32), _p(self.sp, C.c_float), _p(nz, C.c_float), n_steps, C.c_int64(self.n)))
+
+    def _observe(self):
+        ds = np.zeros((self.n, 12), dtype=np.float32)
+        aux = np.zeros((self.n, 4), dtype=np.float32)
+        con = np.zeros(self.n, dtype=np.uint8)
+        self._chk(self.L.hs_observe(_p(self.st, C.c_float), _p(self.ist, C.c_int32), _p(ds, C.c_float), _p(aux, C.c_float), _p(con, C.c_uint8), C.c_int64(self.n)))
+        return ds, aux, con
+
+    def state(self):
+        return self._observe()[0].reshape(self.n, 4, 3).astype(np.float64)
+
+    def aux(self):
+        return self._observe()[1].astype(np.float64)
+
+    def contact(self):
+        return self._observe()[2]
+
+    def precise_pos(self):
+        """hi + lo position words (the fp64 value the kernel carries)."""
+        return (self.st[0:3].astype(np.float64) + self.st[21:24].astype(np.float64)).T
+
+    def env_reset(self, noise):
+        nz = np.ascontiguousarray(noise, dtype=np.float32)
+        obs = np.zeros((self.n, self.obs_dim), dtype=np.float32)
+        self._chk(self.L.hs_env_reset(C.byref(self.model), C.byref(self.env), _p(self.st, C.c_float), _p(self.ist, C.c_int32), _p(self.start_pos, C.c_float), _p(self.start_orn, C.c_float), None, _p(nz, C.c_float), _p(obs, C.c_float), C.c_int64(self.n)))
+        return obs.astype(np.float64)
+
+    def env_step(self, actions, noise):
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        nz = np.ascontiguousarray(noise, dtype=np.float32)
+        obs = np.zeros((self.n, self.obs_dim), dtype=np.float32)
+        rew = np.zeros(self.n, dtype=np.float32)
+        term, trunc, info = (np.zeros(self.n, dtype=np.uint8) for _ in range(3))
+        self._chk(self.L.hs_env_step(C.byref(self.model), C.byref(self.env), _p(self.st, C.c_float), _p(self.ist, C.c_int32), _p(a, C.c_float), _p(nz, C.c_float), _p(obs, C.c_float), _p(rew, C.c_float), _p(term, C.c_uint8), _p(trunc, C.c_uint8), _p(info, C.c_uint8), C.c_int64(self.n)))
+        return obs.astype(np.float64), rew.astype(np.float64), term, trunc, info
+
+
+# ----------------------------------------------------------------------------------------------------
+# fixture replays (shared by every engine)
+# ----------------------------------------------------------------------------------------------------
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name if name.endswith(".npz") else name + ".npz"))
+
+
+def replay_aviary(make_engine, g, every=1):
+    """Replays a quadx_aviary fixture; returns dict of max abs errors vs the reference's outputs."""
+    model = build_model("quadx", str(g["drone_model"]))
+    eng = make_engine(model, None, 1, g["start_pos"][None], g["start_orn"][None])
+    eng.reset()
+    eng.set_mode(int(g["mode"]))
+    T = len(g["state"])
+    noise = g["noise"].reshape(T, eng.ups)
+    err = dict(setpoint=float(np.abs(eng.get_setpoints()[0] - g["setpoint_after_set_mode"]).max()), pos=0.0, euler=0.0, angvel=0.0, linvel=0.0, aux=0.0, contact_mismatch=0)
+    pos_err_t = np.zeros(T)
+    for i in range(T):
+        eng.set_setpoints(g["setpoints"][i][None])
+        eng.aviary_step(noise[i][:, None])
+        if i % every and i != T - 1:
+            continue
+        s = eng.state()[0]
+        ref = g["state"][i]
+        d_eul = np.abs((s[1] - ref[1] + np.pi) % (2 * np.pi) - np.pi)
+        err["angvel"] = max(err["angvel"], float(np.abs(s[0] - ref[0]).max()))
+        err["euler"] = max(err["euler"], float(d_eul.max()))
+        err["linvel"] = max(err["linvel"], float(np.abs(s[2] - ref[2]).max()))
+        pe = float(np.abs(s[3] - ref[3]).max())
+        pos_err_t[i] = pe
+        err["pos"] = max(err["pos"], pe)
+        err["aux"] = max(err["aux"], float(np.abs(eng.aux()[0] - g["aux"][i]).max()))
+        err["contact_mismatch"] += int(bool(eng.contact()[0]) != bool(g["contact"][i]))
+    err["pos_err_t"] = pos_err_t
+    return err
+
+
+def replay_hover(make_engine, g):
+    """Replays a quadx_hover fixture (env.reset + scripted env.step + user-loop resets)."""
+    model = build_model("quadx", "cf2x")
+    env = hover_config(int(g["flight_mode"]), str(g["angle_representation"]), bool(g["sparse"]), float(g["dome"]))
+    eng = make_engine(model, env, 1, np.array([[0.0, 0.0, 1.0]]), np.zeros((1, 3)))
+    noise, splits = g["noise"], g["noise_splits"]
+    cursor = {"i": 0}
+
+    def take():
+        k = cursor["i"]
+        seg = noise[(splits[k - 1] if k > 0 else 0) : splits[k]]
+        cursor["i"] += 1
+        return seg
+
+    per_step = env.env_step_ratio * eng.ups
+    obs = eng.env_reset(take()[:, None])
+    err = dict(obs=float(np.abs(obs[0] - g["reset_obs"]).max()), reward=0.0, flag_mismatch=0, episodes=0)
+    ep_starts = set(g["episode_start"].tolist())
+    k = 0
+    for i in range(len(g["actions"])):
+        seg = take()
+        full = np.zeros((per_step, 1))
+        full[: len(seg), 0] = seg  # an early break consumes fewer draws
+        ob, r, te, tr, inf = eng.env_step(g["actions"][i][None], full)
+        err["obs"] = max(err["obs"], float(np.abs(ob[0] - g["obs"][i]).max()))
+        err["reward"] = max(err["reward"], float(abs(r[0] - g["reward"][i])))
+        err["flag_mismatch"] += int(bool(te[0]) != bool(g["term"][i])) + int(bool(tr[0]) != bool(g["trunc"][i])) + int(int(inf[0]) != int(g["info"][i]))
+        if (i + 1) in ep_starts:
+            ob2 = eng.env_reset(take()[:, None])
+            err["obs"] = max(err["obs"], float(np.abs(ob2[0] - g["after_reset_obs"][k]).max()))
+            k += 1
+            err["episodes"] += 1
+    return err
+
+
+class CudaEngine:
+    """The product path: pyflyt_b200.BatchedAviary -> ctypes -> libpyflyt_b200.so on cuda:0."""
+
+    name = "cuda"
+
+    def __init__(self, model_or_name, env=None, n=1, start_pos=None, start_orn=None, drone_model="cf2x", seed=0):
+        import torch
+
+        from pyflyt_b200.core.aviary import BatchedAviary
+
+        self.torch = torch
+        self.n = n
+        sp = np.ascontiguousarray(np.broadcast_to(np.zeros(3) if start_pos is None else start_pos, (n, 3)), dtype=np.float32)
+        so = np.ascontiguousarray(np.broadcast_to(np.zeros(3) if start_orn is None else start_orn, (n, 3)), dtype=np.float32)
+        self.av = BatchedAviary(sp, so, drone_type="quadx", drone_options=dict(drone_model=drone_model), seed=seed, env_config=env)
+        self.ups = self.av.updates_per_step
+        self.obs_dim = self.av.obs_dim
+
+    def _dev(self, a):
+        return self.torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device=self.av.device)
+
+    def reset(self):
+        self.av.reset()
+
+    def set_mode(self, mode):
+        self.av.set_mode(mode)
+
+    def set_setpoints(self, sp):
+        self.av.set_all_setpoints(self._dev(sp))
+
+    def get_setpoints(self):
+        return self.av.setpoints.double().cpu().numpy()
+
+    def aviary_step(self, noise, n_steps=1):
+        self.av.step(n_steps, noise=self._dev(noise))
+
+    def state(self):
+        return self.av.all_states.double().cpu().numpy()
+
+    def aux(self):
+        return self.av.all_aux_states.double().cpu().numpy()
+
+    def contact(self):
+        return self.av.contact_array.cpu().numpy().astype(np.uint8)
+
+    def env_reset(self, noise):
+        return self.av.env_reset(noise=self._dev(noise)).double().cpu().numpy()
+
+    def env_step(self, actions, noise):
+        self.av.env_step(actions=self._dev(actions), noise=self._dev(noise))
+        a = self.av
+        return (a.obs.double().cpu().numpy(), a.reward.double().cpu().numpy(), a.term.cpu().numpy(), a.trunc.cpu().numpy(), a.info_bits.cpu().numpy())
+
+
+def make_cuda_engine(model, env, n, start_pos, start_orn):
+    """Adapter with the (model, env, n, start_pos, start_orn) factory signature used by the replays."""
+    name = "primitive_drone" if abs(model.mass - 1.0) < 1e-12 else "cf2x"
+    return CudaEngine(model, env, n, start_pos, start_orn, drone_model=name)

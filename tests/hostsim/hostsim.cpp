@@ -1,0 +1,196 @@
+// TEST HARNESS — compiles the per-env kernel body (pyflyt_b200/csrc/pfb_quadx.cuh) for the HOST so the
+// fp32/fp64 precision policy and the control-flow of the CUDA kernels can be studied and unit-tested on
+// a machine without a GPU.  Never linked into, loaded by, or reachable from the product package:
+// libpyflyt_b200.so contains CUDA kernels only and fails loudly without a device.
+// The glue below mirrors the kernels in pfb_lib.cu one-to-one (same loads, same order, same stores).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../pyflyt_b200/csrc/pfb_quadx.cuh"
+
+static char g_err[512];
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return -1;
+}
+#include "../../pyflyt_b200/csrc/pfb_quadx_host.h"
+
+using namespace pfb;
+
+struct HostNoise {
+  const float* ptr;
+  int64_t N;
+  float operator()() {
+    float v = *ptr;
+    ptr += N;
+    return v;
+  }
+};
+
+#define MODE_SWITCH(mode, BODY)                        \
+  switch (mode) {                                      \
+    case -1: { constexpr int MODE = -1; BODY; } break; \
+    case 0: { constexpr int MODE = 0; BODY; } break;   \
+    case 1: { constexpr int MODE = 1; BODY; } break;   \
+    case 2: { constexpr int MODE = 2; BODY; } break;   \
+    case 3: { constexpr int MODE = 3; BODY; } break;   \
+    case 4: { constexpr int MODE = 4; BODY; } break;   \
+    case 5: { constexpr int MODE = 5; BODY; } break;   \
+    case 6: { constexpr int MODE = 6; BODY; } break;   \
+    case 7: { constexpr int MODE = 7; BODY; } break;   \
+    default: return fail("bad mode %d", mode);         \
+  }
+
+static void hover_params(const PfbEnvConfig* env, HoverParams& h) {
+  h.env_step_ratio = env->env_step_ratio;
+  h.max_steps = env->max_steps;
+  h.angle_representation = env->angle_representation;
+  h.sparse_reward = env->sparse_reward;
+  h.warmup_steps = env->warmup_steps;
+  h.flight_mode = env->flight_mode;
+  h.dome = (float)env->flight_dome_size;
+}
+
+#define HS_API extern "C"
+HS_API const char* hs_last_error() { return g_err; }
+HS_API int hs_state_rows() { return QX_ROWS; }
+HS_API int hs_istate_rows() { return QI_ROWS; }
+HS_API int hs_precision_flags() { return PFB_Q_DOUBLE | (PFB_X_DOUBLE << 1) | (PFB_V_DOUBLE << 2) | (PFB_R_DOUBLE << 3); }
+
+HS_API int hs_reset(const PfbModel* m, float* st, int32_t* ist, float* setpoint, const float* start_pos, const float* start_orn,
+             const uint8_t* mask, int64_t N) {
+  for (int64_t i = 0; i < N; ++i) {
+    if (mask && !mask[i]) continue;
+    QuadXRegs s;
+    quadx_reset(s, start_pos[3 * i], start_pos[3 * i + 1], start_pos[3 * i + 2], start_orn[3 * i], start_orn[3 * i + 1],
+                start_orn[3 * i + 2]);
+    quadx_store<7>(st, ist, N, i, s);
+    ist[(int64_t)QI_STEP * N + i] = 0;
+    for (int k = 0; k < 4; ++k) setpoint[4 * i + k] = 0.f;
+  }
+  return 0;
+}
+
+template <int MODE>
+static void set_mode_t(float* st, int32_t* ist, float* setpoint, int64_t N) {
+  for (int64_t i = 0; i < N; ++i) {
+    QuadXRegs s;
+    quadx_load<7>(st, ist, N, i, s);
+    for (int k = 0; k < 4; ++k) s.sp[k] = setpoint[4 * i + k];
+    quadx_set_mode<MODE>(s);
+    quadx_store<7>(st, ist, N, i, s);
+    for (int k = 0; k < 4; ++k) setpoint[4 * i + k] = s.sp[k];
+  }
+}
+HS_API int hs_set_mode(int mode, float* st, int32_t* ist, float* setpoint, int64_t N) {
+  MODE_SWITCH(mode, (set_mode_t<MODE>(st, ist, setpoint, N)));
+  return 0;
+}
+
+template <int MODE>
+static void aviary_step_t(const QuadXParams& p, float* st, int32_t* ist, const float* setpoint, const float* noise,
+                          int n_steps, int64_t N) {
+  for (int64_t i = 0; i < N; ++i) {
+    QuadXRegs s;
+    quadx_load<MODE>(st, ist, N, i, s);
+    for (int k = 0; k < 4; ++k) s.sp[k] = setpoint[4 * i + k];
+    HostNoise nz{noise + i, N};
+    for (int k = 0; k < n_steps; ++k) quadx_aviary_step<MODE>(p, s, nz);
+    quadx_store<MODE>(st, ist, N, i, s);
+    ist[(int64_t)QI_PHYS * N + i] += n_steps * p.ratio;
+  }
+}
+HS_API int hs_aviary_step(const PfbModel* m, int mode, float* st, int32_t* ist, const float* setpoint, const float* noise,
+                   int n_steps, int64_t N) {
+  QuadXParams p;
+  if (build_quadx_params(*m, p)) return -1;
+  MODE_SWITCH(mode, (aviary_step_t<MODE>(p, st, ist, setpoint, noise, n_steps, N)));
+  return 0;
+}
+
+HS_API int hs_observe(const float* st, const int32_t* ist, float* drone_state, float* aux, uint8_t* contact, int64_t N) {
+  for (int64_t i = 0; i < N; ++i) {
+    QuadXRegs s;
+    quadx_load<-1>(st, ist, N, i, s);
+    quadx_drone_state(s, drone_state + 12 * i, aux + 4 * i);
+    contact[i] = (s.flags & FLAG_CONTACT_ARRAY) ? 1 : 0;
+  }
+  return 0;
+}
+
+template <int MODE>
+static void env_reset_t(const QuadXParams& p, const HoverParams& h, float* st, int32_t* ist, const float* start_pos,
+                        const float* start_orn, const uint8_t* mask, const float* noise, float* obs, int64_t N) {
+  const int O = h.angle_representation == 0 ? 20 : 21;
+  for (int64_t i = 0; i < N; ++i) {
+    if (mask && !mask[i]) continue;
+    QuadXRegs s;
+    quadx_reset(s, start_pos[3 * i], start_pos[3 * i + 1], start_pos[3 * i + 2], start_orn[3 * i], start_orn[3 * i + 1],
+                start_orn[3 * i + 2]);
+    quadx_set_mode<MODE>(s);
+    HostNoise nz{noise + i, N};
+    for (int k = 0; k < h.warmup_steps; ++k) quadx_aviary_step<MODE>(p, s, nz);
+    const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+    float my_obs[21];
+    hover_observation(h, s, zero, my_obs);
+    quadx_store<7>(st, ist, N, i, s);
+    ist[(int64_t)QI_STEP * N + i] = 0;
+    ist[(int64_t)QI_PHYS * N + i] += h.warmup_steps * p.ratio;
+    for (int k = 0; k < O; ++k) obs[i * O + k] = my_obs[k];
+  }
+}
+HS_API int hs_env_reset(const PfbModel* m, const PfbEnvConfig* env, float* st, int32_t* ist, const float* start_pos,
+                 const float* start_orn, const uint8_t* mask, const float* noise, float* obs, int64_t N) {
+  QuadXParams p;
+  if (build_quadx_params(*m, p)) return -1;
+  HoverParams h;
+  hover_params(env, h);
+  MODE_SWITCH(env->flight_mode, (env_reset_t<MODE>(p, h, st, ist, start_pos, start_orn, mask, noise, obs, N)));
+  return 0;
+}
+
+template <int MODE>
+static void env_step_t(const QuadXParams& p, const HoverParams& h, float* st, int32_t* ist, const float* actions,
+                       const float* noise, float* obs, float* reward, uint8_t* term, uint8_t* trunc, uint8_t* info, int64_t N) {
+  const int O = h.angle_representation == 0 ? 20 : 21;
+  for (int64_t i = 0; i < N; ++i) {
+    QuadXRegs s;
+    quadx_load<MODE>(st, ist, N, i, s);
+    float act[4];
+    for (int k = 0; k < 4; ++k) { act[k] = actions[4 * i + k]; s.sp[k] = act[k]; }
+    int step_count = ist[(int64_t)QI_STEP * N + i];
+    HostNoise nz{noise + i, N};
+    float rew = -0.1f;
+    int done_steps = 0;
+    for (int k = 0; k < h.env_step_ratio; ++k) {
+      if (s.flags & (FLAG_TERM | FLAG_TRUNC)) break;
+      quadx_aviary_step<MODE>(p, s, nz);
+      hover_term_trunc_reward(h, s, step_count, rew);
+      ++done_steps;
+    }
+    step_count += 1;
+    float my_obs[21];
+    hover_observation(h, s, act, my_obs);
+    quadx_store<MODE>(st, ist, N, i, s);
+    ist[(int64_t)QI_STEP * N + i] = step_count;
+    ist[(int64_t)QI_PHYS * N + i] += done_steps * p.ratio;
+    reward[i] = rew;
+    term[i] = (s.flags & FLAG_TERM) ? 1 : 0;
+    trunc[i] = (s.flags & FLAG_TRUNC) ? 1 : 0;
+    info[i] = (uint8_t)(((s.flags & FLAG_OOB) ? 1 : 0) | ((s.flags & FLAG_COLLISION) ? 2 : 0));
+    for (int k = 0; k < O; ++k) obs[i * O + k] = my_obs[k];
+  }
+}
+HS_API int hs_env_step(const PfbModel* m, const PfbEnvConfig* env, float* st, int32_t* ist, const float* actions, const float* noise,
+                float* obs, float* reward, uint8_t* term, uint8_t* trunc, uint8_t* info, int64_t N) {
+  QuadXParams p;
+  if (build_quadx_params(*m, p)) return -1;
+  HoverParams h;
+  hover_params(env, h);
+  MODE_SWITCH(env->flight_mode, (env_step_t<MODE>(p, h, st, ist, actions, noise, obs, reward, term, trunc, info, N)));
+  return 0;
+}

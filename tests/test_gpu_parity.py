@@ -1,0 +1,217 @@
+"""Parity tests proper: the CUDA path (through the C-ABI) against the golden vectors, the CPU oracle on
+seeded inputs, and size-independent properties at BASELINE.json's full size (65 536 envs)."""
+import numpy as np
+import pytest
+
+from engines import CudaEngine, OracleEngine, build_model, hover_config, load_golden, make_cuda_engine, replay_aviary, replay_hover
+
+pytestmark = pytest.mark.gpu
+POS_TOL = 1e-3  # north_star: |dpos| < 1e-3 m over 1000 env-steps (fp32 tolerance vs the fp64 reference)
+
+
+def test_long_mode0_trajectory_within_tolerance():
+    """BASELINE config 1: 1000 Hover env-steps (3000 Aviary steps, 6000 substeps) of mode-0 flight."""
+    err = replay_aviary(make_cuda_engine, load_golden("quadx_mode0_long"), every=30)
+    assert err["pos"] < POS_TOL, err["pos"]
+    assert err["contact_mismatch"] == 0
+
+
+@pytest.mark.parametrize("mode", [-1, 0, 1, 4, 5, 6])
+@pytest.mark.parametrize("model", ["cf2x", "primitive_drone"])
+def test_flight_modes(model, mode):
+    err = replay_aviary(make_cuda_engine, load_golden(f"quadx_{model}_mode{mode}"), every=3)
+    assert err["setpoint"] < 1e-6 and err["contact_mismatch"] == 0
+    assert err["pos"] < 0.5 * POS_TOL and err["euler"] < 1e-3, err
+
+
+@pytest.mark.parametrize("mode", [2, 3, 7])
+@pytest.mark.parametrize("model", ["cf2x", "primitive_drone"])
+def test_flight_modes_height_hold(model, mode):
+    err = replay_aviary(make_cuda_engine, load_golden(f"quadx_{model}_mode{mode}"), every=3)
+    assert err["contact_mismatch"] == 0 and err["pos"] < POS_TOL, err
+
+
+def test_reference_scenarios_mode7():
+    """tests/test_core.py:13-31 and :65-93 of the reference (hold, two set-points)."""
+    for name in ("quadx_mode7_hold", "quadx_mode7_setpoints"):
+        err = replay_aviary(make_cuda_engine, load_golden(name), every=10)
+        assert err["pos"] < 1e-4 and err["contact_mismatch"] == 0, (name, err)
+
+
+def test_floor_contact():
+    err = replay_aviary(make_cuda_engine, load_golden("quadx_floor_contact"))
+    assert err["contact_mismatch"] == 0 and err["pos"] < 1e-5
+
+
+@pytest.mark.parametrize("name", ["hover_quat_dense", "hover_euler_sparse", "hover_quat_gentle", "hover_mode6"])
+def test_hover_env_golden(name):
+    err = replay_hover(make_cuda_engine, load_golden(name))
+    assert err["flag_mismatch"] == 0
+    assert err["obs"] < 5e-5 and err["reward"] < 5e-5, err
+
+
+def _seeded_batch(n, seed):
+    rng = np.random.default_rng(seed)
+    f = lambda a: a.astype(np.float32).astype(np.float64)  # identical, fp32-representable inputs
+    start = f(np.column_stack([rng.uniform(-1, 1, n), rng.uniform(-1, 1, n), rng.uniform(20, 30, n)]))
+    orn = f(rng.uniform(-0.3, 0.3, (n, 3)))
+    return rng, f, start, orn
+
+
+@pytest.mark.parametrize("mode", [0, 6])
+def test_batch_4096_matches_oracle(mode):
+    """BASELINE config 2 (lower end): 4096 envs, same seeded inputs through oracle and CUDA."""
+    n, steps = 4096, 240
+    rng, f, start, orn = _seeded_batch(n, 11 + mode)
+    model = build_model("quadx", "cf2x")
+    noise = f(rng.normal(4.0, 1.0, (steps * 2, n)))
+    engines = [OracleEngine(model, None, n, start, orn), CudaEngine(model, None, n, start, orn)]
+    for e in engines:
+        e.reset()
+        e.set_mode(mode)
+    lo, hi = ([-1, -1, -1, 0.2], [1, 1, 1, 0.7]) if mode == 0 else ([-1, -1, -0.5, -0.5], [1, 1, 0.5, 0.5])
+    for i in range(0, steps, 20):
+        sp = f(rng.uniform(lo, hi, (n, 4)))
+        for e in engines:
+            e.set_setpoints(sp)
+            e.aviary_step(noise[2 * i : 2 * i + 40], n_steps=20)
+    a, b = engines[0].state(), engines[1].state()
+    assert np.abs(a[:, 3] - b[:, 3]).max() < 2e-4
+    assert np.abs(a[:, 0] - b[:, 0]).max() < 2e-3
+    assert np.array_equal(engines[0].contact(), engines[1].contact())
+
+
+def test_hover_env_batch_matches_oracle():
+    """env.reset + 60 env.step on 4096 envs with scripted actions and injected noise, incl. terminations."""
+    n, steps = 4096, 60
+    rng, f, _, _ = _seeded_batch(n, 5)
+    model = build_model("quadx", "cf2x")
+    env = hover_config(0, "quaternion", False, 3.0)
+    start, orn = np.tile([[0.0, 0.0, 1.0]], (n, 1)), np.zeros((n, 3))
+    orc, cud = OracleEngine(model, env, n, start, orn), CudaEngine(model, env, n, start, orn)
+    nz0 = f(rng.normal(4.0, 1.0, (20, n)))
+    o0, o1 = orc.env_reset(nz0), cud.env_reset(nz0)
+    assert np.abs(o0 - o1).max() < 1e-5
+    n_term = 0
+    for k in range(steps):
+        act = f(rng.uniform([-np.pi, -np.pi, -np.pi, 0.0], [np.pi, np.pi, np.pi, 0.8], (n, 4)) * [0.2, 0.2, 0.2, 1.0])
+        nz = f(rng.normal(4.0, 1.0, (6, n)))
+        ob0, r0, te0, tr0, in0 = orc.env_step(act, nz)
+        ob1, r1, te1, tr1, in1 = cud.env_step(act, nz)
+        # an env whose termination decision sits within fp32 rounding of a threshold may flip; none should
+        assert np.array_equal(te0, te1) and np.array_equal(tr0, tr1) and np.array_equal(in0, in1), k
+        assert np.abs(ob0 - ob1).max() < 1e-4 and np.abs(r0 - r1).max() < 1e-4, k
+        n_term = int(te0.sum())
+    assert n_term > 0  # the scenario does exercise terminations
+
+
+def test_full_size_determinism_and_shard_independence():
+    """65 536 envs: two runs with one seed are bit-identical, and splitting the batch into two handles
+    with env offsets (what each rank does) reproduces the single-handle result exactly."""
+    import torch
+
+    from pyflyt_b200.gym_envs.quadx_hover_env import QuadXHoverVecEnv
+
+    n = 65536
+
+    def run(num, offset):
+        env = QuadXHoverVecEnv(num_envs=num, seed=123, env_offset=offset)
+        env.reset()
+        env.rollout(25)
+        torch.cuda.synchronize()
+        out = (env.aviary.obs.clone(), env.aviary.reward.clone(), env.aviary.state_tensor.clone(), env.aviary.istate_tensor.clone())
+        env.close()
+        return out
+
+    a, b = run(n, 0), run(n, 0)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    lo, hi = run(n // 2, 0), run(n // 2, n // 2)
+    assert torch.equal(torch.cat([lo[0], hi[0]]), a[0])
+    assert torch.equal(torch.cat([lo[1], hi[1]]), a[1])
+    assert torch.equal(torch.cat([lo[2], hi[2]], dim=1), a[2])
+    assert torch.isfinite(a[0]).all() and torch.isfinite(a[2]).all()
+
+
+def test_full_size_autoreset_invariants():
+    import torch
+
+    from pyflyt_b200.gym_envs.quadx_hover_env import QuadXHoverVecEnv
+
+    env = QuadXHoverVecEnv(num_envs=65536, seed=1)
+    obs, _ = env.reset()
+    assert torch.allclose(obs[:, 10:13], torch.tensor([0.0, 0.0, 1.0], device=obs.device).expand(65536, 3), atol=0.05)
+    total_done = 0
+    for _ in range(40):
+        env.rollout(1)
+        done = env.aviary.term.bool() | env.aviary.trunc.bool()
+        total_done += int(done.sum())
+        # SAME_STEP autoreset: every finished env already holds the first observation of a new episode
+        z = env.aviary.obs[done][:, 12]
+        assert bool(((z > 0.9) & (z < 1.0)).all())
+        assert bool((env.aviary.istate_tensor[0][done] == 0).all())
+        assert bool((env.aviary.reward[done] < -50).all())  # -100 overwrite on collision / out of bounds
+    assert total_done > 1000  # random actions crash often
+    flags = env.aviary.istate_tensor[1]
+    assert int((flags & 3).sum()) == 0  # no env is left in a finished state
+    env.close()
+
+
+def test_free_fall_closed_form_at_full_size():
+    """Mode -1 with zero pwm, drag off: z_k = z0 - g dt^2 k(k+1)/2 for all 65 536 envs."""
+    import torch
+
+    from pyflyt_b200.core.aviary import BatchedAviary
+
+    n, k = 65536, 240
+    m = build_model("quadx", "cf2x")
+    m.drag_const[:] = [0.0, 0.0, 0.0]
+    from pyflyt_b200.core import aviary as _av
+
+    real_build = _av.build_model
+    _av.build_model = lambda *a, **kw: m  # hand the edited table to the constructor
+    try:
+        av = BatchedAviary(np.tile([[0.0, 0.0, 500.0]], (n, 1)), np.zeros((n, 3)))
+    finally:
+        _av.build_model = real_build
+    av.set_mode(-1)
+    av.set_all_setpoints(torch.zeros((n, 4), device="cuda"))
+    av.step(k // 2, noise=torch.full((k, n), 4.0, device="cuda"))
+    z = av.all_states[:, 3, 2].double().cpu().numpy()
+    dt, g = 1.0 / 240.0, 9.81
+    assert np.abs(z - (500.0 - g * dt * dt * k * (k + 1) / 2.0)).max() < 2e-4
+    assert np.ptp(z) == 0.0
+
+
+def test_host_buffer_entry_matches_device_entry():
+    import torch
+
+    from pyflyt_b200.gym_envs.quadx_hover_env import QuadXHoverVecEnv
+
+    n = 8192
+    envs = [QuadXHoverVecEnv(num_envs=n, seed=9), QuadXHoverVecEnv(num_envs=n, seed=9)]
+    for e in envs:
+        e.reset()
+    g = torch.Generator().manual_seed(0)
+    act = (torch.rand((n, 4), generator=g) * torch.tensor([0.6, 0.6, 0.6, 0.8])).pin_memory()
+    obs_h = torch.empty((n, envs[0].obs_dim)).pin_memory()
+    rew_h = torch.empty(n).pin_memory()
+    te_h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    tr_h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    for _ in range(5):
+        envs[0].aviary.env_step_host(act, obs_h, rew_h, te_h, tr_h)
+        torch.cuda.synchronize()
+        ob, r, te, tr, _ = envs[1].step(act.cuda())
+        assert torch.equal(ob.cpu(), obs_h) and torch.equal(r.cpu(), rew_h)
+        assert torch.equal(te.cpu(), te_h.bool()) and torch.equal(tr.cpu(), tr_h.bool())
+
+
+def test_single_env_adaptor_signature():
+    from pyflyt_b200.gym_envs.quadx_hover_env import QuadXHoverEnv
+
+    env = QuadXHoverEnv()
+    obs, info = env.reset(seed=0)
+    assert obs.shape == (21,) and obs.dtype == np.float64 and set(info) == {"out_of_bounds", "collision", "env_complete"}
+    obs, rew, term, trunc, info = env.step(np.array([0.0, 0.0, 0.0, 0.4]))
+    assert obs.shape == (21,) and isinstance(rew, float) and isinstance(term, bool) and isinstance(trunc, bool)
+    env.close()
