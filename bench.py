@@ -82,14 +82,15 @@ def cpu_oracle_rate(envs: int, target_seconds: float, threads: int | None = None
     env = hover_config(0, "quaternion", False, 3.0, autoreset=True)
     o = orc_mod.Oracle(model, env, n=envs, seed=1, start_pos=np.array([0.0, 0.0, 1.0]), start_orn=np.zeros(3))
     o.env_reset()
-    o.env_rollout(2)  # warm-up
+    o.env_rollout(5)  # warm-up
+    steps, done, chunk = 0, 0, 20
     t0 = time.perf_counter()
-    o.env_rollout(3)
-    per_step = (time.perf_counter() - t0) / 3
-    steps = max(3, int(target_seconds / max(per_step, 1e-6)))
-    t0 = time.perf_counter()
-    done = o.env_rollout(steps)
-    dt = time.perf_counter() - t0
+    while True:
+        done += o.env_rollout(chunk)
+        steps += chunk
+        dt = time.perf_counter() - t0
+        if dt >= target_seconds:
+            break
     return done / dt, cores, steps, dt
 
 

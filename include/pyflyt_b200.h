@@ -149,7 +149,7 @@ typedef struct PfbEnvConfig {
   int32_t max_steps;         /* agent_hz * max_duration_seconds                                      */
   int32_t angle_representation; /* 0 euler, 1 quaternion                                             */
   int32_t sparse_reward;
-  int32_t autoreset;         /* 1: SAME_STEP autoreset inside pfb_env_step                           */
+  int32_t autoreset;         /* 1: NEXT_STEP autoreset inside pfb_env_step (gymnasium's default)     */
   int32_t warmup_steps;      /* 10 Aviary steps after reset (quadx_base_env.py:209-210)              */
   double flight_dome_size;
   double goal_reach_distance, goal_reach_angle;  /* waypoint envs                                    */
@@ -172,7 +172,7 @@ typedef struct PfbBuffers {
   uint8_t* term;             /* [N]                                                                  */
   uint8_t* trunc;            /* [N]                                                                  */
   uint8_t* info;             /* [N] bit0 out_of_bounds, bit1 collision, bit2 env_complete            */
-  float* final_obs;          /* [N][O] terminal observation of envs that autoreset (nullable)        */
+  float* final_obs;          /* reserved (NEXT_STEP autoreset returns the terminal obs itself)       */
   /* outputs of pfb_observe_state (Aviary.state / aux_state) */
   float* drone_state;        /* [N][12] = state(i) (4,3) flattened: ang_vel_b, euler, lin_vel_b, pos */
   float* aux_state;          /* [N][A]                                                               */

@@ -82,6 +82,14 @@ PFB_HD Vec3 mulT(const Mat3& R, Vec3 v) {
 }
 
 PFB_HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+// a / b to ~2 ulp without the IEEE slow path (used where the reference's result is clipped anyway)
+PFB_HD float fast_div(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fdividef(a, b);
+#else
+  return a / b;
+#endif
+}
 // -sign(v) * k * v^2  ==  -k * v * |v|   (boring_bodies.py:115-119, quadx.py:502-506)
 PFB_HD float signed_square(float v) { return v * fabsf(v); }
 

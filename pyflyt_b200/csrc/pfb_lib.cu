@@ -55,9 +55,11 @@ struct PfbContext {
   PfbBuffers buf;
   bool bound;
   int mode;               // Aviary-level flight mode
-  int32_t* d_counters;    // [4] ping-pong done-list counters
-  int32_t* d_done_list;   // [N]
-  uint64_t step_seq;      // env.step() calls so far (selects the ping-pong counter, seeds random actions)
+  int32_t* d_counters;    // [3] rotating done-list counters: step k appends to [k%3], reads [(k-1)%3], zeroes [(k+1)%3]
+  int32_t* d_done_list;   // [2][N] ping-pong lists of envs that finished on a step
+  uint64_t step_seq;      // env.step() calls so far (selects counters/lists, keys the Philox streams)
+  uint64_t aviary_seq;    // pfb_aviary_step calls so far
+  uint64_t reset_seq;     // pfb_env_reset calls so far
   int64_t launches;
   int sm_count;
   // optional per-step CUDA-event pairs around the dominant kernel (bench.py's roofline leg)
@@ -66,7 +68,8 @@ struct PfbContext {
   int prof_n;
 };
 
-constexpr int kBlock = 64;  // 65536 envs -> 1024 CTAs over 148 SMs: <1.2% wave imbalance
+constexpr int kBlock = 64;     // 65536 envs -> 1024 CTAs over 148 SMs: <1.2% wave imbalance
+constexpr int kMinBlocks = 7;  // 7 CTAs/SM resident (<= 146 regs/thread): all 1024 CTAs in ONE wave
 
 static inline int grid_for(int64_t n) { return (int)((n + kBlock - 1) / kBlock); }
 
@@ -83,28 +86,30 @@ struct InjectedNoise {  // parity tests: the CPU-drawn sequence, [substep][N]
   }
 };
 
-struct PhiloxNoise {  // throughput: N(noise_loc, 1) from a counter RNG keyed by (seed, env, draw index)
-  uint32_t k0, k1, env_lo, env_hi;
-  uint32_t draw;  // physics-step index of the next draw
+// Throughput path: N(noise_loc, 1) from Philox4x32-10, counter = (global env id, call sequence number,
+// stream tag | block).  Stateless: nothing is stored per env, and a trajectory does not depend on how
+// the batch is sharded over GPUs.
+enum { TAG_AVIARY = 0, TAG_ENV_STEP = 1, TAG_RESET = 2, TAG_ACTION = 3 };
+struct PhiloxNoise {
+  uint32_t k0, k1, env_lo, env_hi, seq, tag;
+  uint32_t idx;
   float loc;
-  float cache[4];
-  __device__ __forceinline__ void refill() {
-    U4 r = philox4x32_10(U4{env_lo, env_hi, draw >> 2, 0u}, k0, k1);
-    box_muller(r.x, r.y, cache[0], cache[1]);
-    box_muller(r.z, r.w, cache[2], cache[3]);
-  }
-  __device__ __forceinline__ void init(const RngParams& r, int64_t i, uint32_t draw0, float loc_) {
+  float c0, c1, c2, c3;
+  __device__ __forceinline__ void init(const RngParams& r, int64_t i, uint32_t seq_, uint32_t tag_, float loc_) {
     k0 = r.k0; k1 = r.k1;
     uint64_t g = ((uint64_t)r.env_offset_hi << 32 | r.env_offset_lo) + (uint64_t)i;
     env_lo = (uint32_t)g; env_hi = (uint32_t)(g >> 32);
-    draw = draw0; loc = loc_;
-    refill();
+    seq = seq_; tag = tag_ << 24; idx = 0; loc = loc_;
   }
   __device__ __forceinline__ float operator()() {
-    int k = draw & 3u;
-    float z = k == 0 ? cache[0] : (k == 1 ? cache[1] : (k == 2 ? cache[2] : cache[3]));
-    ++draw;
-    if ((draw & 3u) == 0u) refill();
+    uint32_t k = idx & 3u;
+    if (k == 0u) {
+      U4 r = philox4x32_10(U4{env_lo, env_hi, seq, tag | (idx >> 2)}, k0, k1);
+      box_muller(r.x, r.y, c0, c1);
+      box_muller(r.z, r.w, c2, c3);
+    }
+    ++idx;
+    float z = k == 0u ? c0 : (k == 1u ? c1 : (k == 2u ? c2 : c3));
     return loc + z;
   }
 };
@@ -122,17 +127,18 @@ struct NoiseSel<false> {
 
 template <bool INJECT>
 __device__ __forceinline__ typename NoiseSel<INJECT>::type make_noise(const float* noise, int64_t N, int64_t i,
-                                                                      const RngParams& r, uint32_t draw0, float loc);
+                                                                      const RngParams& r, uint32_t seq, uint32_t tag,
+                                                                      float loc);
 template <>
 __device__ __forceinline__ InjectedNoise make_noise<true>(const float* noise, int64_t N, int64_t i, const RngParams&,
-                                                          uint32_t, float) {
+                                                          uint32_t, uint32_t, float) {
   return InjectedNoise{noise + i, N};
 }
 template <>
 __device__ __forceinline__ PhiloxNoise make_noise<false>(const float*, int64_t, int64_t i, const RngParams& r,
-                                                         uint32_t draw0, float loc) {
+                                                         uint32_t seq, uint32_t tag, float loc) {
   PhiloxNoise n;
-  n.init(r, i, draw0, loc);
+  n.init(r, i, seq, tag, loc);
   return n;
 }
 
@@ -152,7 +158,6 @@ __global__ void __launch_bounds__(kBlock) k_quadx_reset(float* __restrict__ st, 
               start_orn[3 * i + 1], start_orn[3 * i + 2]);
   quadx_store<7>(st, ist, N, i, s);  // mode 7 touches every PID row
   ist[(int64_t)QI_STEP * N + i] = 0;
-  // QI_PHYS (the Philox draw index) is monotonic over the life of the handle: never reset
   if (setpoint) reinterpret_cast<float4*>(setpoint)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
@@ -173,21 +178,19 @@ __global__ void __launch_bounds__(kBlock) k_quadx_set_mode(float* __restrict__ s
 
 // n_steps x Aviary.step() (aviary.py:480-531)
 template <int MODE, bool INJECT>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, kMinBlocks)
     k_quadx_aviary_step(const __grid_constant__ QuadXParams p, const __grid_constant__ RngParams rng,
                         float* __restrict__ st, int32_t* __restrict__ ist, const float* __restrict__ setpoint,
-                        const float* __restrict__ noise, int n_steps, int64_t N) {
+                        const float* __restrict__ noise, int n_steps, uint32_t seq, int64_t N) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   QuadXRegs s;
   quadx_load<MODE>(st, ist, N, i, s);
   float4 sp = __ldg(reinterpret_cast<const float4*>(setpoint) + i);
   s.sp[0] = sp.x; s.sp[1] = sp.y; s.sp[2] = sp.z; s.sp[3] = sp.w;
-  uint32_t phys = (uint32_t)ist[(int64_t)QI_PHYS * N + i];
-  auto nz = make_noise<INJECT>(noise, N, i, rng, phys, p.noise_loc);
+  auto nz = make_noise<INJECT>(noise, N, i, rng, seq, TAG_AVIARY, p.noise_loc);
   for (int k = 0; k < n_steps; ++k) quadx_aviary_step<MODE>(p, s, nz);
   quadx_store<MODE>(st, ist, N, i, s);
-  ist[(int64_t)QI_PHYS * N + i] = (int32_t)(phys + (uint32_t)(n_steps * p.ratio));
 }
 
 // Aviary.state(i) / aux_state(i) / contact_array  -> row-major API buffers
@@ -213,161 +216,155 @@ __global__ void __launch_bounds__(kBlock) k_quadx_observe(const float* __restric
 // ---------------------------------------------------------------------------------------------------
 // kernels — QuadX-Hover env
 // ---------------------------------------------------------------------------------------------------
-constexpr int kObsMax = 21;
 constexpr int kObsStride = 21;  // odd stride: conflict-free shared-memory transpose for O = 20 or 21
 
-// block-cooperative, fully coalesced write of this block's observations into obs[N][O]
-__device__ __forceinline__ void write_obs_block(float* smem, const float* my_obs, bool active, int O,
-                                                float* __restrict__ obs, int64_t block_first, int64_t N) {
-  if (active) {
-#pragma unroll
-    for (int k = 0; k < kObsMax; ++k)
-      if (k < O) smem[threadIdx.x * kObsStride + k] = my_obs[k];
-  }
-  __syncthreads();
-  int64_t rows = N - block_first;
-  if (rows > kBlock) rows = kBlock;
-  int total = (int)rows * O;
-  float* dst = obs + block_first * O;
-  for (int j = threadIdx.x; j < total; j += kBlock) {
-    int r = j / O, c = j - r * O;
-    dst[j] = smem[r * kObsStride + c];
-  }
-}
-
-// env.step(action) for every env (quadx_base_env.py:269-301 + quadx_hover_env.py).
-// RANDACT: actions are drawn on device, uniform in the env's action box (quadx_base_env.py:79-102).
-template <int MODE, bool INJECT, bool RANDACT>
-__global__ void __launch_bounds__(kBlock)
-    k_hover_step(const __grid_constant__ QuadXParams p, const __grid_constant__ HoverParams h,
-                 const __grid_constant__ RngParams rng, float* __restrict__ st, int32_t* __restrict__ ist,
-                 float* __restrict__ actions, const float* __restrict__ noise, float* __restrict__ obs,
-                 float* __restrict__ reward, uint8_t* __restrict__ term, uint8_t* __restrict__ trunc,
-                 uint8_t* __restrict__ info, int32_t* __restrict__ done_count, int32_t* __restrict__ done_list,
-                 uint32_t step_seq, int64_t N) {
-  __shared__ float smem[kBlock * kObsStride];
-  const int64_t block_first = (int64_t)blockIdx.x * kBlock;
-  const int64_t i = block_first + threadIdx.x;
-  const bool active = i < N;
-  const int O = h.angle_representation == 0 ? 20 : 21;
-  float my_obs[kObsMax];
-  if (active) {
-    QuadXRegs s;
-    quadx_load<MODE>(st, ist, N, i, s);
-    float act[4];
-    if (RANDACT) {
-      uint64_t g = ((uint64_t)rng.env_offset_hi << 32 | rng.env_offset_lo) + (uint64_t)i;
-      U4 r = philox4x32_10(U4{(uint32_t)g, (uint32_t)(g >> 32), step_seq, 0x41435431u}, rng.k0, rng.k1);
-      const float pi = 3.14159265358979323846f;
-      if (MODE == -1) {
-        act[0] = 0.8f * u32_to_unit_open(r.x); act[1] = 0.8f * u32_to_unit_open(r.y);
-        act[2] = 0.8f * u32_to_unit_open(r.z); act[3] = 0.8f * u32_to_unit_open(r.w);
-      } else {
-        act[0] = pi * (2.0f * u32_to_unit_open(r.x) - 1.0f); act[1] = pi * (2.0f * u32_to_unit_open(r.y) - 1.0f);
-        act[2] = pi * (2.0f * u32_to_unit_open(r.z) - 1.0f); act[3] = 0.8f * u32_to_unit_open(r.w);
-      }
-      reinterpret_cast<float4*>(actions)[i] = make_float4(act[0], act[1], act[2], act[3]);
-    } else {
-      float4 a4 = __ldg(reinterpret_cast<const float4*>(actions) + i);
-      act[0] = a4.x; act[1] = a4.y; act[2] = a4.z; act[3] = a4.w;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) s.sp[k] = act[k];
-    int step_count = ist[(int64_t)QI_STEP * N + i];
-    uint32_t phys = (uint32_t)ist[(int64_t)QI_PHYS * N + i];
-    auto nz = make_noise<INJECT>(noise, N, i, rng, phys, p.noise_loc);
-    float rew = -0.1f;
-    int done_steps = 0;
-    for (int k = 0; k < h.env_step_ratio; ++k) {
-      if (s.flags & (FLAG_TERM | FLAG_TRUNC)) break;  // quadx_base_env.py:289-290
-      quadx_aviary_step<MODE>(p, s, nz);
-      hover_term_trunc_reward(h, s, step_count, rew);
-      ++done_steps;
-    }
-    step_count += 1;
-    hover_observation(h, s, act, my_obs);
-    quadx_store<MODE>(st, ist, N, i, s);
-    ist[(int64_t)QI_STEP * N + i] = step_count;
-    ist[(int64_t)QI_PHYS * N + i] = (int32_t)(phys + (uint32_t)(done_steps * p.ratio));
-    reward[i] = rew;
-    term[i] = (s.flags & FLAG_TERM) ? 1 : 0;
-    trunc[i] = (s.flags & FLAG_TRUNC) ? 1 : 0;
-    if (info) info[i] = (uint8_t)(((s.flags & FLAG_OOB) ? 1 : 0) | ((s.flags & FLAG_COLLISION) ? 2 : 0));
-    // queue finished episodes for the dense autoreset pass (warp-aggregated append)
-    if (done_list) {
-      bool done = (s.flags & (FLAG_TERM | FLAG_TRUNC)) != 0;
-      unsigned m = __ballot_sync(__activemask(), done);
-      if (done) {
-        int lane = threadIdx.x & 31;
-        int leader = __ffs(m) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(done_count, __popc(m));
-        base = __shfl_sync(m, base, leader);
-        done_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
-      }
-    }
-  }
-  write_obs_block(smem, my_obs, active, O, obs, block_first, N);
-}
-
-// env.reset() body for one env: begin_reset + end_reset (quadx_base_env.py:149-212)
+// env.reset() body for one env: begin_reset + end_reset (quadx_base_env.py:149-212); obs -> `out`
 template <int MODE, bool INJECT>
 __device__ __forceinline__ void hover_reset_env(const QuadXParams& p, const HoverParams& h, const RngParams& rng,
                                                 float* __restrict__ st, int32_t* __restrict__ ist,
                                                 const float* __restrict__ start_pos, const float* __restrict__ start_orn,
-                                                const float* __restrict__ noise, int64_t N, int64_t i, float* my_obs) {
+                                                const float* __restrict__ noise, uint32_t seq, int64_t N, int64_t i,
+                                                float* out) {
   QuadXRegs s;
   quadx_reset(s, start_pos[3 * i + 0], start_pos[3 * i + 1], start_pos[3 * i + 2], start_orn[3 * i + 0],
               start_orn[3 * i + 1], start_orn[3 * i + 2]);
   quadx_set_mode<MODE>(s);
-  uint32_t phys = (uint32_t)ist[(int64_t)QI_PHYS * N + i];
-  auto nz = make_noise<INJECT>(noise, N, i, rng, phys, p.noise_loc);
+  auto nz = make_noise<INJECT>(noise, N, i, rng, seq, TAG_RESET, p.noise_loc);
   for (int k = 0; k < h.warmup_steps; ++k) quadx_aviary_step<MODE>(p, s, nz);
   const float zero[4] = {0.f, 0.f, 0.f, 0.f};  // self.action = zeros (quadx_base_env.py:165)
-  hover_observation(h, s, zero, my_obs);
+  hover_observation(h, s, zero, out);
   quadx_store<7>(st, ist, N, i, s);
   ist[(int64_t)QI_STEP * N + i] = 0;
-  ist[(int64_t)QI_PHYS * N + i] = (int32_t)(phys + (uint32_t)(h.warmup_steps * p.ratio));
 }
 
-// env.reset() for all / masked envs; observations written coalesced
+// env.step(action) for every env (quadx_base_env.py:269-301 + quadx_hover_env.py), ONE launch.
+//   RANDACT   actions are drawn on device, uniform in the env's action box (quadx_base_env.py:79-102)
+//   AUTORESET gymnasium NEXT_STEP autoreset: an env that finished on the previous call is reset on this
+//             one (its action is ignored; obs = first observation, reward 0, flags cleared).  Those envs
+//             were queued by the previous launch and are handled by dense "tail" CTAs placed at the
+//             front of the grid, so the 20 warm-up substeps run in full warps concurrently with the
+//             regular CTAs instead of diverging inside them.
+template <int MODE, bool INJECT, bool RANDACT, bool AUTORESET>
+__global__ void __launch_bounds__(kBlock, kMinBlocks)
+    k_hover_step(const __grid_constant__ QuadXParams p, const __grid_constant__ HoverParams h,
+                 const __grid_constant__ RngParams rng, float* __restrict__ st, int32_t* __restrict__ ist,
+                 float* __restrict__ actions, const float* __restrict__ noise, float* __restrict__ obs,
+                 float* __restrict__ reward, uint8_t* __restrict__ term, uint8_t* __restrict__ trunc,
+                 uint8_t* __restrict__ info, const float* __restrict__ start_pos, const float* __restrict__ start_orn,
+                 const int32_t* __restrict__ prev_count, const int32_t* __restrict__ prev_list,
+                 int32_t* __restrict__ cur_count, int32_t* __restrict__ cur_list, int32_t* __restrict__ next_count,
+                 int tail_blocks, uint32_t step_seq, int64_t N) {
+  __shared__ float smem[kBlock * kObsStride];
+  __shared__ uint8_t row_skip[kBlock];
+  const int O = h.angle_representation == 0 ? 20 : 21;
+
+  if (AUTORESET && (int)blockIdx.x < tail_blocks) {
+    // ---- tail role: reset the envs that finished on the previous call
+    if (blockIdx.x == 0 && threadIdx.x == 0) *next_count = 0;  // arm the counter the NEXT launch appends to
+    const int count = *prev_count;
+    for (int t = blockIdx.x * kBlock + threadIdx.x; t < count; t += tail_blocks * kBlock) {
+      const int64_t i = prev_list[t];
+      float* row = smem + threadIdx.x * kObsStride;
+      hover_reset_env<MODE, false>(p, h, rng, st, ist, start_pos, start_orn, nullptr, step_seq, N, i, row);
+      float* dst = obs + i * O;
+      for (int k = 0; k < O; ++k) dst[k] = row[k];
+      reward[i] = 0.0f;
+      term[i] = 0;
+      trunc[i] = 0;
+      if (info) info[i] = 0;
+    }
+    return;
+  }
+
+  const int64_t block_first = (int64_t)((int)blockIdx.x - (AUTORESET ? tail_blocks : 0)) * kBlock;
+  const int64_t i = block_first + threadIdx.x;
+  const bool active = i < N;
+  bool skip = !active;
+  if (active) {
+    QuadXRegs s;
+    quadx_load<MODE>(st, ist, N, i, s);
+    if (AUTORESET && (s.flags & (FLAG_TERM | FLAG_TRUNC))) {
+      skip = true;  // a tail CTA owns this env for this call
+    } else {
+      float act[4];
+      if (RANDACT) {
+        uint64_t g = ((uint64_t)rng.env_offset_hi << 32 | rng.env_offset_lo) + (uint64_t)i;
+        U4 r = philox4x32_10(U4{(uint32_t)g, (uint32_t)(g >> 32), step_seq, (uint32_t)TAG_ACTION << 24}, rng.k0, rng.k1);
+        const float pi = 3.14159265358979323846f;
+        if (MODE == -1) {
+          act[0] = 0.8f * u32_to_unit_open(r.x); act[1] = 0.8f * u32_to_unit_open(r.y);
+          act[2] = 0.8f * u32_to_unit_open(r.z); act[3] = 0.8f * u32_to_unit_open(r.w);
+        } else {
+          act[0] = pi * (2.0f * u32_to_unit_open(r.x) - 1.0f); act[1] = pi * (2.0f * u32_to_unit_open(r.y) - 1.0f);
+          act[2] = pi * (2.0f * u32_to_unit_open(r.z) - 1.0f); act[3] = 0.8f * u32_to_unit_open(r.w);
+        }
+        reinterpret_cast<float4*>(actions)[i] = make_float4(act[0], act[1], act[2], act[3]);
+      } else {
+        float4 a4 = __ldg(reinterpret_cast<const float4*>(actions) + i);
+        act[0] = a4.x; act[1] = a4.y; act[2] = a4.z; act[3] = a4.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s.sp[k] = act[k];
+      int step_count = ist[(int64_t)QI_STEP * N + i];
+      auto nz = make_noise<INJECT>(noise, N, i, rng, step_seq, TAG_ENV_STEP, p.noise_loc);
+      float rew = -0.1f;
+      for (int k = 0; k < h.env_step_ratio; ++k) {
+        if (s.flags & (FLAG_TERM | FLAG_TRUNC)) break;  // quadx_base_env.py:289-290
+        quadx_aviary_step<MODE>(p, s, nz);
+        hover_term_trunc_reward(h, s, step_count, rew);
+      }
+      step_count += 1;
+      hover_observation(h, s, act, smem + threadIdx.x * kObsStride);
+      quadx_store<MODE>(st, ist, N, i, s);
+      ist[(int64_t)QI_STEP * N + i] = step_count;
+      reward[i] = rew;
+      term[i] = (s.flags & FLAG_TERM) ? 1 : 0;
+      trunc[i] = (s.flags & FLAG_TRUNC) ? 1 : 0;
+      if (info) info[i] = (uint8_t)(((s.flags & FLAG_OOB) ? 1 : 0) | ((s.flags & FLAG_COLLISION) ? 2 : 0));
+      if (AUTORESET) {  // queue finished episodes for the next launch's tail CTAs (warp-aggregated append)
+        bool done = (s.flags & (FLAG_TERM | FLAG_TRUNC)) != 0;
+        unsigned m = __ballot_sync(__activemask(), done);
+        if (done) {
+          int lane = threadIdx.x & 31;
+          int leader = __ffs(m) - 1;
+          int base = 0;
+          if (lane == leader) base = atomicAdd(cur_count, __popc(m));
+          base = __shfl_sync(m, base, leader);
+          cur_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+        }
+      }
+    }
+  }
+  // ---- block-cooperative, fully coalesced write of this CTA's observations into obs[N][O]
+  row_skip[threadIdx.x] = skip ? 1 : 0;
+  __syncthreads();
+  int64_t rows = N - block_first;
+  if (rows > kBlock) rows = kBlock;
+  const int total = (int)rows * O;
+  float* dst = obs + block_first * O;
+  for (int j = threadIdx.x; j < total; j += kBlock) {
+    int r = j / O, c = j - r * O;
+    if (!row_skip[r]) dst[j] = smem[r * kObsStride + c];
+  }
+}
+
+// env.reset() for all / masked envs
 template <int MODE, bool INJECT>
 __global__ void __launch_bounds__(kBlock)
     k_hover_reset(const __grid_constant__ QuadXParams p, const __grid_constant__ HoverParams h,
                   const __grid_constant__ RngParams rng, float* __restrict__ st, int32_t* __restrict__ ist,
                   const float* __restrict__ start_pos, const float* __restrict__ start_orn,
-                  const uint8_t* __restrict__ mask, const float* __restrict__ noise, float* __restrict__ obs, int64_t N) {
+                  const uint8_t* __restrict__ mask, const float* __restrict__ noise, float* __restrict__ obs,
+                  uint32_t seq, int64_t N) {
+  __shared__ float smem[kBlock * kObsStride];
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (i >= N) return;
   if (mask && !mask[i]) return;
   const int O = h.angle_representation == 0 ? 20 : 21;
-  float my_obs[kObsMax];
-  hover_reset_env<MODE, INJECT>(p, h, rng, st, ist, start_pos, start_orn, noise, N, i, my_obs);
+  float* row = smem + threadIdx.x * kObsStride;
+  hover_reset_env<MODE, INJECT>(p, h, rng, st, ist, start_pos, start_orn, noise, seq, N, i, row);
   if (obs) {
-    for (int k = 0; k < O; ++k) obs[i * O + k] = my_obs[k];
-  }
-}
-
-// SAME_STEP autoreset: a dense pass over the envs the step kernel queued.  Threads are assigned to
-// list slots, so the 20 warm-up substeps run in full warps instead of diverging inside k_hover_step.
-template <int MODE>
-__global__ void __launch_bounds__(kBlock)
-    k_hover_autoreset(const __grid_constant__ QuadXParams p, const __grid_constant__ HoverParams h,
-                      const __grid_constant__ RngParams rng, float* __restrict__ st, int32_t* __restrict__ ist,
-                      const float* __restrict__ start_pos, const float* __restrict__ start_orn, float* __restrict__ obs,
-                      float* __restrict__ final_obs, const int32_t* __restrict__ done_count,
-                      const int32_t* __restrict__ done_list, int32_t* __restrict__ next_count, int64_t N) {
-  const int count = *done_count;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *next_count = 0;  // arm the other ping-pong counter
-  const int O = h.angle_representation == 0 ? 20 : 21;
-  for (int t = blockIdx.x * kBlock + threadIdx.x; t < count; t += gridDim.x * kBlock) {
-    const int64_t i = done_list[t];
-    if (final_obs) {
-      for (int k = 0; k < O; ++k) final_obs[i * O + k] = obs[i * O + k];
-    }
-    float my_obs[kObsMax];
-    hover_reset_env<MODE, false>(p, h, rng, st, ist, start_pos, start_orn, nullptr, N, i, my_obs);
-    for (int k = 0; k < O; ++k) obs[i * O + k] = my_obs[k];
+    for (int k = 0; k < O; ++k) obs[i * O + k] = row[k];
   }
 }
 
@@ -434,7 +431,7 @@ int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, i
   c->sm_count = prop.multiProcessorCount;
   CUDA_OK(cudaMalloc(&c->d_counters, 4 * sizeof(int32_t)));
   CUDA_OK(cudaMemset(c->d_counters, 0, 4 * sizeof(int32_t)));
-  CUDA_OK(cudaMalloc(&c->d_done_list, (size_t)n_envs * sizeof(int32_t)));
+  CUDA_OK(cudaMalloc(&c->d_done_list, 2 * (size_t)n_envs * sizeof(int32_t)));
   *out = c;
   return 0;
 }
@@ -512,12 +509,13 @@ int pfb_aviary_step(PfbHandle h, int n_steps, const float* noise, void* stream) 
   if (n_steps <= 0) return fail("n_steps must be positive");
   cudaStream_t s = (cudaStream_t)stream;
   const int mode = h->mode;
+  const uint32_t seq = (uint32_t)h->aviary_seq++;
   if (noise) {
     PFB_MODE_SWITCH(mode, (k_quadx_aviary_step<MODE, true><<<grid_for(h->n), kBlock, 0, s>>>(
-                              h->qx, h->rng, h->buf.state, h->buf.istate, h->buf.setpoint, noise, n_steps, h->n)));
+                              h->qx, h->rng, h->buf.state, h->buf.istate, h->buf.setpoint, noise, n_steps, seq, h->n)));
   } else {
     PFB_MODE_SWITCH(mode, (k_quadx_aviary_step<MODE, false><<<grid_for(h->n), kBlock, 0, s>>>(
-                              h->qx, h->rng, h->buf.state, h->buf.istate, h->buf.setpoint, nullptr, n_steps, h->n)));
+                              h->qx, h->rng, h->buf.state, h->buf.istate, h->buf.setpoint, nullptr, n_steps, seq, h->n)));
   }
   LAUNCH_CHECK(h);
   return 0;
@@ -542,14 +540,16 @@ int pfb_env_reset(PfbHandle h, const uint8_t* mask, const float* noise, void* st
   if (require_env(h)) return -1;
   cudaStream_t s = (cudaStream_t)stream;
   const int mode = h->hover.flight_mode;
+  // resets draw from their own Philox stream; the high bit keeps them apart from in-step autoresets
+  const uint32_t seq = 0x80000000u | (uint32_t)h->reset_seq++;
   if (noise) {
     PFB_MODE_SWITCH(mode, (k_hover_reset<MODE, true><<<grid_for(h->n), kBlock, 0, s>>>(
                               h->qx, h->hover, h->rng, h->buf.state, h->buf.istate, h->buf.start_pos, h->buf.start_orn, mask,
-                              noise, h->buf.obs, h->n)));
+                              noise, h->buf.obs, seq, h->n)));
   } else {
     PFB_MODE_SWITCH(mode, (k_hover_reset<MODE, false><<<grid_for(h->n), kBlock, 0, s>>>(
                               h->qx, h->hover, h->rng, h->buf.state, h->buf.istate, h->buf.start_pos, h->buf.start_orn, mask,
-                              nullptr, h->buf.obs, h->n)));
+                              nullptr, h->buf.obs, seq, h->n)));
   }
   LAUNCH_CHECK(h);
   h->mode = mode;
@@ -559,36 +559,49 @@ int pfb_env_reset(PfbHandle h, const uint8_t* mask, const float* noise, void* st
 static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool randact, cudaStream_t s) {
   const int mode = h->hover.flight_mode;
   const bool autoreset = h->env.autoreset != 0;
-  int32_t* cnt = h->d_counters + (h->step_seq & 1);
-  int32_t* cnt_next = h->d_counters + ((h->step_seq + 1) & 1);
-  int32_t* list = autoreset ? h->d_done_list : nullptr;
-  const uint32_t seq = (uint32_t)h->step_seq;
-#define STEP_ARGS h->qx, h->hover, h->rng, h->buf.state, h->buf.istate, actions, noise, h->buf.obs, h->buf.reward, \
-                  h->buf.term, h->buf.trunc, h->buf.info, cnt, list, seq, h->n
+  const uint64_t k = h->step_seq;
+  int32_t* cnt_cur = h->d_counters + (k % 3);
+  int32_t* cnt_prev = h->d_counters + ((k + 2) % 3);
+  int32_t* cnt_next = h->d_counters + ((k + 1) % 3);
+  int32_t* list_cur = h->d_done_list + (k & 1) * h->n;
+  int32_t* list_prev = h->d_done_list + ((k + 1) & 1) * h->n;
+  const uint32_t seq = (uint32_t)k;
+  // tail CTAs (front of the grid) reset the envs that finished on the previous call; one per SM is
+  // plenty for the ~1-3 % of envs that finish per step, and the loop is grid-strided anyway
+  int tail = 0;
+  if (autoreset) {
+    tail = h->sm_count;
+    int need = grid_for(h->n);
+    if (tail > need) tail = need;
+  }
+  const int grid = grid_for(h->n) + tail;
   const bool prof = h->prof_ev && h->prof_n < h->prof_cap;
   if (prof) CUDA_OK(cudaEventRecord(h->prof_ev[2 * h->prof_n], s));
-  if (noise) {
-    PFB_MODE_SWITCH(mode, (k_hover_step<MODE, true, false><<<grid_for(h->n), kBlock, 0, s>>>(STEP_ARGS)));
-  } else if (randact) {
-    PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, true><<<grid_for(h->n), kBlock, 0, s>>>(STEP_ARGS)));
+#define STEP_ARGS h->qx, h->hover, h->rng, h->buf.state, h->buf.istate, actions, noise, h->buf.obs, h->buf.reward,     \
+                  h->buf.term, h->buf.trunc, h->buf.info, h->buf.start_pos, h->buf.start_orn, cnt_prev, list_prev, \
+                  cnt_cur, list_cur, cnt_next, tail, seq, h->n
+  if (autoreset) {
+    if (noise) {
+      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, true, false, true><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
+    } else if (randact) {
+      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, true, true><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
+    } else {
+      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, false, true><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
+    }
   } else {
-    PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, false><<<grid_for(h->n), kBlock, 0, s>>>(STEP_ARGS)));
+    if (noise) {
+      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, true, false, false><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
+    } else if (randact) {
+      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, true, false><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
+    } else {
+      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, false, false><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
+    }
   }
 #undef STEP_ARGS
   LAUNCH_CHECK(h);
   if (prof) {
     CUDA_OK(cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], s));
     h->prof_n += 1;
-  }
-  if (autoreset) {
-    // a few CTAs per SM are plenty for the ~1-3% of envs that finish per step; grid-strided
-    int blocks = h->sm_count * 2;
-    int need = grid_for(h->n);
-    if (blocks > need) blocks = need;
-    PFB_MODE_SWITCH(mode, (k_hover_autoreset<MODE><<<blocks, kBlock, 0, s>>>(
-                              h->qx, h->hover, h->rng, h->buf.state, h->buf.istate, h->buf.start_pos, h->buf.start_orn,
-                              h->buf.obs, h->buf.final_obs, cnt, h->d_done_list, cnt_next, h->n)));
-    LAUNCH_CHECK(h);
   }
   h->step_seq += 1;
   return 0;

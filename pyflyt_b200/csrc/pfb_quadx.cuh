@@ -81,7 +81,7 @@ enum {
   QX_ROWS = 55
 };
 // istate rows [I][N]
-enum { QI_STEP = 0, QI_FLAGS = 1, QI_PHYS = 2, QI_ROWS = 3 };
+enum { QI_STEP = 0, QI_FLAGS = 1, QI_ROWS = 2 };
 enum { FLAG_TERM = 1, FLAG_TRUNC = 2, FLAG_OOB = 4, FLAG_COLLISION = 8, FLAG_CONTACT_PREV = 16, FLAG_CONTACT_ARRAY = 32 };
 
 template <typename T>
@@ -219,8 +219,8 @@ PFB_HD void quadx_update_control(const QuadXParams& p, QuadXRegs& s) {
   float low = fminf(fminf(m0, m1), fminf(m2, m3));
   if (high != low) {
     float pwm_max = fminf(high, 1.0f), pwm_min = fmaxf(low, 0.05f);
-    float ka = (pwm_min - low) / (pwm_max - low);
-    float ks = (high - pwm_max) / (high - pwm_min);
+    float ka = fast_div(pwm_min - low, pwm_max - low);
+    float ks = fast_div(high - pwm_max, high - pwm_min);
     m0 += ka * (pwm_max - m0) - ks * (m0 - pwm_min);
     m1 += ka * (pwm_max - m1) - ks * (m1 - pwm_min);
     m2 += ka * (pwm_max - m2) - ks * (m2 - pwm_min);
@@ -238,9 +238,9 @@ PFB_HD bool quadx_ground_contact(const QuadXParams& p, const QuadXRegs& s) {
   const float r20 = (float)s.R.m20, r21 = (float)s.R.m21, r22 = (float)s.R.m22;
   const float pz = (float)s.pz;
   bool hit = false;
-#pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    if (k < p.n_shapes) {
+#pragma unroll 1
+  for (int k = 0; k < p.n_shapes; ++k) {
+    {
       float cz = pz + r20 * p.shape_at[k][0] + r21 * p.shape_at[k][1] + r22 * p.shape_at[k][2];
       float extent;
       if (p.shape_kind[k] == 0) {
@@ -320,15 +320,22 @@ PFB_HD void quadx_substep(const QuadXParams& p, QuadXRegs& s, float xi) {
     s.wy = (float)R.m01 * ox + (float)R.m11 * oy + (float)R.m21 * oz;
     s.wz = (float)R.m02 * ox + (float)R.m12 * oy + (float)R.m22 * oz;
   }
-  // ---- attitude: q <- q * dq(w_b dt), exp-map increment in fp32, product + renormalisation in qreal
-  float ang = sqrtf(s.wx * s.wx + s.wy * s.wy + s.wz * s.wz);
+  // ---- attitude: q <- q * dq(w_b dt).  dq = (w sin(h)/|w|, cos h), h = |w| dt / 2.  With
+  // h^2 = |w|^2 dt^2 / 4 <= 0.13 (|w| <= sqrt(3) vmax) both factors are short even series in h^2:
+  // sin(h)/|w| = dt/2 * sinc(h), cos(h) — no sqrt, no division, no range reduction, and the series
+  // IS Bullet's small-angle branch (btTransformUtil), continued to fp32 round-off.
+  float h2 = (s.wx * s.wx + s.wy * s.wy + s.wz * s.wz) * (0.25f * p.dt * p.dt);
   float scale, cw;
-  if (ang < 0.001f) {
-    scale = 0.5f * p.dt - (p.dt * p.dt * p.dt) * 0.020833333333f * ang * ang;
-    cw = 1.0f - 0.125f * (ang * p.dt) * (ang * p.dt);
-  } else {
+  if (h2 <= 0.25f) {
+    float sinc = fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, 2.7557319e-6f, -1.9841270e-4f), 8.3333333e-3f), -1.6666667e-1f), 1.0f);
+    scale = 0.5f * p.dt * sinc;
+    cw = fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, -2.7557319e-7f, 2.4801587e-5f), -1.3888889e-3f), 4.1666667e-2f), -0.5f), 1.0f);
+  } else {  // unreachable with the default velocity clamp; kept for exotic vmax
+    float ang = sqrtf(h2) * (2.0f / p.dt);
+    float lim = 0.78539816339f / p.dt;  // ANGULAR_MOTION_THRESHOLD
+    if (ang > lim) ang = lim;
     float half = 0.5f * ang * p.dt;
-    scale = sinf(half) / ang;
+    scale = sinf(half) / (sqrtf(h2) * (2.0f / p.dt));
     cw = cosf(half);
   }
   qreal dx = (qreal)(s.wx * scale), dy = (qreal)(s.wy * scale), dz = (qreal)(s.wz * scale), dw = (qreal)cw;
@@ -517,17 +524,45 @@ PFB_HD void hover_term_trunc_reward(const HoverParams& h, QuadXRegs& s, int step
 }
 
 // quadx_hover_env.py:85-115: [ang_vel, (euler | quat(euler)), lin_vel, lin_pos, action, aux]
-PFB_HD int hover_observation(const HoverParams& h, const QuadXRegs& s, const float* action, float* obs) {
-  float roll, pitch, yaw;
-  euler_from_quat((float)s.qx, (float)s.qy, (float)s.qz, (float)s.qw, roll, pitch, yaw);
+// The reference's quaternion observation is getQuaternionFromEuler(getEulerFromQuaternion(q)) — the
+// same rotation as q, with the sign that setEulerZYX produces from principal-range angles.  Outside the
+// gimbal-lock branch that is +-q, and the sign follows from half-angle tangents (no trig needed).
+PFB_HD void hover_observation(const HoverParams& h, const QuadXRegs& s, const float* action, float* obs) {
+  const float x = (float)s.qx, y = (float)s.qy, z = (float)s.qz, w = (float)s.qw;
   int o = 0;
   obs[o++] = s.wx; obs[o++] = s.wy; obs[o++] = s.wz;
   if (h.angle_representation == 0) {
+    float roll, pitch, yaw;
+    euler_from_quat(x, y, z, w, roll, pitch, yaw);
     obs[o++] = roll; obs[o++] = pitch; obs[o++] = yaw;
   } else {
-    float x, y, z, w;
-    quat_from_euler(roll, pitch, yaw, x, y, z, w);
-    obs[o++] = x; obs[o++] = y; obs[o++] = z; obs[o++] = w;
+    float sarg = -2.0f * (x * z - w * y);
+    float ox, oy, oz, ow;
+    if (fabsf(sarg) >= 0.99999f) {  // gimbal lock: the reference rebuilds q from clamped angles
+      float roll, pitch, yaw;
+      euler_from_quat(x, y, z, w, roll, pitch, yaw);
+      quat_from_euler(roll, pitch, yaw, ox, oy, oz, ow);
+    } else {
+      float sqx = x * x, sqy = y * y, sqz = z * z, sqw = w * w;
+      float ra = 2.0f * (y * z + w * x), rb = sqw - sqx - sqy + sqz;  // roll = atan2(ra, rb)
+      float ya = 2.0f * (x * y + w * z), yb = sqw + sqx - sqy - sqz;  // yaw  = atan2(ya, yb)
+      // w_e = cr cp cy + sr sp sy with cr, cp, cy >= 0: negative only if the sines' product is negative
+      // and tan(|roll|/2) tan(|pitch|/2) tan(|yaw|/2) > 1;  tan(a/2) = |sin a| / (1 + cos a)
+      float tr_n = fabsf(ra), tr_d = sqrtf(ra * ra + rb * rb) + rb;
+      float ty_n = fabsf(ya), ty_d = sqrtf(ya * ya + yb * yb) + yb;
+      float tp_n = fabsf(sarg), tp_d = 1.0f + sqrtf(fmaxf(0.0f, 1.0f - sarg * sarg));
+      bool sines_negative = (ra * sarg * ya) < 0.0f;
+      bool we_negative = sines_negative && (tr_n * tp_n * ty_n > tr_d * tp_d * ty_d);
+      float sgn = ((w < 0.0f) != we_negative) ? -1.0f : 1.0f;
+      if (w == 0.0f) {  // measure-zero tie: decide on the reference's own formula
+        float roll, pitch, yaw;
+        euler_from_quat(x, y, z, w, roll, pitch, yaw);
+        quat_from_euler(roll, pitch, yaw, ox, oy, oz, ow);
+        sgn = (ox * x + oy * y + oz * z) < 0.0f ? -1.0f : 1.0f;
+      }
+      ox = sgn * x; oy = sgn * y; oz = sgn * z; ow = sgn * w;
+    }
+    obs[o++] = ox; obs[o++] = oy; obs[o++] = oz; obs[o++] = ow;
   }
   obs[o++] = s.vb.x; obs[o++] = s.vb.y; obs[o++] = s.vb.z;
   obs[o++] = (float)s.px; obs[o++] = (float)s.py; obs[o++] = (float)s.pz;
@@ -535,7 +570,6 @@ PFB_HD int hover_observation(const HoverParams& h, const QuadXRegs& s, const flo
   for (int k = 0; k < 4; ++k) obs[o++] = action[k];
 #pragma unroll
   for (int k = 0; k < 4; ++k) obs[o++] = s.thr[k];
-  return o;
 }
 
 }  // namespace pfb

@@ -111,18 +111,16 @@ class QuadXHoverVecEnv:
         return obs, self._info()
 
     def step(self, actions: torch.Tensor, noise=None):
-        """env.step(action) for every env: quadx_base_env.py:269-301.  With ``autoreset`` the envs that
-        finished are reset in the same call (gymnasium's SAME_STEP mode): ``obs`` then holds the first
-        observation of the new episode and ``info['final_obs']`` the terminal one."""
+        """env.step(action) for every env: quadx_base_env.py:269-301.  With ``autoreset`` (gymnasium's
+        default NEXT_STEP mode) an env that terminated / truncated on the previous call is reset on this
+        one: its action is ignored and it returns the first observation of the new episode with reward 0
+        and both flags False — all inside the same kernel launch."""
         a = self.aviary
         if not (torch.is_tensor(actions) and actions.is_cuda and actions.dtype == torch.float32 and actions.is_contiguous()):
             a.setpoints.copy_(torch.as_tensor(actions, dtype=torch.float32, device=self.device).reshape(self.num_envs, 4))
             actions = None
         a.env_step(actions=actions, noise=noise)
-        info = self._info()
-        if self.autoreset:
-            info["final_obs"] = a.final_obs
-        return a.obs, a.reward, a.term.bool(), a.trunc.bool(), info
+        return a.obs, a.reward, a.term.bool(), a.trunc.bool(), self._info()
 
     def rollout(self, n_steps: int) -> None:
         """n_steps env steps with on-device uniform random actions (benchmark shape of BASELINE.json)."""
@@ -154,7 +152,7 @@ class QuadXHoverEnv:
             self.action_space = None
 
     def _np_info(self, info):
-        return {k: bool(v[0].item()) for k, v in info.items() if k != "final_obs"}
+        return {k: bool(v[0].item()) for k, v in info.items()}
 
     def reset(self, *, seed: None | int = None, options: None | dict[str, Any] = dict()):
         if seed is not None and seed != self._seed:

@@ -101,7 +101,6 @@ static void aviary_step_t(const QuadXParams& p, float* st, int32_t* ist, const f
     HostNoise nz{noise + i, N};
     for (int k = 0; k < n_steps; ++k) quadx_aviary_step<MODE>(p, s, nz);
     quadx_store<MODE>(st, ist, N, i, s);
-    ist[(int64_t)QI_PHYS * N + i] += n_steps * p.ratio;
   }
 }
 HS_API int hs_aviary_step(const PfbModel* m, int mode, float* st, int32_t* ist, const float* setpoint, const float* noise,
@@ -139,7 +138,6 @@ static void env_reset_t(const QuadXParams& p, const HoverParams& h, float* st, i
     hover_observation(h, s, zero, my_obs);
     quadx_store<7>(st, ist, N, i, s);
     ist[(int64_t)QI_STEP * N + i] = 0;
-    ist[(int64_t)QI_PHYS * N + i] += h.warmup_steps * p.ratio;
     for (int k = 0; k < O; ++k) obs[i * O + k] = my_obs[k];
   }
 }
@@ -165,19 +163,16 @@ static void env_step_t(const QuadXParams& p, const HoverParams& h, float* st, in
     int step_count = ist[(int64_t)QI_STEP * N + i];
     HostNoise nz{noise + i, N};
     float rew = -0.1f;
-    int done_steps = 0;
     for (int k = 0; k < h.env_step_ratio; ++k) {
       if (s.flags & (FLAG_TERM | FLAG_TRUNC)) break;
       quadx_aviary_step<MODE>(p, s, nz);
       hover_term_trunc_reward(h, s, step_count, rew);
-      ++done_steps;
     }
     step_count += 1;
     float my_obs[21];
     hover_observation(h, s, act, my_obs);
     quadx_store<MODE>(st, ist, N, i, s);
     ist[(int64_t)QI_STEP * N + i] = step_count;
-    ist[(int64_t)QI_PHYS * N + i] += done_steps * p.ratio;
     reward[i] = rew;
     term[i] = (s.flags & FLAG_TERM) ? 1 : 0;
     trunc[i] = (s.flags & FLAG_TRUNC) ? 1 : 0;
@@ -192,5 +187,20 @@ HS_API int hs_env_step(const PfbModel* m, const PfbEnvConfig* env, float* st, in
   HoverParams h;
   hover_params(env, h);
   MODE_SWITCH(env->flight_mode, (env_step_t<MODE>(p, h, st, ist, actions, noise, obs, reward, term, trunc, info, N)));
+  return 0;
+}
+
+// unit hook: the observation quaternion the kernel reports for attitude q (quaternion representation)
+HS_API int hs_obs_quat(const double* q, float* out4) {
+  QuadXRegs s;
+  memset(&s, 0, sizeof(s));
+  s.qx = (qreal)q[0]; s.qy = (qreal)q[1]; s.qz = (qreal)q[2]; s.qw = (qreal)q[3];
+  HoverParams h;
+  memset(&h, 0, sizeof(h));
+  h.angle_representation = 1;
+  const float act[4] = {0, 0, 0, 0};
+  float obs[21];
+  hover_observation(h, s, act, obs);
+  for (int k = 0; k < 4; ++k) out4[k] = obs[3 + k];
   return 0;
 }

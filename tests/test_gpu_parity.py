@@ -76,7 +76,7 @@ def test_batch_4096_matches_oracle(mode):
             e.set_setpoints(sp)
             e.aviary_step(noise[2 * i : 2 * i + 40], n_steps=20)
     a, b = engines[0].state(), engines[1].state()
-    assert np.abs(a[:, 3] - b[:, 3]).max() < 2e-4
+    assert np.abs(a[:, 3] - b[:, 3]).max() < 0.5 * POS_TOL  # 240 Aviary steps, ~50 m travelled
     assert np.abs(a[:, 0] - b[:, 0]).max() < 2e-3
     assert np.array_equal(engines[0].contact(), engines[1].contact())
 
@@ -134,6 +134,9 @@ def test_full_size_determinism_and_shard_independence():
 
 
 def test_full_size_autoreset_invariants():
+    """NEXT_STEP autoreset at 65 536 envs: an env that finished on call k returns, on call k+1, the first
+    observation of a new episode (z just under the 1 m start after the 10 warm-up steps), reward 0 and
+    cleared flags; nobody is ever left in a finished state for more than one call."""
     import torch
 
     from pyflyt_b200.gym_envs.quadx_hover_env import QuadXHoverVecEnv
@@ -141,19 +144,24 @@ def test_full_size_autoreset_invariants():
     env = QuadXHoverVecEnv(num_envs=65536, seed=1)
     obs, _ = env.reset()
     assert torch.allclose(obs[:, 10:13], torch.tensor([0.0, 0.0, 1.0], device=obs.device).expand(65536, 3), atol=0.05)
-    total_done = 0
+    first = obs.clone()
+    total_done, prev_done = 0, torch.zeros(65536, dtype=torch.bool, device=obs.device)
     for _ in range(40):
         env.rollout(1)
-        done = env.aviary.term.bool() | env.aviary.trunc.bool()
+        a = env.aviary
+        done = a.term.bool() | a.trunc.bool()
+        assert not bool((done & prev_done).any())
+        if bool(prev_done.any()):
+            z = a.obs[prev_done][:, 12]
+            assert bool(((z > 0.9) & (z < 1.0)).all())
+            assert bool((a.reward[prev_done] == 0).all())
+            assert bool((a.istate_tensor[0][prev_done] == 0).all())
+            # same start pose, same warm-up dynamics: only the motor-noise draws differ
+            assert float((a.obs[prev_done][:, :13] - first[prev_done][:, :13]).abs().max()) < 1e-2
+        assert bool((a.reward[done & a.term.bool()] < -50).all())  # -100 overwrite on collision / out of bounds
         total_done += int(done.sum())
-        # SAME_STEP autoreset: every finished env already holds the first observation of a new episode
-        z = env.aviary.obs[done][:, 12]
-        assert bool(((z > 0.9) & (z < 1.0)).all())
-        assert bool((env.aviary.istate_tensor[0][done] == 0).all())
-        assert bool((env.aviary.reward[done] < -50).all())  # -100 overwrite on collision / out of bounds
-    assert total_done > 1000  # random actions crash often (SURVEY §8d)
-    flags = env.aviary.istate_tensor[1]
-    assert int((flags & 3).sum()) == 0  # no env is left in a finished state
+        prev_done = done
+    assert total_done > 1000  # random actions crash often (SURVEY 8d)
     env.close()
 
 
