@@ -79,7 +79,8 @@ static inline int grid_for(int64_t n) { return (int)((n + kBlock - 1) / kBlock);
 struct InjectedNoise {  // parity tests: the CPU-drawn sequence, [substep][N]
   const float* ptr;
   int64_t N;
-  __device__ __forceinline__ float operator()() {
+  __device__ __forceinline__ void begin_step() {}
+  __device__ __forceinline__ float get(int) {
     float v = __ldg(ptr);
     ptr += N;
     return v;
@@ -87,29 +88,30 @@ struct InjectedNoise {  // parity tests: the CPU-drawn sequence, [substep][N]
 };
 
 // Throughput path: N(noise_loc, 1) from Philox4x32-10, counter = (global env id, call sequence number,
-// stream tag | block).  Stateless: nothing is stored per env, and a trajectory does not depend on how
-// the batch is sharded over GPUs.
+// stream tag | Aviary-step index).  Stateless: nothing is stored per env, and a trajectory does not depend
+// on how the batch is sharded over GPUs.  One Philox call per Aviary step, issued OUTSIDE the substep loop.
 enum { TAG_AVIARY = 0, TAG_ENV_STEP = 1, TAG_RESET = 2, TAG_ACTION = 3 };
 struct PhiloxNoise {
   uint32_t k0, k1, env_lo, env_hi, seq, tag;
-  uint32_t idx;
+  uint32_t step;
+  int ratio;
   float loc;
-  float c0, c1, c2, c3;
-  __device__ __forceinline__ void init(const RngParams& r, int64_t i, uint32_t seq_, uint32_t tag_, float loc_) {
+  float n0, n1, n2, n3;
+  __device__ __forceinline__ void init(const RngParams& r, int64_t i, uint32_t seq_, uint32_t tag_, float loc_, int ratio_) {
     k0 = r.k0; k1 = r.k1;
     uint64_t g = ((uint64_t)r.env_offset_hi << 32 | r.env_offset_lo) + (uint64_t)i;
     env_lo = (uint32_t)g; env_hi = (uint32_t)(g >> 32);
-    seq = seq_; tag = tag_ << 24; idx = 0; loc = loc_;
+    seq = seq_; tag = tag_ << 24; step = 0; loc = loc_; ratio = ratio_;
+    n2 = n3 = 0.0f;
   }
-  __device__ __forceinline__ float operator()() {
-    uint32_t k = idx & 3u;
-    if (k == 0u) {
-      U4 r = philox4x32_10(U4{env_lo, env_hi, seq, tag | (idx >> 2)}, k0, k1);
-      box_muller(r.x, r.y, c0, c1);
-      box_muller(r.z, r.w, c2, c3);
-    }
-    ++idx;
-    float z = k == 0u ? c0 : (k == 1u ? c1 : (k == 2u ? c2 : c3));
+  __device__ __forceinline__ void begin_step() {
+    U4 r = philox4x32_10(U4{env_lo, env_hi, seq, tag | step}, k0, k1);
+    ++step;
+    box_muller(r.x, r.y, n0, n1);
+    if (ratio > 2) box_muller(r.z, r.w, n2, n3);  // uniform branch; ratio <= 4 is enforced at create
+  }
+  __device__ __forceinline__ float get(int u) {
+    float z = u == 0 ? n0 : (u == 1 ? n1 : (u == 2 ? n2 : n3));
     return loc + z;
   }
 };
@@ -128,17 +130,17 @@ struct NoiseSel<false> {
 template <bool INJECT>
 __device__ __forceinline__ typename NoiseSel<INJECT>::type make_noise(const float* noise, int64_t N, int64_t i,
                                                                       const RngParams& r, uint32_t seq, uint32_t tag,
-                                                                      float loc);
+                                                                      float loc, int ratio);
 template <>
 __device__ __forceinline__ InjectedNoise make_noise<true>(const float* noise, int64_t N, int64_t i, const RngParams&,
-                                                          uint32_t, uint32_t, float) {
+                                                          uint32_t, uint32_t, float, int) {
   return InjectedNoise{noise + i, N};
 }
 template <>
 __device__ __forceinline__ PhiloxNoise make_noise<false>(const float*, int64_t, int64_t i, const RngParams& r,
-                                                         uint32_t seq, uint32_t tag, float loc) {
+                                                         uint32_t seq, uint32_t tag, float loc, int ratio) {
   PhiloxNoise n;
-  n.init(r, i, seq, tag, loc);
+  n.init(r, i, seq, tag, loc, ratio);
   return n;
 }
 
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   quadx_load<MODE>(st, ist, N, i, s);
   float4 sp = __ldg(reinterpret_cast<const float4*>(setpoint) + i);
   s.sp[0] = sp.x; s.sp[1] = sp.y; s.sp[2] = sp.z; s.sp[3] = sp.w;
-  auto nz = make_noise<INJECT>(noise, N, i, rng, seq, TAG_AVIARY, p.noise_loc);
+  auto nz = make_noise<INJECT>(noise, N, i, rng, seq, TAG_AVIARY, p.noise_loc, p.ratio);
   for (int k = 0; k < n_steps; ++k) quadx_aviary_step<MODE>(p, s, nz);
   quadx_store<MODE>(st, ist, N, i, s);
 }
@@ -229,7 +231,7 @@ __device__ __forceinline__ void hover_reset_env(const QuadXParams& p, const Hove
   quadx_reset(s, start_pos[3 * i + 0], start_pos[3 * i + 1], start_pos[3 * i + 2], start_orn[3 * i + 0],
               start_orn[3 * i + 1], start_orn[3 * i + 2]);
   quadx_set_mode<MODE>(s);
-  auto nz = make_noise<INJECT>(noise, N, i, rng, seq, TAG_RESET, p.noise_loc);
+  auto nz = make_noise<INJECT>(noise, N, i, rng, seq, TAG_RESET, p.noise_loc, p.ratio);
   for (int k = 0; k < h.warmup_steps; ++k) quadx_aviary_step<MODE>(p, s, nz);
   const float zero[4] = {0.f, 0.f, 0.f, 0.f};  // self.action = zeros (quadx_base_env.py:165)
   hover_observation(h, s, zero, out);
@@ -242,8 +244,10 @@ __device__ __forceinline__ void hover_reset_env(const QuadXParams& p, const Hove
 //   AUTORESET gymnasium NEXT_STEP autoreset: an env that finished on the previous call is reset on this
 //             one (its action is ignored; obs = first observation, reward 0, flags cleared).  Those envs
 //             were queued by the previous launch and are handled by dense "tail" CTAs placed at the
-//             front of the grid, so the 20 warm-up substeps run in full warps concurrently with the
+//             front of the grid, so the 10 warm-up Aviary steps run in full warps concurrently with the
 //             regular CTAs instead of diverging inside them.
+// Both roles run the SAME code (role-dependent scalars only): the kernel is instruction-fetch bound, so one
+// compact hot loop shared by every warp on the SM matters more than anything else.
 template <int MODE, bool INJECT, bool RANDACT, bool AUTORESET>
 __global__ void __launch_bounds__(kBlock, kMinBlocks)
     k_hover_step(const __grid_constant__ QuadXParams p, const __grid_constant__ HoverParams h,
@@ -257,36 +261,41 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   __shared__ float smem[kBlock * kObsStride];
   __shared__ uint8_t row_skip[kBlock];
   const int O = h.angle_representation == 0 ? 20 : 21;
+  const bool tail = AUTORESET && (int)blockIdx.x < tail_blocks;  // CTA-uniform role
+  const int64_t block_first = tail ? 0 : (int64_t)((int)blockIdx.x - (AUTORESET ? tail_blocks : 0)) * kBlock;
 
-  if (AUTORESET && (int)blockIdx.x < tail_blocks) {
-    // ---- tail role: reset the envs that finished on the previous call
+  // work items: a regular thread owns exactly one env; a tail thread strides over the done list
+  int t, t_end, t_stride;
+  if (tail) {
     if (blockIdx.x == 0 && threadIdx.x == 0) *next_count = 0;  // arm the counter the NEXT launch appends to
-    const int count = *prev_count;
-    for (int t = blockIdx.x * kBlock + threadIdx.x; t < count; t += tail_blocks * kBlock) {
-      const int64_t i = prev_list[t];
-      float* row = smem + threadIdx.x * kObsStride;
-      hover_reset_env<MODE, false>(p, h, rng, st, ist, start_pos, start_orn, nullptr, step_seq, N, i, row);
-      float* dst = obs + i * O;
-      for (int k = 0; k < O; ++k) dst[k] = row[k];
-      reward[i] = 0.0f;
-      term[i] = 0;
-      trunc[i] = 0;
-      if (info) info[i] = 0;
-    }
-    return;
+    t = blockIdx.x * kBlock + threadIdx.x;
+    t_end = *prev_count;
+    t_stride = tail_blocks * kBlock;
+  } else {
+    t = 0;
+    t_end = (block_first + threadIdx.x < N) ? 1 : 0;
+    t_stride = 1;
   }
-
-  const int64_t block_first = (int64_t)((int)blockIdx.x - (AUTORESET ? tail_blocks : 0)) * kBlock;
-  const int64_t i = block_first + threadIdx.x;
-  const bool active = i < N;
-  bool skip = !active;
-  if (active) {
+  bool skip = true;
+  float* row = smem + threadIdx.x * kObsStride;
+#pragma unroll 1
+  for (; t < t_end; t += t_stride) {
+    const int64_t i = tail ? (int64_t)prev_list[t] : block_first + threadIdx.x;
     QuadXRegs s;
-    quadx_load<MODE>(st, ist, N, i, s);
-    if (AUTORESET && (s.flags & (FLAG_TERM | FLAG_TRUNC))) {
-      skip = true;  // a tail CTA owns this env for this call
+    float act[4] = {0.f, 0.f, 0.f, 0.f};
+    int n_aviary, step_count;
+    float rew;
+    if (tail) {
+      // env.reset(): begin_reset + end_reset (quadx_base_env.py:149-212)
+      quadx_reset(s, start_pos[3 * i + 0], start_pos[3 * i + 1], start_pos[3 * i + 2], start_orn[3 * i + 0],
+                  start_orn[3 * i + 1], start_orn[3 * i + 2]);
+      quadx_set_mode<MODE>(s);
+      n_aviary = h.warmup_steps;
+      step_count = 0;
+      rew = 0.0f;
     } else {
-      float act[4];
+      quadx_load<MODE>(st, ist, N, i, s);
+      if (AUTORESET && (s.flags & (FLAG_TERM | FLAG_TRUNC))) continue;  // a tail CTA owns this env on this call
       if (RANDACT) {
         uint64_t g = ((uint64_t)rng.env_offset_hi << 32 | rng.env_offset_lo) + (uint64_t)i;
         U4 r = philox4x32_10(U4{(uint32_t)g, (uint32_t)(g >> 32), step_seq, (uint32_t)TAG_ACTION << 24}, rng.k0, rng.k1);
@@ -305,22 +314,30 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) s.sp[k] = act[k];
-      int step_count = ist[(int64_t)QI_STEP * N + i];
-      auto nz = make_noise<INJECT>(noise, N, i, rng, step_seq, TAG_ENV_STEP, p.noise_loc);
-      float rew = -0.1f;
-      for (int k = 0; k < h.env_step_ratio; ++k) {
-        if (s.flags & (FLAG_TERM | FLAG_TRUNC)) break;  // quadx_base_env.py:289-290
-        quadx_aviary_step<MODE>(p, s, nz);
-        hover_term_trunc_reward(h, s, step_count, rew);
-      }
-      step_count += 1;
-      hover_observation(h, s, act, smem + threadIdx.x * kObsStride);
-      quadx_store<MODE>(st, ist, N, i, s);
-      ist[(int64_t)QI_STEP * N + i] = step_count;
-      reward[i] = rew;
-      term[i] = (s.flags & FLAG_TERM) ? 1 : 0;
-      trunc[i] = (s.flags & FLAG_TRUNC) ? 1 : 0;
-      if (info) info[i] = (uint8_t)(((s.flags & FLAG_OOB) ? 1 : 0) | ((s.flags & FLAG_COLLISION) ? 2 : 0));
+      n_aviary = h.env_step_ratio;
+      step_count = ist[(int64_t)QI_STEP * N + i];
+      rew = -0.1f;
+    }
+    auto nz = make_noise<INJECT>(noise, N, i, rng, step_seq, tail ? TAG_RESET : TAG_ENV_STEP, p.noise_loc, p.ratio);
+#pragma unroll 1
+    for (int k = 0; k < n_aviary; ++k) {
+      if (s.flags & (FLAG_TERM | FLAG_TRUNC)) break;  // quadx_base_env.py:289-290 (never set while resetting)
+      quadx_aviary_step<MODE>(p, s, nz);
+      if (!tail) hover_term_trunc_reward(h, s, step_count, rew);
+    }
+    step_count = tail ? 0 : step_count + 1;
+    hover_observation(h, s, act, row);
+    quadx_store<MODE>(st, ist, N, i, s);
+    ist[(int64_t)QI_STEP * N + i] = step_count;
+    reward[i] = rew;
+    term[i] = (s.flags & FLAG_TERM) ? 1 : 0;
+    trunc[i] = (s.flags & FLAG_TRUNC) ? 1 : 0;
+    if (info) info[i] = (uint8_t)(((s.flags & FLAG_OOB) ? 1 : 0) | ((s.flags & FLAG_COLLISION) ? 2 : 0));
+    if (tail) {
+      float* dst = obs + i * O;  // scattered rows: the tail handles ~1-3 % of the envs
+      for (int k = 0; k < O; ++k) dst[k] = row[k];
+    } else {
+      skip = false;
       if (AUTORESET) {  // queue finished episodes for the next launch's tail CTAs (warp-aggregated append)
         bool done = (s.flags & (FLAG_TERM | FLAG_TRUNC)) != 0;
         unsigned m = __ballot_sync(__activemask(), done);
@@ -335,6 +352,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
       }
     }
   }
+  if (tail) return;
   // ---- block-cooperative, fully coalesced write of this CTA's observations into obs[N][O]
   row_skip[threadIdx.x] = skip ? 1 : 0;
   __syncthreads();
@@ -581,9 +599,8 @@ static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool r
                   h->buf.term, h->buf.trunc, h->buf.info, h->buf.start_pos, h->buf.start_orn, cnt_prev, list_prev, \
                   cnt_cur, list_cur, cnt_next, tail, seq, h->n
   if (autoreset) {
-    if (noise) {
-      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, true, false, true><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
-    } else if (randact) {
+    if (noise) return fail("injected noise (parity mode) is only supported with autoreset = 0");
+    if (randact) {
       PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, true, true><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
     } else {
       PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, false, true><<<grid, kBlock, 0, s>>>(STEP_ARGS)));

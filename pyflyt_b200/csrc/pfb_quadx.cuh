@@ -133,19 +133,59 @@ PFB_HD void quadx_update_state(QuadXRegs& s) {
   s.vb.z = (float)(R.m02 * vx + R.m12 * vy + R.m22 * vz);
 }
 
+// atan2 without the IEEE-division / denormal slow paths: |error| < 2e-7 rad (tests/test_hostsim_parity.py).
+// Octant reduction to a = min/max in [0,1], odd minimax polynomial for atan(a), quadrant fix-ups.
+PFB_HD float atan2_f(float y, float x) {
+  float ax = fabsf(x), ay = fabsf(y);
+  float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  float a = mx > 0.0f ? fast_div(mn, mx) : 0.0f;
+  float t = a * a;
+  float r = 0.00282363896258175373077393f;
+  r = fmaf(r, t, -0.0159569028764963150024414f);
+  r = fmaf(r, t, 0.0425049886107444763183594f);
+  r = fmaf(r, t, -0.0748900920152664184570312f);
+  r = fmaf(r, t, 0.106347933411598205566406f);
+  r = fmaf(r, t, -0.142027363181114196777344f);
+  r = fmaf(r, t, 0.199926957488059997558594f);
+  r = fmaf(r, t, -0.333331018686294555664062f);
+  r = fmaf(r * t, a, a);
+  if (ay > ax) r = 1.57079632679489661923f - r;
+  if (x < 0.0f) r = 3.14159265358979323846f - r;
+  return copysignf(r, y);
+}
+
 // p.getEulerFromQuaternion (btQuaternion::getEulerZYX with the +-0.99999 gimbal-lock branch)
+// asin(s) is evaluated as atan2(s, sqrt(1 - s^2)): same function on (-1, 1), one polynomial to maintain.
 PFB_HD void euler_from_quat(float x, float y, float z, float w, float& roll, float& pitch, float& yaw) {
   float sarg = -2.0f * (x * z - w * y);
-  if (sarg <= -0.99999f) {
-    pitch = -1.57079632679489661923f; roll = 0.0f; yaw = 2.0f * atan2f(x, -y);
-  } else if (sarg >= 0.99999f) {
-    pitch = 1.57079632679489661923f; roll = 0.0f; yaw = 2.0f * atan2f(-x, y);
-  } else {
-    float sqx = x * x, sqy = y * y, sqz = z * z, sqw = w * w;
-    pitch = asinf(sarg);
-    roll = atan2f(2.0f * (y * z + w * x), sqw - sqx - sqy + sqz);
-    yaw = atan2f(2.0f * (x * y + w * z), sqw + sqx - sqy - sqz);
+  float sqx = x * x, sqy = y * y, sqz = z * z, sqw = w * w;
+  float ra = 2.0f * (y * z + w * x), rb = sqw - sqx - sqy + sqz;
+  float ya = 2.0f * (x * y + w * z), yb = sqw + sqx - sqy - sqz;
+  float pa = sarg, pb = sqrtf(fmaxf(0.0f, 1.0f - sarg * sarg));
+  float yscale = 1.0f;
+  if (fabsf(sarg) >= 0.99999f) {  // gimbal lock: roll = 0, pitch = +-pi/2, yaw = 2 atan2(+-x, -+y)
+    float sg = sarg > 0.0f ? 1.0f : -1.0f;
+    ra = 0.0f; rb = 1.0f;
+    pa = sg; pb = 0.0f;
+    ya = -sg * x; yb = sg * y;
+    yscale = 2.0f;
   }
+  roll = atan2_f(ra, rb);
+  pitch = atan2_f(pa, pb);
+  yaw = yscale * atan2_f(ya, yb);
+}
+
+// roll and pitch only (the Hover reward needs nothing else): quadx_hover_env.py:133-134
+PFB_HD void roll_pitch_from_quat(float x, float y, float z, float w, float& roll, float& pitch) {
+  float sarg = -2.0f * (x * z - w * y);
+  float ra = 2.0f * (y * z + w * x), rb = w * w - x * x - y * y + z * z;
+  float pa = sarg, pb = sqrtf(fmaxf(0.0f, 1.0f - sarg * sarg));
+  if (fabsf(sarg) >= 0.99999f) {
+    ra = 0.0f; rb = 1.0f;
+    pa = sarg > 0.0f ? 1.0f : -1.0f; pb = 0.0f;
+  }
+  roll = atan2_f(ra, rb);
+  pitch = atan2_f(pa, pb);
 }
 
 // p.getQuaternionFromEuler (btQuaternion::setEulerZYX)
@@ -256,16 +296,33 @@ PFB_HD bool quadx_ground_contact(const QuadXParams& p, const QuadXRegs& s) {
   return hit;
 }
 
+// Bullet clamps the WORLD angular-velocity coordinates to +-vmax; that can only bite when a body rate
+// exceeds vmax/sqrt(3), so the rotation to the world frame and back lives out of line (cold).  Everything
+// is passed BY VALUE so that the caller's register-resident state never has its address taken.
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+Vec3 quadx_clamp_world_rates(float vmax, Mat3 R, Vec3 w) {
+  Vec3 o = mul(R, w);
+  o.x = clampf(o.x, -vmax, vmax); o.y = clampf(o.y, -vmax, vmax); o.z = clampf(o.z, -vmax, vmax);
+  return mulT(R, o);
+}
+
 // One physics substep: update_physics (quadx.py:495-510) + stepSimulation + update_state.
 // xi = raw draw of np_random.normal(*throttle.shape)  (one scalar ~ N(4, 1) shared by the motors).
+// Written as straight-line code (selects instead of branches): the kernel is instruction-issue bound
+// and the I-cache-resident hot loop is what the whole env step runs in.
 PFB_HD void quadx_substep(const QuadXParams& p, QuadXRegs& s, float xi) {
   // ---- motors (motors.py:130-155): lag, multiplicative noise, rpm^2 thrust + reaction torque
   float Fz = 0.0f, tx = 0.0f, ty = 0.0f, tz = 0.0f;
+  const float gain = xi * p.noise_ratio;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float t = s.thr[i];
     t = fmaf(p.motor_lag, s.pwm[i] - t, t);
-    t = fmaf(xi * t, p.noise_ratio, t);
+    t = fmaf(gain, t, t);
     s.thr[i] = t;
     float a = t * fabsf(t);
     float Ti = p.thrust_k[i] * a;
@@ -279,17 +336,16 @@ PFB_HD void quadx_substep(const QuadXParams& p, QuadXRegs& s, float xi) {
   float Fy = -p.drag_k[1] * signed_square(s.vb.y);
   Fz = fmaf(-p.drag_k[2], signed_square(s.vb.z), Fz);
   // ---- rotational drag unless something touched the floor last step (quadx.py:502-510)
-  if (!(s.flags & FLAG_CONTACT_PREV)) {
-    tx = fmaf(-p.drag_pqr, signed_square(s.wx), tx);
-    ty = fmaf(-p.drag_pqr, signed_square(s.wy), ty);
-    tz = fmaf(-p.drag_pqr, signed_square(s.wz), tz);
-  }
+  const float kpqr = (s.flags & FLAG_CONTACT_PREV) ? 0.0f : -p.drag_pqr;
+  tx = fmaf(kpqr, signed_square(s.wx), tx);
+  ty = fmaf(kpqr, signed_square(s.wy), ty);
+  tz = fmaf(kpqr, signed_square(s.wz), tz);
   // ---- contact flag from the pose at the start of the step (collision detection precedes
   //      integration inside stepSimulation); aviary.py:523-525
-  bool c = quadx_ground_contact(p, s);
+  const bool c = quadx_ground_contact(p, s);
   s.flags = (s.flags & ~(uint32_t)FLAG_CONTACT_PREV) | (c ? (FLAG_CONTACT_PREV | FLAG_CONTACT_ARRAY) : 0u);
 
-  // ---- Newton–Euler about the COM (composite COM offset is zero for the quads; inertia diagonal)
+  // ---- Newton-Euler about the COM (composite COM offset is zero for the quads; inertia diagonal)
   float wdx = (tx - (p.Izz - p.Iyy) * s.wy * s.wz) * p.inv_Ixx;
   float wdy = (ty - (p.Ixx - p.Izz) * s.wz * s.wx) * p.inv_Iyy;
   float wdz = (tz - (p.Iyy - p.Ixx) * s.wx * s.wy) * p.inv_Izz;
@@ -309,35 +365,19 @@ PFB_HD void quadx_substep(const QuadXParams& p, QuadXRegs& s, float xi) {
   s.wx = fmaf(wdx, p.dt, s.wx);
   s.wy = fmaf(wdy, p.dt, s.wy);
   s.wz = fmaf(wdz, p.dt, s.wz);
-  // Bullet clamps the WORLD angular velocity coordinates to +-vmax; only reachable when the body
-  // rate exceeds vmax/sqrt(3) in some axis, so the rotation to the world frame is a cold path.
   if (fmaxf(fmaxf(fabsf(s.wx), fabsf(s.wy)), fabsf(s.wz)) > p.vmax * 0.57735f) {
-    float ox = (float)R.m00 * s.wx + (float)R.m01 * s.wy + (float)R.m02 * s.wz;
-    float oy = (float)R.m10 * s.wx + (float)R.m11 * s.wy + (float)R.m12 * s.wz;
-    float oz = (float)R.m20 * s.wx + (float)R.m21 * s.wy + (float)R.m22 * s.wz;
-    ox = clampf(ox, -p.vmax, p.vmax); oy = clampf(oy, -p.vmax, p.vmax); oz = clampf(oz, -p.vmax, p.vmax);
-    s.wx = (float)R.m00 * ox + (float)R.m10 * oy + (float)R.m20 * oz;
-    s.wy = (float)R.m01 * ox + (float)R.m11 * oy + (float)R.m21 * oz;
-    s.wz = (float)R.m02 * ox + (float)R.m12 * oy + (float)R.m22 * oz;
+    Mat3 Rf{(float)R.m00, (float)R.m01, (float)R.m02, (float)R.m10, (float)R.m11, (float)R.m12, (float)R.m20, (float)R.m21, (float)R.m22};
+    Vec3 w = quadx_clamp_world_rates(p.vmax, Rf, Vec3{s.wx, s.wy, s.wz});
+    s.wx = w.x; s.wy = w.y; s.wz = w.z;
   }
   // ---- attitude: q <- q * dq(w_b dt).  dq = (w sin(h)/|w|, cos h), h = |w| dt / 2.  With
-  // h^2 = |w|^2 dt^2 / 4 <= 0.13 (|w| <= sqrt(3) vmax) both factors are short even series in h^2:
-  // sin(h)/|w| = dt/2 * sinc(h), cos(h) — no sqrt, no division, no range reduction, and the series
-  // IS Bullet's small-angle branch (btTransformUtil), continued to fp32 round-off.
+  // h^2 = |w|^2 dt^2 / 4 <= 0.13 (|w| <= sqrt(3) vmax; checked at create) both factors are short even
+  // series in h^2: sin(h)/|w| = dt/2 * sinc(h) and cos(h) — no sqrt, no division, no range reduction,
+  // and the series IS Bullet's small-angle branch (btTransformUtil), continued to fp32 round-off.
   float h2 = (s.wx * s.wx + s.wy * s.wy + s.wz * s.wz) * (0.25f * p.dt * p.dt);
-  float scale, cw;
-  if (h2 <= 0.25f) {
-    float sinc = fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, 2.7557319e-6f, -1.9841270e-4f), 8.3333333e-3f), -1.6666667e-1f), 1.0f);
-    scale = 0.5f * p.dt * sinc;
-    cw = fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, -2.7557319e-7f, 2.4801587e-5f), -1.3888889e-3f), 4.1666667e-2f), -0.5f), 1.0f);
-  } else {  // unreachable with the default velocity clamp; kept for exotic vmax
-    float ang = sqrtf(h2) * (2.0f / p.dt);
-    float lim = 0.78539816339f / p.dt;  // ANGULAR_MOTION_THRESHOLD
-    if (ang > lim) ang = lim;
-    float half = 0.5f * ang * p.dt;
-    scale = sinf(half) / (sqrtf(h2) * (2.0f / p.dt));
-    cw = cosf(half);
-  }
+  float sinc = fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, 2.7557319e-6f, -1.9841270e-4f), 8.3333333e-3f), -1.6666667e-1f), 1.0f);
+  float scale = 0.5f * p.dt * sinc;
+  float cw = fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, -2.7557319e-7f, 2.4801587e-5f), -1.3888889e-3f), 4.1666667e-2f), -0.5f), 1.0f);
   qreal dx = (qreal)(s.wx * scale), dy = (qreal)(s.wy * scale), dz = (qreal)(s.wz * scale), dw = (qreal)cw;
   qreal nx = s.qw * dx + s.qx * dw + s.qy * dz - s.qz * dy;
   qreal ny = s.qw * dy + s.qy * dw + s.qz * dx - s.qx * dz;
@@ -356,12 +396,16 @@ PFB_HD void quadx_substep(const QuadXParams& p, QuadXRegs& s, float xi) {
   quadx_update_state(s);
 }
 
-// Aviary.step(): one control tick + `ratio` physics substeps (aviary.py:506-531 with one drone)
+// Aviary.step(): one control tick + `ratio` physics substeps (aviary.py:506-531 with one drone).
+// Noise protocol: begin_step() prepares the draws of this Aviary step (outside the substep loop),
+// get(u) hands out the draw of substep u.
 template <int MODE, typename NoiseFn>
 PFB_HD void quadx_aviary_step(const QuadXParams& p, QuadXRegs& s, NoiseFn& noise) {
   s.flags &= ~(uint32_t)FLAG_CONTACT_ARRAY;  // contact_array &= False
+  noise.begin_step();
   quadx_update_control<MODE>(p, s);
-  for (int u = 0; u < p.ratio; ++u) quadx_substep(p, s, noise());
+#pragma unroll 1
+  for (int u = 0; u < p.ratio; ++u) quadx_substep(p, s, noise.get(u));
 }
 
 // quadx.py:233-373: setpoint preset + PID reset on a mode change
@@ -514,8 +558,8 @@ PFB_HD void hover_term_trunc_reward(const HoverParams& h, QuadXRegs& s, int step
   if (!h.sparse_reward) {
     float dz = pz - 1.0f;
     float linear_distance = sqrtf(r2 + dz * dz);
-    float roll, pitch, yaw;
-    euler_from_quat((float)s.qx, (float)s.qy, (float)s.qz, (float)s.qw, roll, pitch, yaw);
+    float roll, pitch;
+    roll_pitch_from_quat((float)s.qx, (float)s.qy, (float)s.qz, (float)s.qw, roll, pitch);
     float angular_distance = sqrtf(roll * roll + pitch * pitch);
     reward -= 0.01f * s.wz * s.wz;
     reward -= linear_distance + angular_distance;

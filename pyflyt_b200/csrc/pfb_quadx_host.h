@@ -65,6 +65,11 @@ static int build_quadx_params(const PfbModel& m, pfb::QuadXParams& q) {
     q.shape_thr[s] = (float)(m.contact_factor * disc);
   }
   q.ratio = (int)(m.physics_hz / m.control_hz);
+  if (q.ratio < 1 || q.ratio > 4) return fail("physics_hz / control_hz must be in 1..4 (got %d)", q.ratio);
+  {  // the exp-map series in quadx_substep needs (|w| dt / 2)^2 <= 0.25 with |w| <= sqrt(3) vmax
+    double hmax = 0.5 * sqrt(3.0) * m.max_coord_velocity / m.physics_hz;
+    if (hmax * hmax > 0.25) return fail("max_coord_velocity * dt too large for the attitude series (h^2 = %g)", hmax * hmax);
+  }
   return 0;
 }
 

@@ -24,7 +24,8 @@ using namespace pfb;
 struct HostNoise {
   const float* ptr;
   int64_t N;
-  float operator()() {
+  void begin_step() {}
+  float get(int) {
     float v = *ptr;
     ptr += N;
     return v;
@@ -204,3 +205,5 @@ HS_API int hs_obs_quat(const double* q, float* out4) {
   for (int k = 0; k < 4; ++k) out4[k] = obs[3 + k];
   return 0;
 }
+
+HS_API float hs_atan2(float y, float x) { return atan2_f(y, x); }
