@@ -82,12 +82,26 @@ PFB_HD Vec3 mulT(const Mat3& R, Vec3 v) {
 }
 
 PFB_HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
-// a / b to ~2 ulp without the IEEE slow path (used where the reference's result is clipped anyway)
-PFB_HD float fast_div(float a, float b) {
+// Single-instruction SFU forms (MUFU.RCP / MUFU.RSQ, flush-to-zero, ~1-2 ulp) without the IEEE
+// denormal/overflow fix-up paths: every use below feeds a clipped control value, a reward distance or
+// a contact margin, never the integrated trajectory state.
+PFB_HD float fast_rcp(float b) {
 #if defined(__CUDA_ARCH__)
-  return __fdividef(a, b);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+  return r;
 #else
-  return a / b;
+  return 1.0f / b;
+#endif
+}
+PFB_HD float fast_div(float a, float b) { return a * fast_rcp(b); }
+PFB_HD float fast_sqrt(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return sqrtf(x);
 #endif
 }
 // -sign(v) * k * v^2  ==  -k * v * |v|   (boring_bodies.py:115-119, quadx.py:502-506)
@@ -139,7 +153,7 @@ PFB_HD void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
   float u1 = u32_to_unit_open(a);
   float u2 = u32_to_unit_open(b);
 #if defined(__CUDA_ARCH__)
-  float r = sqrtf(-2.0f * __logf(u1));
+  float r = fast_sqrt(-2.0f * __logf(u1));
   float s, c;
   __sincosf(6.28318530717958647692f * u2, &s, &c);
 #else

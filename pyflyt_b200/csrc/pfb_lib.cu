@@ -105,14 +105,19 @@ struct PhiloxNoise {
     n2 = n3 = 0.0f;
   }
   __device__ __forceinline__ void begin_step() {
-    U4 r = philox4x32_10(U4{env_lo, env_hi, seq, tag | step}, k0, k1);
+    // ratio <= 2: one Philox call (4 words -> 4 normals) serves two consecutive Aviary steps
+    if (ratio > 2 || (step & 1u) == 0u) {
+      U4 r = philox4x32_10(U4{env_lo, env_hi, seq, tag | step}, k0, k1);
+      box_muller(r.x, r.y, n0, n1);
+      box_muller(r.z, r.w, n2, n3);
+    }
     ++step;
-    box_muller(r.x, r.y, n0, n1);
-    if (ratio > 2) box_muller(r.z, r.w, n2, n3);  // uniform branch; ratio <= 4 is enforced at create
   }
   __device__ __forceinline__ float get(int u) {
-    float z = u == 0 ? n0 : (u == 1 ? n1 : (u == 2 ? n2 : n3));
-    return loc + z;
+    // step was already advanced: odd step-1 -> second half of the 4 normals
+    int idx = ratio > 2 ? u : (int)(((step - 1u) & 1u) << 1) + u;
+    float lo = (idx & 1) ? n1 : n0, hi = (idx & 1) ? n3 : n2;
+    return loc + ((idx & 2) ? hi : lo);
   }
 };
 
@@ -360,9 +365,13 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   if (rows > kBlock) rows = kBlock;
   const int total = (int)rows * O;
   float* dst = obs + block_first * O;
+  // element j = r * O + c of the CTA tile; advancing j by kBlock advances (r, c) by (kBlock / O, kBlock % O)
+  const int dr = kBlock / O, dc = kBlock - dr * O;
+  int r = threadIdx.x / O, c = threadIdx.x - r * O;
   for (int j = threadIdx.x; j < total; j += kBlock) {
-    int r = j / O, c = j - r * O;
     if (!row_skip[r]) dst[j] = smem[r * kObsStride + c];
+    r += dr; c += dc;
+    if (c >= O) { c -= O; ++r; }
   }
 }
 
@@ -436,7 +445,10 @@ int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, i
   c->hover.sparse_reward = env ? env->sparse_reward : 0;
   c->hover.warmup_steps = env ? env->warmup_steps : 0;
   c->hover.flight_mode = env ? env->flight_mode : 0;
-  c->hover.dome = env ? (float)env->flight_dome_size : 1e30f;
+  {
+    double dome = env ? env->flight_dome_size : INFINITY;
+    c->hover.dome2 = (float)(dome * dome);
+  }
   if (env && env->env_kind != PFB_ENV_NONE && env->env_kind != PFB_ENV_QUADX_HOVER) {
     delete c;
     return fail("env kind %d is not built into this library yet", env->env_kind);

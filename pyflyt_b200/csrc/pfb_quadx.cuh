@@ -50,6 +50,7 @@ struct QuadXParams {
   float shape_dims[5][3];
   float shape_at[5][3];
   float shape_thr[5];
+  float contact_zmax;  // base altitude above which no primitive can be within its contact threshold
   int ratio;           // physics substeps per control tick (physics_hz / control_hz)
 };
 
@@ -60,7 +61,7 @@ struct HoverParams {
   int sparse_reward;
   int warmup_steps;
   int flight_mode;
-  float dome;
+  float dome2;  // flight_dome_size squared (inf stays inf)
 };
 
 // PID memory rows inside the state tensor (24 words)
@@ -161,7 +162,7 @@ PFB_HD void euler_from_quat(float x, float y, float z, float w, float& roll, flo
   float sqx = x * x, sqy = y * y, sqz = z * z, sqw = w * w;
   float ra = 2.0f * (y * z + w * x), rb = sqw - sqx - sqy + sqz;
   float ya = 2.0f * (x * y + w * z), yb = sqw + sqx - sqy - sqz;
-  float pa = sarg, pb = sqrtf(fmaxf(0.0f, 1.0f - sarg * sarg));
+  float pa = sarg, pb = fast_sqrt(fmaxf(0.0f, 1.0f - sarg * sarg));
   float yscale = 1.0f;
   if (fabsf(sarg) >= 0.99999f) {  // gimbal lock: roll = 0, pitch = +-pi/2, yaw = 2 atan2(+-x, -+y)
     float sg = sarg > 0.0f ? 1.0f : -1.0f;
@@ -179,7 +180,7 @@ PFB_HD void euler_from_quat(float x, float y, float z, float w, float& roll, flo
 PFB_HD void roll_pitch_from_quat(float x, float y, float z, float w, float& roll, float& pitch) {
   float sarg = -2.0f * (x * z - w * y);
   float ra = 2.0f * (y * z + w * x), rb = w * w - x * x - y * y + z * z;
-  float pa = sarg, pb = sqrtf(fmaxf(0.0f, 1.0f - sarg * sarg));
+  float pa = sarg, pb = fast_sqrt(fmaxf(0.0f, 1.0f - sarg * sarg));
   if (fabsf(sarg) >= 0.99999f) {
     ra = 0.0f; rb = 1.0f;
     pa = sarg > 0.0f ? 1.0f : -1.0f; pb = 0.0f;
@@ -275,8 +276,9 @@ PFB_HD void quadx_update_control(const QuadXParams& p, QuadXRegs& s) {
 // lowest point of the collision primitives against the plane z = 0, with the relative
 // contact-breaking threshold; evaluated on the pose at the START of the substep.
 PFB_HD bool quadx_ground_contact(const QuadXParams& p, const QuadXRegs& s) {
-  const float r20 = (float)s.R.m20, r21 = (float)s.R.m21, r22 = (float)s.R.m22;
   const float pz = (float)s.pz;
+  if (pz > p.contact_zmax) return false;  // higher than any primitive can reach: the common case
+  const float r20 = (float)s.R.m20, r21 = (float)s.R.m21, r22 = (float)s.R.m22;
   bool hit = false;
 #pragma unroll 1
   for (int k = 0; k < p.n_shapes; ++k) {
@@ -286,7 +288,7 @@ PFB_HD bool quadx_ground_contact(const QuadXParams& p, const QuadXRegs& s) {
       if (p.shape_kind[k] == 0) {
         extent = fabsf(r20) * p.shape_dims[k][0] + fabsf(r21) * p.shape_dims[k][1] + fabsf(r22) * p.shape_dims[k][2];
       } else if (p.shape_kind[k] == 1) {
-        extent = p.shape_dims[k][1] * fabsf(r22) + p.shape_dims[k][0] * sqrtf(fmaxf(0.0f, 1.0f - r22 * r22));
+        extent = p.shape_dims[k][1] * fabsf(r22) + p.shape_dims[k][0] * fast_sqrt(fmaxf(0.0f, 1.0f - r22 * r22));
       } else {
         extent = p.shape_dims[k][0];
       }
@@ -355,10 +357,18 @@ PFB_HD void quadx_substep(const QuadXParams& p, QuadXRegs& s, float xi) {
   rreal ax = R.m00 * fx + R.m01 * fy + R.m02 * fz;
   rreal ay = R.m10 * fx + R.m11 * fy + R.m12 * fz;
   rreal az = R.m20 * fx + R.m21 * fy + R.m22 * fz + (rreal)p.gravity;
-  const vreal dt = (vreal)p.dt, vmax = (vreal)p.vmax;
-  s.vx = fmin(fmax(s.vx + (vreal)ax * dt, -vmax), vmax);
-  s.vy = fmin(fmax(s.vy + (vreal)ay * dt, -vmax), vmax);
-  s.vz = fmin(fmax(s.vz + (vreal)az * dt, -vmax), vmax);
+  const vreal dt = (vreal)p.dt;
+  s.vx += (vreal)ax * dt;
+  s.vy += (vreal)ay * dt;
+  s.vz += (vreal)az * dt;
+  // +-vmax clamp per world coordinate (btMultiBody::applyDeltaVeeMultiDof): tested on the fp32 copy,
+  // applied exactly, and only ever taken by a body falling at the 100 m/s limit
+  if (fmaxf(fmaxf(fabsf((float)s.vx), fabsf((float)s.vy)), fabsf((float)s.vz)) >= p.vmax) {
+    const vreal vmax = (vreal)p.vmax;
+    s.vx = fmin(fmax(s.vx, -vmax), vmax);
+    s.vy = fmin(fmax(s.vy, -vmax), vmax);
+    s.vz = fmin(fmax(s.vz, -vmax), vmax);
+  }
   s.px += (xreal)(s.vx * dt);
   s.py += (xreal)(s.vy * dt);
   s.pz += (xreal)(s.vz * dt);
@@ -554,13 +564,13 @@ PFB_HD void hover_term_trunc_reward(const HoverParams& h, QuadXRegs& s, int step
   if (s.flags & FLAG_CONTACT_ARRAY) { reward = -100.0f; s.flags |= FLAG_COLLISION | FLAG_TERM; }
   float px = (float)s.px, py = (float)s.py, pz = (float)s.pz;
   float r2 = px * px + py * py;
-  if (sqrtf(r2 + pz * pz) > h.dome) { reward = -100.0f; s.flags |= FLAG_OOB | FLAG_TERM; }
+  if (r2 + pz * pz > h.dome2) { reward = -100.0f; s.flags |= FLAG_OOB | FLAG_TERM; }  // |x| > dome
   if (!h.sparse_reward) {
     float dz = pz - 1.0f;
-    float linear_distance = sqrtf(r2 + dz * dz);
+    float linear_distance = fast_sqrt(r2 + dz * dz);
     float roll, pitch;
     roll_pitch_from_quat((float)s.qx, (float)s.qy, (float)s.qz, (float)s.qw, roll, pitch);
-    float angular_distance = sqrtf(roll * roll + pitch * pitch);
+    float angular_distance = fast_sqrt(roll * roll + pitch * pitch);
     reward -= 0.01f * s.wz * s.wz;
     reward -= linear_distance + angular_distance;
     reward += 1.0f;
@@ -592,9 +602,9 @@ PFB_HD void hover_observation(const HoverParams& h, const QuadXRegs& s, const fl
       float ya = 2.0f * (x * y + w * z), yb = sqw + sqx - sqy - sqz;  // yaw  = atan2(ya, yb)
       // w_e = cr cp cy + sr sp sy with cr, cp, cy >= 0: negative only if the sines' product is negative
       // and tan(|roll|/2) tan(|pitch|/2) tan(|yaw|/2) > 1;  tan(a/2) = |sin a| / (1 + cos a)
-      float tr_n = fabsf(ra), tr_d = sqrtf(ra * ra + rb * rb) + rb;
-      float ty_n = fabsf(ya), ty_d = sqrtf(ya * ya + yb * yb) + yb;
-      float tp_n = fabsf(sarg), tp_d = 1.0f + sqrtf(fmaxf(0.0f, 1.0f - sarg * sarg));
+      float tr_n = fabsf(ra), tr_d = fast_sqrt(ra * ra + rb * rb) + rb;
+      float ty_n = fabsf(ya), ty_d = fast_sqrt(ya * ya + yb * yb) + yb;
+      float tp_n = fabsf(sarg), tp_d = 1.0f + fast_sqrt(fmaxf(0.0f, 1.0f - sarg * sarg));
       bool sines_negative = (ra * sarg * ya) < 0.0f;
       bool we_negative = sines_negative && (tr_n * tp_n * ty_n > tr_d * tp_d * ty_d);
       float sgn = ((w < 0.0f) != we_negative) ? -1.0f : 1.0f;

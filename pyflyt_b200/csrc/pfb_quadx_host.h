@@ -51,6 +51,7 @@ static int build_quadx_params(const PfbModel& m, pfb::QuadXParams& q) {
     }
   if (m.n_shapes > 5) return fail("quadx stepper supports at most 5 collision primitives, got %d", m.n_shapes);
   q.n_shapes = m.n_shapes;
+  q.contact_zmax = -1e30f;
   for (int s = 0; s < m.n_shapes; ++s) {
     const PfbShape& sh = m.shapes[s];
     const double id[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -63,6 +64,10 @@ static int build_quadx_params(const PfbModel& m, pfb::QuadXParams& q) {
     else disc = sh.dims[0];
     for (int k = 0; k < 3; ++k) { q.shape_dims[s][k] = (float)sh.dims[k]; q.shape_at[s][k] = (float)sh.at[k]; }
     q.shape_thr[s] = (float)(m.contact_factor * disc);
+    {
+      double reach = sqrt(sh.at[0] * sh.at[0] + sh.at[1] * sh.at[1] + sh.at[2] * sh.at[2]) + disc + m.contact_factor * disc;
+      if ((float)(reach * 1.001) > q.contact_zmax) q.contact_zmax = (float)(reach * 1.001);
+    }
   }
   q.ratio = (int)(m.physics_hz / m.control_hz);
   if (q.ratio < 1 || q.ratio > 4) return fail("physics_hz / control_hz must be in 1..4 (got %d)", q.ratio);

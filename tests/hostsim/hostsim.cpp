@@ -53,7 +53,7 @@ static void hover_params(const PfbEnvConfig* env, HoverParams& h) {
   h.sparse_reward = env->sparse_reward;
   h.warmup_steps = env->warmup_steps;
   h.flight_mode = env->flight_mode;
-  h.dome = (float)env->flight_dome_size;
+  h.dome2 = (float)(env->flight_dome_size * env->flight_dome_size);
 }
 
 #define HS_API extern "C"
