@@ -179,7 +179,7 @@ class HostSimEngine:
 # ----------------------------------------------------------------------------------------------------
 # fixture replays (shared by every engine)
 # ----------------------------------------------------------------------------------------------------
-GOLDEN = os.path.join(ROOT, "tests", "golden")
+GOLDEN = os.environ.get("PFB_GOLDEN_DIR", os.path.join(ROOT, "tests", "golden"))
 
 
 def load_golden(name):
