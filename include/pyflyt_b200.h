@@ -166,6 +166,8 @@ typedef struct PfbBuffers {
                               * setpoints here, pfb_reset / pfb_set_mode preset it like the reference  */
   const float* start_pos;    /* [N][3]                                                               */
   const float* start_orn;    /* [N][3] euler                                                         */
+  const float* reset_targets;/* [N][3*num_targets] waypoints to install on env reset (nullable: drawn on
+                              * device like WaypointHandler.reset, waypoint_handler.py:53-83)          */
   /* outputs of pfb_env_step */
   float* obs;                /* [N][O] row-major                                                     */
   float* reward;             /* [N]                                                                  */

@@ -51,6 +51,8 @@ def lib() -> C.CDLL:
         L.orc_get_pwm.argtypes = [vp, dp]
         L.orc_get_contact.argtypes = [vp, u8p]
         L.orc_env_reset.argtypes = [vp, u8p, dp, dp]
+        L.orc_env_reset_targets.argtypes = [vp, u8p, dp, dp, dp]
+        L.orc_obs_dim.argtypes = [vp]
         L.orc_env_step.argtypes = [vp, dp, dp, dp, dp, u8p, u8p, u8p]
         L.orc_env_rollout.restype = i64
         L.orc_env_rollout.argtypes = [vp, C.c_int]
@@ -83,7 +85,7 @@ class Oracle:
         sp = np.zeros((self.n, 3)) if start_pos is None else np.ascontiguousarray(np.broadcast_to(start_pos, (self.n, 3)), dtype=np.float64)
         so = np.zeros((self.n, 3)) if start_orn is None else np.ascontiguousarray(np.broadcast_to(start_orn, (self.n, 3)), dtype=np.float64)
         L.orc_set_start(self._h, _dp(sp), _dp(so))
-        self.obs_dim = 21 if (env_config is not None and env_config.angle_representation == 1) else 20
+        self.obs_dim = L.orc_obs_dim(C.c_void_p(self._h)) if env_config is not None else 21
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -140,11 +142,15 @@ class Oracle:
         return out
 
     # --- gym env level
-    def env_reset(self, mask=None, noise=None):
+    def env_reset(self, mask=None, noise=None, targets=None):
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
         nz = None if noise is None else np.ascontiguousarray(noise, dtype=np.float64)
         obs = np.zeros((self.n, self.obs_dim))
-        lib().orc_env_reset(self._h, _u8(m), _dp(nz), _dp(obs))
+        if targets is not None:
+            tg = np.ascontiguousarray(targets, dtype=np.float64).reshape(self.n, -1)
+            lib().orc_env_reset_targets(self._h, _u8(m), _dp(nz), _dp(tg), _dp(obs))
+        else:
+            lib().orc_env_reset(self._h, _u8(m), _dp(nz), _dp(obs))
         return obs
 
     def env_step(self, actions, noise=None):

@@ -24,6 +24,7 @@ class PfbBuffers(C.Structure):
         ("setpoint", C.c_void_p),
         ("start_pos", C.c_void_p),
         ("start_orn", C.c_void_p),
+        ("reset_targets", C.c_void_p),
         ("obs", C.c_void_p),
         ("reward", C.c_void_p),
         ("term", C.c_void_p),

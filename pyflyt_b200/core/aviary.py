@@ -111,6 +111,8 @@ class BatchedAviary:
         b.obs, b.reward, b.term, b.trunc = self.obs.data_ptr(), self.reward.data_ptr(), self.term.data_ptr(), self.trunc.data_ptr()
         b.info, b.final_obs = self.info_bits.data_ptr(), self.final_obs.data_ptr()
         b.drone_state, b.aux_state, b.contact = self._drone_state.data_ptr(), self._aux_state.data_ptr(), self._contact.data_ptr()
+        b.reset_targets = None
+        self._reset_targets = None
         self._buffers = b
         _lib.check(L.pfb_bind(self._h, C.byref(b)))
         self._state_fresh = False
@@ -150,9 +152,10 @@ class BatchedAviary:
                 raise ValueError("the batched stepper needs one flight mode per batch")
             flight_modes = flight_modes[0]
         mode = int(flight_modes)
-        if mode < -1 or mode > 7:
-            # quadx.py:259-262
-            raise ValueError(f"`mode` must be between -1 and 7 or be registered in self.registered_controllers.keys()=dict_keys([]), got {mode}.")
+        lo, hi = (-1, 7) if self.drone_type == "quadx" else ((-1, 0) if self.drone_type == "fixedwing" else (0, 0))
+        if mode < lo or mode > hi:
+            # quadx.py:259-262, fixedwing.py:216-219, base_drone.py:252-255
+            raise ValueError(f"`mode` must be between {lo} and {hi} or be registered in self.registered_controllers.keys()=dict_keys([]), got {mode}.")
         _lib.check(_lib.lib().pfb_set_mode(self._h, mode, self._s()))
         self._state_fresh = False
 
@@ -209,7 +212,17 @@ class BatchedAviary:
         return int(_lib.lib().pfb_launch_count(self._h))
 
     # ------------------------------------------------------------------ fused env surface
-    def env_reset(self, mask: torch.Tensor | None = None, noise: torch.Tensor | None = None) -> torch.Tensor:
+    def env_reset(self, mask: torch.Tensor | None = None, noise: torch.Tensor | None = None, targets: torch.Tensor | None = None) -> torch.Tensor:
+        """env.reset() for all / masked envs.  ``targets`` [N, 3*num_targets] installs explicit waypoints
+        (parity tests); by default they are drawn on device like ``WaypointHandler.reset``."""
+        if targets is not None:
+            self._reset_targets = torch.as_tensor(targets, dtype=torch.float32, device=self.device).reshape(self.num_drones, -1).contiguous()
+            self._buffers.reset_targets = self._reset_targets.data_ptr()
+            _lib.check(_lib.lib().pfb_bind(self._h, C.byref(self._buffers)))
+        elif self._reset_targets is not None:
+            self._reset_targets = None
+            self._buffers.reset_targets = None
+            _lib.check(_lib.lib().pfb_bind(self._h, C.byref(self._buffers)))
         m = None if mask is None else C.c_void_p(mask.to(torch.uint8).contiguous().data_ptr())
         nz = None if noise is None else C.c_void_p(noise.data_ptr())
         _lib.check(_lib.lib().pfb_env_reset(self._h, m, nz, self._s()))

@@ -95,6 +95,15 @@ PFB_HD float fast_rcp(float b) {
 #endif
 }
 PFB_HD float fast_div(float a, float b) { return a * fast_rcp(b); }
+PFB_HD float fast_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
 PFB_HD float fast_sqrt(float x) {
 #if defined(__CUDA_ARCH__)
   float r;

@@ -1,0 +1,106 @@
+// pfb_context.h — private to libpyflyt_b200: the handle, error plumbing and launch helpers shared by
+// the per-vehicle translation units (pfb_lib.cu, pfb_fixedwing.cu, ...).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/pyflyt_b200.h"
+#include "pfb_fixedwing.cuh"
+#include "pfb_quadx.cuh"
+
+// thread-local error string (pfb_last_error); returns -1
+int pfb_fail(const char* fmt, ...);
+#define fail pfb_fail
+
+#define CUDA_OK(expr)                                                                    \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+struct RngParams {
+  uint32_t k0, k1;        // Philox key (seed)
+  uint32_t env_offset_lo; // global id of local env 0 (multi-GPU sharding keeps streams rank-independent)
+  uint32_t env_offset_hi;
+};
+
+struct PfbContext {
+  PfbModel model;
+  PfbEnvConfig env;
+  int64_t n;
+  int device;
+  pfb::QuadXParams qx;
+  pfb::HoverParams hover;
+  pfb::FixedwingParams fw;
+  pfb::WaypointParams wp;
+  RngParams rng;
+  PfbBuffers buf;
+  bool bound;
+  int mode;               // Aviary-level flight mode
+  int32_t* d_counters;    // [3] rotating done-list counters: step k appends to [k%3], reads [(k-1)%3], zeroes [(k+1)%3]
+  int32_t* d_done_list;   // [2][N] ping-pong lists of envs that finished on a step
+  uint64_t step_seq;      // env.step() calls so far (selects counters/lists, keys the Philox streams)
+  uint64_t aviary_seq;    // pfb_aviary_step calls so far
+  uint64_t reset_seq;     // pfb_env_reset calls so far
+  int64_t launches;
+  int sm_count;
+  // optional per-step CUDA-event pairs around the dominant kernel (bench.py's roofline leg)
+  cudaEvent_t* prof_ev;   // [2 * prof_cap]
+  int prof_cap;
+  int prof_n;
+};
+
+constexpr int kBlock = 64;     // 65536 envs -> 1024 CTAs over 148 SMs: <1.2% wave imbalance
+constexpr int kMinBlocks = 7;  // 7 CTAs/SM resident (<= 146 regs/thread): all 1024 CTAs in ONE wave
+
+static inline int grid_for(int64_t n) { return (int)((n + kBlock - 1) / kBlock); }
+
+#define LAUNCH_CHECK(h)                                                     \
+  do {                                                                      \
+    cudaError_t _e = cudaGetLastError();                                    \
+    if (_e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(_e)); \
+    (h)->launches += 1;                                                     \
+  } while (0)
+
+// per-step bookkeeping shared by every env kind (rotating counters, ping-pong lists, tail CTAs)
+struct StepPlan {
+  int32_t *cnt_cur, *cnt_prev, *cnt_next, *list_cur, *list_prev;
+  uint32_t seq;
+  int tail, grid;
+  bool prof;
+};
+static inline StepPlan plan_step(PfbContext* h) {
+  StepPlan p;
+  const uint64_t k = h->step_seq;
+  p.cnt_cur = h->d_counters + (k % 3);
+  p.cnt_prev = h->d_counters + ((k + 2) % 3);
+  p.cnt_next = h->d_counters + ((k + 1) % 3);
+  p.list_cur = h->d_done_list + (k & 1) * h->n;
+  p.list_prev = h->d_done_list + ((k + 1) & 1) * h->n;
+  p.seq = (uint32_t)k;
+  // tail CTAs (front of the grid) reset the envs that finished on the previous call; one per SM is
+  // plenty for the ~1-3 % of envs that finish per step, and the loop is grid-strided anyway
+  p.tail = 0;
+  if (h->env.autoreset != 0) {
+    p.tail = h->sm_count;
+    int need = grid_for(h->n);
+    if (p.tail > need) p.tail = need;
+  }
+  p.grid = grid_for(h->n) + p.tail;
+  p.prof = h->prof_ev && h->prof_n < h->prof_cap;
+  return p;
+}
+
+// fixedwing translation unit (pfb_fixedwing.cu)
+int fw_build_params(const PfbModel& m, const PfbEnvConfig* env, pfb::FixedwingParams& p, pfb::WaypointParams& w);
+int fw_state_rows();
+int fw_istate_rows();
+int fw_obs_dim(const PfbContext* h);
+int fw_reset(PfbContext* h, const uint8_t* mask, cudaStream_t s);
+int fw_set_mode(PfbContext* h, int mode, cudaStream_t s);
+int fw_aviary_step(PfbContext* h, int n_steps, const float* noise, cudaStream_t s);
+int fw_observe(PfbContext* h, cudaStream_t s);
+int fw_env_reset(PfbContext* h, const uint8_t* mask, const float* noise, cudaStream_t s);
+int fw_env_step(PfbContext* h, float* actions, const float* noise, bool randact, cudaStream_t s);

@@ -12,7 +12,8 @@
 #include <new>
 
 #include "../../include/pyflyt_b200.h"
-#include "pfb_quadx.cuh"
+#include "pfb_context.h"
+#include "pfb_noise.cuh"
 
 using namespace pfb;
 
@@ -20,7 +21,7 @@ using namespace pfb;
 // error plumbing
 // ---------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
-static int fail(const char* fmt, ...) {
+int pfb_fail(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
@@ -28,126 +29,6 @@ static int fail(const char* fmt, ...) {
   return -1;
 }
 #include "pfb_quadx_host.h"
-
-#define CUDA_OK(expr)                                                                    \
-  do {                                                                                   \
-    cudaError_t _e = (expr);                                                             \
-    if (_e != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(_e)); \
-  } while (0)
-
-// ---------------------------------------------------------------------------------------------------
-// context
-// ---------------------------------------------------------------------------------------------------
-struct RngParams {
-  uint32_t k0, k1;        // Philox key (seed)
-  uint32_t env_offset_lo; // global id of local env 0 (multi-GPU sharding keeps streams rank-independent)
-  uint32_t env_offset_hi;
-};
-
-struct PfbContext {
-  PfbModel model;
-  PfbEnvConfig env;
-  int64_t n;
-  int device;
-  QuadXParams qx;
-  HoverParams hover;
-  RngParams rng;
-  PfbBuffers buf;
-  bool bound;
-  int mode;               // Aviary-level flight mode
-  int32_t* d_counters;    // [3] rotating done-list counters: step k appends to [k%3], reads [(k-1)%3], zeroes [(k+1)%3]
-  int32_t* d_done_list;   // [2][N] ping-pong lists of envs that finished on a step
-  uint64_t step_seq;      // env.step() calls so far (selects counters/lists, keys the Philox streams)
-  uint64_t aviary_seq;    // pfb_aviary_step calls so far
-  uint64_t reset_seq;     // pfb_env_reset calls so far
-  int64_t launches;
-  int sm_count;
-  // optional per-step CUDA-event pairs around the dominant kernel (bench.py's roofline leg)
-  cudaEvent_t* prof_ev;   // [2 * prof_cap]
-  int prof_cap;
-  int prof_n;
-};
-
-constexpr int kBlock = 64;     // 65536 envs -> 1024 CTAs over 148 SMs: <1.2% wave imbalance
-constexpr int kMinBlocks = 7;  // 7 CTAs/SM resident (<= 146 regs/thread): all 1024 CTAs in ONE wave
-
-static inline int grid_for(int64_t n) { return (int)((n + kBlock - 1) / kBlock); }
-
-// ---------------------------------------------------------------------------------------------------
-// noise sources: raw draws of np_random.normal(*throttle.shape)  (motors.py:134-138)
-// ---------------------------------------------------------------------------------------------------
-struct InjectedNoise {  // parity tests: the CPU-drawn sequence, [substep][N]
-  const float* ptr;
-  int64_t N;
-  __device__ __forceinline__ void begin_step() {}
-  __device__ __forceinline__ float get(int) {
-    float v = __ldg(ptr);
-    ptr += N;
-    return v;
-  }
-};
-
-// Throughput path: N(noise_loc, 1) from Philox4x32-10, counter = (global env id, call sequence number,
-// stream tag | Aviary-step index).  Stateless: nothing is stored per env, and a trajectory does not depend
-// on how the batch is sharded over GPUs.  One Philox call per Aviary step, issued OUTSIDE the substep loop.
-enum { TAG_AVIARY = 0, TAG_ENV_STEP = 1, TAG_RESET = 2, TAG_ACTION = 3 };
-struct PhiloxNoise {
-  uint32_t k0, k1, env_lo, env_hi, seq, tag;
-  uint32_t step;
-  int ratio;
-  float loc;
-  float n0, n1, n2, n3;
-  __device__ __forceinline__ void init(const RngParams& r, int64_t i, uint32_t seq_, uint32_t tag_, float loc_, int ratio_) {
-    k0 = r.k0; k1 = r.k1;
-    uint64_t g = ((uint64_t)r.env_offset_hi << 32 | r.env_offset_lo) + (uint64_t)i;
-    env_lo = (uint32_t)g; env_hi = (uint32_t)(g >> 32);
-    seq = seq_; tag = tag_ << 24; step = 0; loc = loc_; ratio = ratio_;
-    n2 = n3 = 0.0f;
-  }
-  __device__ __forceinline__ void begin_step() {
-    // ratio <= 2: one Philox call (4 words -> 4 normals) serves two consecutive Aviary steps
-    if (ratio > 2 || (step & 1u) == 0u) {
-      U4 r = philox4x32_10(U4{env_lo, env_hi, seq, tag | step}, k0, k1);
-      box_muller(r.x, r.y, n0, n1);
-      box_muller(r.z, r.w, n2, n3);
-    }
-    ++step;
-  }
-  __device__ __forceinline__ float get(int u) {
-    // step was already advanced: odd step-1 -> second half of the 4 normals
-    int idx = ratio > 2 ? u : (int)(((step - 1u) & 1u) << 1) + u;
-    float lo = (idx & 1) ? n1 : n0, hi = (idx & 1) ? n3 : n2;
-    return loc + ((idx & 2) ? hi : lo);
-  }
-};
-
-template <bool INJECT>
-struct NoiseSel;
-template <>
-struct NoiseSel<true> {
-  typedef InjectedNoise type;
-};
-template <>
-struct NoiseSel<false> {
-  typedef PhiloxNoise type;
-};
-
-template <bool INJECT>
-__device__ __forceinline__ typename NoiseSel<INJECT>::type make_noise(const float* noise, int64_t N, int64_t i,
-                                                                      const RngParams& r, uint32_t seq, uint32_t tag,
-                                                                      float loc, int ratio);
-template <>
-__device__ __forceinline__ InjectedNoise make_noise<true>(const float* noise, int64_t N, int64_t i, const RngParams&,
-                                                          uint32_t, uint32_t, float, int) {
-  return InjectedNoise{noise + i, N};
-}
-template <>
-__device__ __forceinline__ PhiloxNoise make_noise<false>(const float*, int64_t, int64_t i, const RngParams& r,
-                                                         uint32_t seq, uint32_t tag, float loc, int ratio) {
-  PhiloxNoise n;
-  n.init(r, i, seq, tag, loc, ratio);
-  return n;
-}
 
 // ---------------------------------------------------------------------------------------------------
 // kernels — Aviary surface
@@ -424,7 +305,8 @@ int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, i
   if (!model || !out) return fail("pfb_create: null argument");
   if (model->abi_version != PFB_ABI_VERSION) return fail("PfbModel ABI %d != library ABI %d", model->abi_version, PFB_ABI_VERSION);
   if (n_envs <= 0) return fail("n_envs must be positive");
-  if (model->kind != PFB_KIND_QUADX) return fail("vehicle kind %d is not built into this library yet", model->kind);
+  if (model->kind != PFB_KIND_QUADX && model->kind != PFB_KIND_FIXEDWING)
+    return fail("vehicle kind %d is not built into this library yet", model->kind);
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0)
@@ -438,7 +320,11 @@ int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, i
   if (env) c->env = *env;
   c->n = n_envs;
   c->device = device;
-  if (build_quadx_params(*model, c->qx) != 0) { delete c; return -1; }
+  if (model->kind == PFB_KIND_QUADX) {
+    if (build_quadx_params(*model, c->qx) != 0) { delete c; return -1; }
+  } else {
+    if (fw_build_params(*model, env, c->fw, c->wp) != 0) { delete c; return -1; }
+  }
   c->hover.env_step_ratio = env ? env->env_step_ratio : 1;
   c->hover.max_steps = env ? env->max_steps : 0;
   c->hover.angle_representation = env ? env->angle_representation : 1;
@@ -449,9 +335,13 @@ int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, i
     double dome = env ? env->flight_dome_size : INFINITY;
     c->hover.dome2 = (float)(dome * dome);
   }
-  if (env && env->env_kind != PFB_ENV_NONE && env->env_kind != PFB_ENV_QUADX_HOVER) {
-    delete c;
-    return fail("env kind %d is not built into this library yet", env->env_kind);
+  if (env && env->env_kind != PFB_ENV_NONE) {
+    const bool ok = (model->kind == PFB_KIND_QUADX && env->env_kind == PFB_ENV_QUADX_HOVER) ||
+                    (model->kind == PFB_KIND_FIXEDWING && env->env_kind == PFB_ENV_FIXEDWING_WAYPOINTS);
+    if (!ok) {
+      delete c;
+      return fail("env kind %d is not available for vehicle kind %d in this library", env->env_kind, model->kind);
+    }
   }
   c->rng.k0 = (uint32_t)seed;
   c->rng.k1 = (uint32_t)(seed >> 32);
@@ -486,11 +376,12 @@ int pfb_set_env_offset(PfbHandle h, uint64_t first_global_env) {
   return 0;
 }
 
-int pfb_state_rows(PfbHandle h) { (void)h; return QX_ROWS; }
-int pfb_istate_rows(PfbHandle h) { (void)h; return QI_ROWS; }
-int pfb_setpoint_dim(PfbHandle h) { (void)h; return 4; }
-int pfb_obs_dim(PfbHandle h) { return h->hover.angle_representation == 0 ? 20 : 21; }
-int pfb_aux_dim(PfbHandle h) { (void)h; return 4; }
+static inline bool is_fw(PfbHandle h) { return h->model.kind == PFB_KIND_FIXEDWING; }
+int pfb_state_rows(PfbHandle h) { return is_fw(h) ? fw_state_rows() : QX_ROWS; }
+int pfb_istate_rows(PfbHandle h) { return is_fw(h) ? fw_istate_rows() : QI_ROWS; }
+int pfb_setpoint_dim(PfbHandle h) { return (is_fw(h) && h->env.env_kind == PFB_ENV_NONE) ? 6 : 4; }
+int pfb_obs_dim(PfbHandle h) { return is_fw(h) ? fw_obs_dim(h) : (h->hover.angle_representation == 0 ? 20 : 21); }
+int pfb_aux_dim(PfbHandle h) { return is_fw(h) ? 6 : 4; }
 
 int pfb_bind(PfbHandle h, const PfbBuffers* b) {
   if (!h || !b) return fail("pfb_bind: null argument");
@@ -507,16 +398,11 @@ int pfb_bind(PfbHandle h, const PfbBuffers* b) {
   if (!(h)->bound) return fail("buffers not bound: call pfb_bind first"); \
   CUDA_OK(cudaSetDevice((h)->device));
 
-#define LAUNCH_CHECK(h)                                                     \
-  do {                                                                      \
-    cudaError_t _e = cudaGetLastError();                                    \
-    if (_e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(_e)); \
-    (h)->launches += 1;                                                     \
-  } while (0)
 
 int pfb_reset(PfbHandle h, const uint8_t* mask, void* stream) {
   REQUIRE_BOUND(h);
   cudaStream_t s = (cudaStream_t)stream;
+  if (is_fw(h)) return fw_reset(h, mask, s);
   k_quadx_reset<<<grid_for(h->n), kBlock, 0, s>>>(h->buf.state, h->buf.istate, h->buf.setpoint, h->buf.start_pos,
                                                   h->buf.start_orn, mask, h->n);
   LAUNCH_CHECK(h);
@@ -527,6 +413,7 @@ int pfb_reset(PfbHandle h, const uint8_t* mask, void* stream) {
 int pfb_set_mode(PfbHandle h, int mode, void* stream) {
   REQUIRE_BOUND(h);
   cudaStream_t s = (cudaStream_t)stream;
+  if (is_fw(h)) return fw_set_mode(h, mode, s);
   PFB_MODE_SWITCH(mode, (k_quadx_set_mode<MODE><<<grid_for(h->n), kBlock, 0, s>>>(h->buf.state, h->buf.istate,
                                                                                   h->buf.setpoint, h->n)));
   LAUNCH_CHECK(h);
@@ -538,6 +425,7 @@ int pfb_aviary_step(PfbHandle h, int n_steps, const float* noise, void* stream) 
   REQUIRE_BOUND(h);
   if (n_steps <= 0) return fail("n_steps must be positive");
   cudaStream_t s = (cudaStream_t)stream;
+  if (is_fw(h)) return fw_aviary_step(h, n_steps, noise, s);
   const int mode = h->mode;
   const uint32_t seq = (uint32_t)h->aviary_seq++;
   if (noise) {
@@ -553,6 +441,7 @@ int pfb_aviary_step(PfbHandle h, int n_steps, const float* noise, void* stream) 
 
 int pfb_observe_state(PfbHandle h, void* stream) {
   REQUIRE_BOUND(h);
+  if (is_fw(h)) return fw_observe(h, (cudaStream_t)stream);
   k_quadx_observe<<<grid_for(h->n), kBlock, 0, (cudaStream_t)stream>>>(h->buf.state, h->buf.istate, h->buf.drone_state,
                                                                       h->buf.aux_state, h->buf.contact, h->n);
   LAUNCH_CHECK(h);
@@ -560,7 +449,7 @@ int pfb_observe_state(PfbHandle h, void* stream) {
 }
 
 static int require_env(PfbHandle h) {
-  if (h->env.env_kind != PFB_ENV_QUADX_HOVER) return fail("handle was created without an env epilogue");
+  if (h->env.env_kind == PFB_ENV_NONE) return fail("handle was created without an env epilogue");
   if (!h->buf.obs || !h->buf.reward || !h->buf.term || !h->buf.trunc) return fail("obs/reward/term/trunc buffers are not bound");
   return 0;
 }
@@ -569,6 +458,7 @@ int pfb_env_reset(PfbHandle h, const uint8_t* mask, const float* noise, void* st
   REQUIRE_BOUND(h);
   if (require_env(h)) return -1;
   cudaStream_t s = (cudaStream_t)stream;
+  if (is_fw(h)) return fw_env_reset(h, mask, noise, s);
   const int mode = h->hover.flight_mode;
   // resets draw from their own Philox stream; the high bit keeps them apart from in-step autoresets
   const uint32_t seq = 0x80000000u | (uint32_t)h->reset_seq++;
@@ -587,6 +477,7 @@ int pfb_env_reset(PfbHandle h, const uint8_t* mask, const float* noise, void* st
 }
 
 static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool randact, cudaStream_t s) {
+  if (is_fw(h)) return fw_env_step(h, actions, noise, randact, s);
   const int mode = h->hover.flight_mode;
   const bool autoreset = h->env.autoreset != 0;
   const uint64_t k = h->step_seq;

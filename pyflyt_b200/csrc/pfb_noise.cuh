@@ -1,0 +1,84 @@
+// pfb_noise.cuh — device-side noise sources shared by every vehicle's kernels.
+#pragma once
+
+#include "pfb_common.cuh"
+#include "pfb_context.h"
+
+using namespace pfb;
+
+// ---------------------------------------------------------------------------------------------------
+// noise sources: raw draws of np_random.normal(*throttle.shape)  (motors.py:134-138)
+// ---------------------------------------------------------------------------------------------------
+struct InjectedNoise {  // parity tests: the CPU-drawn sequence, [substep][N]
+  const float* ptr;
+  int64_t N;
+  __device__ __forceinline__ void begin_step() {}
+  __device__ __forceinline__ float get(int) {
+    float v = __ldg(ptr);
+    ptr += N;
+    return v;
+  }
+};
+
+// Throughput path: N(noise_loc, 1) from Philox4x32-10, counter = (global env id, call sequence number,
+// stream tag | Aviary-step index).  Stateless: nothing is stored per env, and a trajectory does not depend
+// on how the batch is sharded over GPUs.  One Philox call per Aviary step, issued OUTSIDE the substep loop.
+enum { TAG_AVIARY = 0, TAG_ENV_STEP = 1, TAG_RESET = 2, TAG_ACTION = 3 };
+struct PhiloxNoise {
+  uint32_t k0, k1, env_lo, env_hi, seq, tag;
+  uint32_t step;
+  int ratio;
+  float loc;
+  float n0, n1, n2, n3;
+  __device__ __forceinline__ void init(const RngParams& r, int64_t i, uint32_t seq_, uint32_t tag_, float loc_, int ratio_) {
+    k0 = r.k0; k1 = r.k1;
+    uint64_t g = ((uint64_t)r.env_offset_hi << 32 | r.env_offset_lo) + (uint64_t)i;
+    env_lo = (uint32_t)g; env_hi = (uint32_t)(g >> 32);
+    seq = seq_; tag = tag_ << 24; step = 0; loc = loc_; ratio = ratio_;
+    n2 = n3 = 0.0f;
+  }
+  __device__ __forceinline__ void begin_step() {
+    // ratio <= 2: one Philox call (4 words -> 4 normals) serves two consecutive Aviary steps
+    if (ratio > 2 || (step & 1u) == 0u) {
+      U4 r = philox4x32_10(U4{env_lo, env_hi, seq, tag | step}, k0, k1);
+      box_muller(r.x, r.y, n0, n1);
+      box_muller(r.z, r.w, n2, n3);
+    }
+    ++step;
+  }
+  __device__ __forceinline__ float get(int u) {
+    // step was already advanced: odd step-1 -> second half of the 4 normals
+    int idx = ratio > 2 ? u : (int)(((step - 1u) & 1u) << 1) + u;
+    float lo = (idx & 1) ? n1 : n0, hi = (idx & 1) ? n3 : n2;
+    return loc + ((idx & 2) ? hi : lo);
+  }
+};
+
+template <bool INJECT>
+struct NoiseSel;
+template <>
+struct NoiseSel<true> {
+  typedef InjectedNoise type;
+};
+template <>
+struct NoiseSel<false> {
+  typedef PhiloxNoise type;
+};
+
+template <bool INJECT>
+__device__ __forceinline__ typename NoiseSel<INJECT>::type make_noise(const float* noise, int64_t N, int64_t i,
+                                                                      const RngParams& r, uint32_t seq, uint32_t tag,
+                                                                      float loc, int ratio);
+template <>
+__device__ __forceinline__ InjectedNoise make_noise<true>(const float* noise, int64_t N, int64_t i, const RngParams&,
+                                                          uint32_t, uint32_t, float, int) {
+  return InjectedNoise{noise + i, N};
+}
+template <>
+__device__ __forceinline__ PhiloxNoise make_noise<false>(const float*, int64_t, int64_t i, const RngParams& r,
+                                                         uint32_t seq, uint32_t tag, float loc, int ratio) {
+  PhiloxNoise n;
+  n.init(r, i, seq, tag, loc, ratio);
+  return n;
+}
+

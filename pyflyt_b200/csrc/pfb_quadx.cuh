@@ -302,7 +302,7 @@ PFB_HD bool quadx_ground_contact(const QuadXParams& p, const QuadXRegs& s) {
 // exceeds vmax/sqrt(3), so the rotation to the world frame and back lives out of line (cold).  Everything
 // is passed BY VALUE so that the caller's register-resident state never has its address taken.
 #if defined(__CUDACC__)
-__host__ __device__ __noinline__
+static __host__ __device__ __noinline__
 #else
 inline
 #endif

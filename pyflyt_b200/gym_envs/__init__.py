@@ -3,6 +3,7 @@
 If ``gymnasium`` is importable the single-env adaptors are registered under the reference's ids
 (PyFlyt/gym_envs/__init__.py:8-43) plus the ``-v2`` aliases BASELINE.json uses."""
 
+from .fixedwing_waypoints_env import FixedwingWaypointsVecEnv  # noqa: F401
 from .quadx_hover_env import QuadXHoverEnv, QuadXHoverVecEnv  # noqa: F401
 
 try:  # pragma: no cover - gymnasium is not installed in the build image

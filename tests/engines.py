@@ -46,6 +46,7 @@ class OracleEngine:
         self.o = Oracle(model, env, n=n, start_pos=start_pos, start_orn=start_orn)
         self.n = n
         self.ups = self.o.updates_per_step
+        self.aux_dim = {0: 4, 1: 6, 2: 9}[int(model.kind)]
 
     def reset(self):
         self.o.reset()
@@ -65,14 +66,14 @@ class OracleEngine:
     def state(self):
         return self.o.state()
 
-    def aux(self):
-        return self.o.aux_state()
+    def aux(self, dim=None):
+        return self.o.aux_state(dim or self.aux_dim)
 
     def contact(self):
         return self.o.contact()
 
-    def env_reset(self, noise):
-        return self.o.env_reset(noise=noise)
+    def env_reset(self, noise, targets=None):
+        return self.o.env_reset(noise=noise, targets=targets)
 
     def env_step(self, actions, noise):
         return self.o.env_step(actions, noise)
@@ -87,7 +88,7 @@ def hostsim_lib(flags: str = ""):
     tag = "".join(ch for ch in flags if ch.isalnum())
     out = os.path.join(ROOT, "tests", "_build", f"libpfb_hostsim{tag}.so")
     src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
-    deps = [src] + [os.path.join(ROOT, "pyflyt_b200", "csrc", f) for f in ("pfb_common.cuh", "pfb_quadx.cuh", "pfb_quadx_host.h")]
+    deps = [src] + [os.path.join(ROOT, "pyflyt_b200", "csrc", f) for f in ("pfb_common.cuh", "pfb_quadx.cuh", "pfb_quadx_host.h", "pfb_fixedwing.cuh", "pfb_fixedwing_host.h")]
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-mfma", "-ffp-contract=fast"] + flags.split() + ["-o", out, src]
@@ -108,9 +109,11 @@ class HostSimEngine:
         self.L = hostsim_lib(flags)
         self.model, self.env, self.n = model, env, n
         self.ups = int(model.physics_hz / model.control_hz)
-        self.st = np.zeros((self.L.hs_state_rows(), n), dtype=np.float32)
-        self.ist = np.zeros((self.L.hs_istate_rows(), n), dtype=np.int32)
-        self.sp = np.zeros((n, 4), dtype=np.float32)
+        self.fw = int(model.kind) == 1
+        self.st = np.zeros((self.L.hs_fw_state_rows() if self.fw else self.L.hs_state_rows(), n), dtype=np.float32)
+        self.ist = np.zeros((self.L.hs_fw_istate_rows() if self.fw else self.L.hs_istate_rows(), n), dtype=np.int32)
+        self.sp = np.zeros((n, 6 if self.fw else 4), dtype=np.float32)
+        self.aux_dim = 6 if self.fw else 4
         self.start_pos = np.ascontiguousarray(np.broadcast_to(np.zeros(3) if start_pos is None else start_pos, (n, 3)), dtype=np.float32)
         self.start_orn = np.ascontiguousarray(np.broadcast_to(np.zeros(3) if start_orn is None else start_orn, (n, 3)), dtype=np.float32)
         self.mode = 0
@@ -122,15 +125,24 @@ class HostSimEngine:
 
     def reset(self):
         f, i32 = C.c_float, C.c_int32
+        if self.fw:
+            self._chk(self.L.hs_fw_reset(C.byref(self.model), _p(self.st, f), _p(self.ist, i32), _p(self.sp, f), _p(self.start_pos, f), _p(self.start_orn, f), C.c_int64(self.n)))
+            self.mode = 0
+            return
         self._chk(self.L.hs_reset(C.byref(self.model), _p(self.st, f), _p(self.ist, i32), _p(self.sp, f), _p(self.start_pos, f), _p(self.start_orn, f), None, C.c_int64(self.n)))
         self.mode = 0
 
     def set_mode(self, mode):
+        if self.fw:
+            self.sp[...] = 0.0
+            self.mode = int(mode)
+            return
         self._chk(self.L.hs_set_mode(int(mode), _p(self.st, C.c_float), _p(self.ist, C.c_int32), _p(self.sp, C.c_float), C.c_int64(self.n)))
         self.mode = int(mode)
 
     def set_setpoints(self, sp):
-        self.sp[...] = np.asarray(sp, dtype=np.float32)
+        sp = np.asarray(sp, dtype=np.float32)
+        self.sp[:, : sp.shape[1]] = sp
 
     def get_setpoints(self):
         return self.sp.astype(np.float64)
@@ -138,12 +150,18 @@ class HostSimEngine:
     def aviary_step(self, noise, n_steps=1):
         nz = np.ascontiguousarray(noise, dtype=np.float32)
         assert nz.shape == (n_steps * self.ups, self.n)
+        if self.fw:
+            self._chk(self.L.hs_fw_aviary_step(C.byref(self.model), self.mode, _p(self.st, C.c_float), _p(self.ist, C.c_int32), _p(self.sp, C.c_float), _p(nz, C.c_float), n_steps, C.c_int64(self.n)))
+            return
         self._chk(self.L.hs_aviary_step(C.byref(self.model), self.mode, _p(self.st, C.c_float), _p(self.ist, C.c_int32), _p(self.sp, C.c_float), _p(nz, C.c_float), n_steps, C.c_int64(self.n)))
 
     def _observe(self):
         ds = np.zeros((self.n, 12), dtype=np.float32)
-        aux = np.zeros((self.n, 4), dtype=np.float32)
+        aux = np.zeros((self.n, self.aux_dim), dtype=np.float32)
         con = np.zeros(self.n, dtype=np.uint8)
+        if self.fw:
+            self._chk(self.L.hs_fw_observe(_p(self.st, C.c_float), _p(self.ist, C.c_int32), _p(ds, C.c_float), _p(aux, C.c_float), _p(con, C.c_uint8), C.c_int64(self.n)))
+            return ds, aux, con
         self._chk(self.L.hs_observe(_p(self.st, C.c_float), _p(self.ist, C.c_int32), _p(ds, C.c_float), _p(aux, C.c_float), _p(con, C.c_uint8), C.c_int64(self.n)))
         return ds, aux, con
 
@@ -160,7 +178,7 @@ class HostSimEngine:
         """hi + lo position words (the fp64 value the kernel carries)."""
         return (self.st[0:3].astype(np.float64) + self.st[21:24].astype(np.float64)).T
 
-    def env_reset(self, noise):
+    def env_reset(self, noise, targets=None):
         nz = np.ascontiguousarray(noise, dtype=np.float32)
         obs = np.zeros((self.n, self.obs_dim), dtype=np.float32)
         self._chk(self.L.hs_env_reset(C.byref(self.model), C.byref(self.env), _p(self.st, C.c_float), _p(self.ist, C.c_int32), _p(self.start_pos, C.c_float), _p(self.start_orn, C.c_float), None, _p(nz, C.c_float), _p(obs, C.c_float), C.c_int64(self.n)))
@@ -256,7 +274,7 @@ class CudaEngine:
 
     name = "cuda"
 
-    def __init__(self, model_or_name, env=None, n=1, start_pos=None, start_orn=None, drone_model="cf2x", seed=0):
+    def __init__(self, model_or_name, env=None, n=1, start_pos=None, start_orn=None, drone_model="cf2x", seed=0, drone_type="quadx", drone_options=None):
         import torch
 
         from pyflyt_b200.core.aviary import BatchedAviary
@@ -265,7 +283,8 @@ class CudaEngine:
         self.n = n
         sp = np.ascontiguousarray(np.broadcast_to(np.zeros(3) if start_pos is None else start_pos, (n, 3)), dtype=np.float32)
         so = np.ascontiguousarray(np.broadcast_to(np.zeros(3) if start_orn is None else start_orn, (n, 3)), dtype=np.float32)
-        self.av = BatchedAviary(sp, so, drone_type="quadx", drone_options=dict(drone_model=drone_model), seed=seed, env_config=env)
+        self.av = BatchedAviary(sp, so, drone_type=drone_type, drone_options=dict(drone_model=drone_model, **(drone_options or {})), seed=seed, env_config=env)
+        self.aux_dim = self.av.aux_dim
         self.ups = self.av.updates_per_step
         self.obs_dim = self.av.obs_dim
 
@@ -279,7 +298,10 @@ class CudaEngine:
         self.av.set_mode(mode)
 
     def set_setpoints(self, sp):
-        self.av.set_all_setpoints(self._dev(sp))
+        sp = np.asarray(sp, dtype=np.float32)
+        full = np.zeros((self.n, self.av.setpoint_dim), dtype=np.float32)
+        full[:, : sp.shape[1]] = sp
+        self.av.set_all_setpoints(self._dev(full))
 
     def get_setpoints(self):
         return self.av.setpoints.double().cpu().numpy()
@@ -296,8 +318,9 @@ class CudaEngine:
     def contact(self):
         return self.av.contact_array.cpu().numpy().astype(np.uint8)
 
-    def env_reset(self, noise):
-        return self.av.env_reset(noise=self._dev(noise)).double().cpu().numpy()
+    def env_reset(self, noise, targets=None):
+        tg = None if targets is None else self._dev(np.asarray(targets).reshape(self.n, -1))
+        return self.av.env_reset(noise=self._dev(noise), targets=tg).double().cpu().numpy()
 
     def env_step(self, actions, noise):
         self.av.env_step(actions=self._dev(actions), noise=self._dev(noise))
@@ -307,5 +330,97 @@ class CudaEngine:
 
 def make_cuda_engine(model, env, n, start_pos, start_orn):
     """Adapter with the (model, env, n, start_pos, start_orn) factory signature used by the replays."""
+    if int(model.kind) == 1:
+        name = "acrowing" if abs(model.com[0] + 0.39574468) < 1e-6 else "fixedwing"
+        return CudaEngine(model, env, n, start_pos, start_orn, drone_model=name, drone_type="fixedwing",
+                          drone_options=dict(starting_velocity=list(model.starting_velocity)))
     name = "primitive_drone" if abs(model.mass - 1.0) < 1e-12 else "cf2x"
     return CudaEngine(model, env, n, start_pos, start_orn, drone_model=name)
+
+
+def model_for_fixture(g):
+    import json
+
+    kind = str(g["drone_type"]) if "drone_type" in g.files else "quadx"
+    opts = json.loads(str(g["drone_options"])) if "drone_options" in g.files else {}
+    return build_model(kind, str(g["drone_model"]), **opts)
+
+
+def replay_vehicle(make_engine, g, every=1):
+    """Replays a fixedwing_aviary / rocket_aviary fixture; max abs errors vs the reference's outputs."""
+    model = model_for_fixture(g)
+    eng = make_engine(model, None, 1, g["start_pos"][None], g["start_orn"][None])
+    eng.reset()
+    eng.set_mode(int(g["mode"]))
+    T = len(g["state"])
+    noise = g["noise"].reshape(T, -1)
+    err = dict(pos=0.0, euler=0.0, angvel=0.0, linvel=0.0, aux=0.0, contact_mismatch=0)
+    for i in range(T):
+        eng.set_setpoints(g["setpoints"][i][None])
+        eng.aviary_step(noise[i][:, None])
+        if i % every and i != T - 1:
+            continue
+        s = eng.state()[0]
+        ref = g["state"][i]
+        d_eul = np.abs((s[1] - ref[1] + np.pi) % (2 * np.pi) - np.pi)
+        err["angvel"] = max(err["angvel"], float(np.abs(s[0] - ref[0]).max()))
+        err["euler"] = max(err["euler"], float(d_eul.max()))
+        err["linvel"] = max(err["linvel"], float(np.abs(s[2] - ref[2]).max()))
+        err["pos"] = max(err["pos"], float(np.abs(s[3] - ref[3]).max()))
+        err["aux"] = max(err["aux"], float(np.abs(eng.aux()[0][: len(g["aux"][i])] - g["aux"][i]).max()))
+        err["contact_mismatch"] += int(bool(eng.contact()[0]) != bool(g["contact"][i]))
+    return err
+
+
+def waypoints_config(angle_representation="quaternion", sparse=False, num_targets=4, goal_reach_distance=2.0, dome=100.0,
+                     agent_hz=30, max_duration=120.0, autoreset=False):
+    e = PfbEnvConfig()
+    e.env_kind = 3
+    e.flight_mode = 0
+    e.env_step_ratio = int(120 / agent_hz)
+    e.max_steps = int(agent_hz * max_duration)
+    e.angle_representation = 1 if angle_representation == "quaternion" else 0
+    e.sparse_reward = int(bool(sparse))
+    e.autoreset = int(bool(autoreset))
+    e.warmup_steps = 10
+    e.flight_dome_size = float(dome)
+    e.goal_reach_distance = float(goal_reach_distance)
+    e.goal_reach_angle = float("inf")
+    e.num_targets = int(num_targets)
+    e.use_yaw_targets = 0
+    return e
+
+
+def replay_waypoints(make_engine, g):
+    """Replays a fixedwing_waypoints fixture: env.reset (targets injected) + scripted env.step + user-loop resets."""
+    model = build_model("fixedwing", "fixedwing")
+    env = waypoints_config(str(g["angle_representation"]), bool(g["sparse"]), int(g["num_targets"]), float(g["goal_reach_distance"]), float(g["dome"]))
+    eng = make_engine(model, env, 1, np.array([[0.0, 0.0, 10.0]]), np.zeros((1, 3)))
+    noise, splits = g["noise"], g["noise_splits"]
+    cursor = {"i": 0}
+
+    def take():
+        k = cursor["i"]
+        seg = noise[(splits[k - 1] if k > 0 else 0) : splits[k]]
+        cursor["i"] += 1
+        return seg
+
+    per_step = env.env_step_ratio * eng.ups
+    obs = eng.env_reset(take()[:, None], targets=g["targets"][0][None])
+    err = dict(obs=float(np.abs(obs[0] - g["reset_obs"]).max()), reward=0.0, flag_mismatch=0, episodes=0)
+    ep_starts = set(g["episode_start"].tolist())
+    k = 0
+    for i in range(len(g["actions"])):
+        seg = take()
+        full = np.zeros((per_step, 1))
+        full[: len(seg), 0] = seg
+        ob, r, te, tr, inf = eng.env_step(g["actions"][i][None], full)
+        err["obs"] = max(err["obs"], float(np.abs(ob[0] - g["obs"][i]).max()))
+        err["reward"] = max(err["reward"], float(abs(r[0] - g["reward"][i])))
+        err["flag_mismatch"] += int(bool(te[0]) != bool(g["term"][i])) + int(bool(tr[0]) != bool(g["trunc"][i])) + int(int(inf[0]) != int(g["info"][i]))
+        if (i + 1) in ep_starts:
+            k += 1
+            ob2 = eng.env_reset(take()[:, None], targets=g["targets"][k][None])
+            err["obs"] = max(err["obs"], float(np.abs(ob2[0] - g["after_reset_obs"][k - 1]).max()))
+            err["episodes"] += 1
+    return err

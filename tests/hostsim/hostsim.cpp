@@ -18,6 +18,7 @@ static int fail(const char* fmt, ...) {
   return -1;
 }
 #include "../../pyflyt_b200/csrc/pfb_quadx_host.h"
+#include "../../pyflyt_b200/csrc/pfb_fixedwing_host.h"
 
 using namespace pfb;
 
@@ -207,3 +208,48 @@ HS_API int hs_obs_quat(const double* q, float* out4) {
 }
 
 HS_API float hs_atan2(float y, float x) { return atan2_f(y, x); }
+
+// ---- fixedwing (Aviary level) -------------------------------------------------------------------
+HS_API int hs_fw_state_rows() { return FW_ROWS; }
+HS_API int hs_fw_istate_rows() { return FI_ROWS; }
+
+HS_API int hs_fw_reset(const PfbModel* m, float* st, int32_t* ist, float* setpoint, const float* start_pos, const float* start_orn, int64_t N) {
+  FixedwingParams p;
+  WaypointParams w;
+  if (fw_build_params_impl(*m, nullptr, p, w)) return -1;
+  for (int64_t i = 0; i < N; ++i) {
+    FixedwingRegs s;
+    fixedwing_reset(p, s, start_pos[3 * i], start_pos[3 * i + 1], start_pos[3 * i + 2], start_orn[3 * i], start_orn[3 * i + 1], start_orn[3 * i + 2]);
+    fixedwing_store(st, ist, N, i, s);
+    ist[(int64_t)FI_STEP * N + i] = 0;
+    for (int k = 0; k < 6; ++k) setpoint[6 * i + k] = 0.f;
+  }
+  return 0;
+}
+
+HS_API int hs_fw_aviary_step(const PfbModel* m, int mode, float* st, int32_t* ist, const float* setpoint, const float* noise, int n_steps, int64_t N) {
+  FixedwingParams p;
+  WaypointParams w;
+  if (fw_build_params_impl(*m, nullptr, p, w)) return -1;
+  for (int64_t i = 0; i < N; ++i) {
+    FixedwingRegs s;
+    fixedwing_load(st, ist, N, i, s);
+    for (int k = 0; k < 6; ++k) s.sp[k] = setpoint[6 * i + k];
+    HostNoise nz{noise + i, N};
+    for (int k = 0; k < n_steps; ++k) {
+      if (mode == 0) fixedwing_aviary_step<0>(p, s, nz); else fixedwing_aviary_step<-1>(p, s, nz);
+    }
+    fixedwing_store(st, ist, N, i, s);
+  }
+  return 0;
+}
+
+HS_API int hs_fw_observe(const float* st, const int32_t* ist, float* drone_state, float* aux, uint8_t* contact, int64_t N) {
+  for (int64_t i = 0; i < N; ++i) {
+    FixedwingRegs s;
+    fixedwing_load(st, ist, N, i, s);
+    fixedwing_drone_state(s, drone_state + 12 * i, aux + 6 * i);
+    contact[i] = (s.flags & FLAG_CONTACT_ARRAY) ? 1 : 0;
+  }
+  return 0;
+}

@@ -10,6 +10,7 @@ CUDA path are both replayed against these with the same injected draws.
 Scenarios mirror the reference's own tests: tests/test_core.py:13-31 (mode-7 hold),
 :65-93 (two set-points), tests/test_gym_envs.py:92-112 (env determinism contract).
 """
+import json
 import os
 import sys
 
@@ -70,6 +71,99 @@ def fly_quadx(name, mode, drone_model, start_pos, start_orn, setpoint_schedule, 
     print(name, "final pos", states[-1][3], "draws", len(rng.normal_log))
 
 
+def fly_vehicle(name, drone_type, drone_model, mode, start_pos, start_orn, setpoint_schedule, n_steps, seed, drone_options=None, pre_hook=None):
+    """Aviary-level flight of a fixedwing / rocket; setpoint_schedule: {step: setpoint} applied before the step."""
+    rng = ril.ScriptedNoise(seed)
+    opts = dict(drone_model=drone_model, **(drone_options or {}))
+    env = Aviary(
+        start_pos=np.array([start_pos], dtype=np.float64),
+        start_orn=np.array([start_orn], dtype=np.float64),
+        drone_type=drone_type,
+        drone_options=opts,
+        np_random=rng,
+    )
+    env.set_mode(mode)
+    if pre_hook is not None:
+        pre_hook(env)
+    d = env.drones[0]
+    sp_dim = len(np.atleast_1d(d.setpoint))
+    states, auxs, contacts, raws, sps = [], [], [], [], []
+    for i in range(n_steps):
+        if i in setpoint_schedule:
+            env.set_setpoint(0, np.array(setpoint_schedule[i], dtype=np.float64))
+        sps.append(np.array(d.setpoint, dtype=np.float64))
+        env.step()
+        states.append(np.array(d.state))
+        auxs.append(np.array(d.aux_state, dtype=np.float64))
+        contacts.append(bool(np.any(env.contact_array[env.planeId])))
+        pos, quat = env.getBasePositionAndOrientation(d.Id)
+        v, w = env.getBaseVelocity(d.Id)
+        raws.append(np.concatenate([pos, quat, v, w]))
+    np.savez_compressed(
+        os.path.join(OUT, f"{name}.npz"),
+        kind=f"{drone_type}_aviary",
+        mode=mode,
+        drone_type=drone_type,
+        drone_model=drone_model,
+        drone_options=json.dumps({k: (list(v) if hasattr(v, "__len__") else v) for k, v in (drone_options or {}).items()}),
+        start_pos=np.array(start_pos, dtype=np.float64),
+        start_orn=np.array(start_orn, dtype=np.float64),
+        setpoint_dim=sp_dim,
+        setpoints=np.array(sps),
+        noise=np.array(rng.normal_log),
+        state=np.array(states),
+        aux=np.array(auxs),
+        contact=np.array(contacts),
+        raw=np.array(raws),
+    )
+    print(name, "final pos", states[-1][3], "draws", len(rng.normal_log))
+
+
+def fly_waypoints(name, seed, n_steps, action_seed, angle_representation="quaternion", sparse=False, num_targets=4,
+                  goal_reach_distance=2.0, dome=100.0, action_scale=1.0):
+    """FixedwingWaypointsEnv (fixedwing_waypoints_env.py) with scripted actions and user-loop resets."""
+    from PyFlyt.gym_envs.fixedwing_envs.fixedwing_waypoints_env import FixedwingWaypointsEnv
+
+    env = FixedwingWaypointsEnv(sparse_reward=sparse, num_targets=num_targets, goal_reach_distance=goal_reach_distance,
+                                flight_dome_size=dome, angle_representation=angle_representation)
+    rng = ril.ScriptedNoise(seed)
+    env._np_random = rng
+
+    def flat(state):
+        d = np.asarray(state["target_deltas"], dtype=np.float64).reshape(-1)
+        pad = np.zeros(3 * num_targets)
+        pad[: len(d)] = d
+        return np.concatenate([state["attitude"], pad])
+
+    state0, _ = env.reset()
+    targets = [np.array(env.waypoints.targets, dtype=np.float64)]
+    arng = np.random.default_rng(action_seed)
+    obs, rew, term, trunc, info, acts, episode_start, resets_obs = [], [], [], [], [], [], [], []
+    noise_splits = [len(rng.normal_log)]
+    for i in range(n_steps):
+        a = arng.uniform(-1.0, 1.0, 4) * action_scale
+        a[3] = arng.uniform(0.2, 1.0)
+        o, r, te, tr, inf = env.step(a)
+        acts.append(a); obs.append(flat(o)); rew.append(r); term.append(te); trunc.append(tr)
+        info.append(int(inf["out_of_bounds"]) | (int(inf["collision"]) << 1) | (int(inf["env_complete"]) << 2) | (int(inf["num_targets_reached"]) << 3))
+        noise_splits.append(len(rng.normal_log))
+        if te or tr:
+            o2, _ = env.reset()
+            targets.append(np.array(env.waypoints.targets, dtype=np.float64))
+            resets_obs.append(flat(o2))
+            episode_start.append(i + 1)
+            noise_splits.append(len(rng.normal_log))
+    np.savez_compressed(
+        os.path.join(OUT, f"{name}.npz"), kind="fixedwing_waypoints", sparse=sparse, dome=dome, num_targets=num_targets,
+        goal_reach_distance=goal_reach_distance, angle_representation=angle_representation, reset_obs=flat(state0),
+        targets=np.array(targets), actions=np.array(acts), obs=np.array(obs), reward=np.array(rew), term=np.array(term),
+        trunc=np.array(trunc), info=np.array(info), noise=np.array(rng.normal_log), noise_splits=np.array(noise_splits),
+        episode_start=np.array(episode_start, dtype=np.int64),
+        after_reset_obs=np.array(resets_obs) if resets_obs else np.zeros((0, 23 + 3 * num_targets)),
+    )
+    print(name, "steps", n_steps, "episodes", len(episode_start) + 1, "max targets reached", max(v >> 3 for v in info), "draws", len(rng.normal_log))
+
+
 def fly_hover(name, seed, n_steps, action_seed, angle_representation, flight_mode=0, sparse=False, dome=3.0, action_scale=1.0):
     from PyFlyt.gym_envs.quadx_envs.quadx_hover_env import QuadXHoverEnv
 
@@ -122,6 +216,31 @@ def fly_hover(name, seed, n_steps, action_seed, angle_representation, flight_mod
     print(name, "steps", n_steps, "episodes", len(episode_start) + 1, "draws", len(rng.normal_log))
 
 
+def fixedwing_fixtures():
+    # Fixedwing (lifting surfaces + one motor), both airframes, mode 0 (RPYT mixing) and -1 (raw surfaces)
+    r = np.random.default_rng(21)
+    for model in ["fixedwing", "acrowing"]:
+        sched0 = {}
+        for k in range(0, 600, 40):
+            sched0[k] = np.concatenate([r.uniform(-0.6, 0.6, 3), r.uniform(0.3, 1.0, 1)])
+        fly_vehicle(f"fixedwing_{model}_mode0", "fixedwing", model, 0, [0, 0, 60.0], [0.05, -0.1, 0.4], sched0, 600, seed=31)
+        schedm = {}
+        for k in range(0, 400, 50):
+            schedm[k] = np.concatenate([r.uniform(-0.8, 0.8, 5), r.uniform(0.0, 1.0, 1)])
+        fly_vehicle(f"fixedwing_{model}_mode-1", "fixedwing", model, -1, [0, 0, 80.0], [0.0, 0.2, -1.0], schedm, 400, seed=32)
+    # deep stall / tumbling: large attitude offsets and zero airspeed at spawn exercise the post-stall branches
+    fly_vehicle(
+        "fixedwing_stall", "fixedwing", "fixedwing", 0, [0, 0, 120.0], [1.2, 0.9, -2.0],
+        {0: [0.9, -0.9, 0.5, 0.0], 150: [-0.9, 0.9, -0.5, 1.0]}, 500, seed=33, drone_options=dict(starting_velocity=np.array([0.0, 0.0, 0.0])),
+    )
+    # dive into the floor: contact flag from the link boxes
+    fly_vehicle("fixedwing_floor", "fixedwing", "fixedwing", 0, [0, 0, 3.0], [0.0, 0.6, 0.0], {0: [0.0, 0.5, 0.0, 0.2]}, 120, seed=34)
+    # Fixedwing-Waypoints env (BASELINE configs[2]); the wide goal radius makes scripted flights reach targets
+    fly_waypoints("fwwp_quat_dense", seed=41, n_steps=300, action_seed=5, action_scale=0.3)
+    fly_waypoints("fwwp_wide_goal", seed=42, n_steps=400, action_seed=6, goal_reach_distance=70.0, action_scale=0.15, num_targets=3)
+    fly_waypoints("fwwp_euler_sparse", seed=43, n_steps=200, action_seed=7, angle_representation="euler", sparse=True, action_scale=0.5)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     # A: tests/test_core.py:13-31
@@ -164,4 +283,9 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "quadx"):
+        main()
+    if which in ("all", "fixedwing"):
+        fixedwing_fixtures()
