@@ -154,6 +154,9 @@ typedef struct PfbEnvConfig {
   double flight_dome_size;
   double goal_reach_distance, goal_reach_angle;  /* waypoint envs                                    */
   int32_t num_targets, use_yaw_targets;
+  /* Rocket-Landing (gym_envs/rocket_envs/rocket_landing_env.py:33-67, rocket_base_env.py:192-226) */
+  double ceiling, max_displacement;
+  int32_t randomize_drop, accelerate_drop;
 } PfbEnvConfig;
 
 /* Caller-owned DEVICE buffers.  Any pointer may be NULL if the env kind does not use it. */
@@ -216,6 +219,9 @@ int pfb_set_mode(PfbHandle h, int mode, void* stream);
 /* n_steps × Aviary.step() (aviary.py:480-531).  noise: device [n_steps*updates_per_step][N] raw
  * draws of np_random.normal(*throttle.shape) (motors.py:134-138), or NULL → on-device Philox.        */
 int pfb_aviary_step(PfbHandle h, int n_steps, const float* noise, void* stream);
+/* p.resetBaseVelocity for every env (gym_envs/rocket_envs/rocket_base_env.py:228): device [N][3] world-
+ * frame linear and angular velocities.                                                                */
+int pfb_set_base_velocity(PfbHandle h, const float* lin_vel, const float* ang_vel, void* stream);
 /* Fills drone_state / aux_state / contact (Aviary.state(i), aux_state(i), contact_array).            */
 int pfb_observe_state(PfbHandle h, void* stream);
 

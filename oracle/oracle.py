@@ -46,6 +46,8 @@ def lib() -> C.CDLL:
         L.orc_get_setpoints.argtypes = [vp, dp, C.c_int]
         L.orc_aviary_step.argtypes = [vp, C.c_int, dp]
         L.orc_get_raw.argtypes = [vp, dp, dp, dp, dp]
+        L.orc_set_base_velocity.argtypes = [vp, dp, dp]
+        L.orc_update_state.argtypes = [vp]
         L.orc_get_state.argtypes = [vp, dp]
         L.orc_get_aux.argtypes = [vp, dp, C.c_int]
         L.orc_get_pwm.argtypes = [vp, dp]
@@ -116,6 +118,14 @@ class Oracle:
             assert nz.shape == (n_steps * self.updates_per_step, self.n), nz.shape
         lib().orc_aviary_step(self._h, n_steps, _dp(nz))
 
+    def set_base_velocity(self, lin, ang):
+        lin = np.ascontiguousarray(np.broadcast_to(lin, (self.n, 3)), dtype=np.float64)
+        ang = np.ascontiguousarray(np.broadcast_to(ang, (self.n, 3)), dtype=np.float64)
+        lib().orc_set_base_velocity(self._h, _dp(lin), _dp(ang))
+
+    def update_state(self):
+        lib().orc_update_state(self._h)
+
     def raw(self):
         pos, quat, v, w = np.zeros((self.n, 3)), np.zeros((self.n, 4)), np.zeros((self.n, 3)), np.zeros((self.n, 3))
         lib().orc_get_raw(self._h, _dp(pos), _dp(quat), _dp(v), _dp(w))
@@ -152,6 +162,11 @@ class Oracle:
         else:
             lib().orc_env_reset(self._h, _u8(m), _dp(nz), _dp(obs))
         return obs
+
+    def set_start(self, start_pos, start_orn):
+        sp = np.ascontiguousarray(np.broadcast_to(start_pos, (self.n, 3)), dtype=np.float64)
+        so = np.ascontiguousarray(np.broadcast_to(start_orn, (self.n, 3)), dtype=np.float64)
+        lib().orc_set_start(self._h, _dp(sp), _dp(so))
 
     def env_step(self, actions, noise=None):
         a = np.ascontiguousarray(actions, dtype=np.float64)

@@ -72,6 +72,7 @@ def lib() -> C.CDLL:
     L.pfb_set_mode.argtypes = [vp, i32, vp]
     L.pfb_aviary_step.argtypes = [vp, i32, vp, vp]
     L.pfb_observe_state.argtypes = [vp, vp]
+    L.pfb_set_base_velocity.argtypes = [vp, vp, vp, vp]
     L.pfb_env_reset.argtypes = [vp, vp, vp, vp]
     L.pfb_env_step.argtypes = [vp, vp, vp, vp]
     L.pfb_env_rollout.argtypes = [vp, i32, vp]
@@ -95,6 +96,7 @@ EXPORTS = [
     "pfb_last_error", "pfb_abi_version", "pfb_sizeof_model", "pfb_sizeof_env_config", "pfb_sizeof_buffers",
     "pfb_create", "pfb_destroy", "pfb_set_env_offset", "pfb_state_rows", "pfb_istate_rows", "pfb_setpoint_dim",
     "pfb_obs_dim", "pfb_aux_dim", "pfb_bind", "pfb_reset", "pfb_set_mode", "pfb_aviary_step", "pfb_observe_state",
+    "pfb_set_base_velocity",
     "pfb_env_reset", "pfb_env_step", "pfb_env_rollout", "pfb_env_step_host", "pfb_launch_count",
     "pfb_profile_begin", "pfb_profile_read",
 ]  # every symbol include/pyflyt_b200.h declares

@@ -179,6 +179,13 @@ class BatchedAviary:
         self.elapsed_time = self.physics_steps / self.physics_hz
         self._state_fresh = False
 
+    def set_base_velocity(self, lin_vel: torch.Tensor, ang_vel: torch.Tensor) -> None:
+        """``p.resetBaseVelocity`` for every drone (used by rocket_base_env.py:228): [N, 3] world-frame tensors."""
+        lin = torch.as_tensor(lin_vel, dtype=torch.float32, device=self.device).reshape(self.num_drones, 3).contiguous()
+        ang = torch.as_tensor(ang_vel, dtype=torch.float32, device=self.device).reshape(self.num_drones, 3).contiguous()
+        _lib.check(_lib.lib().pfb_set_base_velocity(self._h, C.c_void_p(lin.data_ptr()), C.c_void_p(ang.data_ptr()), self._s()))
+        self._state_fresh = False
+
     def _refresh(self):
         if not self._state_fresh:
             _lib.check(_lib.lib().pfb_observe_state(self._h, self._s()))

@@ -9,6 +9,7 @@
 #include "../../include/pyflyt_b200.h"
 #include "pfb_fixedwing.cuh"
 #include "pfb_quadx.cuh"
+#include "pfb_rocket.cuh"
 
 // thread-local error string (pfb_last_error); returns -1
 int pfb_fail(const char* fmt, ...);
@@ -35,6 +36,8 @@ struct PfbContext {
   pfb::HoverParams hover;
   pfb::FixedwingParams fw;
   pfb::WaypointParams wp;
+  pfb::RocketParams rk;
+  pfb::LandingParams land;
   RngParams rng;
   PfbBuffers buf;
   bool bound;
@@ -104,3 +107,16 @@ int fw_aviary_step(PfbContext* h, int n_steps, const float* noise, cudaStream_t 
 int fw_observe(PfbContext* h, cudaStream_t s);
 int fw_env_reset(PfbContext* h, const uint8_t* mask, const float* noise, cudaStream_t s);
 int fw_env_step(PfbContext* h, float* actions, const float* noise, bool randact, cudaStream_t s);
+
+// rocket translation unit (pfb_rocket.cu)
+int rk_build_params(const PfbModel& m, const PfbEnvConfig* env, pfb::RocketParams& p, pfb::LandingParams& l);
+int rk_state_rows();
+int rk_istate_rows();
+int rk_obs_dim(const PfbContext* h);
+int rk_reset(PfbContext* h, const uint8_t* mask, cudaStream_t s);
+int rk_set_mode(PfbContext* h, int mode, cudaStream_t s);
+int rk_set_velocity(PfbContext* h, const float* lin, const float* ang, cudaStream_t s);
+int rk_aviary_step(PfbContext* h, int n_steps, const float* noise, cudaStream_t s);
+int rk_observe(PfbContext* h, cudaStream_t s);
+int rk_env_reset(PfbContext* h, const uint8_t* mask, const float* noise, cudaStream_t s);
+int rk_env_step(PfbContext* h, float* actions, const float* noise, bool randact, cudaStream_t s);

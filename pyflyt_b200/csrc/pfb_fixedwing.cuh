@@ -46,12 +46,14 @@ struct RigidParams {
   float Ainv[36];
 };
 
+constexpr int kMaxShapes = 12;
 struct ContactParams {
   int n_shapes;
-  int kind[8];
-  float dims[8][3];
-  float at[8][3];
-  float thr[8];
+  int kind[kMaxShapes];
+  float dims[kMaxShapes][3];
+  float at[kMaxShapes][3];
+  float rot[kMaxShapes][9];  // primitive axes in the base frame (row-major)
+  float thr[kMaxShapes];
   float zmax;
 };
 
@@ -168,17 +170,23 @@ PFB_HD void surface_force(const SurfaceParams& sf, float& act, float cmd, Vec3 v
 }
 
 // ground-contact flag over a list of axis-aligned primitives (shared helper)
-PFB_HD bool ground_contact(const ContactParams& cp, float pz, float r20, float r21, float r22) {
-  if (pz > cp.zmax) return false;
+// `top` = height of the surface tested (0 for the ground plane, 0.15 for the landing pad)
+PFB_HD bool ground_contact(const ContactParams& cp, float pz, float r20, float r21, float r22, float top = 0.0f) {
+  if (pz - top > cp.zmax) return false;
   bool hit = false;
 #pragma unroll 1
   for (int k = 0; k < cp.n_shapes; ++k) {
     float cz = pz + r20 * cp.at[k][0] + r21 * cp.at[k][1] + r22 * cp.at[k][2];
+    // world-z components of the primitive's own axes: third row of (R * rot)
+    const float* q = cp.rot[k];
+    float z0 = r20 * q[0] + r21 * q[3] + r22 * q[6];
+    float z1 = r20 * q[1] + r21 * q[4] + r22 * q[7];
+    float z2 = r20 * q[2] + r21 * q[5] + r22 * q[8];
     float extent;
-    if (cp.kind[k] == 0) extent = fabsf(r20) * cp.dims[k][0] + fabsf(r21) * cp.dims[k][1] + fabsf(r22) * cp.dims[k][2];
-    else if (cp.kind[k] == 1) extent = cp.dims[k][1] * fabsf(r22) + cp.dims[k][0] * fast_sqrt(fmaxf(0.0f, 1.0f - r22 * r22));
+    if (cp.kind[k] == 0) extent = fabsf(z0) * cp.dims[k][0] + fabsf(z1) * cp.dims[k][1] + fabsf(z2) * cp.dims[k][2];
+    else if (cp.kind[k] == 1) extent = cp.dims[k][1] * fabsf(z2) + cp.dims[k][0] * fast_sqrt(fmaxf(0.0f, 1.0f - z2 * z2));
     else extent = cp.dims[k][0];
-    hit = hit || (cz - extent < cp.thr[k]);
+    hit = hit || (cz - extent - top < cp.thr[k]);
   }
   return hit;
 }

@@ -71,14 +71,12 @@ static int pfb_build_surface(const PfbSurface& s, pfb::SurfaceParams& o) {
 }
 
 static int pfb_build_contact(const PfbModel& m, pfb::ContactParams& c) {
-  if (m.n_shapes > 8) return fail("at most 8 collision primitives are supported, got %d", m.n_shapes);
+  if (m.n_shapes > pfb::kMaxShapes) return fail("at most %d collision primitives are supported, got %d", pfb::kMaxShapes, m.n_shapes);
   c.n_shapes = m.n_shapes;
   c.zmax = -1e30f;
   for (int s = 0; s < m.n_shapes; ++s) {
     const PfbShape& sh = m.shapes[s];
-    const double id[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    for (int k = 0; k < 9; ++k)
-      if (fabs(sh.rot[k] - id[k]) > 1e-12) return fail("collision primitives must be axis-aligned in the base frame");
+    for (int k = 0; k < 9; ++k) c.rot[s][k] = (float)sh.rot[k];
     double disc;
     if (sh.kind == PFB_SHAPE_BOX) disc = sqrt(sh.dims[0] * sh.dims[0] + sh.dims[1] * sh.dims[1] + sh.dims[2] * sh.dims[2]);
     else if (sh.kind == PFB_SHAPE_CYLINDER) disc = sqrt(sh.dims[0] * sh.dims[0] + sh.dims[1] * sh.dims[1]);

@@ -305,8 +305,8 @@ int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, i
   if (!model || !out) return fail("pfb_create: null argument");
   if (model->abi_version != PFB_ABI_VERSION) return fail("PfbModel ABI %d != library ABI %d", model->abi_version, PFB_ABI_VERSION);
   if (n_envs <= 0) return fail("n_envs must be positive");
-  if (model->kind != PFB_KIND_QUADX && model->kind != PFB_KIND_FIXEDWING)
-    return fail("vehicle kind %d is not built into this library yet", model->kind);
+  if (model->kind != PFB_KIND_QUADX && model->kind != PFB_KIND_FIXEDWING && model->kind != PFB_KIND_ROCKET)
+    return fail("unknown vehicle kind %d", model->kind);
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0)
@@ -322,8 +322,10 @@ int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, i
   c->device = device;
   if (model->kind == PFB_KIND_QUADX) {
     if (build_quadx_params(*model, c->qx) != 0) { delete c; return -1; }
-  } else {
+  } else if (model->kind == PFB_KIND_FIXEDWING) {
     if (fw_build_params(*model, env, c->fw, c->wp) != 0) { delete c; return -1; }
+  } else {
+    if (rk_build_params(*model, env, c->rk, c->land) != 0) { delete c; return -1; }
   }
   c->hover.env_step_ratio = env ? env->env_step_ratio : 1;
   c->hover.max_steps = env ? env->max_steps : 0;
@@ -337,7 +339,8 @@ int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, i
   }
   if (env && env->env_kind != PFB_ENV_NONE) {
     const bool ok = (model->kind == PFB_KIND_QUADX && env->env_kind == PFB_ENV_QUADX_HOVER) ||
-                    (model->kind == PFB_KIND_FIXEDWING && env->env_kind == PFB_ENV_FIXEDWING_WAYPOINTS);
+                    (model->kind == PFB_KIND_FIXEDWING && env->env_kind == PFB_ENV_FIXEDWING_WAYPOINTS) ||
+                    (model->kind == PFB_KIND_ROCKET && env->env_kind == PFB_ENV_ROCKET_LANDING);
     if (!ok) {
       delete c;
       return fail("env kind %d is not available for vehicle kind %d in this library", env->env_kind, model->kind);
@@ -377,11 +380,12 @@ int pfb_set_env_offset(PfbHandle h, uint64_t first_global_env) {
 }
 
 static inline bool is_fw(PfbHandle h) { return h->model.kind == PFB_KIND_FIXEDWING; }
-int pfb_state_rows(PfbHandle h) { return is_fw(h) ? fw_state_rows() : QX_ROWS; }
-int pfb_istate_rows(PfbHandle h) { return is_fw(h) ? fw_istate_rows() : QI_ROWS; }
-int pfb_setpoint_dim(PfbHandle h) { return (is_fw(h) && h->env.env_kind == PFB_ENV_NONE) ? 6 : 4; }
-int pfb_obs_dim(PfbHandle h) { return is_fw(h) ? fw_obs_dim(h) : (h->hover.angle_representation == 0 ? 20 : 21); }
-int pfb_aux_dim(PfbHandle h) { return is_fw(h) ? 6 : 4; }
+static inline bool is_rk(PfbHandle h) { return h->model.kind == PFB_KIND_ROCKET; }
+int pfb_state_rows(PfbHandle h) { return is_rk(h) ? rk_state_rows() : (is_fw(h) ? fw_state_rows() : QX_ROWS); }
+int pfb_istate_rows(PfbHandle h) { return is_rk(h) ? rk_istate_rows() : (is_fw(h) ? fw_istate_rows() : QI_ROWS); }
+int pfb_setpoint_dim(PfbHandle h) { return is_rk(h) ? 7 : ((is_fw(h) && h->env.env_kind == PFB_ENV_NONE) ? 6 : 4); }
+int pfb_obs_dim(PfbHandle h) { return is_rk(h) ? rk_obs_dim(h) : (is_fw(h) ? fw_obs_dim(h) : (h->hover.angle_representation == 0 ? 20 : 21)); }
+int pfb_aux_dim(PfbHandle h) { return is_rk(h) ? 9 : (is_fw(h) ? 6 : 4); }
 
 int pfb_bind(PfbHandle h, const PfbBuffers* b) {
   if (!h || !b) return fail("pfb_bind: null argument");
@@ -403,6 +407,7 @@ int pfb_reset(PfbHandle h, const uint8_t* mask, void* stream) {
   REQUIRE_BOUND(h);
   cudaStream_t s = (cudaStream_t)stream;
   if (is_fw(h)) return fw_reset(h, mask, s);
+  if (is_rk(h)) return rk_reset(h, mask, s);
   k_quadx_reset<<<grid_for(h->n), kBlock, 0, s>>>(h->buf.state, h->buf.istate, h->buf.setpoint, h->buf.start_pos,
                                                   h->buf.start_orn, mask, h->n);
   LAUNCH_CHECK(h);
@@ -414,6 +419,7 @@ int pfb_set_mode(PfbHandle h, int mode, void* stream) {
   REQUIRE_BOUND(h);
   cudaStream_t s = (cudaStream_t)stream;
   if (is_fw(h)) return fw_set_mode(h, mode, s);
+  if (is_rk(h)) return rk_set_mode(h, mode, s);
   PFB_MODE_SWITCH(mode, (k_quadx_set_mode<MODE><<<grid_for(h->n), kBlock, 0, s>>>(h->buf.state, h->buf.istate,
                                                                                   h->buf.setpoint, h->n)));
   LAUNCH_CHECK(h);
@@ -426,6 +432,7 @@ int pfb_aviary_step(PfbHandle h, int n_steps, const float* noise, void* stream) 
   if (n_steps <= 0) return fail("n_steps must be positive");
   cudaStream_t s = (cudaStream_t)stream;
   if (is_fw(h)) return fw_aviary_step(h, n_steps, noise, s);
+  if (is_rk(h)) return rk_aviary_step(h, n_steps, noise, s);
   const int mode = h->mode;
   const uint32_t seq = (uint32_t)h->aviary_seq++;
   if (noise) {
@@ -439,9 +446,17 @@ int pfb_aviary_step(PfbHandle h, int n_steps, const float* noise, void* stream) 
   return 0;
 }
 
+int pfb_set_base_velocity(PfbHandle h, const float* lin_vel, const float* ang_vel, void* stream) {
+  REQUIRE_BOUND(h);
+  if (!lin_vel || !ang_vel) return fail("pfb_set_base_velocity: null argument");
+  if (is_rk(h)) return rk_set_velocity(h, lin_vel, ang_vel, (cudaStream_t)stream);
+  return fail("pfb_set_base_velocity is only built for the rocket (the one vehicle whose env calls resetBaseVelocity)");
+}
+
 int pfb_observe_state(PfbHandle h, void* stream) {
   REQUIRE_BOUND(h);
   if (is_fw(h)) return fw_observe(h, (cudaStream_t)stream);
+  if (is_rk(h)) return rk_observe(h, (cudaStream_t)stream);
   k_quadx_observe<<<grid_for(h->n), kBlock, 0, (cudaStream_t)stream>>>(h->buf.state, h->buf.istate, h->buf.drone_state,
                                                                       h->buf.aux_state, h->buf.contact, h->n);
   LAUNCH_CHECK(h);
@@ -459,6 +474,7 @@ int pfb_env_reset(PfbHandle h, const uint8_t* mask, const float* noise, void* st
   if (require_env(h)) return -1;
   cudaStream_t s = (cudaStream_t)stream;
   if (is_fw(h)) return fw_env_reset(h, mask, noise, s);
+  if (is_rk(h)) return rk_env_reset(h, mask, noise, s);
   const int mode = h->hover.flight_mode;
   // resets draw from their own Philox stream; the high bit keeps them apart from in-step autoresets
   const uint32_t seq = 0x80000000u | (uint32_t)h->reset_seq++;
@@ -478,6 +494,7 @@ int pfb_env_reset(PfbHandle h, const uint8_t* mask, const float* noise, void* st
 
 static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool randact, cudaStream_t s) {
   if (is_fw(h)) return fw_env_step(h, actions, noise, randact, s);
+  if (is_rk(h)) return rk_env_step(h, actions, noise, randact, s);
   const int mode = h->hover.flight_mode;
   const bool autoreset = h->env.autoreset != 0;
   const uint64_t k = h->step_seq;
@@ -548,7 +565,7 @@ int pfb_env_step_host(PfbHandle h, const float* host_actions, float* host_obs, f
   if (require_env(h)) return -1;
   cudaStream_t s = (cudaStream_t)stream;
   const int O = pfb_obs_dim(h);
-  CUDA_OK(cudaMemcpyAsync(h->buf.setpoint, host_actions, (size_t)h->n * 4 * sizeof(float), cudaMemcpyHostToDevice, s));
+  CUDA_OK(cudaMemcpyAsync(h->buf.setpoint, host_actions, (size_t)h->n * pfb_setpoint_dim(h) * sizeof(float), cudaMemcpyHostToDevice, s));
   if (env_step_impl(h, h->buf.setpoint, nullptr, false, s)) return -1;
   CUDA_OK(cudaMemcpyAsync(host_obs, h->buf.obs, (size_t)h->n * O * sizeof(float), cudaMemcpyDeviceToHost, s));
   CUDA_OK(cudaMemcpyAsync(host_reward, h->buf.reward, (size_t)h->n * sizeof(float), cudaMemcpyDeviceToHost, s));

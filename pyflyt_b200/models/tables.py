@@ -128,6 +128,10 @@ class PfbEnvConfig(C.Structure):
         ("goal_reach_angle", C.c_double),
         ("num_targets", C.c_int32),
         ("use_yaw_targets", C.c_int32),
+        ("ceiling", C.c_double),
+        ("max_displacement", C.c_double),
+        ("randomize_drop", C.c_int32),
+        ("accelerate_drop", C.c_int32),
     ]
 
 
@@ -333,7 +337,7 @@ def build_model(
         m.gimbal_dt_over_tau = dt / bp["gimbal_tau"]
         r = math.radians(bp["gimbal_range_degrees"])
         m.gimbal_range_rad[:] = [r, r]
-        m.starting_fuel_ratio = float(options.get("starting_fuel_ratio", 1.0))  # rocket.py:47 default
+        m.starting_fuel_ratio = float(options.get("starting_fuel_ratio", 0.05))  # rocket.py:47 default
     return m
 
 

@@ -60,6 +60,13 @@ class OracleEngine:
     def get_setpoints(self):
         return self.o.get_setpoints()
 
+    def set_base_velocity(self, lin, ang):
+        self.o.set_base_velocity(lin, ang)
+        self.o.update_state()  # the fixtures call drone.update_state() after resetBaseVelocity
+
+    def set_start(self, pos, orn):
+        self.o.set_start(pos, orn)
+
     def aviary_step(self, noise, n_steps=1):
         self.o.aviary_step(n_steps, noise)
 
@@ -88,7 +95,7 @@ def hostsim_lib(flags: str = ""):
     tag = "".join(ch for ch in flags if ch.isalnum())
     out = os.path.join(ROOT, "tests", "_build", f"libpfb_hostsim{tag}.so")
     src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
-    deps = [src] + [os.path.join(ROOT, "pyflyt_b200", "csrc", f) for f in ("pfb_common.cuh", "pfb_quadx.cuh", "pfb_quadx_host.h", "pfb_fixedwing.cuh", "pfb_fixedwing_host.h")]
+    deps = [src] + [os.path.join(ROOT, "pyflyt_b200", "csrc", f) for f in ("pfb_common.cuh", "pfb_quadx.cuh", "pfb_quadx_host.h", "pfb_fixedwing.cuh", "pfb_fixedwing_host.h", "pfb_rocket.cuh", "pfb_rocket_host.h")]
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-mfma", "-ffp-contract=fast"] + flags.split() + ["-o", out, src]
@@ -110,10 +117,12 @@ class HostSimEngine:
         self.model, self.env, self.n = model, env, n
         self.ups = int(model.physics_hz / model.control_hz)
         self.fw = int(model.kind) == 1
-        self.st = np.zeros((self.L.hs_fw_state_rows() if self.fw else self.L.hs_state_rows(), n), dtype=np.float32)
-        self.ist = np.zeros((self.L.hs_fw_istate_rows() if self.fw else self.L.hs_istate_rows(), n), dtype=np.int32)
-        self.sp = np.zeros((n, 6 if self.fw else 4), dtype=np.float32)
-        self.aux_dim = 6 if self.fw else 4
+        self.rk = int(model.kind) == 2
+        pre = "hs_rk_" if self.rk else ("hs_fw_" if self.fw else "hs_")
+        self.st = np.zeros((getattr(self.L, pre + "state_rows")(), n), dtype=np.float32)
+        self.ist = np.zeros((getattr(self.L, pre + "istate_rows")(), n), dtype=np.int32)
+        self.sp = np.zeros((n, 7 if self.rk else (6 if self.fw else 4)), dtype=np.float32)
+        self.aux_dim = 9 if self.rk else (6 if self.fw else 4)
         self.start_pos = np.ascontiguousarray(np.broadcast_to(np.zeros(3) if start_pos is None else start_pos, (n, 3)), dtype=np.float32)
         self.start_orn = np.ascontiguousarray(np.broadcast_to(np.zeros(3) if start_orn is None else start_orn, (n, 3)), dtype=np.float32)
         self.mode = 0
@@ -125,14 +134,23 @@ class HostSimEngine:
 
     def reset(self):
         f, i32 = C.c_float, C.c_int32
-        if self.fw:
-            self._chk(self.L.hs_fw_reset(C.byref(self.model), _p(self.st, f), _p(self.ist, i32), _p(self.sp, f), _p(self.start_pos, f), _p(self.start_orn, f), C.c_int64(self.n)))
+        if self.fw or self.rk:
+            fn = self.L.hs_rk_reset if self.rk else self.L.hs_fw_reset
+            self._chk(fn(C.byref(self.model), _p(self.st, f), _p(self.ist, i32), _p(self.sp, f), _p(self.start_pos, f), _p(self.start_orn, f), C.c_int64(self.n)))
             self.mode = 0
             return
         self._chk(self.L.hs_reset(C.byref(self.model), _p(self.st, f), _p(self.ist, i32), _p(self.sp, f), _p(self.start_pos, f), _p(self.start_orn, f), None, C.c_int64(self.n)))
         self.mode = 0
 
+    def set_base_velocity(self, lin, ang):
+        lin = np.ascontiguousarray(np.broadcast_to(lin, (self.n, 3)), dtype=np.float32)
+        ang = np.ascontiguousarray(np.broadcast_to(ang, (self.n, 3)), dtype=np.float32)
+        self._chk(self.L.hs_rk_set_velocity(_p(self.st, C.c_float), _p(self.ist, C.c_int32), _p(lin, C.c_float), _p(ang, C.c_float), C.c_int64(self.n)))
+
     def set_mode(self, mode):
+        if self.rk:
+            self.mode = int(mode)
+            return
         if self.fw:
             self.sp[...] = 0.0
             self.mode = int(mode)
@@ -150,6 +168,9 @@ class HostSimEngine:
     def aviary_step(self, noise, n_steps=1):
         nz = np.ascontiguousarray(noise, dtype=np.float32)
         assert nz.shape == (n_steps * self.ups, self.n)
+        if self.rk:
+            self._chk(self.L.hs_rk_aviary_step(C.byref(self.model), _p(self.st, C.c_float), _p(self.ist, C.c_int32), _p(self.sp, C.c_float), _p(nz, C.c_float), n_steps, C.c_int64(self.n)))
+            return
         if self.fw:
             self._chk(self.L.hs_fw_aviary_step(C.byref(self.model), self.mode, _p(self.st, C.c_float), _p(self.ist, C.c_int32), _p(self.sp, C.c_float), _p(nz, C.c_float), n_steps, C.c_int64(self.n)))
             return
@@ -159,6 +180,9 @@ class HostSimEngine:
         ds = np.zeros((self.n, 12), dtype=np.float32)
         aux = np.zeros((self.n, self.aux_dim), dtype=np.float32)
         con = np.zeros(self.n, dtype=np.uint8)
+        if self.rk:
+            self._chk(self.L.hs_rk_observe(_p(self.st, C.c_float), _p(self.ist, C.c_int32), _p(ds, C.c_float), _p(aux, C.c_float), _p(con, C.c_uint8), C.c_int64(self.n)))
+            return ds, aux, con
         if self.fw:
             self._chk(self.L.hs_fw_observe(_p(self.st, C.c_float), _p(self.ist, C.c_int32), _p(ds, C.c_float), _p(aux, C.c_float), _p(con, C.c_uint8), C.c_int64(self.n)))
             return ds, aux, con
@@ -306,6 +330,15 @@ class CudaEngine:
     def get_setpoints(self):
         return self.av.setpoints.double().cpu().numpy()
 
+    def set_base_velocity(self, lin, ang):
+        lin = self._dev(np.broadcast_to(lin, (self.n, 3)))
+        ang = self._dev(np.broadcast_to(ang, (self.n, 3)))
+        self.av.set_base_velocity(lin, ang)
+
+    def set_start(self, pos, orn):
+        self.av.start_pos.copy_(self._dev(np.broadcast_to(pos, (self.n, 3))))
+        self.av.start_orn.copy_(self._dev(np.broadcast_to(orn, (self.n, 3))))
+
     def aviary_step(self, noise, n_steps=1):
         self.av.step(n_steps, noise=self._dev(noise))
 
@@ -330,6 +363,9 @@ class CudaEngine:
 
 def make_cuda_engine(model, env, n, start_pos, start_orn):
     """Adapter with the (model, env, n, start_pos, start_orn) factory signature used by the replays."""
+    if int(model.kind) == 2:
+        return CudaEngine(model, env, n, start_pos, start_orn, drone_model="rocket", drone_type="rocket",
+                          drone_options=dict(starting_fuel_ratio=float(model.starting_fuel_ratio)))
     if int(model.kind) == 1:
         name = "acrowing" if abs(model.com[0] + 0.39574468) < 1e-6 else "fixedwing"
         return CudaEngine(model, env, n, start_pos, start_orn, drone_model=name, drone_type="fixedwing",
@@ -352,6 +388,8 @@ def replay_vehicle(make_engine, g, every=1):
     eng = make_engine(model, None, 1, g["start_pos"][None], g["start_orn"][None])
     eng.reset()
     eng.set_mode(int(g["mode"]))
+    if "has_pre_hook" in g.files and bool(g["has_pre_hook"]):
+        eng.set_base_velocity(g["start_lin_vel"][None], g["start_ang_vel"][None])  # p.resetBaseVelocity + drone.update_state()
     T = len(g["state"])
     noise = g["noise"].reshape(T, -1)
     err = dict(pos=0.0, euler=0.0, angvel=0.0, linvel=0.0, aux=0.0, contact_mismatch=0)
@@ -421,6 +459,63 @@ def replay_waypoints(make_engine, g):
         if (i + 1) in ep_starts:
             k += 1
             ob2 = eng.env_reset(take()[:, None], targets=g["targets"][k][None])
+            err["obs"] = max(err["obs"], float(np.abs(ob2[0] - g["after_reset_obs"][k - 1]).max()))
+            err["episodes"] += 1
+    return err
+
+
+def landing_config(angle_representation="quaternion", sparse=False, randomize_drop=False, accelerate_drop=False, ceiling=500.0,
+                   max_displacement=200.0, agent_hz=40, max_duration=30.0, autoreset=False):
+    e = PfbEnvConfig()
+    e.env_kind = 4
+    e.flight_mode = 0
+    e.env_step_ratio = int(120 / agent_hz)
+    e.max_steps = int(agent_hz * max_duration)
+    e.angle_representation = 1 if angle_representation == "quaternion" else 0
+    e.sparse_reward = int(bool(sparse))
+    e.autoreset = int(bool(autoreset))
+    e.warmup_steps = 10
+    e.ceiling = float(ceiling)
+    e.max_displacement = float(max_displacement)
+    e.randomize_drop = int(bool(randomize_drop))
+    e.accelerate_drop = int(bool(accelerate_drop))
+    e.flight_dome_size = float("inf")
+    return e
+
+
+def replay_landing(make_engine, g, max_steps=None):
+    """Replays a rocket_landing fixture: every episode's spawn pose is installed explicitly."""
+    model = build_model("rocket", "rocket", starting_fuel_ratio=0.05)  # rocket_landing_env.py:104
+    env = landing_config(str(g["angle_representation"]), bool(g["sparse"]), False, bool(g["accelerate_drop"]))
+    sp = g["spawns"]
+    eng = make_engine(model, env, 1, sp[0][None, :3], sp[0][None, 3:])
+    noise, splits = g["noise"], g["noise_splits"]
+    cursor = {"i": 0}
+
+    def take():
+        k = cursor["i"]
+        seg = noise[(splits[k - 1] if k > 0 else 0) : splits[k]]
+        cursor["i"] += 1
+        return seg
+
+    per_step = env.env_step_ratio * eng.ups
+    obs = eng.env_reset(take()[:, None])
+    err = dict(obs=float(np.abs(obs[0] - g["reset_obs"]).max()), reward=0.0, flag_mismatch=0, episodes=0)
+    ep_starts = set(g["episode_start"].tolist())
+    k = 0
+    T = len(g["actions"]) if max_steps is None else min(max_steps, len(g["actions"]))
+    for i in range(T):
+        seg = take()
+        full = np.zeros((per_step, 1))
+        full[: len(seg), 0] = seg
+        ob, r, te, tr, inf = eng.env_step(g["actions"][i][None], full)
+        err["obs"] = max(err["obs"], float(np.abs(ob[0] - g["obs"][i]).max()))
+        err["reward"] = max(err["reward"], float(abs(r[0] - g["reward"][i])))
+        err["flag_mismatch"] += int(bool(te[0]) != bool(g["term"][i])) + int(bool(tr[0]) != bool(g["trunc"][i])) + int(int(inf[0]) != int(g["info"][i]))
+        if (i + 1) in ep_starts:
+            k += 1
+            eng.set_start(sp[k][None, :3], sp[k][None, 3:])
+            ob2 = eng.env_reset(take()[:, None])
             err["obs"] = max(err["obs"], float(np.abs(ob2[0] - g["after_reset_obs"][k - 1]).max()))
             err["episodes"] += 1
     return err

@@ -19,6 +19,7 @@ static int fail(const char* fmt, ...) {
 }
 #include "../../pyflyt_b200/csrc/pfb_quadx_host.h"
 #include "../../pyflyt_b200/csrc/pfb_fixedwing_host.h"
+#include "../../pyflyt_b200/csrc/pfb_rocket_host.h"
 
 using namespace pfb;
 
@@ -249,6 +250,64 @@ HS_API int hs_fw_observe(const float* st, const int32_t* ist, float* drone_state
     FixedwingRegs s;
     fixedwing_load(st, ist, N, i, s);
     fixedwing_drone_state(s, drone_state + 12 * i, aux + 6 * i);
+    contact[i] = (s.flags & FLAG_CONTACT_ARRAY) ? 1 : 0;
+  }
+  return 0;
+}
+
+// ---- rocket (Aviary level) ------------------------------------------------------------------------
+HS_API int hs_rk_state_rows() { return RK_ROWS; }
+HS_API int hs_rk_istate_rows() { return RI_ROWS; }
+
+HS_API int hs_rk_reset(const PfbModel* m, float* st, int32_t* ist, float* setpoint, const float* start_pos, const float* start_orn, int64_t N) {
+  RocketParams p;
+  LandingParams l;
+  if (rk_build_params_impl(*m, nullptr, p, l)) return -1;
+  for (int64_t i = 0; i < N; ++i) {
+    RocketRegs s;
+    rocket_reset(p, s, start_pos[3 * i], start_pos[3 * i + 1], start_pos[3 * i + 2], start_orn[3 * i], start_orn[3 * i + 1], start_orn[3 * i + 2]);
+    rocket_store(st, ist, N, i, s);
+    ist[(int64_t)RI_STEP * N + i] = 0;
+    for (int k = 0; k < 7; ++k) setpoint[7 * i + k] = 0.f;
+  }
+  return 0;
+}
+
+HS_API int hs_rk_set_velocity(float* st, int32_t* ist, const float* lin, const float* ang, int64_t N) {
+  for (int64_t i = 0; i < N; ++i) {
+    RocketRegs s;
+    rocket_load(st, ist, N, i, s);
+    s.vx = lin[3 * i]; s.vy = lin[3 * i + 1]; s.vz = lin[3 * i + 2];
+    float ox = ang[3 * i], oy = ang[3 * i + 1], oz = ang[3 * i + 2];
+    const Rot<rreal>& R = s.R;
+    s.wx = (float)R.m00 * ox + (float)R.m10 * oy + (float)R.m20 * oz;
+    s.wy = (float)R.m01 * ox + (float)R.m11 * oy + (float)R.m21 * oz;
+    s.wz = (float)R.m02 * ox + (float)R.m12 * oy + (float)R.m22 * oz;
+    rocket_store(st, ist, N, i, s);
+  }
+  return 0;
+}
+
+HS_API int hs_rk_aviary_step(const PfbModel* m, float* st, int32_t* ist, const float* setpoint, const float* noise, int n_steps, int64_t N) {
+  RocketParams p;
+  LandingParams l;
+  if (rk_build_params_impl(*m, nullptr, p, l)) return -1;
+  for (int64_t i = 0; i < N; ++i) {
+    RocketRegs s;
+    rocket_load(st, ist, N, i, s);
+    for (int k = 0; k < 7; ++k) s.sp[k] = setpoint[7 * i + k];
+    HostNoise nz{noise + i, N};
+    for (int k = 0; k < n_steps; ++k) rocket_aviary_step(p, s, nz, false);
+    rocket_store(st, ist, N, i, s);
+  }
+  return 0;
+}
+
+HS_API int hs_rk_observe(const float* st, const int32_t* ist, float* drone_state, float* aux, uint8_t* contact, int64_t N) {
+  for (int64_t i = 0; i < N; ++i) {
+    RocketRegs s;
+    rocket_load(st, ist, N, i, s);
+    rocket_drone_state(s, drone_state + 12 * i, aux + 9 * i);
     contact[i] = (s.flags & FLAG_CONTACT_ARRAY) ? 1 : 0;
   }
   return 0;

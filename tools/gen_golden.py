@@ -85,7 +85,9 @@ def fly_vehicle(name, drone_type, drone_model, mode, start_pos, start_orn, setpo
     env.set_mode(mode)
     if pre_hook is not None:
         pre_hook(env)
+        env.drones[0].update_state()  # resetBaseVelocity alone leaves the drone's cached velocities stale
     d = env.drones[0]
+    v0, w0 = env.getBaseVelocity(d.Id)
     sp_dim = len(np.atleast_1d(d.setpoint))
     states, auxs, contacts, raws, sps = [], [], [], [], []
     for i in range(n_steps):
@@ -109,6 +111,9 @@ def fly_vehicle(name, drone_type, drone_model, mode, start_pos, start_orn, setpo
         start_pos=np.array(start_pos, dtype=np.float64),
         start_orn=np.array(start_orn, dtype=np.float64),
         setpoint_dim=sp_dim,
+        start_lin_vel=np.array(v0, dtype=np.float64),
+        start_ang_vel=np.array(w0, dtype=np.float64),
+        has_pre_hook=pre_hook is not None,
         setpoints=np.array(sps),
         noise=np.array(rng.normal_log),
         state=np.array(states),
@@ -162,6 +167,43 @@ def fly_waypoints(name, seed, n_steps, action_seed, angle_representation="quater
         after_reset_obs=np.array(resets_obs) if resets_obs else np.zeros((0, 23 + 3 * num_targets)),
     )
     print(name, "steps", n_steps, "episodes", len(episode_start) + 1, "max targets reached", max(v >> 3 for v in info), "draws", len(rng.normal_log))
+
+
+def fly_landing(name, seed, n_steps, action_seed, options, angle_representation="quaternion", sparse=False, ignite_p=0.7):
+    """RocketLandingEnv (rocket_landing_env.py) with scripted actions and user-loop resets; ``options`` as in
+    env.reset(options=...): None = randomised + accelerated drop, {} = the plain 450 m hover-drop."""
+    from PyFlyt.gym_envs.rocket_envs.rocket_landing_env import RocketLandingEnv
+
+    env = RocketLandingEnv(sparse_reward=sparse, angle_representation=angle_representation)
+    rng = ril.ScriptedNoise(seed)
+    env._np_random = rng
+    obs0, _ = env.reset(options=None if options is None else dict(options))
+    spawns = [np.concatenate([env.start_pos[0], env.start_orn[0]])]
+    arng = np.random.default_rng(action_seed)
+    lo, hi = env.action_space.low, env.action_space.high
+    obs, rew, term, trunc, info, acts, episode_start, resets_obs = [], [], [], [], [], [], [], []
+    noise_splits = [len(rng.normal_log)]
+    for i in range(n_steps):
+        a = arng.uniform(lo, hi)
+        a[3] = 1.0 if arng.random() < ignite_p else 0.0
+        o, r, te, tr, inf = env.step(a)
+        acts.append(a); obs.append(np.array(o)); rew.append(r); term.append(te); trunc.append(tr)
+        info.append(int(inf["out_of_bounds"]) | (int(inf["fatal_collision"]) << 1) | (int(inf["env_complete"]) << 2))
+        noise_splits.append(len(rng.normal_log))
+        if te or tr:
+            o2, _ = env.reset(options=None if options is None else dict(options))
+            spawns.append(np.concatenate([env.start_pos[0], env.start_orn[0]]))
+            resets_obs.append(np.array(o2))
+            episode_start.append(i + 1)
+            noise_splits.append(len(rng.normal_log))
+    np.savez_compressed(
+        os.path.join(OUT, f"{name}.npz"), kind="rocket_landing", sparse=sparse, angle_representation=angle_representation,
+        randomize_drop=options is None, accelerate_drop=options is None, spawns=np.array(spawns), reset_obs=np.array(obs0),
+        actions=np.array(acts), obs=np.array(obs), reward=np.array(rew), term=np.array(term), trunc=np.array(trunc), info=np.array(info),
+        noise=np.array(rng.normal_log), noise_splits=np.array(noise_splits), episode_start=np.array(episode_start, dtype=np.int64),
+        after_reset_obs=np.array(resets_obs) if resets_obs else np.zeros((0, len(obs0))),
+    )
+    print(name, "steps", n_steps, "episodes", len(episode_start) + 1, "infos", sorted(set(info)), "draws", len(rng.normal_log))
 
 
 def fly_hover(name, seed, n_steps, action_seed, angle_representation, flight_mode=0, sparse=False, dome=3.0, action_scale=1.0):
@@ -241,6 +283,40 @@ def fixedwing_fixtures():
     fly_waypoints("fwwp_euler_sparse", seed=43, n_steps=200, action_seed=7, angle_representation="euler", sparse=True, action_scale=0.5)
 
 
+def rocket_fixtures():
+    r = np.random.default_rng(51)
+
+    def sched(n, every, ign_p=0.8):
+        out = {}
+        for k in range(0, n, every):
+            out[k] = np.concatenate([r.uniform(-1, 1, 3), [1.0 if r.random() < ign_p else 0.0], r.uniform(0, 1, 1), r.uniform(-1, 1, 2)])
+        return out
+
+    # powered flight from rest: gimbal, fins, throttle changes, full tank (mass/inertia vary slowly)
+    fly_vehicle("rocket_powered", "rocket", "rocket", 0, [0, 0, 100.0], [0.05, -0.04, 0.3], sched(600, 40), 600, seed=61)
+    # Rocket-Landing style drop: 5 % fuel runs dry (hard cut-off), -100 m/s start hits Bullet's velocity clamp
+    def drop(env):
+        env.resetBaseVelocity(env.drones[0].Id, [3.0, -2.0, -100.0], [0.2, -0.1, 0.3])
+    fly_vehicle("rocket_drop", "rocket", "rocket", 0, [5.0, -8.0, 420.0], [0.2, -0.15, 0.1], sched(500, 25, 0.6), 500, seed=62,
+                drone_options=dict(starting_fuel_ratio=0.05), pre_hook=drop)
+    # tumbling, engine off: finlets + body drag at large angles of attack
+    def spin(env):
+        env.resetBaseVelocity(env.drones[0].Id, [20.0, 10.0, -30.0], [1.5, -1.0, 0.5])
+    s3 = sched(300, 30, 0.0)
+    fly_vehicle("rocket_tumble", "rocket", "rocket", 0, [0, 0, 300.0], [1.0, 0.5, 0.0], s3, 300, seed=63, pre_hook=spin)
+    # ground strike (legs / body primitives)
+    fly_vehicle("rocket_ground", "rocket", "rocket", 0, [30.0, 0, 6.0], [0.3, 0.0, 0.0], {0: [0, 0, 0, 0, 0, 0, 0]}, 150, seed=64)
+    # full tank: the composite mass / COM / inertia change every substep while the booster burns
+    fly_vehicle("rocket_full_tank", "rocket", "rocket", 0, [0, 0, 50.0], [0.0, 0.05, 0.0], sched(480, 60, 1.0), 480, seed=65,
+                drone_options=dict(starting_fuel_ratio=1.0))
+    # Rocket-Landing env (BASELINE configs[3]): randomised accelerated drops (options=None) and the plain drop ({})
+    fly_landing("landing_random_drop", seed=71, n_steps=500, action_seed=8, options=None)
+    fly_landing("landing_plain_euler", seed=72, n_steps=400, action_seed=9, options={}, angle_representation="euler", ignite_p=0.2)
+    fly_landing("landing_sparse", seed=73, n_steps=300, action_seed=10, options=None, sparse=True, ignite_p=0.0)
+    # unpowered plain drop straight onto the pad: pad-contact reward, fatal touchdown speed, next episode
+    fly_landing("landing_pad_strike", seed=74, n_steps=450, action_seed=11, options={}, ignite_p=0.0)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     # A: tests/test_core.py:13-31
@@ -289,3 +365,5 @@ if __name__ == "__main__":
         main()
     if which in ("all", "fixedwing"):
         fixedwing_fixtures()
+    if which in ("all", "rocket"):
+        rocket_fixtures()
