@@ -7,7 +7,7 @@
 One "step" = one env.step() of every env of this rank's shard = one k_hover_step launch (6 physics
 substeps, 3 control ticks, reward/termination/observation fused) + one k_hover_autoreset launch.
 Workload (config.workload): QuadX-Hover-v4, mode 0, 65 536 envs per GPU, uniform random actions in the
-env's action box, same-step autoreset — BASELINE.json configs[1].  Prints ONE JSON line on rank 0.
+env's action box, NEXT_STEP autoreset — BASELINE.json configs[1].  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -75,8 +75,7 @@ def cpu_oracle_rate(envs: int, target_seconds: float, threads: int | None = None
     from oracle import oracle as orc_mod
 
     L = orc_mod.lib()
-    if threads:
-        L.orc_set_num_threads(int(threads))
+    L.orc_set_num_threads(int(threads) if threads else (os.cpu_count() or 1))
     cores = int(L.orc_num_threads())
     model = build_model("quadx", "cf2x")
     env = hover_config(0, "quaternion", False, 3.0, autoreset=True)
@@ -107,6 +106,7 @@ def run_reference(args, rank, world):
     from oracle import oracle as orc_mod
 
     L = orc_mod.lib()
+    L.orc_set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: use every host thread anyway
     cores = int(L.orc_num_threads())
     model = build_model("quadx", "cf2x")
     env = hover_config(0, "quaternion", False, 3.0, autoreset=True)
@@ -123,7 +123,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "QuadX-Hover-v4 mode 0, 65536 envs, uniform random actions, same-step autoreset", "envs": envs},
+        "config": {"workload": "QuadX-Hover-v4 mode 0, 65536 envs, uniform random actions, NEXT_STEP autoreset", "envs": envs},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} steps x {envs} envs of the full workload (oracle/pfb_oracle.c, OpenMP)"},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -225,7 +225,7 @@ def run_ours(args, rank, local_rank, world):
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {
-                "workload": "QuadX-Hover-v4 (BASELINE configs[1]): flight mode 0, 65536 envs per GPU, uniform random actions, same-step autoreset, 6 physics substeps + 3 control ticks per env-step",
+                "workload": "QuadX-Hover-v4 (BASELINE configs[1]): flight mode 0, 65536 envs per GPU, uniform random actions, NEXT_STEP autoreset, 6 physics substeps + 3 control ticks per env-step",
                 "envs_per_gpu": n, "global_envs": world * n, "parallelism": f"env-shard x{world} (no data-path collective)",
                 "l2": "flushed between timed steps (256 MiB write outside the event pairs); per-step CUDA-event pairs summed",
                 "precision": "fp32 forces/control/obs; quaternion, position, velocity carried as fp64 (hi+lo fp32 words in HBM)",
