@@ -157,6 +157,11 @@ typedef struct PfbEnvConfig {
   /* Rocket-Landing (gym_envs/rocket_envs/rocket_landing_env.py:33-67, rocket_base_env.py:192-226) */
   double ceiling, max_displacement;
   int32_t randomize_drop, accelerate_drop;
+  /* MAFixedwingDogfight (pz_envs/fixedwing_envs/ma_fixedwing_dogfight_env.py:42-62): an arena is
+   * 2*team_size CONSECUTIVE envs of the batch; the first team_size of them are team 0                 */
+  int32_t team_size, _pad_df;
+  double damage_per_hit, lethal_distance, lethal_angle, aggressiveness, cooperativeness;
+  double spawn_min_radius, spawn_max_radius, spawn_min_height, spawn_max_height;
 } PfbEnvConfig;
 
 /* Caller-owned DEVICE buffers.  Any pointer may be NULL if the env kind does not use it. */

@@ -132,6 +132,17 @@ class PfbEnvConfig(C.Structure):
         ("max_displacement", C.c_double),
         ("randomize_drop", C.c_int32),
         ("accelerate_drop", C.c_int32),
+        ("team_size", C.c_int32),
+        ("_pad_df", C.c_int32),
+        ("damage_per_hit", C.c_double),
+        ("lethal_distance", C.c_double),
+        ("lethal_angle", C.c_double),
+        ("aggressiveness", C.c_double),
+        ("cooperativeness", C.c_double),
+        ("spawn_min_radius", C.c_double),
+        ("spawn_max_radius", C.c_double),
+        ("spawn_min_height", C.c_double),
+        ("spawn_max_height", C.c_double),
     ]
 
 

@@ -519,3 +519,54 @@ def replay_landing(make_engine, g, max_steps=None):
             err["obs"] = max(err["obs"], float(np.abs(ob2[0] - g["after_reset_obs"][k - 1]).max()))
             err["episodes"] += 1
     return err
+
+
+def dogfight_config(team_size=1, sparse=False, lethal_distance=20.0, lethal_angle=0.07, damage_per_hit=0.003, aggressiveness=0.5,
+                    cooperativeness=0.5, dome=800.0, agent_hz=30, max_duration=60.0, autoreset=False,
+                    spawn_min_radius=10.0, spawn_max_radius=50.0, spawn_min_height=20.0, spawn_max_height=50.0):
+    e = PfbEnvConfig()
+    e.env_kind = 5
+    e.flight_mode = 0
+    e.env_step_ratio = int(120 / agent_hz)
+    e.max_steps = int(agent_hz * max_duration)
+    e.angle_representation = 0
+    e.sparse_reward = int(bool(sparse))
+    e.autoreset = int(bool(autoreset))
+    e.warmup_steps = 10
+    e.flight_dome_size = float(dome)
+    e.team_size = int(team_size)
+    e.damage_per_hit, e.lethal_distance, e.lethal_angle = float(damage_per_hit), float(lethal_distance), float(lethal_angle)
+    e.aggressiveness, e.cooperativeness = float(aggressiveness), float(cooperativeness)
+    e.spawn_min_radius, e.spawn_max_radius = float(spawn_min_radius), float(spawn_max_radius)
+    e.spawn_min_height, e.spawn_max_height = float(spawn_min_height), float(spawn_max_height)
+    return e
+
+
+def replay_dogfight(make_engine, g):
+    """Replays a dogfight fixture arena by arena: spawn poses and noise injected, dead agents keep flying."""
+    ts = int(g["team_size"])
+    A = 2 * ts
+    model = build_model("fixedwing", "acrowing")  # ma_fixedwing_base_env.py:192-195
+    env = dogfight_config(ts, bool(g["sparse"]), float(g["lethal_distance"]), float(g["lethal_angle"]), float(g["damage_per_hit"]) if "damage_per_hit" in g.files else 0.003)
+    err = dict(obs=0.0, reward=0.0, flag_mismatch=0, episodes=int(g["n_episodes"]))
+    eng = None
+    for k in range(int(g["n_episodes"])):
+        spawn = g[f"ep{k}_spawn"]
+        if eng is None:
+            eng = make_engine(model, env, A, spawn[:, :3], spawn[:, 3:])
+        else:
+            eng.set_start(spawn[:, :3], spawn[:, 3:])
+        per_sub = A
+        rn = g[f"ep{k}_reset_noise"].reshape(-1, per_sub)
+        obs = eng.env_reset(rn)
+        err["obs"] = max(err["obs"], float(np.abs(obs - g[f"ep{k}_reset_obs"]).max()))
+        T = len(g[f"ep{k}_actions"])
+        for i in range(T):
+            nz = g[f"ep{k}_noise"][i].reshape(-1, per_sub)
+            ob, r, te, tr, _ = eng.env_step(g[f"ep{k}_actions"][i], nz)
+            alive = g[f"ep{k}_alive"][i]
+            ref_o, ref_r = g[f"ep{k}_obs"][i], g[f"ep{k}_reward"][i]
+            err["obs"] = max(err["obs"], float(np.abs(ob[alive] - ref_o[alive]).max()))
+            err["reward"] = max(err["reward"], float(np.abs(r[alive] - ref_r[alive]).max()))
+            err["flag_mismatch"] += int((te[alive].astype(bool) != g[f"ep{k}_term"][i][alive]).sum()) + int((tr[alive].astype(bool) != g[f"ep{k}_trunc"][i][alive]).sum())
+    return err

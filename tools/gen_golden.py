@@ -206,6 +206,71 @@ def fly_landing(name, seed, n_steps, action_seed, options, angle_representation=
     print(name, "steps", n_steps, "episodes", len(episode_start) + 1, "infos", sorted(set(info)), "draws", len(rng.normal_log))
 
 
+def fly_dogfight(name, seed, n_steps, action_seed, team_size=1, sparse=False, action_scale=0.6, lethal_distance=20.0, lethal_angle=0.07,
+                 spawn_min_radius=10.0, spawn_max_radius=50.0, damage_per_hit=0.003, pitch_bias=0.0):
+    """MAFixedwingDogfightEnv (pz_envs/fixedwing_envs/ma_fixedwing_dogfight_env.py) with scripted actions; a new
+    episode is started whenever every agent is done.  The Aviary's own generator (seeded by reset(seed)) is
+    wrapped so that its motor-noise draws are recorded."""
+    from PyFlyt.pz_envs.fixedwing_envs.ma_fixedwing_dogfight_env import MAFixedwingDogfightEnv
+
+    env = MAFixedwingDogfightEnv(team_size=team_size, sparse_reward=sparse, lethal_distance=lethal_distance, lethal_angle_radians=lethal_angle,
+                                 spawn_min_radius=spawn_min_radius, spawn_max_radius=spawn_max_radius, damage_per_hit=damage_per_hit)
+    A = 2 * team_size
+    real_default_rng = np.random.default_rng
+    loggers = []
+
+    def reset(seed_):
+        def patched(s=None):
+            lg = ril.ScriptedNoise.__new__(ril.ScriptedNoise)
+            lg._rng = real_default_rng(s)
+            lg.normal_log = []
+            loggers.append(lg)
+            return lg
+        np.random.default_rng = patched
+        try:
+            obs, _ = env.reset(seed=seed_)
+        finally:
+            np.random.default_rng = real_default_rng
+        return np.stack([obs[f"uav_{i}"] for i in range(A)])
+
+    def drained():
+        lg = loggers[-1]
+        out = np.array(lg.normal_log)
+        lg.normal_log.clear()
+        return out
+
+    arng = real_default_rng(action_seed)
+    episodes = []
+    ep_seed = seed
+    obs0 = reset(ep_seed)
+    ep = dict(spawn=np.concatenate([env.start_pos, env.start_orn], axis=1), reset_obs=obs0, reset_noise=drained(), actions=[], obs=[], reward=[], term=[], trunc=[], noise=[])
+    for i in range(n_steps):
+        alive = set(env.agents)
+        act = arng.uniform(-1.0, 1.0, (A, 4)) * action_scale
+        act[:, 1] = np.clip(act[:, 1] + pitch_bias, -1.0, 1.0)
+        o, r, te, tr, _ = env.step({f"uav_{k}": act[k] for k in range(A) if f"uav_{k}" in alive})
+        ep["actions"].append(act)
+        ep["noise"].append(drained())
+        row = lambda d, default: np.array([d.get(f"uav_{k}", default) for k in range(A)])  # noqa: E731
+        ep["obs"].append(np.stack([o.get(f"uav_{k}", np.full(obs0.shape[1], np.nan)) for k in range(A)]))
+        ep["reward"].append(row(r, np.nan)); ep["term"].append(row(te, True)); ep["trunc"].append(row(tr, False))
+        ep["alive"] = ep.get("alive", []) + [np.array([f"uav_{k}" in alive for k in range(A)])]
+        if len(env.agents) == 0:
+            episodes.append(ep)
+            ep_seed += 1
+            obs0 = reset(ep_seed)
+            ep = dict(spawn=np.concatenate([env.start_pos, env.start_orn], axis=1), reset_obs=obs0, reset_noise=drained(), actions=[], obs=[], reward=[], term=[], trunc=[], noise=[])
+    if ep["actions"]:
+        episodes.append(ep)
+    flat = {}
+    for k, e in enumerate(episodes):
+        for key, v in e.items():
+            flat[f"ep{k}_{key}"] = np.array(v)
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), kind="dogfight", team_size=team_size, sparse=sparse, n_episodes=len(episodes),
+                        lethal_distance=lethal_distance, lethal_angle=lethal_angle, damage_per_hit=damage_per_hit, **flat)
+    print(name, "episodes", len(episodes), "steps", [len(e["actions"]) for e in episodes], "reward range", min(np.nanmin(e["reward"]) for e in episodes), max(np.nanmax(e["reward"]) for e in episodes))
+
+
 def fly_hover(name, seed, n_steps, action_seed, angle_representation, flight_mode=0, sparse=False, dome=3.0, action_scale=1.0):
     from PyFlyt.gym_envs.quadx_envs.quadx_hover_env import QuadXHoverEnv
 
@@ -317,6 +382,18 @@ def rocket_fixtures():
     fly_landing("landing_pad_strike", seed=74, n_steps=450, action_seed=11, options={}, ignite_p=0.0)
 
 
+def dogfight_fixtures():
+    # MAFixedwingDogfight (BASELINE configs[4]): 1-vs-1 arenas; a wide lethal cone makes scripted flights score hits
+    fly_dogfight("dogfight_1v1", seed=81, n_steps=260, action_seed=12)
+    fly_dogfight("dogfight_1v1_wide_cone", seed=83, n_steps=260, action_seed=13, lethal_distance=150.0, lethal_angle=1.2, action_scale=0.3)
+    fly_dogfight("dogfight_1v1_sparse", seed=85, n_steps=150, action_seed=14, sparse=True)
+    # nose-down bias: ground collisions (-1000), the survivor's team win (+300), several episodes
+    fly_dogfight("dogfight_1v1_crash", seed=91, n_steps=250, action_seed=17, action_scale=0.2, pitch_bias=0.8)
+    # heavy damage in a 2-vs-2: deaths by health, team wins, dead agents that keep flying
+    fly_dogfight("dogfight_2v2_lethal", seed=87, n_steps=200, action_seed=15, team_size=2, lethal_distance=120.0, lethal_angle=0.9, action_scale=0.3, damage_per_hit=0.05)
+    fly_dogfight("dogfight_2v2", seed=87, n_steps=200, action_seed=15, team_size=2, lethal_distance=120.0, lethal_angle=0.9, action_scale=0.3)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     # A: tests/test_core.py:13-31
@@ -367,3 +444,5 @@ if __name__ == "__main__":
         fixedwing_fixtures()
     if which in ("all", "rocket"):
         rocket_fixtures()
+    if which in ("all", "dogfight"):
+        dogfight_fixtures()
