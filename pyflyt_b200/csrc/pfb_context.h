@@ -36,6 +36,7 @@ struct PfbContext {
   pfb::HoverParams hover;
   pfb::FixedwingParams fw;
   pfb::WaypointParams wp;
+  pfb::DogfightParams df;
   pfb::RocketParams rk;
   pfb::LandingParams land;
   RngParams rng;
@@ -120,3 +121,9 @@ int rk_aviary_step(PfbContext* h, int n_steps, const float* noise, cudaStream_t 
 int rk_observe(PfbContext* h, cudaStream_t s);
 int rk_env_reset(PfbContext* h, const uint8_t* mask, const float* noise, cudaStream_t s);
 int rk_env_step(PfbContext* h, float* actions, const float* noise, bool randact, cudaStream_t s);
+
+// dogfight translation unit (pfb_dogfight.cu): fixedwing vehicles, arenas of 2*team_size adjacent envs
+int df_build_params(const PfbEnvConfig* env, pfb::DogfightParams& d);
+int df_obs_dim(const PfbContext* h);
+int df_env_reset(PfbContext* h, const uint8_t* mask, const float* noise, cudaStream_t s);
+int df_env_step(PfbContext* h, float* actions, const float* noise, bool randact, cudaStream_t s);

@@ -1,0 +1,466 @@
+// pfb_dogfight.cu — MAFixedwingDogfight on the batched stepper (BASELINE.json configs[4]).
+//
+// Replaces /root/reference/PyFlyt/pz_envs/fixedwing_envs/ma_fixedwing_dogfight_env.py:346-721 and
+// ma_fixedwing_base_env.py:166-338 for many arenas at once.  One thread = one aircraft; an arena is
+// A = 2*team_size ADJACENT lanes of a warp (A in {2, 4}), so the pairwise combat state — separation,
+// engagement angle, hits, healths — is exchanged with warp shuffles inside the same launch that integrates
+// the aircraft: no shared memory, no second kernel, no collective.  (The cross-rank variant, where an arena's
+// agents live on different GPUs, exchanges the same 16-float payload through an NCCL all-gather between two
+// kernels: see DESIGN.md §7; it is not built yet.)
+#include <cmath>
+#include <cstring>
+
+#include "pfb_context.h"
+#include "pfb_noise.cuh"
+
+using namespace pfb;
+
+// per-agent dogfight rows alias the (unused) waypoint-target rows of the fixedwing state tensor
+enum {
+  DF_HEALTH = FW_TARGETS + 0, DF_REWARD = FW_TARGETS + 1, DF_PAST = FW_TARGETS + 2 /*4*/, DF_CUR = FW_TARGETS + 6 /*4*/,
+  DF_DIST = FW_TARGETS + 10 /*7*/, DF_ANG = FW_TARGETS + 17 /*7*/
+};
+enum { FLAG_AGENT_DONE = 1024 /* popped out of self.agents */, FLAG_DF_DEAD = 2048, FLAG_DF_WIN = 4096 };
+enum { DI_STEP = 0, DI_FLAGS = 1, DI_HITS = 2 };
+
+constexpr int kDfObsMax = 23 + 14 * 3;   // A = 4
+constexpr int kDfObsStride = kDfObsMax | 1;
+
+int df_build_params(const PfbEnvConfig* env, DogfightParams& d) {
+  memset(&d, 0, sizeof(d));
+  if (!env) return 0;
+  d.team_size = env->team_size;
+  if (env->env_kind == PFB_ENV_DOGFIGHT && d.team_size != 1 && d.team_size != 2)
+    return fail("the fused dogfight kernel supports team_size 1 or 2 (arenas of 2 or 4 adjacent lanes), got %d", d.team_size);
+  d.env_step_ratio = env->env_step_ratio;
+  d.max_steps = env->max_steps;
+  d.sparse_reward = env->sparse_reward;
+  d.warmup_steps = env->warmup_steps;
+  d.dome = (float)env->flight_dome_size;
+  d.damage_per_hit = (float)env->damage_per_hit;
+  d.lethal_distance = (float)env->lethal_distance;
+  d.lethal_angle = (float)env->lethal_angle;
+  d.aggressiveness = (float)env->aggressiveness;
+  d.cooperativeness = (float)env->cooperativeness;
+  d.spawn_min_radius = (float)env->spawn_min_radius;
+  d.spawn_max_radius = (float)env->spawn_max_radius;
+  return 0;
+}
+int df_obs_dim(const PfbContext* h) { return 23 + 14 * (2 * h->df.team_size - 1); }
+
+struct DfAgent {
+  float health, acc_reward;
+  float past[4], cur[4];
+  float dist[3], ang[3];   // current_distances / current_angles towards partner slot k (other agents in index order)
+  int hits;                // received_hits
+};
+
+// update_states for the calling agent: _compute_observation + _compute_term_trunc_rew_info.
+// `li` = index inside the arena, `base` = lane of agent 0, `full` = lanes taking part (whole arenas only).
+// Partners are addressed RELATIVELY (r = 1 .. A-1 -> agent (li + r) mod A) so that every per-partner array is
+// indexed by a compile-time constant and stays in registers; slot r-1 is this agent's persistent slot for it.
+template <int A>
+__device__ __forceinline__ void df_update_states(const DogfightParams& d, FixedwingRegs& s, DfAgent& ag, int li, int base, int step_count,
+                                                 bool write_obs, float* obs, unsigned full) {
+  constexpr int ts = A / 2;
+  const Rot<rreal>& R = s.R;
+  // forward vector = first column of R; the reported position is shifted 0.35 m back along it (:390)
+  const float fx = (float)R.m00, fy = (float)R.m10, fz = (float)R.m20;
+  const float px = (float)s.px - 0.35f * fx, py = (float)s.py - 0.35f * fy, pz = (float)s.pz - 0.35f * fz;
+  const float gvx = (float)s.vx, gvy = (float)s.vy, gvz = (float)s.vz;  // rotation @ lin_vel == world velocity
+  float roll = 0.f, pitch = 0.f, yaw = 0.f;
+  if (write_obs) euler_from_quat((float)s.qx, (float)s.qy, (float)s.qz, (float)s.qw, roll, pitch, yaw);
+  const bool my_team = li >= ts;
+  const float dorigin = sqrtf(px * px + py * py + pz * pz);
+
+  int hits_made = 0, received = 0, team_hits_others = 0;
+  float er = 0.0f, close_pen = 0.0f;
+  int pj[A - 1];
+  float p_sep[A - 1][3], p_gv[A - 1][3], p_speed2[A - 1], p_z[A - 1];
+  bool p_hit_ij[A - 1];
+#pragma unroll
+  for (int r = 1; r < A; ++r) {
+    const int k = r - 1;
+    const int j = (li + r) & (A - 1);
+    const int src = base + j;
+    pj[k] = j;
+    const float jx = __shfl_sync(full, px, src), jy = __shfl_sync(full, py, src), jz = __shfl_sync(full, pz, src);
+    const float jfx = __shfl_sync(full, fx, src), jfy = __shfl_sync(full, fy, src), jfz = __shfl_sync(full, fz, src);
+    p_gv[k][0] = __shfl_sync(full, gvx, src); p_gv[k][1] = __shfl_sync(full, gvy, src); p_gv[k][2] = __shfl_sync(full, gvz, src);
+    p_speed2[k] = p_gv[k][0] * p_gv[k][0] + p_gv[k][1] * p_gv[k][1] + p_gv[k][2] * p_gv[k][2];
+    p_z[k] = jz;
+    // pairwise combat state, my row (i -> j) and my column (j -> i); :393-415
+    const float sx = jx - px, sy = jy - py, sz = jz - pz;
+    p_sep[k][0] = sx; p_sep[k][1] = sy; p_sep[k][2] = sz;
+    const float dist = sqrtf(sx * sx + sy * sy + sz * sz);
+    // arccos(sep . fwd / |sep|) evaluated as atan2(|sep x fwd|, sep . fwd): accurate near 0 where the cone test lives
+    const float cx = sy * fz - sz * fy, cy = sz * fx - sx * fz, cz = sx * fy - sy * fx;
+    const float ang = atan2_f(sqrtf(cx * cx + cy * cy + cz * cz), sx * fx + sy * fy + sz * fz);
+    const float dx = sy * jfz - sz * jfy, dy = sz * jfx - sx * jfz, dz = sx * jfy - sy * jfx;
+    const float ang_ji = atan2_f(sqrtf(dx * dx + dy * dy + dz * dz), -(sx * jfx + sy * jfy + sz * jfz));
+    const bool ffm = (j >= ts) != my_team;  // friendly-fire mask: only opponents can be hit
+    const bool rng = dist < d.lethal_distance;
+    const bool ch_ij = fabsf(ang) < 1.57079632679f, ch_ji = fabsf(ang_ji) < 1.57079632679f;
+    const bool h_ij = (ang < d.lethal_angle) && rng && ch_ij && ffm;
+    const bool h_ji = (ang_ji < d.lethal_angle) && rng && ch_ji && ffm;
+    p_hit_ij[k] = h_ij;
+    hits_made += h_ij ? 1 : 0;
+    received += h_ji ? 1 : 0;
+    // engagement rewards, row i (:552-600)
+    if (!d.sparse_reward) {
+      const float dd = fmaxf(ag.dist[k] - dist, 0.0f);  // previous - current
+      er += (!rng && ch_ij && ffm) ? 4.0f * dd : 0.0f;
+      float da = (rng && ffm) ? (ag.ang[k] - ang) : 0.0f;
+      if (da < 0.0f) da *= d.aggressiveness;
+      er += 30.0f * da;
+      const float inv_ij = (ffm && rng && ch_ij) ? fast_rcp(ang + 0.1f) : 0.0f;
+      const float inv_ji = (ffm && rng && ch_ji) ? fast_rcp(ang_ji + 0.1f) : 0.0f;
+      er += 3.0f * (inv_ij - (1.0f - d.aggressiveness) * inv_ji);
+      close_pen += dist < 5.0f ? 10.0f * (5.0f - dist) : 0.0f;
+    }
+    er += 20.0f * ((h_ij ? 1.0f : 0.0f) - (1.0f - d.aggressiveness) * (h_ji ? 1.0f : 0.0f));
+    ag.dist[k] = dist;
+    ag.ang[k] = ang;
+  }
+  // healths (:486-489)
+  ag.hits += received;
+  ag.health = fmaxf(ag.health - d.damage_per_hit * (float)received, 0.0f);
+  const bool collided = (s.flags & FLAG_CONTACT_ARRAY) != 0;
+  const bool oob = dorigin > d.dome;
+  const float h_final = (collided || oob) ? 0.0f : ag.health;
+  // second exchange: post-damage health (observation), final health (team wins), hits made (team bonus)
+  float n_h[A - 1];
+  bool own_alive = h_final > 0.0f;
+#pragma unroll
+  for (int r = 1; r < A; ++r) {
+    const int k = r - 1;
+    const int src = base + pj[k];
+    n_h[k] = __shfl_sync(full, ag.health, src);
+    const float hf = __shfl_sync(full, h_final, src);
+    const int hm = __shfl_sync(full, hits_made, src);
+    const bool same_team = (pj[k] >= ts) == my_team;
+    team_hits_others += same_team ? hm : 0;
+    own_alive = own_alive || (same_team && hf > 0.0f);
+  }
+  // the opponent paired with me by the reference's elementwise team_wins (:684-691)
+  const int opp = (my_team ? 0 : ts) + (li - (my_team ? ts : 0));
+  const float opp_h = __shfl_sync(full, h_final, base + opp);
+
+  if (write_obs) {  // :503-529: "self", then every other ACTIVE agent in ascending index order, zero padding
+    int n = 0;
+    obs[n++] = s.wx; obs[n++] = s.wy; obs[n++] = s.wz;
+    obs[n++] = roll; obs[n++] = pitch; obs[n++] = yaw;
+    obs[n++] = s.vb.x; obs[n++] = s.vb.y; obs[n++] = s.vb.z;
+    obs[n++] = px; obs[n++] = py; obs[n++] = pz;
+#pragma unroll
+    for (int k = 0; k < kMaxSurfaces; ++k) obs[n++] = s.act[k];
+    obs[n++] = s.thr;
+    obs[n++] = ag.health;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) obs[n++] = ag.past[k];
+    constexpr int O = 23 + 14 * (A - 1);
+    for (int k = n; k < O; ++k) obs[k] = 0.0f;  // the row lives in shared memory: dynamic indexing is free
+    bool inactive[A - 1];
+#pragma unroll
+    for (int k = 0; k < A - 1; ++k) inactive[k] = (n_h[k] <= 0.0f) && (p_z[k] < 2.0f) && (p_speed2[k] < 0.01f);
+#pragma unroll
+    for (int r = 1; r < A; ++r) {
+      const int k = r - 1;
+      const int src = base + pj[k];
+      // these shuffles must be executed by every lane of the arena, active partner or not
+      const float jwx = __shfl_sync(full, s.wx, src), jwy = __shfl_sync(full, s.wy, src), jwz = __shfl_sync(full, s.wz, src);
+      const float jr = __shfl_sync(full, roll, src), jp = __shfl_sync(full, pitch, src), jyw = __shfl_sync(full, yaw, src);
+      if (inactive[k]) continue;
+      int pos = 0;  // active partners with a smaller index come first
+#pragma unroll
+      for (int q = 0; q < A - 1; ++q) pos += (q != k && !inactive[q] && pj[q] < pj[k]) ? 1 : 0;
+      float* o = obs + 23 + 14 * pos;
+      o[0] = jwx; o[1] = jwy; o[2] = jwz;
+      o[3] = jr - roll; o[4] = jp - pitch; o[5] = jyw - yaw;
+      // partner's world velocity and the separation, both in MY body frame (x @ rotation == R^T x)
+      const float vx = p_gv[k][0], vy = p_gv[k][1], vz = p_gv[k][2];
+      o[6] = ((float)R.m00 * vx + (float)R.m10 * vy + (float)R.m20 * vz) - s.vb.x;
+      o[7] = ((float)R.m01 * vx + (float)R.m11 * vy + (float)R.m21 * vz) - s.vb.y;
+      o[8] = ((float)R.m02 * vx + (float)R.m12 * vy + (float)R.m22 * vz) - s.vb.z;
+      const float sx = p_sep[k][0], sy = p_sep[k][1], sz = p_sep[k][2];
+      o[9] = (float)R.m00 * sx + (float)R.m10 * sy + (float)R.m20 * sz;
+      o[10] = (float)R.m01 * sx + (float)R.m11 * sy + (float)R.m21 * sz;
+      o[11] = (float)R.m02 * sx + (float)R.m12 * sy + (float)R.m22 * sz;
+      o[12] = n_h[k];
+      o[13] = ((pj[k] >= ts) == my_team) ? 1.0f : 0.0f;
+    }
+  }
+  // team bonus (:601-610) and boundary rewards (:614-639)
+  er += d.cooperativeness * (float)(hits_made + team_hits_others);
+  float br = 0.0f;
+  if (!d.sparse_reward) br = tanhf(0.1f * pz - 1.0f) - tanhf(0.0025f * dorigin - 1.0f) - close_pen;
+  ag.acc_reward += er + br;
+  // terminations (:655-692)
+  if (step_count > d.max_steps) s.flags |= FLAG_TRUNC;
+  if (ag.health <= 1e-3f) s.flags |= FLAG_TERM | FLAG_DF_DEAD;
+  if (collided) { s.flags |= FLAG_TERM | FLAG_COLLISION; ag.acc_reward = -1000.0f; }
+  if (oob) { s.flags |= FLAG_TERM | FLAG_OOB; ag.acc_reward = -1000.0f; }
+  ag.health = h_final;
+  if (opp_h <= 0.0f && own_alive) { s.flags |= FLAG_TERM | FLAG_DF_WIN; ag.acc_reward = 300.0f; }
+  (void)p_hit_ij;
+}
+
+__device__ __forceinline__ void df_load_agent(const float* __restrict__ st, const int32_t* __restrict__ ist, int64_t N, int64_t i, DfAgent& ag) {
+  auto F = [&](int row) { return st[(int64_t)row * N + i]; };
+  ag.health = F(DF_HEALTH); ag.acc_reward = F(DF_REWARD);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { ag.past[k] = F(DF_PAST + k); ag.cur[k] = F(DF_CUR + k); }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { ag.dist[k] = F(DF_DIST + k); ag.ang[k] = F(DF_ANG + k); }
+  ag.hits = ist[(int64_t)DI_HITS * N + i];
+}
+__device__ __forceinline__ void df_store_agent(float* __restrict__ st, int32_t* __restrict__ ist, int64_t N, int64_t i, const DfAgent& ag) {
+  auto S = [&](int row, float v) { st[(int64_t)row * N + i] = v; };
+  S(DF_HEALTH, ag.health); S(DF_REWARD, ag.acc_reward);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { S(DF_PAST + k, ag.past[k]); S(DF_CUR + k, ag.cur[k]); }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { S(DF_DIST + k, ag.dist[k]); S(DF_ANG + k, ag.ang[k]); }
+  ist[(int64_t)DI_HITS * N + i] = ag.hits;
+}
+
+// reset of the calling agent's arena (:219-344): spawn pose from the bound buffers or drawn on device
+template <int A, bool INJECT>
+__device__ __forceinline__ void df_reset_agent(const FixedwingParams& p, const DogfightParams& d, const RngParams& rng,
+                                               const float* __restrict__ start_pos, const float* __restrict__ start_orn,
+                                               const float* __restrict__ noise, uint32_t seq, bool random_spawn, int64_t N, int64_t i, int li,
+                                               int base, FixedwingRegs& s, DfAgent& ag, float* obs, unsigned lanes) {
+  float sx = start_pos[3 * i], sy = start_pos[3 * i + 1], sz = start_pos[3 * i + 2];
+  float yaw = start_orn[3 * i + 2], roll = start_orn[3 * i], pitch = start_orn[3 * i + 1];
+  if (random_spawn) {  // _get_start_pos_orn (:177-217): one base angle per arena, per-agent radius / height / heading jitter
+    const uint64_t g0 = ((uint64_t)rng.env_offset_hi << 32 | rng.env_offset_lo) + (uint64_t)(i - li);
+    U4 a = philox4x32_10(U4{(uint32_t)g0, (uint32_t)(g0 >> 32), seq, 6u << 24}, rng.k0, rng.k1);
+    const uint64_t g = g0 + (uint64_t)li;
+    U4 b = philox4x32_10(U4{(uint32_t)g, (uint32_t)(g >> 32), seq, (6u << 24) | 1u}, rng.k0, rng.k1);
+    const float two_pi = 6.28318530717958647692f;
+    float rad = (two_pi / (float)A) * (float)li + two_pi * u32_to_unit_open(a.x);  // pi / team_size * index + U(0, 2 pi)
+    float radius = d.spawn_min_radius + (d.spawn_max_radius - d.spawn_min_radius) * u32_to_unit_open(b.x);
+    float height = d.spawn_min_radius + (d.spawn_max_radius - d.spawn_min_radius) * u32_to_unit_open(b.y);  // (sic) radius range, :199-203
+    float sn, cs;
+    sincos_f(fmodf(rad, two_pi), sn, cs);
+    sx = radius * cs; sy = radius * sn; sz = height;
+    roll = 0.0f; pitch = 0.0f;
+    yaw = rad + u32_to_unit_open(b.z) * 0.39269908169872414f;
+  }
+  fixedwing_reset(p, s, sx, sy, sz, roll, pitch, yaw);
+  // starting_velocity = 20 m/s along the heading (:235-239)
+  s.vx = (vreal)(20.0f * (float)s.R.m00); s.vy = (vreal)(20.0f * (float)s.R.m10); s.vz = (vreal)(20.0f * (float)s.R.m20);
+  body_update_state(s);
+  ag.health = 1.0f; ag.acc_reward = 0.0f; ag.hits = 0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { ag.dist[k] = 0.0f; ag.ang[k] = 0.0f; }
+  // current_actions / past_actions survive a reset in the reference (they are only created in __init__)
+  auto nz = make_noise<INJECT>(noise, N, i, rng, seq, TAG_RESET, p.noise_loc, p.ratio);
+  for (int k = 0; k < d.warmup_steps; ++k) fixedwing_aviary_step<0>(p, s, nz);
+  df_update_states<A>(d, s, ag, li, base, 0, true, obs, lanes);
+}
+
+template <int A, bool INJECT, bool RANDACT, bool AUTORESET>
+__global__ void __launch_bounds__(kBlock, kMinBlocks)
+    k_df_step(const __grid_constant__ FixedwingParams p, const __grid_constant__ DogfightParams d, const __grid_constant__ RngParams rng,
+              float* __restrict__ st, int32_t* __restrict__ ist, float* __restrict__ actions, const float* __restrict__ noise,
+              float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ term, uint8_t* __restrict__ trunc,
+              uint8_t* __restrict__ info, const float* __restrict__ start_pos, const float* __restrict__ start_orn,
+              const int32_t* __restrict__ prev_count, const int32_t* __restrict__ prev_list, int32_t* __restrict__ cur_count,
+              int32_t* __restrict__ cur_list, int32_t* __restrict__ next_count, int tail_blocks, uint32_t step_seq, int64_t N) {
+  __shared__ float smem[kBlock * kDfObsStride];
+  __shared__ uint8_t row_skip[kBlock];
+  constexpr int O = 23 + 14 * (A - 1);
+  const bool tail = AUTORESET && (int)blockIdx.x < tail_blocks;
+  const int64_t block_first = tail ? 0 : (int64_t)((int)blockIdx.x - (AUTORESET ? tail_blocks : 0)) * kBlock;
+  const int li = threadIdx.x % A;                 // agent index inside its arena
+  const int base = (threadIdx.x & 31) - li;       // lane of the arena's agent 0
+  // work items are whole arenas: a regular lane owns one agent; tail lanes stride over the done-arena list
+  int t, t_end, t_stride;
+  if (tail) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *next_count = 0;
+    t = (blockIdx.x * kBlock + threadIdx.x) / A;
+    t_end = *prev_count;
+    t_stride = tail_blocks * kBlock / A;
+  } else {
+    t = 0;
+    t_end = (block_first + threadIdx.x < N) ? 1 : 0;  // N is a multiple of A: an arena is never cut
+    t_stride = 1;
+  }
+  bool skip = true;
+  float* row = smem + threadIdx.x * kDfObsStride;
+#pragma unroll 1
+  for (;; t += t_stride) {
+    // whole arenas enter or leave together (t is arena-uniform), so every shuffle below names exactly the
+    // lanes that are present
+    const bool go = t < t_end;
+    unsigned lanes = __ballot_sync(0xffffffffu, go);
+    if (lanes == 0u) break;
+    if (!go) continue;
+    const int64_t i = tail ? (int64_t)prev_list[t] + li : block_first + threadIdx.x;
+    FixedwingRegs s;
+    DfAgent ag;
+    float rew_out = 0.0f;
+    int step_count = 0;
+    if (tail) {
+      df_load_agent(st, ist, N, i, ag);  // keeps current / past actions across the reset, like the reference
+      df_reset_agent<A, false>(p, d, rng, start_pos, start_orn, nullptr, step_seq, true, N, i, li, base, s, ag, row, lanes);
+      s.flags &= ~(uint32_t)(FLAG_AGENT_DONE);
+    } else {
+      fixedwing_load(st, ist, N, i, s);
+      df_load_agent(st, ist, N, i, ag);
+      // an arena whose agents are all done is reset by a tail CTA on this call
+      const unsigned arena_mask = ((1u << A) - 1u) << base;
+      const bool i_done = (s.flags & FLAG_AGENT_DONE) != 0;
+      const bool arena_done = (__ballot_sync(lanes, i_done) & arena_mask) == arena_mask;
+      lanes = __ballot_sync(lanes, !(AUTORESET && arena_done));
+      if (AUTORESET && arena_done) continue;
+      float act[4];
+      if (RANDACT) {
+        uint64_t g = ((uint64_t)rng.env_offset_hi << 32 | rng.env_offset_lo) + (uint64_t)i;
+        U4 r = philox4x32_10(U4{(uint32_t)g, (uint32_t)(g >> 32), step_seq, (uint32_t)TAG_ACTION << 24}, rng.k0, rng.k1);
+        act[0] = 2.0f * u32_to_unit_open(r.x) - 1.0f; act[1] = 2.0f * u32_to_unit_open(r.y) - 1.0f;
+        act[2] = 2.0f * u32_to_unit_open(r.z) - 1.0f; act[3] = 2.0f * u32_to_unit_open(r.w) - 1.0f;
+        reinterpret_cast<float4*>(actions)[i] = make_float4(act[0], act[1], act[2], act[3]);
+      } else {
+        float4 a4 = __ldg(reinterpret_cast<const float4*>(actions) + i);
+        act[0] = a4.x; act[1] = a4.y; act[2] = a4.z; act[3] = a4.w;
+      }
+      // ma_fixedwing_base_env.py:299-308: past <- current, current <- action of the agents still in self.agents
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { ag.past[k] = ag.cur[k]; ag.cur[k] = i_done ? 0.0f : act[k]; }
+      s.sp[0] = ag.cur[0]; s.sp[1] = ag.cur[1]; s.sp[2] = ag.cur[2]; s.sp[3] = ag.cur[3] * 0.5f + 0.5f;
+      step_count = ist[(int64_t)DI_STEP * N + i];
+      auto nz = make_noise<INJECT>(noise, N, i, rng, step_seq, TAG_ENV_STEP, p.noise_loc, p.ratio);
+#pragma unroll 1
+      for (int k = 0; k < d.env_step_ratio; ++k) {  // parallel envs do not break out of the loop (:312-314)
+        fixedwing_aviary_step<0>(p, s, nz);
+        df_update_states<A>(d, s, ag, li, base, step_count, k == d.env_step_ratio - 1, row, lanes);
+      }
+      rew_out = ag.acc_reward;
+      if (!i_done) ag.acc_reward = 0.0f;  // pop_term_trunc_rew_info_by_id only runs for agents still in self.agents
+      step_count += 1;
+    }
+    fixedwing_store(st, ist, N, i, s);
+    // fixedwing_store wrote the flags; mark agents that just left self.agents
+    uint32_t flags = s.flags;
+    if (!tail && (flags & (FLAG_TERM | FLAG_TRUNC))) flags |= FLAG_AGENT_DONE;
+    ist[(int64_t)DI_FLAGS * N + i] = (int32_t)flags;
+    df_store_agent(st, ist, N, i, ag);
+    ist[(int64_t)DI_STEP * N + i] = step_count;
+    reward[i] = rew_out;
+    term[i] = (flags & FLAG_TERM) ? 1 : 0;
+    trunc[i] = (flags & FLAG_TRUNC) ? 1 : 0;
+    if (info)
+      info[i] = (uint8_t)(((flags & FLAG_OOB) ? 1 : 0) | ((flags & FLAG_COLLISION) ? 2 : 0) | ((flags & FLAG_DF_DEAD) ? 4 : 0) | ((flags & FLAG_DF_WIN) ? 8 : 0));
+    if (tail) {
+      float* dst = obs + i * O;
+      for (int k = 0; k < O; ++k) dst[k] = row[k];
+    } else {
+      skip = false;
+      if (AUTORESET) {  // queue arenas whose agents have ALL left self.agents (the arena's first lane speaks for it)
+        const unsigned arena_mask = ((1u << A) - 1u) << base;
+        const unsigned done_lanes = __ballot_sync(lanes, (flags & FLAG_AGENT_DONE) != 0);
+        const bool leader_done = (li == 0) && ((done_lanes & arena_mask) == arena_mask);
+        unsigned m = __ballot_sync(lanes, leader_done);
+        if (leader_done) {
+          int lane = threadIdx.x & 31;
+          int leader = __ffs(m) - 1;
+          int b0 = 0;
+          if (lane == leader) b0 = atomicAdd(cur_count, __popc(m));
+          b0 = __shfl_sync(m, b0, leader);
+          cur_list[b0 + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+        }
+      }
+    }
+  }
+  if (tail) return;
+  row_skip[threadIdx.x] = skip ? 1 : 0;
+  __syncthreads();
+  int64_t rows = N - block_first;
+  if (rows > kBlock) rows = kBlock;
+  const int total = (int)rows * O;
+  float* dst = obs + block_first * O;
+  const int dr = kBlock / O, dc = kBlock - dr * O;
+  int r = threadIdx.x / O, c = threadIdx.x - r * O;
+  for (int j = threadIdx.x; j < total; j += kBlock) {
+    if (!row_skip[r]) dst[j] = smem[r * kDfObsStride + c];
+    r += dr; c += dc;
+    if (c >= O) { c -= O; ++r; }
+  }
+}
+
+template <int A, bool INJECT>
+__global__ void __launch_bounds__(kBlock)
+    k_df_reset(const __grid_constant__ FixedwingParams p, const __grid_constant__ DogfightParams d, const __grid_constant__ RngParams rng,
+               float* __restrict__ st, int32_t* __restrict__ ist, const float* __restrict__ start_pos, const float* __restrict__ start_orn,
+               const uint8_t* __restrict__ mask, const float* __restrict__ noise, float* __restrict__ obs, uint32_t seq, int random_spawn,
+               int64_t N) {
+  __shared__ float smem[kBlock * kDfObsStride];
+  constexpr int O = 23 + 14 * (A - 1);
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  const int li = threadIdx.x % A;
+  const int base = (threadIdx.x & 31) - li;
+  // N and kBlock are multiples of A: whole arenas drop out together; the mask is per arena (first agent's entry)
+  const bool go = (i < N) && !(mask && !mask[i - li]);
+  const unsigned lanes = __ballot_sync(0xffffffffu, go);
+  if (!go) return;
+  FixedwingRegs s;
+  DfAgent ag;
+  df_load_agent(st, ist, N, i, ag);
+  float* row = smem + threadIdx.x * kDfObsStride;
+  df_reset_agent<A, INJECT>(p, d, rng, start_pos, start_orn, noise, seq, random_spawn != 0, N, i, li, base, s, ag, row, lanes);
+  fixedwing_store(st, ist, N, i, s);
+  df_store_agent(st, ist, N, i, ag);
+  ist[(int64_t)DI_STEP * N + i] = 0;
+  if (obs)
+    for (int k = 0; k < O; ++k) obs[i * O + k] = row[k];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------
+int df_env_reset(PfbContext* h, const uint8_t* mask, const float* noise, cudaStream_t s) {
+  const uint32_t seq = 0x80000000u | (uint32_t)h->reset_seq++;
+  const int g = grid_for(h->n);
+  const int A = 2 * h->df.team_size;
+  if (h->n % A) return fail("the number of envs (%lld) must be a multiple of the arena size %d", (long long)h->n, A);
+  const int rnd = h->env.randomize_drop;  // reused as "draw the spawn on device" for the dogfight
+#define DR_ARGS h->fw, h->df, h->rng, h->buf.state, h->buf.istate, h->buf.start_pos, h->buf.start_orn, mask, noise, h->buf.obs, seq, rnd, h->n
+  if (A == 2) { if (noise) k_df_reset<2, true><<<g, kBlock, 0, s>>>(DR_ARGS); else k_df_reset<2, false><<<g, kBlock, 0, s>>>(DR_ARGS); }
+  else { if (noise) k_df_reset<4, true><<<g, kBlock, 0, s>>>(DR_ARGS); else k_df_reset<4, false><<<g, kBlock, 0, s>>>(DR_ARGS); }
+#undef DR_ARGS
+  LAUNCH_CHECK(h);
+  h->mode = 0;
+  return 0;
+}
+
+int df_env_step(PfbContext* h, float* actions, const float* noise, bool randact, cudaStream_t s) {
+  StepPlan pl = plan_step(h);
+  const int A = 2 * h->df.team_size;
+  if (h->n % A) return fail("the number of envs (%lld) must be a multiple of the arena size %d", (long long)h->n, A);
+  if (pl.prof) CUDA_OK(cudaEventRecord(h->prof_ev[2 * h->prof_n], s));
+#define DF_ARGS h->fw, h->df, h->rng, h->buf.state, h->buf.istate, actions, noise, h->buf.obs, h->buf.reward, h->buf.term, h->buf.trunc, \
+                h->buf.info, h->buf.start_pos, h->buf.start_orn, pl.cnt_prev, pl.list_prev, pl.cnt_cur, pl.list_cur, pl.cnt_next, pl.tail, \
+                pl.seq, h->n
+#define DF_LAUNCH(AA)                                                                                         \
+  if (h->env.autoreset) {                                                                                     \
+    if (noise) return fail("injected noise (parity mode) is only supported with autoreset = 0");              \
+    if (randact) k_df_step<AA, false, true, true><<<pl.grid, kBlock, 0, s>>>(DF_ARGS);                        \
+    else k_df_step<AA, false, false, true><<<pl.grid, kBlock, 0, s>>>(DF_ARGS);                               \
+  } else {                                                                                                    \
+    if (noise) k_df_step<AA, true, false, false><<<pl.grid, kBlock, 0, s>>>(DF_ARGS);                         \
+    else if (randact) k_df_step<AA, false, true, false><<<pl.grid, kBlock, 0, s>>>(DF_ARGS);                  \
+    else k_df_step<AA, false, false, false><<<pl.grid, kBlock, 0, s>>>(DF_ARGS);                              \
+  }
+  if (A == 2) { DF_LAUNCH(2) } else { DF_LAUNCH(4) }
+#undef DF_LAUNCH
+#undef DF_ARGS
+  LAUNCH_CHECK(h);
+  if (pl.prof) {
+    CUDA_OK(cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], s));
+    h->prof_n += 1;
+  }
+  h->step_seq += 1;
+  return 0;
+}

@@ -76,6 +76,13 @@ struct WaypointParams {
   float dome2, dome, goal_reach_distance, min_height;
 };
 
+// MAFixedwingDogfight constants (pz_envs/fixedwing_envs/ma_fixedwing_dogfight_env.py:42-62)
+struct DogfightParams {
+  int team_size, env_step_ratio, max_steps, sparse_reward, warmup_steps;
+  float dome, damage_per_hit, lethal_distance, lethal_angle, aggressiveness, cooperativeness;
+  float spawn_min_radius, spawn_max_radius;
+};
+
 // state tensor rows [F][N] for Fixedwing
 enum {
   FW_POS = 0, FW_QUAT = 3, FW_VEL = 7, FW_ANGVEL = 10, FW_ACT = 13 /*5*/, FW_THR = 18, FW_POS_LO = 19, FW_QUAT_LO = 22,

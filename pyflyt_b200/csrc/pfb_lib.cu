@@ -324,6 +324,11 @@ int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, i
     if (build_quadx_params(*model, c->qx) != 0) { delete c; return -1; }
   } else if (model->kind == PFB_KIND_FIXEDWING) {
     if (fw_build_params(*model, env, c->fw, c->wp) != 0) { delete c; return -1; }
+    if (df_build_params(env, c->df) != 0) { delete c; return -1; }
+    if (env && env->env_kind == PFB_ENV_DOGFIGHT && (n_envs % (2 * env->team_size)) != 0) {
+      delete c;
+      return fail("n_envs (%lld) must be a multiple of the arena size 2*team_size = %d", (long long)n_envs, 2 * env->team_size);
+    }
   } else {
     if (rk_build_params(*model, env, c->rk, c->land) != 0) { delete c; return -1; }
   }
@@ -340,6 +345,7 @@ int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, i
   if (env && env->env_kind != PFB_ENV_NONE) {
     const bool ok = (model->kind == PFB_KIND_QUADX && env->env_kind == PFB_ENV_QUADX_HOVER) ||
                     (model->kind == PFB_KIND_FIXEDWING && env->env_kind == PFB_ENV_FIXEDWING_WAYPOINTS) ||
+                    (model->kind == PFB_KIND_FIXEDWING && env->env_kind == PFB_ENV_DOGFIGHT) ||
                     (model->kind == PFB_KIND_ROCKET && env->env_kind == PFB_ENV_ROCKET_LANDING);
     if (!ok) {
       delete c;
@@ -381,10 +387,11 @@ int pfb_set_env_offset(PfbHandle h, uint64_t first_global_env) {
 
 static inline bool is_fw(PfbHandle h) { return h->model.kind == PFB_KIND_FIXEDWING; }
 static inline bool is_rk(PfbHandle h) { return h->model.kind == PFB_KIND_ROCKET; }
+static inline bool is_df(PfbHandle h) { return h->model.kind == PFB_KIND_FIXEDWING && h->env.env_kind == PFB_ENV_DOGFIGHT; }
 int pfb_state_rows(PfbHandle h) { return is_rk(h) ? rk_state_rows() : (is_fw(h) ? fw_state_rows() : QX_ROWS); }
 int pfb_istate_rows(PfbHandle h) { return is_rk(h) ? rk_istate_rows() : (is_fw(h) ? fw_istate_rows() : QI_ROWS); }
 int pfb_setpoint_dim(PfbHandle h) { return is_rk(h) ? 7 : ((is_fw(h) && h->env.env_kind == PFB_ENV_NONE) ? 6 : 4); }
-int pfb_obs_dim(PfbHandle h) { return is_rk(h) ? rk_obs_dim(h) : (is_fw(h) ? fw_obs_dim(h) : (h->hover.angle_representation == 0 ? 20 : 21)); }
+int pfb_obs_dim(PfbHandle h) { return is_df(h) ? df_obs_dim(h) : is_rk(h) ? rk_obs_dim(h) : (is_fw(h) ? fw_obs_dim(h) : (h->hover.angle_representation == 0 ? 20 : 21)); }
 int pfb_aux_dim(PfbHandle h) { return is_rk(h) ? 9 : (is_fw(h) ? 6 : 4); }
 
 int pfb_bind(PfbHandle h, const PfbBuffers* b) {
@@ -473,6 +480,7 @@ int pfb_env_reset(PfbHandle h, const uint8_t* mask, const float* noise, void* st
   REQUIRE_BOUND(h);
   if (require_env(h)) return -1;
   cudaStream_t s = (cudaStream_t)stream;
+  if (is_df(h)) return df_env_reset(h, mask, noise, s);
   if (is_fw(h)) return fw_env_reset(h, mask, noise, s);
   if (is_rk(h)) return rk_env_reset(h, mask, noise, s);
   const int mode = h->hover.flight_mode;
@@ -493,6 +501,7 @@ int pfb_env_reset(PfbHandle h, const uint8_t* mask, const float* noise, void* st
 }
 
 static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool randact, cudaStream_t s) {
+  if (is_df(h)) return df_env_step(h, actions, noise, randact, s);
   if (is_fw(h)) return fw_env_step(h, actions, noise, randact, s);
   if (is_rk(h)) return rk_env_step(h, actions, noise, randact, s);
   const int mode = h->hover.flight_mode;

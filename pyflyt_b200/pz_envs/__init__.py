@@ -1,0 +1,2 @@
+"""Vectorised mirrors of ``PyFlyt.pz_envs`` (hot-path rows of SURVEY.md §8 only)."""
+from .ma_fixedwing_dogfight_env import MAFixedwingDogfightVecEnv  # noqa: F401

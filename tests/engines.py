@@ -367,7 +367,7 @@ def make_cuda_engine(model, env, n, start_pos, start_orn):
         return CudaEngine(model, env, n, start_pos, start_orn, drone_model="rocket", drone_type="rocket",
                           drone_options=dict(starting_fuel_ratio=float(model.starting_fuel_ratio)))
     if int(model.kind) == 1:
-        name = "acrowing" if abs(model.com[0] + 0.39574468) < 1e-6 else "fixedwing"
+        name = "acrowing" if abs(model.com[0] + 0.39574468) < 1e-5 else "fixedwing"
         return CudaEngine(model, env, n, start_pos, start_orn, drone_model=name, drone_type="fixedwing",
                           drone_options=dict(starting_velocity=list(model.starting_velocity)))
     name = "primitive_drone" if abs(model.mass - 1.0) < 1e-12 else "cf2x"
