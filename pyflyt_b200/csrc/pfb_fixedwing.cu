@@ -15,6 +15,7 @@ int fw_build_params(const PfbModel& m, const PfbEnvConfig* env, FixedwingParams&
   return fw_build_params_impl(m, env, p, w);
 }
 
+static inline int fw_setpoint_dim(const PfbContext* h) { return h->env.env_kind == PFB_ENV_NONE ? 6 : 4; }
 int fw_state_rows() { return FW_ROWS; }
 int fw_istate_rows() { return FI_ROWS; }
 int fw_obs_dim(const PfbContext* h) { return (h->wp.angle_representation == 0 ? 22 : 23) + 3 * h->wp.num_targets; }
@@ -25,7 +26,7 @@ int fw_obs_dim(const PfbContext* h) { return (h->wp.angle_representation == 0 ? 
 __global__ void __launch_bounds__(kBlock) k_fw_reset(const __grid_constant__ FixedwingParams p, float* __restrict__ st,
                                                      int32_t* __restrict__ ist, float* __restrict__ setpoint,
                                                      const float* __restrict__ start_pos, const float* __restrict__ start_orn,
-                                                     const uint8_t* __restrict__ mask, int64_t N) {
+                                                     const uint8_t* __restrict__ mask, int sp_dim, int64_t N) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   if (mask && !mask[i]) return;
@@ -34,21 +35,21 @@ __global__ void __launch_bounds__(kBlock) k_fw_reset(const __grid_constant__ Fix
                   start_orn[3 * i + 2]);
   fixedwing_store(st, ist, N, i, s);
   ist[(int64_t)FI_STEP * N + i] = 0;
-  if (setpoint)
-    for (int k = 0; k < 6; ++k) setpoint[6 * i + k] = 0.0f;
+  if (setpoint)  // the caller's buffer is [N][sp_dim]: 6 on the Aviary surface, 4 behind an env
+    for (int k = 0; k < sp_dim; ++k) setpoint[(int64_t)sp_dim * i + k] = 0.0f;
 }
 
 template <int MODE, bool INJECT>
 __global__ void __launch_bounds__(kBlock, kMinBlocks)
     k_fw_aviary_step(const __grid_constant__ FixedwingParams p, const __grid_constant__ RngParams rng, float* __restrict__ st,
                      int32_t* __restrict__ ist, const float* __restrict__ setpoint, const float* __restrict__ noise,
-                     int n_steps, uint32_t seq, int64_t N) {
+                     int n_steps, uint32_t seq, int sp_dim, int64_t N) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   FixedwingRegs s;
   fixedwing_load(st, ist, N, i, s);
 #pragma unroll
-  for (int k = 0; k < 6; ++k) s.sp[k] = __ldg(setpoint + 6 * i + k);
+  for (int k = 0; k < 6; ++k) s.sp[k] = k < sp_dim ? __ldg(setpoint + (int64_t)sp_dim * i + k) : 0.0f;
   auto nz = make_noise<INJECT>(noise, N, i, rng, seq, TAG_AVIARY, p.noise_loc, p.ratio);
   for (int k = 0; k < n_steps; ++k) fixedwing_aviary_step<MODE>(p, s, nz);
   fixedwing_store(st, ist, N, i, s);
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(kBlock)
 // ---------------------------------------------------------------------------------------------------
 int fw_reset(PfbContext* h, const uint8_t* mask, cudaStream_t s) {
   k_fw_reset<<<grid_for(h->n), kBlock, 0, s>>>(h->fw, h->buf.state, h->buf.istate, h->buf.setpoint, h->buf.start_pos,
-                                               h->buf.start_orn, mask, h->n);
+                                               h->buf.start_orn, mask, fw_setpoint_dim(h), h->n);
   LAUNCH_CHECK(h);
   if (!mask) h->mode = 0;
   return 0;
@@ -352,7 +353,8 @@ int fw_reset(PfbContext* h, const uint8_t* mask, cudaStream_t s) {
 int fw_set_mode(PfbContext* h, int mode, cudaStream_t s) {
   if (mode < -1 || mode > 0)  // fixedwing.py:216-219
     return fail("`mode` must be between -1 and 0 or be registered in self.registered_controllers.keys()=dict_keys([]), got %d.", mode);
-  CUDA_OK(cudaMemsetAsync(h->buf.setpoint, 0, (size_t)h->n * 6 * sizeof(float), s));  // fixedwing.py:224-227
+  if (mode == -1 && fw_setpoint_dim(h) < 6) return fail("mode -1 needs the 6-wide setpoint buffer of the Aviary surface");
+  CUDA_OK(cudaMemsetAsync(h->buf.setpoint, 0, (size_t)h->n * fw_setpoint_dim(h) * sizeof(float), s));  // fixedwing.py:224-227
   h->mode = mode;
   return 0;
 }
@@ -360,7 +362,7 @@ int fw_set_mode(PfbContext* h, int mode, cudaStream_t s) {
 int fw_aviary_step(PfbContext* h, int n_steps, const float* noise, cudaStream_t s) {
   const uint32_t seq = (uint32_t)h->aviary_seq++;
   const int g = grid_for(h->n);
-#define FW_ARGS h->fw, h->rng, h->buf.state, h->buf.istate, h->buf.setpoint, noise, n_steps, seq, h->n
+#define FW_ARGS h->fw, h->rng, h->buf.state, h->buf.istate, h->buf.setpoint, noise, n_steps, seq, fw_setpoint_dim(h), h->n
   if (h->mode == 0) {
     if (noise) k_fw_aviary_step<0, true><<<g, kBlock, 0, s>>>(FW_ARGS);
     else k_fw_aviary_step<0, false><<<g, kBlock, 0, s>>>(FW_ARGS);
