@@ -42,13 +42,14 @@ def test_cuda_arenas_match_oracle(team_size):
     rng = np.random.default_rng(9 + team_size)
     f = lambda a: a.astype(np.float32).astype(np.float64)  # noqa: E731
     model = build_model("fixedwing", "acrowing")
-    env = dogfight_config(team_size, False, lethal_distance=150.0, lethal_angle=1.0, damage_per_hit=0.01)
-    # spawn like _get_start_pos_orn: agents on a circle, heading outwards
+    env = dogfight_config(team_size, False, lethal_distance=150.0, lethal_angle=1.0, damage_per_hit=0.05)
+    # spawn like _get_start_pos_orn: agents on a circle; every other arena heads INWARDS so that the aircraft meet nose to nose
     base = rng.uniform(0, 2 * np.pi, n_arenas)[:, None] + np.pi / team_size * np.arange(A)[None, :]
     radius = rng.uniform(10, 50, (n_arenas, A))
     pos = f(np.stack([radius * np.cos(base), radius * np.sin(base), rng.uniform(10, 50, (n_arenas, A))], axis=-1).reshape(n, 3))
     orn = np.zeros((n, 3))
-    orn[:, 2] = (base + rng.random((n_arenas, A)) * np.pi / 8).reshape(n)
+    inward = (np.arange(n_arenas) % 2 == 0)[:, None] * np.pi
+    orn[:, 2] = (base + inward + rng.random((n_arenas, A)) * np.pi / 8).reshape(n)
     orn = f(orn)
     orc, cud = OracleEngine(model, env, n, pos, orn), make_cuda_engine(model, env, n, pos, orn)
     nz0 = f(rng.normal(1.0, 1.0, (20, n)))
