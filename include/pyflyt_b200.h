@@ -246,6 +246,19 @@ int pfb_env_rollout(PfbHandle h, int n_steps, void* stream);
 int pfb_env_step_host(PfbHandle h, const float* host_actions, float* host_obs, float* host_reward,
                       uint8_t* host_term, uint8_t* host_trunc, void* stream);
 
+/* ---- MAFixedwingDogfight with an arena's agents on DIFFERENT ranks (ma_fixedwing_dogfight_env.py:346-465):
+ * global agent id = member * num_arenas + arena; this handle owns ids [first_global_agent, +n_envs).  Per Aviary
+ * step the caller runs  pfb_dogfight_physics -> all-gather of the payload table (NCCL) -> pfb_dogfight_combat.
+ *   physics: integrates one Aviary step (or, with do_reset, the reset + warm-up) and writes
+ *            payload_out [n_envs][pfb_dogfight_payload_dim()]; `first` = this is the first Aviary step of an
+ *            env.step (actions are latched), `aviary_index` = 0..env_step_ratio-1 (noise stream position);
+ *   combat:  payload_table [num_arenas*2][dim] gathered from every rank; `last` = 1 on the last Aviary step of
+ *            the env.step (writes obs / reward / term / trunc / info), 2 after a reset (obs only), else 0. */
+int pfb_dogfight_payload_dim(void);
+int pfb_dogfight_physics(PfbHandle h, const float* actions, const float* noise, float* payload_out, int first, int do_reset,
+                         int aviary_index, void* stream);
+int pfb_dogfight_combat(PfbHandle h, const float* payload_table, int64_t first_global_agent, int64_t num_arenas, int last,
+                        void* stream);
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches).                  */
 int64_t pfb_launch_count(PfbHandle h);
 /* Measurement aid: record a CUDA-event pair around the dominant kernel of each of the next

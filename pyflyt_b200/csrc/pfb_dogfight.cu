@@ -464,3 +464,201 @@ int df_env_step(PfbContext* h, float* actions, const float* noise, bool randact,
   h->step_seq += 1;
   return 0;
 }
+
+// ===================================================================================================
+// Split ("agent-major") variant — BASELINE.json configs[4] as written: the agents of one arena live on
+// DIFFERENT ranks, so the combat state needs one exchange per Aviary step.  Per Aviary step:
+//     k_df_split_physics  (integrate my aircraft, publish a 20-float payload per agent)
+//     ncclAllGather       (torch.distributed.all_gather_into_tensor on the payload table, host side)
+//     k_df_split_combat   (pairwise combat state, health, rewards, terminations from the gathered table)
+// Global agent id gid = k * num_arenas + g (member k of arena g); rank r owns gids [r*n_local, (r+1)*n_local).
+// 1-vs-1 arenas (team_size 1).  No in-kernel autoreset: reset() is a collective call.
+// ===================================================================================================
+constexpr int kPayload = 20;  // pos'(3) fwd(3) gv(3) w(3) euler(3) health(1) contact(1) + pad to 5 float4
+enum { PL_POS = 0, PL_FWD = 3, PL_GV = 6, PL_W = 9, PL_EUL = 12, PL_HEALTH = 15, PL_CONTACT = 16 };
+
+__device__ __forceinline__ void df_publish(const FixedwingRegs& s, const DfAgent& ag, float* __restrict__ out) {
+  const Rot<rreal>& R = s.R;
+  const float fx = (float)R.m00, fy = (float)R.m10, fz = (float)R.m20;
+  float roll, pitch, yaw;
+  euler_from_quat((float)s.qx, (float)s.qy, (float)s.qz, (float)s.qw, roll, pitch, yaw);
+  float4* o = reinterpret_cast<float4*>(out);
+  o[0] = make_float4((float)s.px - 0.35f * fx, (float)s.py - 0.35f * fy, (float)s.pz - 0.35f * fz, fx);
+  o[1] = make_float4(fy, fz, (float)s.vx, (float)s.vy);
+  o[2] = make_float4((float)s.vz, s.wx, s.wy, s.wz);
+  o[3] = make_float4(roll, pitch, yaw, ag.health);
+  o[4] = make_float4((s.flags & FLAG_CONTACT_ARRAY) ? 1.0f : 0.0f, 0.f, 0.f, 0.f);
+}
+
+// first = 1: take the action, roll past/current actions (start of env.step); warm = 1: reset + warm-up
+template <bool INJECT>
+__global__ void __launch_bounds__(kBlock, kMinBlocks)
+    k_df_split_physics(const __grid_constant__ FixedwingParams p, const __grid_constant__ DogfightParams d, const __grid_constant__ RngParams rng,
+                       float* __restrict__ st, int32_t* __restrict__ ist, const float* __restrict__ actions, const float* __restrict__ noise,
+                       const float* __restrict__ start_pos, const float* __restrict__ start_orn, float* __restrict__ payload, int first,
+                       int do_reset, uint32_t seq, uint32_t sub, int64_t N) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= N) return;
+  FixedwingRegs s;
+  DfAgent ag;
+  df_load_agent(st, ist, N, i, ag);
+  if (do_reset) {
+    fixedwing_reset(p, s, start_pos[3 * i], start_pos[3 * i + 1], start_pos[3 * i + 2], start_orn[3 * i], start_orn[3 * i + 1], start_orn[3 * i + 2]);
+    s.vx = (vreal)(20.0f * (float)s.R.m00); s.vy = (vreal)(20.0f * (float)s.R.m10); s.vz = (vreal)(20.0f * (float)s.R.m20);
+    body_update_state(s);
+    ag.health = 1.0f; ag.acc_reward = 0.0f; ag.hits = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { ag.dist[k] = 0.0f; ag.ang[k] = 0.0f; }
+    auto nz = make_noise<INJECT>(noise, N, i, rng, seq, TAG_RESET, p.noise_loc, p.ratio);
+    for (int k = 0; k < d.warmup_steps; ++k) fixedwing_aviary_step<0>(p, s, nz);
+    ist[(int64_t)DI_STEP * N + i] = 0;
+  } else {
+    fixedwing_load(st, ist, N, i, s);
+    if (first) {
+      const bool i_done = (s.flags & FLAG_AGENT_DONE) != 0;
+      float4 a4 = __ldg(reinterpret_cast<const float4*>(actions) + i);
+      const float act[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { ag.past[k] = ag.cur[k]; ag.cur[k] = i_done ? 0.0f : act[k]; }
+    }
+    s.sp[0] = ag.cur[0]; s.sp[1] = ag.cur[1]; s.sp[2] = ag.cur[2]; s.sp[3] = ag.cur[3] * 0.5f + 0.5f;
+    // one Aviary step; the noise stream position is (env-step sequence, Aviary step index)
+    auto nz = make_noise<INJECT>(noise, N, i, rng, seq, TAG_ENV_STEP, p.noise_loc, 4);  // ratio > 2 path: one call per step
+    nz.seek(sub);
+    fixedwing_aviary_step<0>(p, s, nz);
+  }
+  fixedwing_store(st, ist, N, i, s);
+  df_store_agent(st, ist, N, i, ag);
+  df_publish(s, ag, payload + (int64_t)kPayload * i);
+}
+
+// combat state for 1-vs-1 arenas from the gathered payload table [num_agents][kPayload]
+__global__ void __launch_bounds__(kBlock, kMinBlocks)
+    k_df_split_combat(const __grid_constant__ DogfightParams d, float* __restrict__ st, int32_t* __restrict__ ist,
+                      const float* __restrict__ table, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ term,
+                      uint8_t* __restrict__ trunc, uint8_t* __restrict__ info, int64_t first_gid, int64_t num_arenas, int last, int64_t N) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= N) return;
+  const int64_t gid = first_gid + i;
+  const int li = (int)(gid / num_arenas);
+  const int64_t g = gid - (int64_t)li * num_arenas;
+  const int64_t pid = (int64_t)(1 - li) * num_arenas + g;  // my opponent
+  const float* me = table + kPayload * gid;
+  const float* ot = table + kPayload * pid;
+  FixedwingRegs s;
+  DfAgent ag;
+  fixedwing_load(st, ist, N, i, s);
+  df_load_agent(st, ist, N, i, ag);
+  const int step_count = ist[(int64_t)DI_STEP * N + i];
+  const float px = me[PL_POS], py = me[PL_POS + 1], pz = me[PL_POS + 2];
+  const float fx = me[PL_FWD], fy = me[PL_FWD + 1], fz = me[PL_FWD + 2];
+  const float jx = ot[PL_POS], jy = ot[PL_POS + 1], jz = ot[PL_POS + 2];
+  const float jfx = ot[PL_FWD], jfy = ot[PL_FWD + 1], jfz = ot[PL_FWD + 2];
+  const float sx = jx - px, sy = jy - py, sz = jz - pz;
+  const float dist = sqrtf(sx * sx + sy * sy + sz * sz);
+  const float cx = sy * fz - sz * fy, cy = sz * fx - sx * fz, cz = sx * fy - sy * fx;
+  const float ang = atan2_f(sqrtf(cx * cx + cy * cy + cz * cz), sx * fx + sy * fy + sz * fz);
+  const float dx = sy * jfz - sz * jfy, dy = sz * jfx - sx * jfz, dz = sx * jfy - sy * jfx;
+  const float ang_ji = atan2_f(sqrtf(dx * dx + dy * dy + dz * dz), -(sx * jfx + sy * jfy + sz * jfz));
+  const bool rng = dist < d.lethal_distance;
+  const bool ch_ij = fabsf(ang) < 1.57079632679f, ch_ji = fabsf(ang_ji) < 1.57079632679f;
+  const bool h_ij = (ang < d.lethal_angle) && rng && ch_ij;
+  const bool h_ji = (ang_ji < d.lethal_angle) && rng && ch_ji;
+  float er = 0.0f, close_pen = 0.0f;
+  if (!d.sparse_reward) {
+    er += (!rng && ch_ij) ? 4.0f * fmaxf(ag.dist[0] - dist, 0.0f) : 0.0f;
+    float da = rng ? (ag.ang[0] - ang) : 0.0f;
+    if (da < 0.0f) da *= d.aggressiveness;
+    er += 30.0f * da;
+    const float inv_ij = (rng && ch_ij) ? fast_rcp(ang + 0.1f) : 0.0f;
+    const float inv_ji = (rng && ch_ji) ? fast_rcp(ang_ji + 0.1f) : 0.0f;
+    er += 3.0f * (inv_ij - (1.0f - d.aggressiveness) * inv_ji);
+    close_pen = dist < 5.0f ? 10.0f * (5.0f - dist) : 0.0f;
+  }
+  er += 20.0f * ((h_ij ? 1.0f : 0.0f) - (1.0f - d.aggressiveness) * (h_ji ? 1.0f : 0.0f));
+  ag.dist[0] = dist; ag.ang[0] = ang;
+  // healths: mine from the hit I received; the opponent's is recomputed from the hit I made
+  ag.hits += h_ji ? 1 : 0;
+  ag.health = fmaxf(ag.health - d.damage_per_hit * (h_ji ? 1.0f : 0.0f), 0.0f);
+  const float n_h = fmaxf(ot[PL_HEALTH] - d.damage_per_hit * (h_ij ? 1.0f : 0.0f), 0.0f);
+  const float dorigin = sqrtf(px * px + py * py + pz * pz), j_dorigin = sqrtf(jx * jx + jy * jy + jz * jz);
+  const bool collided = me[PL_CONTACT] != 0.0f, oob = dorigin > d.dome;
+  const float h_final = (collided || oob) ? 0.0f : ag.health;
+  const float opp_h = (ot[PL_CONTACT] != 0.0f || j_dorigin > d.dome) ? 0.0f : n_h;
+  if (last) {
+    const Rot<rreal>& R = s.R;
+    float* o = obs + 37 * i;
+    int n = 0;
+    o[n++] = s.wx; o[n++] = s.wy; o[n++] = s.wz;
+    o[n++] = me[PL_EUL]; o[n++] = me[PL_EUL + 1]; o[n++] = me[PL_EUL + 2];
+    o[n++] = s.vb.x; o[n++] = s.vb.y; o[n++] = s.vb.z;
+    o[n++] = px; o[n++] = py; o[n++] = pz;
+    for (int k = 0; k < kMaxSurfaces; ++k) o[n++] = s.act[k];
+    o[n++] = s.thr;
+    o[n++] = ag.health;
+    for (int k = 0; k < 4; ++k) o[n++] = ag.past[k];
+    const float vx = ot[PL_GV], vy = ot[PL_GV + 1], vz = ot[PL_GV + 2];
+    const bool inactive = (n_h <= 0.0f) && (jz < 2.0f) && (vx * vx + vy * vy + vz * vz < 0.01f);
+    if (!inactive) {
+      o[n++] = ot[PL_W]; o[n++] = ot[PL_W + 1]; o[n++] = ot[PL_W + 2];
+      o[n++] = ot[PL_EUL] - me[PL_EUL]; o[n++] = ot[PL_EUL + 1] - me[PL_EUL + 1]; o[n++] = ot[PL_EUL + 2] - me[PL_EUL + 2];
+      o[n++] = ((float)R.m00 * vx + (float)R.m10 * vy + (float)R.m20 * vz) - s.vb.x;
+      o[n++] = ((float)R.m01 * vx + (float)R.m11 * vy + (float)R.m21 * vz) - s.vb.y;
+      o[n++] = ((float)R.m02 * vx + (float)R.m12 * vy + (float)R.m22 * vz) - s.vb.z;
+      o[n++] = (float)R.m00 * sx + (float)R.m10 * sy + (float)R.m20 * sz;
+      o[n++] = (float)R.m01 * sx + (float)R.m11 * sy + (float)R.m21 * sz;
+      o[n++] = (float)R.m02 * sx + (float)R.m12 * sy + (float)R.m22 * sz;
+      o[n++] = n_h;
+      o[n++] = 0.0f;
+    }
+    while (n < 37) o[n++] = 0.0f;
+  }
+  er += d.cooperativeness * (h_ij ? 1.0f : 0.0f);
+  float br = 0.0f;
+  if (!d.sparse_reward) br = tanhf(0.1f * pz - 1.0f) - tanhf(0.0025f * dorigin - 1.0f) - close_pen;
+  ag.acc_reward += er + br;
+  if (step_count > d.max_steps) s.flags |= FLAG_TRUNC;
+  if (ag.health <= 1e-3f) s.flags |= FLAG_TERM | FLAG_DF_DEAD;
+  if (collided) { s.flags |= FLAG_TERM | FLAG_COLLISION; ag.acc_reward = -1000.0f; }
+  if (oob) { s.flags |= FLAG_TERM | FLAG_OOB; ag.acc_reward = -1000.0f; }
+  ag.health = h_final;
+  if (opp_h <= 0.0f && h_final > 0.0f) { s.flags |= FLAG_TERM | FLAG_DF_WIN; ag.acc_reward = 300.0f; }
+  uint32_t flags = s.flags;
+  if (last == 1) {
+    const bool was_done = (flags & FLAG_AGENT_DONE) != 0;
+    reward[i] = ag.acc_reward;
+    if (!was_done) ag.acc_reward = 0.0f;
+    ist[(int64_t)DI_STEP * N + i] = step_count + 1;
+    if (flags & (FLAG_TERM | FLAG_TRUNC)) flags |= FLAG_AGENT_DONE;
+    term[i] = (flags & FLAG_TERM) ? 1 : 0;
+    trunc[i] = (flags & FLAG_TRUNC) ? 1 : 0;
+    if (info)
+      info[i] = (uint8_t)(((flags & FLAG_OOB) ? 1 : 0) | ((flags & FLAG_COLLISION) ? 2 : 0) | ((flags & FLAG_DF_DEAD) ? 4 : 0) | ((flags & FLAG_DF_WIN) ? 8 : 0));
+  }
+  ist[(int64_t)DI_FLAGS * N + i] = (int32_t)flags;
+  df_store_agent(st, ist, N, i, ag);
+}
+
+int df_split_physics(PfbContext* h, const float* actions, const float* noise, float* payload, int first, int do_reset, int sub, cudaStream_t s) {
+  if (h->df.team_size != 1) return fail("the split (all-gather) dogfight path is built for team_size 1");
+  const uint32_t seq = do_reset ? (0x80000000u | (uint32_t)h->reset_seq) : (uint32_t)h->step_seq;
+  if (do_reset) h->reset_seq += 1;
+  const int g = grid_for(h->n);
+  if (noise)
+    k_df_split_physics<true><<<g, kBlock, 0, s>>>(h->fw, h->df, h->rng, h->buf.state, h->buf.istate, actions, noise, h->buf.start_pos,
+                                                  h->buf.start_orn, payload, first, do_reset, seq, (uint32_t)sub, h->n);
+  else
+    k_df_split_physics<false><<<g, kBlock, 0, s>>>(h->fw, h->df, h->rng, h->buf.state, h->buf.istate, actions, nullptr, h->buf.start_pos,
+                                                   h->buf.start_orn, payload, first, do_reset, seq, (uint32_t)sub, h->n);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int df_split_combat(PfbContext* h, const float* table, int64_t first_gid, int64_t num_arenas, int last, cudaStream_t s) {
+  if (h->df.team_size != 1) return fail("the split (all-gather) dogfight path is built for team_size 1");
+  k_df_split_combat<<<grid_for(h->n), kBlock, 0, s>>>(h->df, h->buf.state, h->buf.istate, table, h->buf.obs, h->buf.reward, h->buf.term,
+                                                      h->buf.trunc, h->buf.info, first_gid, num_arenas, last, h->n);
+  LAUNCH_CHECK(h);
+  if (last) h->step_seq += 1;
+  return 0;
+}

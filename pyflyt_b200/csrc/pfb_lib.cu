@@ -583,6 +583,24 @@ int pfb_env_step_host(PfbHandle h, const float* host_actions, float* host_obs, f
   return 0;
 }
 
+// ---- MAFixedwingDogfight, split variant: an arena's agents on different ranks
+int pfb_dogfight_payload_dim(void) { return 20; }
+
+int pfb_dogfight_physics(PfbHandle h, const float* actions, const float* noise, float* payload_out, int first, int do_reset, int aviary_index,
+                         void* stream) {
+  REQUIRE_BOUND(h);
+  if (!is_df(h)) return fail("handle is not a dogfight env");
+  if (!payload_out) return fail("pfb_dogfight_physics: null payload buffer");
+  return df_split_physics(h, actions ? actions : h->buf.setpoint, noise, payload_out, first, do_reset, aviary_index, (cudaStream_t)stream);
+}
+
+int pfb_dogfight_combat(PfbHandle h, const float* payload_table, int64_t first_global_agent, int64_t num_arenas, int last, void* stream) {
+  REQUIRE_BOUND(h);
+  if (!is_df(h)) return fail("handle is not a dogfight env");
+  if (require_env(h)) return -1;
+  return df_split_combat(h, payload_table, first_global_agent, num_arenas, last, (cudaStream_t)stream);
+}
+
 int64_t pfb_launch_count(PfbHandle h) { return h ? h->launches : 0; }
 
 int pfb_profile_begin(PfbHandle h, int capacity) {

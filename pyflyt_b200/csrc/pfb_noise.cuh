@@ -13,6 +13,7 @@ struct InjectedNoise {  // parity tests: the CPU-drawn sequence, [substep][N]
   const float* ptr;
   int64_t N;
   __device__ __forceinline__ void begin_step() {}
+  __device__ __forceinline__ void seek(uint32_t) {}  // the caller passes the pointer already positioned
   __device__ __forceinline__ float get(int) {
     float v = __ldg(ptr);
     ptr += N;
@@ -37,6 +38,7 @@ struct PhiloxNoise {
     seq = seq_; tag = tag_ << 24; step = 0; loc = loc_; ratio = ratio_;
     n2 = n3 = 0.0f;
   }
+  __device__ __forceinline__ void seek(uint32_t s) { step = s; }
   __device__ __forceinline__ void begin_step() {
     // ratio <= 2: one Philox call (4 words -> 4 normals) serves two consecutive Aviary steps
     if (ratio > 2 || (step & 1u) == 0u) {

@@ -1,2 +1,3 @@
 """Vectorised mirrors of ``PyFlyt.pz_envs`` (hot-path rows of SURVEY.md §8 only)."""
 from .ma_fixedwing_dogfight_env import MAFixedwingDogfightVecEnv  # noqa: F401
+from .ma_fixedwing_dogfight_split import MAFixedwingDogfightSplitEnv, split_agent_range, spawn_poses  # noqa: F401
