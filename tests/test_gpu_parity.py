@@ -223,3 +223,39 @@ def test_single_env_adaptor_signature():
     obs, rew, term, trunc, info = env.step(np.array([0.0, 0.0, 0.0, 0.4]))
     assert obs.shape == (21,) and isinstance(rew, float) and isinstance(term, bool) and isinstance(trunc, bool)
     env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 6])
+def test_reset_cache_is_exact(mode):
+    """The memoised post-warm-up state (PfbBuffers.reset_cache) must give bit-identical rollouts to re-integrating the
+    warm-up on every autoreset; in mode 6 the motors spin during the warm-up, so the cache must declare itself invalid."""
+    import torch
+
+    from pyflyt_b200.gym_envs.quadx_hover_env import QuadXHoverVecEnv
+
+    n = 8192
+    rng = np.random.default_rng(3)
+    sp = np.zeros((n, 3), dtype=np.float32)
+    sp[:, 2] = rng.uniform(0.6, 1.4, n)  # per-env start heights: the cache is per env
+    so = np.zeros((n, 3), dtype=np.float32)
+    so[:, 2] = rng.uniform(-1, 1, n)
+    outs = []
+    for use_cache in (True, False):
+        env = QuadXHoverVecEnv(num_envs=n, flight_mode=mode, seed=5, start_pos=sp, start_orn=so, reset_cache=use_cache)
+        env.reset()
+        resets = 0
+        for k in range(120):
+            env.rollout(1)
+            resets += int((env.aviary.term | env.aviary.trunc).sum())
+            if k == 60:  # move every other env's start pose: stale cache entries must be recomputed, not reused
+                env.aviary.start_pos[::2, 2] += 0.25
+        torch.cuda.synchronize()
+        outs.append((env.aviary.obs.clone(), env.aviary.reward.clone(), env.aviary.state_tensor.clone(), resets))
+        if use_cache:
+            valid = env.aviary.reset_cache[55 + 6]
+            assert bool((valid == 1).all()) if mode == 0 else bool((valid == 0).all())
+        env.close()
+    (o0, r0, s0, n0), (o1, r1, s1, n1) = outs
+    assert n0 == n1 and n0 > n  # every env was reset at least once on average
+    assert torch.equal(o0, o1) and torch.equal(r0, r1) and torch.equal(s0, s1)
