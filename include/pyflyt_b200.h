@@ -182,14 +182,7 @@ typedef struct PfbBuffers {
   uint8_t* term;             /* [N]                                                                  */
   uint8_t* trunc;            /* [N]                                                                  */
   uint8_t* info;             /* [N] bit0 out_of_bounds, bit1 collision, bit2 env_complete            */
-  float* reset_cache;        /* optional [pfb_reset_cache_rows()][N]: memoised post-warm-up state of each env.
-                              * env.reset() = start pose + `warmup_steps` Aviary steps at zero setpoint
-                              * (quadx_base_env.py:149-212); when the motors stay at exactly zero throttle
-                              * through that warm-up no noise draw can act, the result depends on the start
-                              * pose alone, and the in-launch autoreset reloads it instead of re-integrating.
-                              * Entries are filled by the first reset that computes them, checked against the
-                              * current start pose on every use, and skipped (recompute) when the motors spun.
-                              * NULL = always recompute.                                                     */
+  float* final_obs;          /* reserved (NEXT_STEP autoreset returns the terminal obs itself)       */
   /* outputs of pfb_observe_state (Aviary.state / aux_state) */
   float* drone_state;        /* [N][12] = state(i) (4,3) flattened: ang_vel_b, euler, lin_vel_b, pos */
   float* aux_state;          /* [N][A]                                                               */
@@ -218,8 +211,7 @@ int pfb_state_rows(PfbHandle h);     /* F of PfbBuffers.state                   
 int pfb_istate_rows(PfbHandle h);    /* I of PfbBuffers.istate                                        */
 int pfb_setpoint_dim(PfbHandle h);   /* S                                                             */
 int pfb_obs_dim(PfbHandle h);        /* O                                                             */
-int pfb_aux_dim(PfbHandle h);
-int pfb_reset_cache_rows(PfbHandle h); /* rows of PfbBuffers.reset_cache for this handle (0 = not used by this env kind) */        /* A                                                             */
+int pfb_aux_dim(PfbHandle h);        /* A                                                             */
 int pfb_bind(PfbHandle h, const PfbBuffers* buffers);
 
 /* ---- Aviary surface ------------------------------------------------------------------------------ */

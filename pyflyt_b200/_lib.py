@@ -30,7 +30,7 @@ class PfbBuffers(C.Structure):
         ("term", C.c_void_p),
         ("trunc", C.c_void_p),
         ("info", C.c_void_p),
-        ("reset_cache", C.c_void_p),
+        ("final_obs", C.c_void_p),
         ("drone_state", C.c_void_p),
         ("aux_state", C.c_void_p),
         ("contact", C.c_void_p),
@@ -65,7 +65,7 @@ def lib() -> C.CDLL:
     L.pfb_create.argtypes = [vp, vp, i64, i32, u64, C.POINTER(vp)]
     L.pfb_destroy.argtypes = [vp]
     L.pfb_set_env_offset.argtypes = [vp, u64]
-    for name in ("pfb_state_rows", "pfb_istate_rows", "pfb_setpoint_dim", "pfb_obs_dim", "pfb_aux_dim", "pfb_reset_cache_rows"):
+    for name in ("pfb_state_rows", "pfb_istate_rows", "pfb_setpoint_dim", "pfb_obs_dim", "pfb_aux_dim"):
         getattr(L, name).argtypes = [vp]
     L.pfb_bind.argtypes = [vp, vp]
     L.pfb_reset.argtypes = [vp, vp, vp]
@@ -97,7 +97,7 @@ def check(rc: int) -> None:
 EXPORTS = [
     "pfb_last_error", "pfb_abi_version", "pfb_sizeof_model", "pfb_sizeof_env_config", "pfb_sizeof_buffers",
     "pfb_create", "pfb_destroy", "pfb_set_env_offset", "pfb_state_rows", "pfb_istate_rows", "pfb_setpoint_dim",
-    "pfb_obs_dim", "pfb_aux_dim", "pfb_reset_cache_rows", "pfb_bind", "pfb_reset", "pfb_set_mode", "pfb_aviary_step", "pfb_observe_state",
+    "pfb_obs_dim", "pfb_aux_dim", "pfb_bind", "pfb_reset", "pfb_set_mode", "pfb_aviary_step", "pfb_observe_state",
     "pfb_set_base_velocity",
     "pfb_env_reset", "pfb_env_step", "pfb_env_rollout", "pfb_env_step_host", "pfb_launch_count",
     "pfb_profile_begin", "pfb_profile_read", "pfb_dogfight_payload_dim", "pfb_dogfight_physics", "pfb_dogfight_combat",

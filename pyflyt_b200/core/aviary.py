@@ -51,7 +51,6 @@ class BatchedAviary:
         device: str | torch.device = "cuda:0",
         env_config: PfbEnvConfig | None = None,
         env_offset: int = 0,
-        reset_cache: bool = True,
     ):
         start_pos = np.asarray(start_pos, dtype=np.float32)
         start_orn = np.asarray(start_orn, dtype=np.float32)
@@ -102,8 +101,7 @@ class BatchedAviary:
         self.term = torch.zeros((n,), dtype=torch.uint8, device=dev)
         self.trunc = torch.zeros((n,), dtype=torch.uint8, device=dev)
         self.info_bits = torch.zeros((n,), dtype=torch.uint8, device=dev)
-        rows = int(_lib.lib().pfb_reset_cache_rows(self._h)) if reset_cache else 0
-        self.reset_cache = torch.zeros((rows, n), **f32) if rows else None
+        self.final_obs = torch.zeros((n, self.obs_dim), **f32)
         self._drone_state = torch.zeros((n, 12), **f32)
         self._aux_state = torch.zeros((n, self.aux_dim), **f32)
         self._contact = torch.zeros((n,), dtype=torch.uint8, device=dev)
@@ -111,8 +109,7 @@ class BatchedAviary:
         b.state, b.istate = self.state_tensor.data_ptr(), self.istate_tensor.data_ptr()
         b.setpoint, b.start_pos, b.start_orn = self.setpoints.data_ptr(), self.start_pos.data_ptr(), self.start_orn.data_ptr()
         b.obs, b.reward, b.term, b.trunc = self.obs.data_ptr(), self.reward.data_ptr(), self.term.data_ptr(), self.trunc.data_ptr()
-        b.info = self.info_bits.data_ptr()
-        b.reset_cache = self.reset_cache.data_ptr() if self.reset_cache is not None else None
+        b.info, b.final_obs = self.info_bits.data_ptr(), self.final_obs.data_ptr()
         b.drone_state, b.aux_state, b.contact = self._drone_state.data_ptr(), self._aux_state.data_ptr(), self._contact.data_ptr()
         b.reset_targets = None
         self._reset_targets = None

@@ -306,13 +306,17 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
       df_load_agent(st, ist, N, i, ag);  // keeps current / past actions across the reset, like the reference
       df_reset_agent<A, false>(p, d, rng, start_pos, start_orn, nullptr, step_seq, true, N, i, li, base, s, ag, row, lanes);
       s.flags &= ~(uint32_t)(FLAG_AGENT_DONE);
+      s.flags |= fresh_tag(step_seq);
     } else {
       fixedwing_load(st, ist, N, i, s);
       df_load_agent(st, ist, N, i, ag);
-      // an arena whose agents are all done is reset by a tail CTA on this call
+      // an arena whose agents are all done is reset by a tail CTA on this call; an agent that CTA has already rewritten
+      // carries this launch's fresh tag instead of AGENT_DONE (pfb_quadx.cuh, FLAG_FRESH*)
       const unsigned arena_mask = ((1u << A) - 1u) << base;
       const bool i_done = (s.flags & FLAG_AGENT_DONE) != 0;
-      const bool arena_done = (__ballot_sync(lanes, i_done) & arena_mask) == arena_mask;
+      const bool owned = (s.flags & (FLAG_AGENT_DONE | fresh_tag(step_seq))) != 0;
+      s.flags &= ~(uint32_t)FLAG_FRESH_ANY;
+      const bool arena_done = (__ballot_sync(lanes, owned) & arena_mask) == arena_mask;
       lanes = __ballot_sync(lanes, !(AUTORESET && arena_done));
       if (AUTORESET && arena_done) continue;
       float act[4];

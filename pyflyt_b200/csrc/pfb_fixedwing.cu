@@ -235,9 +235,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
     float rew = 0.0f;
     if (tail) {
       wp_reset_env<false>(p, w, rng, st, ist, start_pos, start_orn, nullptr, nullptr, step_seq, N, i, s, wp);
+      s.flags |= fresh_tag(step_seq);
     } else {
       fixedwing_load(st, ist, N, i, s);
-      if (AUTORESET && (s.flags & (FLAG_TERM | FLAG_TRUNC))) continue;
+      if (AUTORESET && (s.flags & (FLAG_TERM | FLAG_TRUNC | fresh_tag(step_seq)))) continue;  // a tail CTA owns this env
+      s.flags &= ~(uint32_t)FLAG_FRESH_ANY;
       if (RANDACT) {
         uint64_t g = ((uint64_t)rng.env_offset_hi << 32 | rng.env_offset_lo) + (uint64_t)i;
         U4 r = philox4x32_10(U4{(uint32_t)g, (uint32_t)(g >> 32), step_seq, (uint32_t)TAG_ACTION << 24}, rng.k0, rng.k1);

@@ -107,39 +107,12 @@ __global__ void __launch_bounds__(kBlock) k_quadx_observe(const float* __restric
 constexpr int kObsStride = 21;  // odd stride: conflict-free shared-memory transpose for O = 20 or 21
 
 // env.reset() body for one env: begin_reset + end_reset (quadx_base_env.py:149-212); obs -> `out`
-// ---- reset cache: rows [0, QX_ROWS) = post-warm-up state, then start pose (6), valid (1), flags bits (1)
-__device__ __forceinline__ bool hover_cache_hit(const float* __restrict__ cache, const float* __restrict__ start_pos,
-                                                const float* __restrict__ start_orn, int64_t N, int64_t i) {
-  const float* c = cache + (int64_t)QX_ROWS * N + i;
-  bool ok = c[6 * N] != 0.0f;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) ok = ok && (c[k * N] == start_pos[3 * i + k]) && (c[(3 + k) * N] == start_orn[3 * i + k]);
-  return ok;
-}
-template <int MODE>
-__device__ __forceinline__ void hover_cache_fill(float* __restrict__ cache, int32_t* __restrict__ ist, const float* __restrict__ start_pos,
-                                                 const float* __restrict__ start_orn, int64_t N, int64_t i, const QuadXRegs& s) {
-  // valid only if no motor ever spun (throttle follows pwm with a lag < 1, so "zero now" means "zero throughout")
-  const bool quiet = s.thr[0] == 0.0f && s.thr[1] == 0.0f && s.thr[2] == 0.0f && s.thr[3] == 0.0f && s.pwm[0] == 0.0f &&
-                     s.pwm[1] == 0.0f && s.pwm[2] == 0.0f && s.pwm[3] == 0.0f;
-  float* c = cache + (int64_t)QX_ROWS * N + i;
-  c[6 * N] = 0.0f;
-  if (!quiet) return;
-  const int32_t keep = ist[(int64_t)QI_FLAGS * N + i];
-  quadx_store<7>(cache, ist, N, i, s);  // every row: any mode may read the cache back
-  ist[(int64_t)QI_FLAGS * N + i] = keep;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { c[k * N] = start_pos[3 * i + k]; c[(3 + k) * N] = start_orn[3 * i + k]; }
-  c[7 * N] = __uint_as_float(s.flags);
-  c[6 * N] = 1.0f;
-}
-
 template <int MODE, bool INJECT>
 __device__ __forceinline__ void hover_reset_env(const QuadXParams& p, const HoverParams& h, const RngParams& rng,
                                                 float* __restrict__ st, int32_t* __restrict__ ist,
                                                 const float* __restrict__ start_pos, const float* __restrict__ start_orn,
                                                 const float* __restrict__ noise, uint32_t seq, int64_t N, int64_t i,
-                                                float* out, float* __restrict__ cache) {
+                                                float* out) {
   QuadXRegs s;
   quadx_reset(s, start_pos[3 * i + 0], start_pos[3 * i + 1], start_pos[3 * i + 2], start_orn[3 * i + 0],
               start_orn[3 * i + 1], start_orn[3 * i + 2]);
@@ -150,9 +123,7 @@ __device__ __forceinline__ void hover_reset_env(const QuadXParams& p, const Hove
   hover_observation(h, s, zero, out);
   quadx_store<7>(st, ist, N, i, s);
   ist[(int64_t)QI_STEP * N + i] = 0;
-  if (cache) hover_cache_fill<MODE>(cache, ist, start_pos, start_orn, N, i, s);
 }
-
 
 // env.step(action) for every env (quadx_base_env.py:269-301 + quadx_hover_env.py), ONE launch.
 //   RANDACT   actions are drawn on device, uniform in the env's action box (quadx_base_env.py:79-102)
@@ -172,7 +143,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
                  uint8_t* __restrict__ info, const float* __restrict__ start_pos, const float* __restrict__ start_orn,
                  const int32_t* __restrict__ prev_count, const int32_t* __restrict__ prev_list,
                  int32_t* __restrict__ cur_count, int32_t* __restrict__ cur_list, int32_t* __restrict__ next_count,
-                 float* __restrict__ cache, int tail_blocks, uint32_t step_seq, int64_t N) {
+                 int tail_blocks, uint32_t step_seq, int64_t N) {
   __shared__ float smem[kBlock * kObsStride];
   __shared__ uint8_t row_skip[kBlock];
   const int O = h.angle_representation == 0 ? 20 : 21;
@@ -200,12 +171,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
     float act[4] = {0.f, 0.f, 0.f, 0.f};
     int n_aviary, step_count;
     float rew;
-    // reset cache: the post-warm-up state of env i is a pure function of its start pose whenever the
-    // motors stay at exactly zero throttle during the warm-up (then no noise draw can act); it is stored by the
-    // first reset that computes it and reused while the start pose is unchanged
-    bool hit = false;
-    if (tail && cache) hit = hover_cache_hit(cache, start_pos, start_orn, N, i);
-    if (tail && !hit) {
+    if (tail) {
       // env.reset(): begin_reset + end_reset (quadx_base_env.py:149-212)
       quadx_reset(s, start_pos[3 * i + 0], start_pos[3 * i + 1], start_pos[3 * i + 2], start_orn[3 * i + 0],
                   start_orn[3 * i + 1], start_orn[3 * i + 2]);
@@ -213,15 +179,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
       n_aviary = h.warmup_steps;
       step_count = 0;
       rew = 0.0f;
-    } else if (tail) {
-      quadx_load<MODE>(cache, ist, N, i, s);
-      s.flags = __float_as_uint(cache[(int64_t)(QX_ROWS + 7) * N + i]);
-      n_aviary = 0;
-      step_count = 0;
-      rew = 0.0f;
+      s.flags |= fresh_tag(step_seq);
     } else {
       quadx_load<MODE>(st, ist, N, i, s);
-      if (AUTORESET && (s.flags & (FLAG_TERM | FLAG_TRUNC))) continue;  // a tail CTA owns this env on this call
+      if (AUTORESET && (s.flags & (FLAG_TERM | FLAG_TRUNC | fresh_tag(step_seq)))) continue;  // a tail CTA owns this env on this call
+      s.flags &= ~(uint32_t)FLAG_FRESH_ANY;
       if (RANDACT) {
         uint64_t g = ((uint64_t)rng.env_offset_hi << 32 | rng.env_offset_lo) + (uint64_t)i;
         U4 r = philox4x32_10(U4{(uint32_t)g, (uint32_t)(g >> 32), step_seq, (uint32_t)TAG_ACTION << 24}, rng.k0, rng.k1);
@@ -262,7 +224,6 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
     if (tail) {
       float* dst = obs + i * O;  // scattered rows: the tail handles ~1-3 % of the envs
       for (int k = 0; k < O; ++k) dst[k] = row[k];
-      if (cache && !hit) hover_cache_fill<MODE>(cache, ist, start_pos, start_orn, N, i, s);
     } else {
       skip = false;
       if (AUTORESET) {  // queue finished episodes for the next launch's tail CTAs (warp-aggregated append)
@@ -304,14 +265,14 @@ __global__ void __launch_bounds__(kBlock)
                   const __grid_constant__ RngParams rng, float* __restrict__ st, int32_t* __restrict__ ist,
                   const float* __restrict__ start_pos, const float* __restrict__ start_orn,
                   const uint8_t* __restrict__ mask, const float* __restrict__ noise, float* __restrict__ obs,
-                  float* __restrict__ cache, uint32_t seq, int64_t N) {
+                  uint32_t seq, int64_t N) {
   __shared__ float smem[kBlock * kObsStride];
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (i >= N) return;
   if (mask && !mask[i]) return;
   const int O = h.angle_representation == 0 ? 20 : 21;
   float* row = smem + threadIdx.x * kObsStride;
-  hover_reset_env<MODE, INJECT>(p, h, rng, st, ist, start_pos, start_orn, noise, seq, N, i, row, cache);
+  hover_reset_env<MODE, INJECT>(p, h, rng, st, ist, start_pos, start_orn, noise, seq, N, i, row);
   if (obs) {
     for (int k = 0; k < O; ++k) obs[i * O + k] = row[k];
   }
@@ -433,7 +394,6 @@ int pfb_state_rows(PfbHandle h) { return is_rk(h) ? rk_state_rows() : (is_fw(h) 
 int pfb_istate_rows(PfbHandle h) { return is_rk(h) ? rk_istate_rows() : (is_fw(h) ? fw_istate_rows() : QI_ROWS); }
 int pfb_setpoint_dim(PfbHandle h) { return is_rk(h) ? 7 : ((is_fw(h) && h->env.env_kind == PFB_ENV_NONE) ? 6 : 4); }
 int pfb_obs_dim(PfbHandle h) { return is_df(h) ? df_obs_dim(h) : is_rk(h) ? rk_obs_dim(h) : (is_fw(h) ? fw_obs_dim(h) : (h->hover.angle_representation == 0 ? 20 : 21)); }
-int pfb_reset_cache_rows(PfbHandle h) { return (h && h->env.env_kind == PFB_ENV_QUADX_HOVER) ? QX_ROWS + 8 : 0; }
 int pfb_aux_dim(PfbHandle h) { return is_rk(h) ? 9 : (is_fw(h) ? 6 : 4); }
 
 int pfb_bind(PfbHandle h, const PfbBuffers* b) {
@@ -531,11 +491,11 @@ int pfb_env_reset(PfbHandle h, const uint8_t* mask, const float* noise, void* st
   if (noise) {
     PFB_MODE_SWITCH(mode, (k_hover_reset<MODE, true><<<grid_for(h->n), kBlock, 0, s>>>(
                               h->qx, h->hover, h->rng, h->buf.state, h->buf.istate, h->buf.start_pos, h->buf.start_orn, mask,
-                              noise, h->buf.obs, h->buf.reset_cache, seq, h->n)));
+                              noise, h->buf.obs, seq, h->n)));
   } else {
     PFB_MODE_SWITCH(mode, (k_hover_reset<MODE, false><<<grid_for(h->n), kBlock, 0, s>>>(
                               h->qx, h->hover, h->rng, h->buf.state, h->buf.istate, h->buf.start_pos, h->buf.start_orn, mask,
-                              nullptr, h->buf.obs, h->buf.reset_cache, seq, h->n)));
+                              nullptr, h->buf.obs, seq, h->n)));
   }
   LAUNCH_CHECK(h);
   h->mode = mode;
@@ -568,7 +528,7 @@ static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool r
   if (prof) CUDA_OK(cudaEventRecord(h->prof_ev[2 * h->prof_n], s));
 #define STEP_ARGS h->qx, h->hover, h->rng, h->buf.state, h->buf.istate, actions, noise, h->buf.obs, h->buf.reward,     \
                   h->buf.term, h->buf.trunc, h->buf.info, h->buf.start_pos, h->buf.start_orn, cnt_prev, list_prev, \
-                  cnt_cur, list_cur, cnt_next, h->buf.reset_cache, tail, seq, h->n
+                  cnt_cur, list_cur, cnt_next, tail, seq, h->n
   if (autoreset) {
     if (noise) return fail("injected noise (parity mode) is only supported with autoreset = 0");
     if (randact) {

@@ -38,7 +38,15 @@ struct PhiloxNoise {
     seq = seq_; tag = tag_ << 24; step = 0; loc = loc_; ratio = ratio_;
     n2 = n3 = 0.0f;
   }
-  __device__ __forceinline__ void seek(uint32_t s) { step = s; }
+  // continue a stream at Aviary step s (a spare's warm-up is integrated in pieces over several launches)
+  __device__ __forceinline__ void seek(uint32_t s) {
+    step = s;
+    if (ratio <= 2 && (s & 1u)) {  // the pair (s-1, s) shares one Philox call
+      U4 r = philox4x32_10(U4{env_lo, env_hi, seq, tag | (s - 1u)}, k0, k1);
+      box_muller(r.x, r.y, n0, n1);
+      box_muller(r.z, r.w, n2, n3);
+    }
+  }
   __device__ __forceinline__ void begin_step() {
     // ratio <= 2: one Philox call (4 words -> 4 normals) serves two consecutive Aviary steps
     if (ratio > 2 || (step & 1u) == 0u) {

@@ -84,6 +84,12 @@ enum {
 // istate rows [I][N]
 enum { QI_STEP = 0, QI_FLAGS = 1, QI_ROWS = 2 };
 enum { FLAG_TERM = 1, FLAG_TRUNC = 2, FLAG_OOB = 4, FLAG_COLLISION = 8, FLAG_CONTACT_PREV = 16, FLAG_CONTACT_ARRAY = 32 };
+// In-launch autoreset: a tail CTA that resets an env on launch k tags the new episode with FLAG_FRESH0 << (k & 1).  The
+// env's regular thread of the SAME launch may read the flags before or after the tail CTA rewrote them (a later wave of
+// a large grid): it stands down on TERM/TRUNC (not yet rewritten) and on this launch's tag (already rewritten).  The
+// tag of the other parity is from the previous launch and is cleared by the regular thread's store.
+enum { FLAG_FRESH0 = 1 << 14, FLAG_FRESH1 = 1 << 15, FLAG_FRESH_ANY = FLAG_FRESH0 | FLAG_FRESH1 };
+PFB_HD uint32_t fresh_tag(uint32_t step_seq) { return (uint32_t)FLAG_FRESH0 << (step_seq & 1u); }
 
 template <typename T>
 struct Rot {

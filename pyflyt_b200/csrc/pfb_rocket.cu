@@ -213,9 +213,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
     bool pad_obs = false;
     if (tail) {
       landing_reset_env<false>(p, l, rng, start_pos, start_orn, nullptr, step_seq, l.randomize_drop != 0, N, i, s);
+      s.flags |= fresh_tag(step_seq);
     } else {
       rocket_load(st, ist, N, i, s);
-      if (AUTORESET && (s.flags & (FLAG_TERM | FLAG_TRUNC))) continue;
+      if (AUTORESET && (s.flags & (FLAG_TERM | FLAG_TRUNC | fresh_tag(step_seq)))) continue;  // a tail CTA owns this env
+      s.flags &= ~(uint32_t)FLAG_FRESH_ANY;
       if (RANDACT) {  // rocket_base_env.py:82-107: [-1,1]^3, ignition {0..1}, throttle [0,1], gimbal [-1,1]^2
         uint64_t g = ((uint64_t)rng.env_offset_hi << 32 | rng.env_offset_lo) + (uint64_t)i;
         U4 a = philox4x32_10(U4{(uint32_t)g, (uint32_t)(g >> 32), step_seq, (uint32_t)TAG_ACTION << 24}, rng.k0, rng.k1);

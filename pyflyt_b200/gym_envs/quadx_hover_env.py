@@ -43,7 +43,6 @@ class QuadXHoverVecEnv:
         seed: int | None = None,
         device: str | torch.device = "cuda:0",
         env_offset: int = 0,
-        reset_cache: bool = True,
     ):
         if 120 % agent_hz != 0:  # quadx_base_env.py:47-52
             lowest = int(120 / (int(120 / agent_hz) + 1))
@@ -81,8 +80,7 @@ class QuadXHoverVecEnv:
         sp = np.ascontiguousarray(np.broadcast_to(sp.reshape(-1, 3) if sp.size == 3 else sp, (self.num_envs, 3)))
         so = np.ascontiguousarray(np.broadcast_to(so.reshape(-1, 3) if so.size == 3 else so, (self.num_envs, 3)))
         self.aviary = BatchedAviary(
-            sp, so, drone_type="quadx", drone_options=drone_options, seed=seed, device=device, env_config=cfg, env_offset=env_offset,
-            reset_cache=reset_cache,
+            sp, so, drone_type="quadx", drone_options=drone_options, seed=seed, device=device, env_config=cfg, env_offset=env_offset
         )
         self.device = self.aviary.device
         self.obs_dim = self.aviary.obs_dim
