@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
                  const int32_t* __restrict__ prev_count, const int32_t* __restrict__ prev_list,
                  int32_t* __restrict__ cur_count, int32_t* __restrict__ cur_list, int32_t* __restrict__ next_count,
                  int tail_blocks, uint32_t step_seq, int64_t N) {
-  __shared__ float smem[kBlock * kObsStride];
+  __shared__ __align__(16) float smem[kBlock * kObsStride];
   __shared__ uint8_t row_skip[kBlock];
   const int O = h.angle_representation == 0 ? 20 : 21;
   const bool tail = AUTORESET && (int)blockIdx.x < tail_blocks;  // CTA-uniform role
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
     t_stride = 1;
   }
   bool skip = true;
-  float* row = smem + threadIdx.x * kObsStride;
+  float* row = smem + threadIdx.x * O;  // dense [kBlock][O] tile: copied out below as float4
 #pragma unroll 1
   for (; t < t_end; t += t_stride) {
     const int64_t i = tail ? (int64_t)prev_list[t] : block_first + threadIdx.x;
@@ -241,21 +241,38 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
     }
   }
   if (tail) return;
-  // ---- block-cooperative, fully coalesced write of this CTA's observations into obs[N][O]
+  // ---- block-cooperative write of this CTA's observation tile obs[block_first .. +rows][O]: the tile is contiguous in
+  //      global memory and 16-byte aligned (kBlock * O * 4 bytes per CTA), so it goes out as float4; rows of envs that a
+  //      tail CTA owns on this launch are left alone
   row_skip[threadIdx.x] = skip ? 1 : 0;
-  __syncthreads();
+  const int any_skip = __syncthreads_or(skip ? 1 : 0);
   int64_t rows = N - block_first;
   if (rows > kBlock) rows = kBlock;
   const int total = (int)rows * O;
+  const int nvec = total >> 2;
   float* dst = obs + block_first * O;
-  // element j = r * O + c of the CTA tile; advancing j by kBlock advances (r, c) by (kBlock / O, kBlock % O)
-  const int dr = kBlock / O, dc = kBlock - dr * O;
-  int r = threadIdx.x / O, c = threadIdx.x - r * O;
-  for (int j = threadIdx.x; j < total; j += kBlock) {
-    if (!row_skip[r]) dst[j] = smem[r * kObsStride + c];
-    r += dr; c += dc;
-    if (c >= O) { c -= O; ++r; }
+  const float4* src4 = reinterpret_cast<const float4*>(smem);
+  float4* dst4 = reinterpret_cast<float4*>(dst);
+  if (!any_skip) {
+    for (int v = threadIdx.x; v < nvec; v += kBlock) dst4[v] = src4[v];
+  } else {
+    for (int v = threadIdx.x; v < nvec; v += kBlock) {
+      const int j = v << 2;
+      const int r0 = (O == 21) ? j / 21 : j / 20, r1 = (O == 21) ? (j + 3) / 21 : (j + 3) / 20;
+      const float4 val = src4[v];
+      if (!row_skip[r0] && !row_skip[r1]) {
+        dst4[v] = val;
+      } else {  // the vector straddles a skipped row: element-wise
+        const int split = r1 * O - j;  // elements [0, split) belong to row r0
+        const float e[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (!row_skip[q < split ? r0 : r1]) dst[j + q] = e[q];
+      }
+    }
   }
+  for (int j = (nvec << 2) + threadIdx.x; j < total; j += kBlock)  // ragged last CTA only
+    if (!row_skip[(O == 21) ? j / 21 : j / 20]) dst[j] = smem[j];
 }
 
 // env.reset() for all / masked envs

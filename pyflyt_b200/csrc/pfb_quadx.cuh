@@ -318,6 +318,22 @@ Vec3 quadx_clamp_world_rates(float vmax, Mat3 R, Vec3 w) {
   return mulT(R, o);
 }
 
+// Bullet's +-vmax clamp of the world linear velocity (btMultiBody::applyDeltaVeeMultiDof): only ever taken by a body
+// falling at the 100 m/s limit.  Out of line for the same reason as above: inlined, the compiler if-converts it into
+// ~45 predicated fp64 instructions that occupy issue slots on every substep.
+struct Vel3 { vreal x, y, z; };
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+inline
+#endif
+Vel3 quadx_clamp_world_velocity(vreal vmax, Vel3 v) {
+  v.x = fmin(fmax(v.x, -vmax), vmax);
+  v.y = fmin(fmax(v.y, -vmax), vmax);
+  v.z = fmin(fmax(v.z, -vmax), vmax);
+  return v;
+}
+
 // One physics substep: update_physics (quadx.py:495-510) + stepSimulation + update_state.
 // xi = raw draw of np_random.normal(*throttle.shape)  (one scalar ~ N(4, 1) shared by the motors).
 // Written as straight-line code (selects instead of branches): the kernel is instruction-issue bound
@@ -370,10 +386,8 @@ PFB_HD void quadx_substep(const QuadXParams& p, QuadXRegs& s, float xi) {
   // +-vmax clamp per world coordinate (btMultiBody::applyDeltaVeeMultiDof): tested on the fp32 copy,
   // applied exactly, and only ever taken by a body falling at the 100 m/s limit
   if (fmaxf(fmaxf(fabsf((float)s.vx), fabsf((float)s.vy)), fabsf((float)s.vz)) >= p.vmax) {
-    const vreal vmax = (vreal)p.vmax;
-    s.vx = fmin(fmax(s.vx, -vmax), vmax);
-    s.vy = fmin(fmax(s.vy, -vmax), vmax);
-    s.vz = fmin(fmax(s.vz, -vmax), vmax);
+    Vel3 c = quadx_clamp_world_velocity((vreal)p.vmax, Vel3{s.vx, s.vy, s.vz});
+    s.vx = c.x; s.vy = c.y; s.vz = c.z;
   }
   s.px += (xreal)(s.vx * dt);
   s.py += (xreal)(s.vy * dt);
