@@ -159,7 +159,9 @@ typedef struct PfbEnvConfig {
   int32_t randomize_drop, accelerate_drop;
   /* MAFixedwingDogfight (pz_envs/fixedwing_envs/ma_fixedwing_dogfight_env.py:42-62): an arena is
    * 2*team_size CONSECUTIVE envs of the batch; the first team_size of them are team 0                 */
-  int32_t team_size, _pad_df;
+  int32_t team_size;
+  int32_t inline_reset;      /* QuadX-Hover autoreset: 1 = integrate every warm-up inside the step launch instead of
+                              * copying the env's spare post-reset state (same results, longer launches; tests)  */
   double damage_per_hit, lethal_distance, lethal_angle, aggressiveness, cooperativeness;
   double spawn_min_radius, spawn_max_radius, spawn_min_height, spawn_max_height;
 } PfbEnvConfig;

@@ -50,6 +50,12 @@ struct PfbContext {
   uint64_t reset_seq;     // pfb_env_reset calls so far
   int64_t launches;
   int sm_count;
+  // QuadX-Hover reset pipeline (pfb_lib.cu, "spare post-reset states"): library-owned spares + the side stream that rebuilds them
+  float* d_spare;          // [SP_ROWS][N], zero-initialised; nullptr = warm-ups run inline
+  cudaStream_t side;       // k_hover_spare runs here, concurrently with the following step launches
+  cudaEvent_t ev_step;     // recorded on the caller's stream after a step launch; the side stream waits on it
+  cudaEvent_t ev_spare[4]; // ev_spare[k % 4]: spares consumed by step k are rebuilt; step k + 2 waits on it
+  int64_t side_launches;
   // optional per-step CUDA-event pairs around the dominant kernel (bench.py's roofline leg)
   cudaEvent_t* prof_ev;   // [2 * prof_cap]
   int prof_cap;

@@ -104,7 +104,43 @@ __global__ void __launch_bounds__(kBlock) k_quadx_observe(const float* __restric
 // ---------------------------------------------------------------------------------------------------
 // kernels — QuadX-Hover env
 // ---------------------------------------------------------------------------------------------------
-constexpr int kObsStride = 21;  // odd stride: conflict-free shared-memory transpose for O = 20 or 21
+constexpr int kObsStride = 21;
+// 10 CTAs of 64 threads per SM (<= 96 registers): the 1024 regular + tail CTAs of a 65 536-env step and the CTAs of the
+// concurrent spare rebuild must all be resident at once, or the stragglers form a second wave
+constexpr int kHoverBlocks = 10;  // odd stride: conflict-free shared-memory transpose for O = 20 or 21
+
+// ---- spare post-reset states ("reset pipeline") ---------------------------------------
+// env.reset() = start pose + `warmup_steps` Aviary steps (quadx_base_env.py:149-212): 3.3x the work of an env step and a
+// strictly serial chain; reset inline, even one finished env stretches the launch to the length of that chain.  So each
+// env owns a SPARE, the post-warm-up state of its NEXT episode, with noise keyed by (env id, episode number, Aviary
+// step) so that it does not matter when it is computed.  The step kernel's tail CTAs only COPY the spare of a finished
+// env; a second launch of the SAME kernel in build mode (all CTAs are tail CTAs, same compiled warm-up loop, hence
+// bit-identical results) rebuilds the spares just consumed on a side stream, concurrently with the following step
+// launches (the step two launches later waits for it: an env cannot finish again sooner).  If the start pose was
+// edited since a spare was built it is ignored and the warm-up runs inline (same episode number, same result).
+// Library-owned buffer [SP_ROWS][N]: rows [0, QX_ROWS) the spare's state, then:
+enum { SP_POSE = QX_ROWS, SP_VALID = QX_ROWS + 6, SP_FLAGS = QX_ROWS + 7, SP_EPISODE = QX_ROWS + 8, SP_ROWS = QX_ROWS + 9 };
+
+__device__ __forceinline__ bool spare_usable(const float* __restrict__ spare, const float* __restrict__ start_pos,
+                                             const float* __restrict__ start_orn, int64_t N, int64_t i) {
+  const float* c = spare + (int64_t)SP_POSE * N + i;
+  bool ok = c[6 * N] != 0.0f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) ok = ok && (c[k * N] == start_pos[3 * i + k]) && (c[(3 + k) * N] == start_orn[3 * i + k]);
+  return ok;
+}
+
+// the pose rows are written by the caller at reset time, from the very values the warm-up started from (the user may
+// edit start_pos / start_orn while a rebuild is in flight on the side stream)
+template <int MODE>
+__device__ __forceinline__ void spare_store(float* __restrict__ spare, int32_t* __restrict__ ist, int64_t N, int64_t i,
+                                            const QuadXRegs& s, uint32_t episode) {
+  quadx_store<MODE>(spare, ist, N, i, s, false);
+  float* c = spare + (int64_t)SP_POSE * N + i;
+  c[7 * N] = __uint_as_float(s.flags);
+  c[8 * N] = __uint_as_float(episode);
+  c[6 * N] = 1.0f;
+}
 
 // env.reset() body for one env: begin_reset + end_reset (quadx_base_env.py:149-212); obs -> `out`
 template <int MODE, bool INJECT>
@@ -135,7 +171,7 @@ __device__ __forceinline__ void hover_reset_env(const QuadXParams& p, const Hove
 // Both roles run the SAME code (role-dependent scalars only): the kernel is instruction-fetch bound, so one
 // compact hot loop shared by every warp on the SM matters more than anything else.
 template <int MODE, bool INJECT, bool RANDACT, bool AUTORESET>
-__global__ void __launch_bounds__(kBlock, kMinBlocks)
+__global__ void __launch_bounds__(kBlock, kHoverBlocks)
     k_hover_step(const __grid_constant__ QuadXParams p, const __grid_constant__ HoverParams h,
                  const __grid_constant__ RngParams rng, float* __restrict__ st, int32_t* __restrict__ ist,
                  float* __restrict__ actions, const float* __restrict__ noise, float* __restrict__ obs,
@@ -143,7 +179,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
                  uint8_t* __restrict__ info, const float* __restrict__ start_pos, const float* __restrict__ start_orn,
                  const int32_t* __restrict__ prev_count, const int32_t* __restrict__ prev_list,
                  int32_t* __restrict__ cur_count, int32_t* __restrict__ cur_list, int32_t* __restrict__ next_count,
-                 int tail_blocks, uint32_t step_seq, int64_t N) {
+                 float* __restrict__ spare, int spare_copy, int build, int tail_blocks, uint32_t step_seq, int64_t N) {
   __shared__ __align__(16) float smem[kBlock * kObsStride];
   __shared__ uint8_t row_skip[kBlock];
   const int O = h.angle_representation == 0 ? 20 : 21;
@@ -153,9 +189,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   // work items: a regular thread owns exactly one env; a tail thread strides over the done list
   int t, t_end, t_stride;
   if (tail) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *next_count = 0;  // arm the counter the NEXT launch appends to
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !build) *next_count = 0;  // arm the counter the NEXT launch appends to
     t = blockIdx.x * kBlock + threadIdx.x;
-    t_end = *prev_count;
+    t_end = prev_list ? *prev_count : (int)N;  // build mode after a user reset: every env
     t_stride = tail_blocks * kBlock;
   } else {
     t = 0;
@@ -166,20 +202,41 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   float* row = smem + threadIdx.x * O;  // dense [kBlock][O] tile: copied out below as float4
 #pragma unroll 1
   for (; t < t_end; t += t_stride) {
-    const int64_t i = tail ? (int64_t)prev_list[t] : block_first + threadIdx.x;
+    const int64_t i = tail ? (prev_list ? (int64_t)prev_list[t] : (int64_t)t) : block_first + threadIdx.x;
     QuadXRegs s;
     float act[4] = {0.f, 0.f, 0.f, 0.f};
     int n_aviary, step_count;
     float rew;
+    uint32_t nseq = step_seq;
     if (tail) {
-      // env.reset(): begin_reset + end_reset (quadx_base_env.py:149-212)
-      quadx_reset(s, start_pos[3 * i + 0], start_pos[3 * i + 1], start_pos[3 * i + 2], start_orn[3 * i + 0],
-                  start_orn[3 * i + 1], start_orn[3 * i + 2]);
-      quadx_set_mode<MODE>(s);
-      n_aviary = h.warmup_steps;
+      // env.reset(): begin_reset + end_reset (quadx_base_env.py:149-212) — normally a copy of the env's spare
+      nseq = step_seq | 0x40000000u;
+      bool hit = false;
+      if (spare) {
+        nseq = __float_as_uint(spare[(int64_t)SP_EPISODE * N + i]) + (build ? 1u : 0u);  // episode number: keys the warm-up noise
+        hit = !build && spare_copy && spare_usable(spare, start_pos, start_orn, N, i);
+      }
+      if (hit) {
+        quadx_load<MODE>(spare, ist, N, i, s);
+        s.flags = __float_as_uint(spare[(int64_t)SP_FLAGS * N + i]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s.sp[k] = 0.0f;
+        n_aviary = 0;
+      } else {
+        const float px = start_pos[3 * i + 0], py = start_pos[3 * i + 1], pz = start_pos[3 * i + 2];
+        const float ox = start_orn[3 * i + 0], oy = start_orn[3 * i + 1], oz = start_orn[3 * i + 2];
+        if (build) {
+          float* c = spare + (int64_t)SP_POSE * N + i;
+          c[6 * N] = 0.0f;  // invalid until the warm-up below is stored
+          c[0] = px; c[N] = py; c[2 * N] = pz; c[3 * N] = ox; c[4 * N] = oy; c[5 * N] = oz;
+        }
+        quadx_reset(s, px, py, pz, ox, oy, oz);
+        quadx_set_mode<MODE>(s);
+        n_aviary = h.warmup_steps;
+      }
       step_count = 0;
       rew = 0.0f;
-      s.flags |= fresh_tag(step_seq);
+      if (!build) s.flags |= fresh_tag(step_seq);
     } else {
       quadx_load<MODE>(st, ist, N, i, s);
       if (AUTORESET && (s.flags & (FLAG_TERM | FLAG_TRUNC | fresh_tag(step_seq)))) continue;  // a tail CTA owns this env on this call
@@ -206,7 +263,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
       step_count = ist[(int64_t)QI_STEP * N + i];
       rew = -0.1f;
     }
-    auto nz = make_noise<INJECT>(noise, N, i, rng, step_seq, tail ? TAG_RESET : TAG_ENV_STEP, p.noise_loc, p.ratio);
+    auto nz = make_noise<INJECT>(noise, N, i, rng, nseq, tail ? TAG_RESET : TAG_ENV_STEP, p.noise_loc, p.ratio);
 #pragma unroll 1
     for (int k = 0; k < n_aviary; ++k) {
       if (s.flags & (FLAG_TERM | FLAG_TRUNC)) break;  // quadx_base_env.py:289-290 (never set while resetting)
@@ -214,6 +271,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
       if (!tail) hover_term_trunc_reward(h, s, step_count, rew);
     }
     step_count = tail ? 0 : step_count + 1;
+    if (tail && build) {  // build mode: the warm-up result is the env's new spare
+      spare_store<MODE>(spare, ist, N, i, s, nseq);
+      continue;
+    }
+    if (tail && n_aviary > 0) quadx_requantize(s);  // an inline warm-up must leave exactly what a copied spare holds
     hover_observation(h, s, act, row);
     quadx_store<MODE>(st, ist, N, i, s);
     ist[(int64_t)QI_STEP * N + i] = step_count;
@@ -379,7 +441,16 @@ int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, i
   c->sm_count = prop.multiProcessorCount;
   CUDA_OK(cudaMalloc(&c->d_counters, 4 * sizeof(int32_t)));
   CUDA_OK(cudaMemset(c->d_counters, 0, 4 * sizeof(int32_t)));
-  CUDA_OK(cudaMalloc(&c->d_done_list, 2 * (size_t)n_envs * sizeof(int32_t)));
+  CUDA_OK(cudaMalloc(&c->d_done_list, 4 * (size_t)n_envs * sizeof(int32_t)));
+  if (env && env->env_kind == PFB_ENV_QUADX_HOVER && env->autoreset) {
+    CUDA_OK(cudaMalloc(&c->d_spare, (size_t)SP_ROWS * (size_t)n_envs * sizeof(float)));
+    CUDA_OK(cudaMemset(c->d_spare, 0, (size_t)SP_ROWS * (size_t)n_envs * sizeof(float)));
+    int prio_lo = 0, prio_hi = 0;  // the rebuild is small and latency-critical: let its CTAs go first when slots free up
+    CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CUDA_OK(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_hi));
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_step, cudaEventDisableTiming));
+    for (int k = 0; k < 4; ++k) CUDA_OK(cudaEventCreateWithFlags(&c->ev_spare[k], cudaEventDisableTiming));
+  }
   *out = c;
   return 0;
 }
@@ -387,6 +458,13 @@ int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, i
 int pfb_destroy(PfbHandle h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
+  if (h->d_spare) {
+    cudaStreamSynchronize(h->side);
+    cudaStreamDestroy(h->side);
+    cudaEventDestroy(h->ev_step);
+    for (int k = 0; k < 4; ++k) cudaEventDestroy(h->ev_spare[k]);
+    cudaFree(h->d_spare);
+  }
   cudaFree(h->d_counters);
   cudaFree(h->d_done_list);
   if (h->prof_ev) {
@@ -505,6 +583,10 @@ int pfb_env_reset(PfbHandle h, const uint8_t* mask, const float* noise, void* st
   const int mode = h->hover.flight_mode;
   // resets draw from their own Philox stream; the high bit keeps them apart from in-step autoresets
   const uint32_t seq = 0x80000000u | (uint32_t)h->reset_seq++;
+  if (h->d_spare) {  // the reset kernel rewrites spares: let the side stream's last rebuild finish first
+    if (h->step_seq > 0) CUDA_OK(cudaStreamWaitEvent(s, h->ev_spare[(h->step_seq - 1) % 4], 0));
+    if (!mask) CUDA_OK(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(int32_t), s));  // a full reset empties the autoreset queues
+  }
   if (noise) {
     PFB_MODE_SWITCH(mode, (k_hover_reset<MODE, true><<<grid_for(h->n), kBlock, 0, s>>>(
                               h->qx, h->hover, h->rng, h->buf.state, h->buf.istate, h->buf.start_pos, h->buf.start_orn, mask,
@@ -515,6 +597,14 @@ int pfb_env_reset(PfbHandle h, const uint8_t* mask, const float* noise, void* st
                               nullptr, h->buf.obs, seq, h->n)));
   }
   LAUNCH_CHECK(h);
+  if (h->d_spare) {  // every env gets a fresh spare (build mode of the step kernel over all envs, same stream)
+    const int g = grid_for(h->n);
+    PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, false, true><<<g, kBlock, 0, s>>>(
+                              h->qx, h->hover, h->rng, h->buf.state, h->buf.istate, h->buf.setpoint, nullptr, h->buf.obs, h->buf.reward,
+                              h->buf.term, h->buf.trunc, h->buf.info, h->buf.start_pos, h->buf.start_orn, nullptr, nullptr, nullptr, nullptr,
+                              nullptr, h->d_spare, 0, 1, g, 0u, h->n)));
+    LAUNCH_CHECK(h);
+  }
   h->mode = mode;
   return 0;
 }
@@ -526,12 +616,17 @@ static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool r
   const int mode = h->hover.flight_mode;
   const bool autoreset = h->env.autoreset != 0;
   const uint64_t k = h->step_seq;
-  int32_t* cnt_cur = h->d_counters + (k % 3);
-  int32_t* cnt_prev = h->d_counters + ((k + 2) % 3);
-  int32_t* cnt_next = h->d_counters + ((k + 1) % 3);
-  int32_t* list_cur = h->d_done_list + (k & 1) * h->n;
-  int32_t* list_prev = h->d_done_list + ((k + 1) & 1) * h->n;
+  // four rotating done lists / counters: step k appends to [k % 4], its tail CTAs and the side-stream spare rebuild read
+  // [(k - 1) % 4], and it zeroes counter [(k + 1) % 4] (last read by the rebuild of step k - 2, which step k waits for)
+  int32_t* cnt_cur = h->d_counters + (k % 4);
+  int32_t* cnt_prev = h->d_counters + ((k + 3) % 4);
+  int32_t* cnt_next = h->d_counters + ((k + 1) % 4);
+  int32_t* list_cur = h->d_done_list + (k % 4) * h->n;
+  int32_t* list_prev = h->d_done_list + ((k + 3) % 4) * h->n;
   const uint32_t seq = (uint32_t)k;
+  const bool spares = autoreset && h->d_spare != nullptr;
+  const int spare_copy = (spares && !h->env.inline_reset) ? 1 : 0;
+  if (spares && k >= 2) CUDA_OK(cudaStreamWaitEvent(s, h->ev_spare[(k - 2) % 4], 0));
   // tail CTAs (front of the grid) reset the envs that finished on the previous call; one per SM is
   // plenty for the ~1-3 % of envs that finish per step, and the loop is grid-strided anyway
   int tail = 0;
@@ -545,7 +640,7 @@ static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool r
   if (prof) CUDA_OK(cudaEventRecord(h->prof_ev[2 * h->prof_n], s));
 #define STEP_ARGS h->qx, h->hover, h->rng, h->buf.state, h->buf.istate, actions, noise, h->buf.obs, h->buf.reward,     \
                   h->buf.term, h->buf.trunc, h->buf.info, h->buf.start_pos, h->buf.start_orn, cnt_prev, list_prev, \
-                  cnt_cur, list_cur, cnt_next, tail, seq, h->n
+                  cnt_cur, list_cur, cnt_next, h->d_spare, spare_copy, 0, tail, seq, h->n
   if (autoreset) {
     if (noise) return fail("injected noise (parity mode) is only supported with autoreset = 0");
     if (randact) {
@@ -567,6 +662,16 @@ static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool r
   if (prof) {
     CUDA_OK(cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], s));
     h->prof_n += 1;
+  }
+  if (spares) {  // rebuild the spares this launch consumed, on the side stream, while the next launches run
+    CUDA_OK(cudaEventRecord(h->ev_step, s));
+    CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_step, 0));
+    PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, false, true><<<h->sm_count, kBlock, 0, h->side>>>(
+                              h->qx, h->hover, h->rng, h->buf.state, h->buf.istate, actions, nullptr, h->buf.obs, h->buf.reward, h->buf.term,
+                              h->buf.trunc, h->buf.info, h->buf.start_pos, h->buf.start_orn, cnt_prev, list_prev, cnt_cur, list_cur, cnt_next,
+                              h->d_spare, 0, 1, h->sm_count, seq, h->n)));
+    LAUNCH_CHECK(h);
+    CUDA_OK(cudaEventRecord(h->ev_spare[k % 4], h->side));
   }
   h->step_seq += 1;
   return 0;

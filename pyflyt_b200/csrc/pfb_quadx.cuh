@@ -530,7 +530,8 @@ PFB_HD void quadx_load(const float* __restrict__ st, const int32_t* __restrict__
 }
 
 template <int MODE>
-PFB_HD void quadx_store(float* __restrict__ st, int32_t* __restrict__ ist, int64_t N, int64_t i, const QuadXRegs& s) {
+PFB_HD void quadx_store(float* __restrict__ st, int32_t* __restrict__ ist, int64_t N, int64_t i, const QuadXRegs& s,
+                        bool with_flags = true) {
   auto S = [&](int row, float v) { st[(int64_t)row * N + i] = v; };
   float hi, lo;
 #if PFB_X_DOUBLE
@@ -562,7 +563,31 @@ PFB_HD void quadx_store(float* __restrict__ st, int32_t* __restrict__ ist, int64
 #pragma unroll
   for (int k = 0; k < PID_WORDS; ++k)
     if (pid_row_used<MODE>(k)) S(QX_PID + k, s.pid[k]);
-  ist[(int64_t)QI_FLAGS * N + i] = (int32_t)s.flags;
+  if (with_flags) ist[(int64_t)QI_FLAGS * N + i] = (int32_t)s.flags;
+}
+
+// Round the fp64-carried fields to what the state tensor holds (hi + lo fp32 words) and re-derive R / body velocity:
+// afterwards the registers equal what quadx_store followed by quadx_load would produce.
+PFB_HD void quadx_requantize(QuadXRegs& s) {
+  float hi, lo;
+#if PFB_X_DOUBLE
+  split_hi_lo(s.px, hi, lo); s.px = join_hi_lo(hi, lo);
+  split_hi_lo(s.py, hi, lo); s.py = join_hi_lo(hi, lo);
+  split_hi_lo(s.pz, hi, lo); s.pz = join_hi_lo(hi, lo);
+#endif
+#if PFB_Q_DOUBLE
+  split_hi_lo(s.qx, hi, lo); s.qx = join_hi_lo(hi, lo);
+  split_hi_lo(s.qy, hi, lo); s.qy = join_hi_lo(hi, lo);
+  split_hi_lo(s.qz, hi, lo); s.qz = join_hi_lo(hi, lo);
+  split_hi_lo(s.qw, hi, lo); s.qw = join_hi_lo(hi, lo);
+#endif
+#if PFB_V_DOUBLE
+  split_hi_lo(s.vx, hi, lo); s.vx = join_hi_lo(hi, lo);
+  split_hi_lo(s.vy, hi, lo); s.vy = join_hi_lo(hi, lo);
+  split_hi_lo(s.vz, hi, lo); s.vz = join_hi_lo(hi, lo);
+#endif
+  (void)hi; (void)lo;
+  quadx_update_state(s);
 }
 
 // ---- Aviary.state(i) (4,3) + aux_state -----------------------------------------------------------

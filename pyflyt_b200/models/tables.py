@@ -133,7 +133,7 @@ class PfbEnvConfig(C.Structure):
         ("randomize_drop", C.c_int32),
         ("accelerate_drop", C.c_int32),
         ("team_size", C.c_int32),
-        ("_pad_df", C.c_int32),
+        ("inline_reset", C.c_int32),
         ("damage_per_hit", C.c_double),
         ("lethal_distance", C.c_double),
         ("lethal_angle", C.c_double),

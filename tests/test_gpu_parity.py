@@ -224,3 +224,48 @@ def test_single_env_adaptor_signature():
     obs, rew, term, trunc, info = env.step(np.array([0.0, 0.0, 0.0, 0.4]))
     assert obs.shape == (21,) and isinstance(rew, float) and isinstance(term, bool) and isinstance(trunc, bool)
     env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,max_seconds", [(0, 10.0), (6, 10.0), (0, 0.05)])
+def test_spare_reset_equals_inline_reset(mode, max_seconds):
+    """In-launch autoreset copies the env's spare post-warm-up state, rebuilt on a side stream with noise keyed by
+    (env, episode).  It must be bit-identical to integrating every warm-up inside the step launch (inline_reset=True),
+    also when the start pose is edited mid-run (stale spares are ignored) and with 3-step episodes (max_seconds=0.05)."""
+    import torch
+
+    from pyflyt_b200.gym_envs.quadx_hover_env import QuadXHoverVecEnv
+
+    n = 8192
+    rng = np.random.default_rng(3)
+    sp = np.zeros((n, 3), dtype=np.float32)
+    sp[:, 2] = rng.uniform(0.6, 1.4, n)
+    so = np.zeros((n, 3), dtype=np.float32)
+    so[:, 2] = rng.uniform(-1, 1, n)
+    outs = []
+    for inline in (False, True):
+        env = QuadXHoverVecEnv(num_envs=n, flight_mode=mode, seed=5, start_pos=sp, start_orn=so, inline_reset=inline, max_duration_seconds=max_seconds)
+        env.reset()
+        resets, trace = 0, []
+        for k in range(90):
+            env.rollout(1)
+            resets += int((env.aviary.term | env.aviary.trunc).sum())
+            trace.append(env.aviary.obs.sum().item())
+            if k == 40:  # move every other env's start pose
+                env.aviary.start_pos[::2, 2] += 0.25
+        torch.cuda.synchronize()
+        outs.append((env.aviary.obs.clone(), env.aviary.reward.clone(), env.aviary.state_tensor.clone(), resets, trace))
+        env.close()
+    a, b = outs
+    assert a[3] > n // 4, a[3]  # plenty of resets (position control in mode 6 keeps many envs alive for the whole run)
+    assert a[3] == b[3] and a[4] == b[4]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    # the edited start pose is what later resets use
+    env = QuadXHoverVecEnv(num_envs=256, flight_mode=mode, seed=5, max_duration_seconds=0.05)
+    env.reset()
+    env.aviary.start_pos[:, 2] = 2.0
+    for _ in range(12):
+        env.rollout(1)
+    torch.cuda.synchronize()
+    assert float(env.aviary.state_tensor[2].min()) > 1.5
+    env.close()
