@@ -227,11 +227,12 @@ def test_single_env_adaptor_signature():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode,max_seconds", [(0, 10.0), (6, 10.0), (0, 0.05)])
+@pytest.mark.parametrize("mode,max_seconds", [(0, 10.0), (6, 0.25), (0, 0.05)])
 def test_spare_reset_equals_inline_reset(mode, max_seconds):
     """In-launch autoreset copies the env's spare post-warm-up state, rebuilt on a side stream with noise keyed by
     (env, episode).  It must be bit-identical to integrating every warm-up inside the step launch (inline_reset=True),
-    also when the start pose is edited mid-run (stale spares are ignored) and with 3-step episodes (max_seconds=0.05)."""
+    also when the start pose is edited mid-run (stale spares are ignored), with 3-step episodes (max_seconds=0.05), and in
+    mode 6 (position control: motors spin during the warm-up; episodes cut to 11 steps so that resets happen)."""
     import torch
 
     from pyflyt_b200.gym_envs.quadx_hover_env import QuadXHoverVecEnv
