@@ -208,6 +208,9 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
     int n_aviary, step_count;
     float rew;
     uint32_t nseq = step_seq;
+    // ONE load site for every role: a regular thread reads its env's state, a tail thread the env's spare.  The loads are
+    // issued before the spare's pose / validity words are examined, so a cold tail thread pays one round trip, not two.
+    quadx_load<MODE>((tail && spare) ? spare : st, ist, N, i, s);
     if (tail) {
       // env.reset(): begin_reset + end_reset (quadx_base_env.py:149-212) — normally a copy of the env's spare
       nseq = step_seq | 0x40000000u;
@@ -217,7 +220,6 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
         hit = !build && spare_copy && spare_usable(spare, start_pos, start_orn, N, i);
       }
       if (hit) {
-        quadx_load<MODE>(spare, ist, N, i, s);
         s.flags = __float_as_uint(spare[(int64_t)SP_FLAGS * N + i]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) s.sp[k] = 0.0f;
@@ -238,7 +240,6 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
       rew = 0.0f;
       if (!build) s.flags |= fresh_tag(step_seq);
     } else {
-      quadx_load<MODE>(st, ist, N, i, s);
       if (AUTORESET && (s.flags & (FLAG_TERM | FLAG_TRUNC | fresh_tag(step_seq)))) continue;  // a tail CTA owns this env on this call
       s.flags &= ~(uint32_t)FLAG_FRESH_ANY;
       if (RANDACT) {
