@@ -429,11 +429,40 @@ def waypoints_config(angle_representation="quaternion", sparse=False, num_target
     return e
 
 
+def quadx_waypoints_config(g_or_none=None, *, flight_mode=0, angle_representation="quaternion", sparse=False, num_targets=4,
+                           use_yaw_targets=False, goal_reach_distance=0.2, goal_reach_angle=0.1, dome=5.0, agent_hz=30,
+                           max_duration=10.0, autoreset=False):
+    """QuadXWaypointsEnv.__init__ defaults (quadx_waypoints_env.py:38-52)."""
+    e = PfbEnvConfig()
+    e.env_kind = 2
+    e.flight_mode = int(flight_mode)
+    e.env_step_ratio = int(120 / agent_hz)
+    e.max_steps = int(agent_hz * max_duration)
+    e.angle_representation = 1 if angle_representation == "quaternion" else 0
+    e.sparse_reward = int(bool(sparse))
+    e.autoreset = int(bool(autoreset))
+    e.warmup_steps = 10
+    e.flight_dome_size = float(dome)
+    e.goal_reach_distance = float(goal_reach_distance)
+    e.goal_reach_angle = float(goal_reach_angle)
+    e.num_targets = int(num_targets)
+    e.use_yaw_targets = int(bool(use_yaw_targets))
+    return e
+
+
 def replay_waypoints(make_engine, g):
-    """Replays a fixedwing_waypoints fixture: env.reset (targets injected) + scripted env.step + user-loop resets."""
-    model = build_model("fixedwing", "fixedwing")
-    env = waypoints_config(str(g["angle_representation"]), bool(g["sparse"]), int(g["num_targets"]), float(g["goal_reach_distance"]), float(g["dome"]))
-    eng = make_engine(model, env, 1, np.array([[0.0, 0.0, 10.0]]), np.zeros((1, 3)))
+    """Replays a fixedwing_waypoints / quadx_waypoints fixture: env.reset (targets injected) + scripted env.step +
+    user-loop resets."""
+    if str(g["kind"]) == "quadx_waypoints":
+        model = build_model("quadx", "cf2x")
+        env = quadx_waypoints_config(flight_mode=int(g["flight_mode"]), angle_representation=str(g["angle_representation"]), sparse=bool(g["sparse"]),
+                                     num_targets=int(g["num_targets"]), use_yaw_targets=bool(g["use_yaw_targets"]),
+                                     goal_reach_distance=float(g["goal_reach_distance"]), goal_reach_angle=float(g["goal_reach_angle"]), dome=float(g["dome"]))
+        eng = make_engine(model, env, 1, np.array([[0.0, 0.0, 1.0]]), np.zeros((1, 3)))
+    else:
+        model = build_model("fixedwing", "fixedwing")
+        env = waypoints_config(str(g["angle_representation"]), bool(g["sparse"]), int(g["num_targets"]), float(g["goal_reach_distance"]), float(g["dome"]))
+        eng = make_engine(model, env, 1, np.array([[0.0, 0.0, 10.0]]), np.zeros((1, 3)))
     noise, splits = g["noise"], g["noise_splits"]
     cursor = {"i": 0}
 

@@ -169,6 +169,65 @@ def fly_waypoints(name, seed, n_steps, action_seed, angle_representation="quater
     print(name, "steps", n_steps, "episodes", len(episode_start) + 1, "max targets reached", max(v >> 3 for v in info), "draws", len(rng.normal_log))
 
 
+def fly_qx_waypoints(name, seed, n_steps, action_seed, flight_mode=0, angle_representation="quaternion", sparse=False, num_targets=4,
+                     use_yaw_targets=False, goal_reach_distance=0.2, goal_reach_angle=0.1, dome=5.0, chase=False, action_scale=1.0):
+    """QuadXWaypointsEnv (quadx_waypoints_env.py) with scripted actions and user-loop resets.  ``chase``: in a position
+    flight mode (7: x, y, yaw, z) the action is the next target (+ jitter), so that waypoints ARE reached."""
+    from PyFlyt.gym_envs.quadx_envs.quadx_waypoints_env import QuadXWaypointsEnv
+
+    env = QuadXWaypointsEnv(sparse_reward=sparse, num_targets=num_targets, use_yaw_targets=use_yaw_targets,
+                            goal_reach_distance=goal_reach_distance, goal_reach_angle=goal_reach_angle, flight_mode=flight_mode,
+                            flight_dome_size=dome, angle_representation=angle_representation)
+    rng = ril.ScriptedNoise(seed)
+    env._np_random = rng
+    T = 4 if use_yaw_targets else 3
+
+    def flat(state):
+        d = np.asarray(state["target_deltas"], dtype=np.float64).reshape(-1)
+        pad = np.zeros(T * num_targets)
+        pad[: len(d)] = d
+        return np.concatenate([state["attitude"], pad])
+
+    def cur_targets():
+        t = np.array(env.waypoints.targets, dtype=np.float64).reshape(-1, 3)
+        if use_yaw_targets:
+            t = np.concatenate([t, np.array(env.waypoints.yaw_targets, dtype=np.float64)[:, None]], axis=-1)
+        return t
+
+    state0, _ = env.reset()
+    targets = [cur_targets()]
+    arng = np.random.default_rng(action_seed)
+    obs, rew, term, trunc, info, acts, episode_start, resets_obs = [], [], [], [], [], [], [], []
+    noise_splits = [len(rng.normal_log)]
+    for i in range(n_steps):
+        if chase and len(env.waypoints.targets) > 0:
+            t = np.asarray(env.waypoints.targets[0], dtype=np.float64)
+            yaw = float(env.waypoints.yaw_targets[0]) if use_yaw_targets else 0.0
+            a = np.array([t[0], t[1], yaw, t[2]]) + arng.normal(0.0, 0.02, 4)
+        else:
+            a = arng.uniform([-np.pi, -np.pi, -np.pi, 0.0], [np.pi, np.pi, np.pi, 0.8]) * np.array([action_scale] * 3 + [1.0])
+        o, r, te, tr, inf = env.step(a)
+        acts.append(a); obs.append(flat(o)); rew.append(r); term.append(te); trunc.append(tr)
+        info.append(int(inf["out_of_bounds"]) | (int(inf["collision"]) << 1) | (int(inf["env_complete"]) << 2) | (int(inf["num_targets_reached"]) << 3))
+        noise_splits.append(len(rng.normal_log))
+        if te or tr:
+            o2, _ = env.reset()
+            targets.append(cur_targets())
+            resets_obs.append(flat(o2))
+            episode_start.append(i + 1)
+            noise_splits.append(len(rng.normal_log))
+    att = 21 if angle_representation == "quaternion" else 20
+    np.savez_compressed(
+        os.path.join(OUT, f"{name}.npz"), kind="quadx_waypoints", sparse=sparse, dome=dome, num_targets=num_targets,
+        use_yaw_targets=use_yaw_targets, goal_reach_distance=goal_reach_distance, goal_reach_angle=goal_reach_angle, flight_mode=flight_mode,
+        angle_representation=angle_representation, reset_obs=flat(state0), targets=np.array(targets), actions=np.array(acts),
+        obs=np.array(obs), reward=np.array(rew), term=np.array(term), trunc=np.array(trunc), info=np.array(info),
+        noise=np.array(rng.normal_log), noise_splits=np.array(noise_splits), episode_start=np.array(episode_start, dtype=np.int64),
+        after_reset_obs=np.array(resets_obs) if resets_obs else np.zeros((0, att + T * num_targets)),
+    )
+    print(name, "steps", n_steps, "episodes", len(episode_start) + 1, "max targets reached", max(v >> 3 for v in info), "draws", len(rng.normal_log))
+
+
 def fly_landing(name, seed, n_steps, action_seed, options, angle_representation="quaternion", sparse=False, ignite_p=0.7):
     """RocketLandingEnv (rocket_landing_env.py) with scripted actions and user-loop resets; ``options`` as in
     env.reset(options=...): None = randomised + accelerated drop, {} = the plain 450 m hover-drop."""
@@ -382,6 +441,16 @@ def rocket_fixtures():
     fly_landing("landing_pad_strike", seed=74, n_steps=450, action_seed=11, options={}, ignite_p=0.0)
 
 
+def quadx_waypoints_fixtures():
+    # QuadX-Waypoints: rate mode with random actions (crashes, no targets), position mode chasing the
+    # targets (reached targets, env_complete), yaw targets, euler + sparse
+    fly_qx_waypoints("qxwp_mode0_random", seed=101, n_steps=300, action_seed=21, action_scale=0.3)
+    fly_qx_waypoints("qxwp_mode7_chase", seed=102, n_steps=500, action_seed=22, flight_mode=7, chase=True, goal_reach_distance=0.3, num_targets=3)
+    fly_qx_waypoints("qxwp_mode7_yaw_targets", seed=103, n_steps=500, action_seed=23, flight_mode=7, chase=True, use_yaw_targets=True,
+                     goal_reach_distance=0.4, goal_reach_angle=0.3, num_targets=2)
+    fly_qx_waypoints("qxwp_euler_sparse", seed=104, n_steps=200, action_seed=24, angle_representation="euler", sparse=True, action_scale=0.5)
+
+
 def dogfight_fixtures():
     # MAFixedwingDogfight (BASELINE configs[4]): 1-vs-1 arenas; a wide lethal cone makes scripted flights score hits
     fly_dogfight("dogfight_1v1", seed=81, n_steps=260, action_seed=12)
@@ -446,3 +515,5 @@ if __name__ == "__main__":
         rocket_fixtures()
     if which in ("all", "dogfight"):
         dogfight_fixtures()
+    if which in ("all", "qxwp"):
+        quadx_waypoints_fixtures()
