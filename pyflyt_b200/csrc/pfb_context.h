@@ -49,6 +49,7 @@ struct PfbContext {
   uint64_t aviary_seq;    // pfb_aviary_step calls so far
   uint64_t reset_seq;     // pfb_env_reset calls so far
   int64_t launches;
+  pfb::QxWaypointParams qwp;
   int sm_count;
   // QuadX-Hover reset pipeline (pfb_lib.cu, "spare post-reset states"): library-owned spares + the side stream that rebuilds them
   float* d_spare;          // [SP_ROWS][N], zero-initialised; nullptr = warm-ups run inline
@@ -135,3 +136,10 @@ int df_env_reset(PfbContext* h, const uint8_t* mask, const float* noise, cudaStr
 int df_env_step(PfbContext* h, float* actions, const float* noise, bool randact, cudaStream_t s);
 int df_split_physics(PfbContext* h, const float* actions, const float* noise, float* payload, int first, int do_reset, int sub, cudaStream_t s);
 int df_split_combat(PfbContext* h, const float* table, int64_t first_gid, int64_t num_arenas, int last, cudaStream_t s);
+
+// QuadX-Waypoints translation unit (pfb_quadx_wp.cu)
+int qwp_state_rows();
+int qwp_istate_rows();
+int qwp_obs_dim(const PfbContext* h);
+int qwp_env_reset(PfbContext* h, const uint8_t* mask, const float* noise, cudaStream_t s);
+int qwp_env_step(PfbContext* h, float* actions, const float* noise, bool randact, cudaStream_t s);

@@ -426,6 +426,7 @@ int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, i
   }
   if (env && env->env_kind != PFB_ENV_NONE) {
     const bool ok = (model->kind == PFB_KIND_QUADX && env->env_kind == PFB_ENV_QUADX_HOVER) ||
+                    (model->kind == PFB_KIND_QUADX && env->env_kind == PFB_ENV_QUADX_WAYPOINTS) ||
                     (model->kind == PFB_KIND_FIXEDWING && env->env_kind == PFB_ENV_FIXEDWING_WAYPOINTS) ||
                     (model->kind == PFB_KIND_FIXEDWING && env->env_kind == PFB_ENV_DOGFIGHT) ||
                     (model->kind == PFB_KIND_ROCKET && env->env_kind == PFB_ENV_ROCKET_LANDING);
@@ -433,6 +434,23 @@ int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, i
       delete c;
       return fail("env kind %d is not available for vehicle kind %d in this library", env->env_kind, model->kind);
     }
+  }
+  if (env && env->env_kind == PFB_ENV_QUADX_WAYPOINTS) {
+    if (env->num_targets < 1 || env->num_targets > kMaxTargets) {
+      delete c;
+      return fail("num_targets must be in 1..%d, got %d", kMaxTargets, env->num_targets);
+    }
+    c->qwp.env_step_ratio = env->env_step_ratio;
+    c->qwp.max_steps = env->max_steps;
+    c->qwp.sparse_reward = env->sparse_reward;
+    c->qwp.warmup_steps = env->warmup_steps;
+    c->qwp.num_targets = env->num_targets;
+    c->qwp.use_yaw_targets = env->use_yaw_targets ? 1 : 0;
+    c->qwp.dome = (float)env->flight_dome_size;
+    c->qwp.dome2 = (float)(env->flight_dome_size * env->flight_dome_size);
+    c->qwp.goal_reach_distance = (float)env->goal_reach_distance;
+    c->qwp.goal_reach_angle = (float)env->goal_reach_angle;
+    c->qwp.min_height = 0.1f;  // quadx_waypoints_env.py:88
   }
   c->rng.k0 = (uint32_t)seed;
   c->rng.k1 = (uint32_t)(seed >> 32);
@@ -485,11 +503,12 @@ int pfb_set_env_offset(PfbHandle h, uint64_t first_global_env) {
 
 static inline bool is_fw(PfbHandle h) { return h->model.kind == PFB_KIND_FIXEDWING; }
 static inline bool is_rk(PfbHandle h) { return h->model.kind == PFB_KIND_ROCKET; }
+static inline bool is_qwp(PfbHandle h) { return h->model.kind == PFB_KIND_QUADX && h->env.env_kind == PFB_ENV_QUADX_WAYPOINTS; }
 static inline bool is_df(PfbHandle h) { return h->model.kind == PFB_KIND_FIXEDWING && h->env.env_kind == PFB_ENV_DOGFIGHT; }
-int pfb_state_rows(PfbHandle h) { return is_rk(h) ? rk_state_rows() : (is_fw(h) ? fw_state_rows() : QX_ROWS); }
-int pfb_istate_rows(PfbHandle h) { return is_rk(h) ? rk_istate_rows() : (is_fw(h) ? fw_istate_rows() : QI_ROWS); }
+int pfb_state_rows(PfbHandle h) { return is_rk(h) ? rk_state_rows() : (is_fw(h) ? fw_state_rows() : (is_qwp(h) ? qwp_state_rows() : QX_ROWS)); }
+int pfb_istate_rows(PfbHandle h) { return is_rk(h) ? rk_istate_rows() : (is_fw(h) ? fw_istate_rows() : (is_qwp(h) ? qwp_istate_rows() : QI_ROWS)); }
 int pfb_setpoint_dim(PfbHandle h) { return is_rk(h) ? 7 : ((is_fw(h) && h->env.env_kind == PFB_ENV_NONE) ? 6 : 4); }
-int pfb_obs_dim(PfbHandle h) { return is_df(h) ? df_obs_dim(h) : is_rk(h) ? rk_obs_dim(h) : (is_fw(h) ? fw_obs_dim(h) : (h->hover.angle_representation == 0 ? 20 : 21)); }
+int pfb_obs_dim(PfbHandle h) { return is_df(h) ? df_obs_dim(h) : is_rk(h) ? rk_obs_dim(h) : (is_fw(h) ? fw_obs_dim(h) : (is_qwp(h) ? qwp_obs_dim(h) : (h->hover.angle_representation == 0 ? 20 : 21))); }
 int pfb_aux_dim(PfbHandle h) { return is_rk(h) ? 9 : (is_fw(h) ? 6 : 4); }
 
 int pfb_bind(PfbHandle h, const PfbBuffers* b) {
@@ -581,6 +600,7 @@ int pfb_env_reset(PfbHandle h, const uint8_t* mask, const float* noise, void* st
   if (is_df(h)) return df_env_reset(h, mask, noise, s);
   if (is_fw(h)) return fw_env_reset(h, mask, noise, s);
   if (is_rk(h)) return rk_env_reset(h, mask, noise, s);
+  if (is_qwp(h)) return qwp_env_reset(h, mask, noise, s);
   const int mode = h->hover.flight_mode;
   // resets draw from their own Philox stream; the high bit keeps them apart from in-step autoresets
   const uint32_t seq = 0x80000000u | (uint32_t)h->reset_seq++;
@@ -614,6 +634,7 @@ static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool r
   if (is_df(h)) return df_env_step(h, actions, noise, randact, s);
   if (is_fw(h)) return fw_env_step(h, actions, noise, randact, s);
   if (is_rk(h)) return rk_env_step(h, actions, noise, randact, s);
+  if (is_qwp(h)) return qwp_env_step(h, actions, noise, randact, s);
   const int mode = h->hover.flight_mode;
   const bool autoreset = h->env.autoreset != 0;
   const uint64_t k = h->step_seq;

@@ -64,6 +64,13 @@ struct HoverParams {
   float dome2;  // flight_dome_size squared (inf stays inf)
 };
 
+// QuadX-Waypoints constants (gym_envs/quadx_envs/quadx_waypoints_env.py:38-52, utils/waypoint_handler.py)
+struct QxWaypointParams {
+  int env_step_ratio, max_steps, sparse_reward, warmup_steps;
+  int num_targets, use_yaw_targets;
+  float dome2, dome, goal_reach_distance, goal_reach_angle, min_height;
+};
+
 // PID memory rows inside the state tensor (24 words)
 enum { PID_P0 = 0, PID_P1 = 6, PID_P2 = 12, PID_P3 = 16, PID_ZV = 20, PID_ZP = 22, PID_WORDS = 24 };
 

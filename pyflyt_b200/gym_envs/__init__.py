@@ -5,6 +5,7 @@ If ``gymnasium`` is importable the single-env adaptors are registered under the 
 
 from .fixedwing_waypoints_env import FixedwingWaypointsVecEnv  # noqa: F401
 from .quadx_hover_env import QuadXHoverEnv, QuadXHoverVecEnv  # noqa: F401
+from .quadx_waypoints_env import QuadXWaypointsVecEnv  # noqa: F401
 from .rocket_landing_env import RocketLandingVecEnv  # noqa: F401
 
 try:  # pragma: no cover - gymnasium is not installed in the build image
