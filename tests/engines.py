@@ -474,7 +474,8 @@ def replay_waypoints(make_engine, g):
 
     per_step = env.env_step_ratio * eng.ups
     obs = eng.env_reset(take()[:, None], targets=g["targets"][0][None])
-    err = dict(obs=float(np.abs(obs[0] - g["reset_obs"]).max()), reward=0.0, flag_mismatch=0, episodes=0)
+    p0 = 10 if str(g["angle_representation"]) == "quaternion" else 9  # lin_pos columns of the attitude block
+    err = dict(obs=float(np.abs(obs[0] - g["reset_obs"]).max()), pos=0.0, reward=0.0, flag_mismatch=0, episodes=0)
     ep_starts = set(g["episode_start"].tolist())
     k = 0
     for i in range(len(g["actions"])):
@@ -483,6 +484,7 @@ def replay_waypoints(make_engine, g):
         full[: len(seg), 0] = seg
         ob, r, te, tr, inf = eng.env_step(g["actions"][i][None], full)
         err["obs"] = max(err["obs"], float(np.abs(ob[0] - g["obs"][i]).max()))
+        err["pos"] = max(err["pos"], float(np.abs(ob[0][p0 : p0 + 3] - g["obs"][i][p0 : p0 + 3]).max()))
         err["reward"] = max(err["reward"], float(abs(r[0] - g["reward"][i])))
         err["flag_mismatch"] += int(bool(te[0]) != bool(g["term"][i])) + int(bool(tr[0]) != bool(g["trunc"][i])) + int(int(inf[0]) != int(g["info"][i]))
         if (i + 1) in ep_starts:
