@@ -195,10 +195,9 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- timed region B: end to end through the host-buffer entry of the C-ABI (pinned host memory)
     act_h = [actions[k].cpu().pin_memory() for k in range(4)]
-    obs_h = torch.empty((n, env.obs_dim), dtype=torch.float32).pin_memory()
-    rew_h = torch.empty(n, dtype=torch.float32).pin_memory()
-    te_h = torch.empty(n, dtype=torch.uint8).pin_memory()
-    tr_h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    # one pinned slab, obs | reward | term | trunc back to back like the device side: the library returns it in one D2H copy
+    slab_h = torch.empty(av.out_slab_bytes(n, env.obs_dim), dtype=torch.uint8).pin_memory()
+    obs_h, rew_h, te_h, tr_h = av.slab_views(slab_h, n, env.obs_dim)
     for k in range(3):
         av.env_step_host(act_h[k % 4], obs_h, rew_h, te_h, tr_h)
     barrier()

@@ -244,7 +244,8 @@ int pfb_env_step(PfbHandle h, const float* actions, const float* noise, void* st
 int pfb_env_rollout(PfbHandle h, int n_steps, void* stream);
 
 /* Host-buffer convenience used for the end-to-end measurement: H2D(actions) → pfb_env_step →
- * D2H(obs, reward, term, trunc).  Host pointers should be pinned.                                    */
+ * D2H(obs, reward, term, trunc).  Host pointers should be pinned.  If obs | reward | term | trunc are laid out back to
+ * back both in the bound device buffers and in the host pointers, they are returned with a single copy.   */
 int pfb_env_step_host(PfbHandle h, const float* host_actions, float* host_obs, float* host_reward,
                       uint8_t* host_term, uint8_t* host_trunc, void* stream);
 

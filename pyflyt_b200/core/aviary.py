@@ -96,10 +96,9 @@ class BatchedAviary:
         self.setpoints = torch.zeros((n, self.setpoint_dim), **f32)
         self.start_pos = torch.from_numpy(start_pos).to(dev).contiguous()
         self.start_orn = torch.from_numpy(start_orn).to(dev).contiguous()
-        self.obs = torch.zeros((n, self.obs_dim), **f32)
-        self.reward = torch.zeros((n,), **f32)
-        self.term = torch.zeros((n,), dtype=torch.uint8, device=dev)
-        self.trunc = torch.zeros((n,), dtype=torch.uint8, device=dev)
+        # obs | reward | term | trunc live in ONE slab: pfb_env_step_host then returns them with a single D2H copy
+        self._out_slab = torch.zeros(self.out_slab_bytes(n, self.obs_dim), dtype=torch.uint8, device=dev)
+        self.obs, self.reward, self.term, self.trunc = self.slab_views(self._out_slab, n, self.obs_dim)
         self.info_bits = torch.zeros((n,), dtype=torch.uint8, device=dev)
         self.final_obs = torch.zeros((n, self.obs_dim), **f32)
         self._drone_state = torch.zeros((n, 12), **f32)
@@ -246,6 +245,20 @@ class BatchedAviary:
         nz = None if noise is None else C.c_void_p(noise.data_ptr())
         _lib.check(_lib.lib().pfb_env_step(self._h, act, nz, self._s()))
         self._state_fresh = False
+
+    @staticmethod
+    def out_slab_bytes(n: int, obs_dim: int) -> int:
+        return n * obs_dim * 4 + n * 4 + n + n
+
+    @staticmethod
+    def slab_views(slab: torch.Tensor, n: int, obs_dim: int):
+        """(obs [n, O] f32, reward [n] f32, term [n] u8, trunc [n] u8) views of a contiguous uint8 slab (device or pinned host)."""
+        o = n * obs_dim * 4
+        obs = slab[:o].view(torch.float32).view(n, obs_dim)
+        reward = slab[o : o + 4 * n].view(torch.float32)
+        term = slab[o + 4 * n : o + 5 * n]
+        trunc = slab[o + 5 * n : o + 6 * n]
+        return obs, reward, term, trunc
 
     def dogfight_physics(self, payload: torch.Tensor, actions: torch.Tensor | None = None, noise: torch.Tensor | None = None,
                          first: bool = False, do_reset: bool = False, aviary_index: int = 0) -> None:

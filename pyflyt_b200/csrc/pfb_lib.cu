@@ -722,10 +722,21 @@ int pfb_env_step_host(PfbHandle h, const float* host_actions, float* host_obs, f
   const int O = pfb_obs_dim(h);
   CUDA_OK(cudaMemcpyAsync(h->buf.setpoint, host_actions, (size_t)h->n * pfb_setpoint_dim(h) * sizeof(float), cudaMemcpyHostToDevice, s));
   if (env_step_impl(h, h->buf.setpoint, nullptr, false, s)) return -1;
-  CUDA_OK(cudaMemcpyAsync(host_obs, h->buf.obs, (size_t)h->n * O * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CUDA_OK(cudaMemcpyAsync(host_reward, h->buf.reward, (size_t)h->n * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CUDA_OK(cudaMemcpyAsync(host_term, h->buf.term, (size_t)h->n, cudaMemcpyDeviceToHost, s));
-  CUDA_OK(cudaMemcpyAsync(host_trunc, h->buf.trunc, (size_t)h->n, cudaMemcpyDeviceToHost, s));
+  // obs | reward | term | trunc laid out back to back on both sides (what the Python mirror allocates): one copy, one
+  // PCIe transaction stream instead of four latency-bound ones
+  const size_t ob = (size_t)h->n * O * sizeof(float), rb = (size_t)h->n * sizeof(float), fb = (size_t)h->n;
+  const char* d0 = (const char*)h->buf.obs;
+  char* h0 = (char*)host_obs;
+  const bool packed = (const char*)h->buf.reward == d0 + ob && (const char*)h->buf.term == d0 + ob + rb && (const char*)h->buf.trunc == d0 + ob + rb + fb &&
+                      (char*)host_reward == h0 + ob && (char*)host_term == h0 + ob + rb && (char*)host_trunc == h0 + ob + rb + fb;
+  if (packed) {
+    CUDA_OK(cudaMemcpyAsync(host_obs, h->buf.obs, ob + rb + 2 * fb, cudaMemcpyDeviceToHost, s));
+    return 0;
+  }
+  CUDA_OK(cudaMemcpyAsync(host_obs, h->buf.obs, ob, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaMemcpyAsync(host_reward, h->buf.reward, rb, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaMemcpyAsync(host_term, h->buf.term, fb, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaMemcpyAsync(host_trunc, h->buf.trunc, fb, cudaMemcpyDeviceToHost, s));
   return 0;
 }
 
