@@ -66,6 +66,45 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads() -> int:
+    """Threads this process may actually use: affinity mask and cgroup CPU quota, not just the core count."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    try:  # cgroup v2, then v1
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        try:
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0:
+                n = max(1, min(n, quota // period))
+        except Exception:
+            pass
+    return n
+
+
+def tune_oracle_threads(o, L) -> int:
+    """The CPU arm gets its best thread count: short probes at 1x, 1/2x, 1/4x, 1/8x of the usable threads (SMT siblings and
+    memory bandwidth make 'all of them' the wrong answer on some hosts)."""
+    n = host_threads()
+    best, best_rate = n, 0.0
+    for t in sorted({n, max(1, n // 2), max(1, n // 4), max(1, n // 8)}, reverse=True):
+        L.orc_set_num_threads(t)
+        o.env_rollout(2)
+        t0 = time.perf_counter()
+        done = o.env_rollout(6)
+        rate = done / (time.perf_counter() - t0)
+        if rate > best_rate:
+            best, best_rate = t, rate
+    L.orc_set_num_threads(best)
+    return best
+
+
 def cpu_oracle_rate(envs: int, target_seconds: float, threads: int | None = None):
     """env-steps/s of the CPU oracle port on the host cores; bounded sample of the same workload."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -75,12 +114,14 @@ def cpu_oracle_rate(envs: int, target_seconds: float, threads: int | None = None
     from oracle import oracle as orc_mod
 
     L = orc_mod.lib()
-    L.orc_set_num_threads(int(threads) if threads else (os.cpu_count() or 1))
-    cores = int(L.orc_num_threads())
+    L.orc_set_num_threads(int(threads) if threads else host_threads())
     model = build_model("quadx", "cf2x")
     env = hover_config(0, "quaternion", False, 3.0, autoreset=True)
     o = orc_mod.Oracle(model, env, n=envs, seed=1, start_pos=np.array([0.0, 0.0, 1.0]), start_orn=np.zeros(3))
     o.env_reset()
+    if not threads:
+        tune_oracle_threads(o, L)
+    cores = int(L.orc_num_threads())
     o.env_rollout(5)  # warm-up
     steps, done, chunk = 0, 0, 20
     t0 = time.perf_counter()
@@ -106,12 +147,13 @@ def run_reference(args, rank, world):
     from oracle import oracle as orc_mod
 
     L = orc_mod.lib()
-    L.orc_set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: use every host thread anyway
-    cores = int(L.orc_num_threads())
+    L.orc_set_num_threads(host_threads())  # torchrun exports OMP_NUM_THREADS=1: use the host's threads anyway
     model = build_model("quadx", "cf2x")
     env = hover_config(0, "quaternion", False, 3.0, autoreset=True)
     o = orc_mod.Oracle(model, env, n=envs, seed=1, start_pos=np.array([0.0, 0.0, 1.0]), start_orn=np.zeros(3))
     o.env_reset()
+    tune_oracle_threads(o, L)
+    cores = int(L.orc_num_threads())
     for _ in range(args.warmup):
         o.env_rollout(1)
     t0 = time.perf_counter()
@@ -244,10 +286,10 @@ def run_ours(args, rank, local_rank, world):
             },
         }
         if world == 1 and not args.no_cpu_baseline:
-            rate, cores, steps, dt = cpu_oracle_rate(4096, args.cpu_seconds)
+            rate, cores, steps, dt = cpu_oracle_rate(16384, args.cpu_seconds)
             line["cpu_baseline"] = {
                 "value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                "sample": f"{steps} env-steps x 4096 envs ({dt:.1f} s) of the same workload on oracle/pfb_oracle.c (fp64, OpenMP)",
+                "sample": f"{steps} env-steps x 16384 envs ({dt:.1f} s) of the same workload on oracle/pfb_oracle.c (fp64, OpenMP; thread count tuned by a short probe)",
             }
         print(json.dumps(line), flush=True)
     if world > 1:
