@@ -270,3 +270,35 @@ def test_spare_reset_equals_inline_reset(mode, max_seconds):
     torch.cuda.synchronize()
     assert float(env.aviary.state_tensor[2].min()) > 1.5
     env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("drone_model", ["cf2x", "primitive_drone"])
+def test_north_star_parity_4096_envs_1000_env_steps(drone_model):
+    """BASELINE.json's bar at scale: |dpos| < 1e-3 m against the fp64 oracle over 1000 env-steps (3000 Aviary steps,
+    6000 physics substeps) for 4096 drones flying different scripted rate / thrust commands with the same noise draws."""
+    n, chunks, per = 4096, 10, 300
+    rng = np.random.default_rng(2024)
+    f = lambda a: a.astype(np.float32).astype(np.float64)  # noqa: E731
+    model = build_model("quadx", drone_model)
+    pos0 = f(np.stack([rng.uniform(-2, 2, n), rng.uniform(-2, 2, n), rng.uniform(50, 60, n)], axis=-1))
+    orn0 = f(np.stack([rng.uniform(-0.2, 0.2, n), rng.uniform(-0.2, 0.2, n), rng.uniform(-3, 3, n)], axis=-1))
+    orc = OracleEngine(model, None, n, pos0, orn0)
+    cud = CudaEngine(model, None, n, pos0, orn0, drone_model=drone_model)
+    for e in (orc, cud):
+        e.reset()
+        e.set_mode(0)
+    worst, travelled = 0.0, np.zeros(n)
+    prev = pos0.copy()
+    for c in range(chunks):
+        sp = f(np.concatenate([rng.uniform(-0.6, 0.6, (n, 3)), rng.uniform(0.25, 0.55, (n, 1))], axis=-1))  # body rates, thrust
+        noise = f(rng.normal(4.0, 1.0, (per * 2, n)))
+        for e in (orc, cud):
+            e.set_setpoints(sp)
+            e.aviary_step(noise, per)
+        p0, p1 = orc.state()[:, 3, :], cud.state()[:, 3, :]
+        worst = max(worst, float(np.abs(p0 - p1).max()))
+        travelled += np.linalg.norm(p0 - prev, axis=1)
+        prev = p0
+    assert np.isfinite(worst) and worst < 1e-3, worst
+    assert np.median(travelled) > 50.0  # these are real flights, not hovering drones

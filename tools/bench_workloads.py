@@ -70,6 +70,15 @@ def main():
         env.reset()
         report("Fixedwing-Waypoints-v4, 16384 envs/GPU (configs[2]), random actions, NEXT_STEP autoreset", n, time_steps(lambda: env.rollout(1), K, W, dev, world), 1)
         env.close()
+    if want("quadx-waypoints"):
+        from pyflyt_b200.gym_envs import QuadXWaypointsVecEnv
+
+        n = 65536
+        env = QuadXWaypointsVecEnv(num_envs=n, seed=1, device=dev, env_offset=rank * n)
+        env.reset()
+        report("QuadX-Waypoints-v4, 65536 envs/GPU (SURVEY 8f #1), mode 0, random actions, NEXT_STEP autoreset (inline warm-ups)", n,
+               time_steps(lambda: env.rollout(1), K, W, dev, world), 1)
+        env.close()
     if want("rocket-landing"):
         n = 16384
         env = RocketLandingVecEnv(num_envs=n, seed=1, device=dev, env_offset=rank * n)
