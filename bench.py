@@ -32,6 +32,24 @@ def load_peaks():
     return 6650.0, "fallback"
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "r01_k_hover_step_ncu_summary.txt")
+    try:
+        total, seen = 0.0, 0
+        for line in open(path):
+            f = line.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[2]]
+                total += float(f[1]) * mult
+                seen += 1
+                if seen == 2:  # the first kernel block of the summary is the step launch
+                    return total
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
 
@@ -279,10 +297,11 @@ def run_ours(args, rank, local_rank, world):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {
-                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                 "kernel": "k_hover_step<0,false,false>", "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
                 "kernel_avg_us": kern_avg_s * 1e6, "peak_source": peak_src,
                 "note": "issue/FMA-bound kernel: the HBM fraction is reported because BASELINE.json asks for it; see DESIGN.md",
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the step launch in profiles/r01_k_hover_step_ncu_summary.txt (ncu replays with a warm L2: state written by the previous replay is still resident, so traffic < algorithmic bytes)",
             },
         }
         if world == 1 and not args.no_cpu_baseline:
