@@ -118,15 +118,18 @@ constexpr int kHoverBlocks = 640 / kBlock;
 // bit-identical results) rebuilds the spares just consumed on a side stream, concurrently with the following step
 // launches (the step two launches later waits for it: an env cannot finish again sooner).  If the start pose was
 // edited since a spare was built it is ignored and the warm-up runs inline (same episode number, same result).
-// Library-owned buffer [SP_ROWS][N]: rows [0, QX_ROWS) the spare's state, then:
-enum { SP_POSE = QX_ROWS, SP_VALID = QX_ROWS + 6, SP_FLAGS = QX_ROWS + 7, SP_EPISODE = QX_ROWS + 8, SP_ROWS = QX_ROWS + 9 };
+// Library-owned buffer [N][SP_ROWS], ENV-MAJOR (a 256-byte record per env: a tail thread touches 2-3 lines of DRAM instead of
+// one 32-byte sector per field; measured 9 MB -> ~1 MB of DRAM reads per launch with ~2200 resets): words [0, QX_ROWS) the
+// spare's state, then:
+enum { SP_POSE = QX_ROWS, SP_VALID = QX_ROWS + 6, SP_FLAGS = QX_ROWS + 7, SP_EPISODE = QX_ROWS + 8, SP_ROWS = 64 };
+static_assert(QX_ROWS + 9 <= SP_ROWS, "spare record too small");
 
 __device__ __forceinline__ bool spare_usable(const float* __restrict__ spare, const float* __restrict__ start_pos,
                                              const float* __restrict__ start_orn, int64_t N, int64_t i) {
-  const float* c = spare + (int64_t)SP_POSE * N + i;
-  bool ok = c[6 * N] != 0.0f;
+  const float* c = spare + i * SP_ROWS + SP_POSE;
+  bool ok = c[6] != 0.0f;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) ok = ok && (c[k * N] == start_pos[3 * i + k]) && (c[(3 + k) * N] == start_orn[3 * i + k]);
+  for (int k = 0; k < 3; ++k) ok = ok && (c[k] == start_pos[3 * i + k]) && (c[3 + k] == start_orn[3 * i + k]);
   return ok;
 }
 
@@ -135,11 +138,11 @@ __device__ __forceinline__ bool spare_usable(const float* __restrict__ spare, co
 template <int MODE>
 __device__ __forceinline__ void spare_store(float* __restrict__ spare, int32_t* __restrict__ ist, int64_t N, int64_t i,
                                             const QuadXRegs& s, uint32_t episode) {
-  quadx_store<MODE>(spare, ist, N, i, s, false);
-  float* c = spare + (int64_t)SP_POSE * N + i;
-  c[7 * N] = __uint_as_float(s.flags);
-  c[8 * N] = __uint_as_float(episode);
-  c[6 * N] = 1.0f;
+  quadx_store<MODE>(spare + i * SP_ROWS, ist, N, i, s, false, 1, 0);
+  float* c = spare + i * SP_ROWS + SP_POSE;
+  c[7] = __uint_as_float(s.flags);
+  c[8] = __uint_as_float(episode);
+  c[6] = 1.0f;
 }
 
 // env.reset() body for one env: begin_reset + end_reset (quadx_base_env.py:149-212); obs -> `out`
@@ -210,17 +213,18 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
     uint32_t nseq = step_seq;
     // ONE load site for every role: a regular thread reads its env's state, a tail thread the env's spare.  The loads are
     // issued before the spare's pose / validity words are examined, so a cold tail thread pays one round trip, not two.
-    quadx_load<MODE>((tail && spare) ? spare : st, ist, N, i, s);
+    const bool from_spare = tail && spare;  // env-major record vs field-major state rows: same loads, different strides
+    quadx_load<MODE>(from_spare ? spare + i * SP_ROWS : st, ist, N, i, s, from_spare ? 1 : N, from_spare ? 0 : i);
     if (tail) {
       // env.reset(): begin_reset + end_reset (quadx_base_env.py:149-212) — normally a copy of the env's spare
       nseq = step_seq | 0x40000000u;
       bool hit = false;
       if (spare) {
-        nseq = __float_as_uint(spare[(int64_t)SP_EPISODE * N + i]) + (build ? 1u : 0u);  // episode number: keys the warm-up noise
+        nseq = __float_as_uint(spare[i * SP_ROWS + SP_EPISODE]) + (build ? 1u : 0u);  // episode number: keys the warm-up noise
         hit = !build && spare_copy && spare_usable(spare, start_pos, start_orn, N, i);
       }
       if (hit) {
-        s.flags = __float_as_uint(spare[(int64_t)SP_FLAGS * N + i]);
+        s.flags = __float_as_uint(spare[i * SP_ROWS + SP_FLAGS]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) s.sp[k] = 0.0f;
         n_aviary = 0;
@@ -228,9 +232,9 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
         const float px = start_pos[3 * i + 0], py = start_pos[3 * i + 1], pz = start_pos[3 * i + 2];
         const float ox = start_orn[3 * i + 0], oy = start_orn[3 * i + 1], oz = start_orn[3 * i + 2];
         if (build) {
-          float* c = spare + (int64_t)SP_POSE * N + i;
-          c[6 * N] = 0.0f;  // invalid until the warm-up below is stored
-          c[0] = px; c[N] = py; c[2 * N] = pz; c[3 * N] = ox; c[4 * N] = oy; c[5 * N] = oz;
+          float* c = spare + i * SP_ROWS + SP_POSE;
+          c[6] = 0.0f;  // invalid until the warm-up below is stored
+          c[0] = px; c[1] = py; c[2] = pz; c[3] = ox; c[4] = oy; c[5] = oz;
         }
         quadx_reset(s, px, py, pz, ox, oy, oz);
         quadx_set_mode<MODE>(s);

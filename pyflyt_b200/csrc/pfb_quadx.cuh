@@ -503,8 +503,12 @@ PFB_HD bool pid_row_used(int k) {
 }
 
 template <int MODE>
-PFB_HD void quadx_load(const float* __restrict__ st, const int32_t* __restrict__ ist, int64_t N, int64_t i, QuadXRegs& s) {
-  auto F = [&](int row) { return st[(int64_t)row * N + i]; };
+// `st` is field-major [F][N] (row stride N) by default; `rs` / `ci` let a caller read an env-major record instead
+// (row stride 1, base already advanced to the env's record): the spare states of the reset pipeline.
+PFB_HD void quadx_load(const float* __restrict__ st, const int32_t* __restrict__ ist, int64_t N, int64_t i, QuadXRegs& s,
+                       int64_t rs = -1, int64_t ci = -1) {
+  if (rs < 0) { rs = N; ci = i; }
+  auto F = [&](int row) { return st[(int64_t)row * rs + ci]; };
 #if PFB_X_DOUBLE
   s.px = join_hi_lo(F(QX_POS + 0), F(QX_POS_LO + 0));
   s.py = join_hi_lo(F(QX_POS + 1), F(QX_POS_LO + 1));
@@ -538,8 +542,9 @@ PFB_HD void quadx_load(const float* __restrict__ st, const int32_t* __restrict__
 
 template <int MODE>
 PFB_HD void quadx_store(float* __restrict__ st, int32_t* __restrict__ ist, int64_t N, int64_t i, const QuadXRegs& s,
-                        bool with_flags = true) {
-  auto S = [&](int row, float v) { st[(int64_t)row * N + i] = v; };
+                        bool with_flags = true, int64_t rs = -1, int64_t ci = -1) {
+  if (rs < 0) { rs = N; ci = i; }
+  auto S = [&](int row, float v) { st[(int64_t)row * rs + ci] = v; };
   float hi, lo;
 #if PFB_X_DOUBLE
   split_hi_lo(s.px, hi, lo); S(QX_POS + 0, hi); S(QX_POS_LO + 0, lo);
