@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
       if (hit) {
         s.flags = __float_as_uint(spare[i * SP_ROWS + SP_FLAGS]);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) s.sp[k] = 0.0f;
+        for (int k = 0; k < 4; ++k) { s.sp[k] = 0.0f; s.pwm[k] = spare[i * SP_ROWS + QX_PWM + k]; }  // quadx_load skips the pwm words
         n_aviary = 0;
       } else {
         const float px = start_pos[3 * i + 0], py = start_pos[3 * i + 1], pz = start_pos[3 * i + 2];

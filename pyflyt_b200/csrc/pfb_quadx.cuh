@@ -533,7 +533,9 @@ PFB_HD void quadx_load(const float* __restrict__ st, const int32_t* __restrict__
 #endif
   s.wx = F(QX_ANGVEL + 0); s.wy = F(QX_ANGVEL + 1); s.wz = F(QX_ANGVEL + 2);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) { s.thr[k] = F(QX_THR + k); s.pwm[k] = F(QX_PWM + k); }
+  // the pwm rows are write-only: every Aviary step starts with a control tick that recomputes pwm before any
+  // substep reads it (aviary.py:506-531 with physics_control_ratio == updates_per_step), so they are not loaded
+  for (int k = 0; k < 4; ++k) { s.thr[k] = F(QX_THR + k); s.pwm[k] = 0.0f; }
 #pragma unroll
   for (int k = 0; k < PID_WORDS; ++k) s.pid[k] = pid_row_used<MODE>(k) ? F(QX_PID + k) : 0.0f;
   s.flags = (uint32_t)ist[(int64_t)QI_FLAGS * N + i];
