@@ -7,6 +7,7 @@ from .fixedwing_waypoints_env import FixedwingWaypointsVecEnv  # noqa: F401
 from .quadx_hover_env import QuadXHoverEnv, QuadXHoverVecEnv  # noqa: F401
 from .quadx_waypoints_env import QuadXWaypointsVecEnv  # noqa: F401
 from .rocket_landing_env import RocketLandingVecEnv  # noqa: F401
+from .single_env import FixedwingWaypointsEnv, QuadXWaypointsEnv, RocketLandingEnv  # noqa: F401
 
 try:  # pragma: no cover - gymnasium is not installed in the build image
     from gymnasium.envs.registration import register

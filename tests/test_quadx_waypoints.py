@@ -110,3 +110,25 @@ def test_cuda_autoreset_and_determinism():
     for x, y in zip(a, b):
         assert torch.equal(x, y)
     assert torch.isfinite(a[0]).all() and da == db and da > 1000
+
+
+@pytest.mark.gpu
+def test_single_env_adaptors():
+    """numpy-in / numpy-out adaptors with the reference's signatures (Dict observation for the waypoint envs)."""
+    from pyflyt_b200.gym_envs import FixedwingWaypointsEnv, QuadXWaypointsEnv, RocketLandingEnv
+
+    env = QuadXWaypointsEnv(num_targets=3, use_yaw_targets=True, seed=1)
+    obs, info = env.reset()
+    assert obs["attitude"].shape == (21,) and obs["target_deltas"].shape == (3, 4) and info["num_targets_reached"] == 0
+    obs, rew, term, trunc, info = env.step(np.array([0.0, 0.0, 0.0, 0.5]))
+    assert obs["attitude"].dtype == np.float64 and isinstance(rew, float) and isinstance(term, bool) and set(info) == {"out_of_bounds", "collision", "env_complete", "num_targets_reached"}
+    env.close()
+    env = FixedwingWaypointsEnv(seed=1)
+    obs, _ = env.reset()
+    assert obs["attitude"].shape == (23,) and obs["target_deltas"].shape == (4, 3)
+    env.close()
+    env = RocketLandingEnv(seed=1)
+    obs, info = env.reset()
+    obs2, rew, term, trunc, info = env.step(np.array([0.0, 0.0, 0.0, 1.0, 0.5, 0.0, 0.0]))
+    assert obs.shape == obs2.shape and obs.ndim == 1 and set(info) == {"out_of_bounds", "fatal_collision", "env_complete"}
+    env.close()
