@@ -88,11 +88,13 @@ struct StepPlan {
 static inline StepPlan plan_step(PfbContext* h) {
   StepPlan p;
   const uint64_t k = h->step_seq;
-  p.cnt_cur = h->d_counters + (k % 3);
-  p.cnt_prev = h->d_counters + ((k + 2) % 3);
-  p.cnt_next = h->d_counters + ((k + 1) % 3);
-  p.list_cur = h->d_done_list + (k & 1) * h->n;
-  p.list_prev = h->d_done_list + ((k + 1) & 1) * h->n;
+  // four rotating done lists / counters: step k appends to [k % 4], its tail CTAs (and the side-stream spare rebuild, for the
+  // envs that have one) read [(k - 1) % 4], and it zeroes counter [(k + 1) % 4]
+  p.cnt_cur = h->d_counters + (k % 4);
+  p.cnt_prev = h->d_counters + ((k + 3) % 4);
+  p.cnt_next = h->d_counters + ((k + 1) % 4);
+  p.list_cur = h->d_done_list + (k % 4) * h->n;
+  p.list_prev = h->d_done_list + ((k + 3) % 4) * h->n;
   p.seq = (uint32_t)k;
   // tail CTAs (front of the grid) reset the envs that finished on the previous call; one per SM is
   // plenty for the ~1-3 % of envs that finish per step, and the loop is grid-strided anyway
@@ -106,6 +108,27 @@ static inline StepPlan plan_step(PfbContext* h) {
   p.prof = h->prof_ev && h->prof_n < h->prof_cap;
   return p;
 }
+
+// ---- reset pipeline plumbing shared by the env kinds that keep spare post-reset states ----------------
+// before step k: the rebuild of the spares consumed by step k - 2 must be complete (an env cannot finish again sooner)
+#define SPARE_BEFORE_STEP(h, s)                                                                          \
+  do {                                                                                                   \
+    if ((h)->d_spare && (h)->env.autoreset && (h)->step_seq >= 2)                                        \
+      CUDA_OK(cudaStreamWaitEvent((s), (h)->ev_spare[((h)->step_seq - 2) % 4], 0));                      \
+  } while (0)
+// after step k was launched on `s`: order the side stream behind it; the caller then launches the build-mode kernel on
+// (h)->side and calls SPARE_REBUILD_DONE
+#define SPARE_REBUILD_BEGIN(h, s)                              \
+  do {                                                         \
+    CUDA_OK(cudaEventRecord((h)->ev_step, (s)));               \
+    CUDA_OK(cudaStreamWaitEvent((h)->side, (h)->ev_step, 0));  \
+  } while (0)
+#define SPARE_REBUILD_DONE(h) CUDA_OK(cudaEventRecord((h)->ev_spare[(h)->step_seq % 4], (h)->side))
+// before a user reset rewrites the spares: the last rebuild must have finished
+#define SPARE_BEFORE_RESET(h, s)                                                                         \
+  do {                                                                                                   \
+    if ((h)->d_spare && (h)->step_seq > 0) CUDA_OK(cudaStreamWaitEvent((s), (h)->ev_spare[((h)->step_seq - 1) % 4], 0)); \
+  } while (0)
 
 // fixedwing translation unit (pfb_fixedwing.cu)
 int fw_build_params(const PfbModel& m, const PfbEnvConfig* env, pfb::FixedwingParams& p, pfb::WaypointParams& w);

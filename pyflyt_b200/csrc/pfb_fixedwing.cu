@@ -78,8 +78,10 @@ constexpr int kWpObsMax = 23 + 3 * kMaxTargets;
 constexpr int kWpObsStride = kWpObsMax | 1;
 
 // WaypointHandler.reset (waypoint_handler.py:53-83): polar sampling of the targets, on-device Philox stream
+// Target words are addressed as tb[row * ts]: tb = st + i, ts = N for the field-major state tensor, tb = the env's spare
+// record, ts = 1 while a spare is being built.
 __device__ __forceinline__ void wp_sample_targets(const WaypointParams& w, const RngParams& rng, int64_t i, uint32_t seq,
-                                                  float* __restrict__ st, int64_t N) {
+                                                  float* __restrict__ tb, int64_t ts) {
   uint64_t g = ((uint64_t)rng.env_offset_hi << 32 | rng.env_offset_lo) + (uint64_t)i;
   for (int k = 0; k < w.num_targets; ++k) {
     U4 r = philox4x32_10(U4{(uint32_t)g, (uint32_t)(g >> 32), seq, (4u << 24) | (uint32_t)k}, rng.k0, rng.k1);
@@ -90,9 +92,9 @@ __device__ __forceinline__ void wp_sample_targets(const WaypointParams& w, const
     sincos_f(theta, st_, ct);
     sincos_f(phi, sp, cp);
     float z = fabsf(dist * cp);
-    st[(int64_t)(FW_TARGETS + 3 * k + 0) * N + i] = dist * sp * ct;
-    st[(int64_t)(FW_TARGETS + 3 * k + 1) * N + i] = dist * sp * st_;
-    st[(int64_t)(FW_TARGETS + 3 * k + 2) * N + i] = z > w.min_height ? z : w.min_height;
+    tb[(int64_t)(FW_TARGETS + 3 * k + 0) * ts] = dist * sp * ct;
+    tb[(int64_t)(FW_TARGETS + 3 * k + 1) * ts] = dist * sp * st_;
+    tb[(int64_t)(FW_TARGETS + 3 * k + 2) * ts] = z > w.min_height ? z : w.min_height;
   }
 }
 
@@ -103,10 +105,10 @@ struct WpState {
   bool reached_now;     // a target was reached on the most recent Aviary step
 };
 
-__device__ __forceinline__ void wp_load_target0(const float* __restrict__ st, int64_t N, int64_t i, WpState& wp) {
-  wp.t0x = st[(int64_t)(FW_TARGETS + 3 * wp.first + 0) * N + i];
-  wp.t0y = st[(int64_t)(FW_TARGETS + 3 * wp.first + 1) * N + i];
-  wp.t0z = st[(int64_t)(FW_TARGETS + 3 * wp.first + 2) * N + i];
+__device__ __forceinline__ void wp_load_target0(const float* __restrict__ tb, int64_t ts, WpState& wp) {
+  wp.t0x = tb[(int64_t)(FW_TARGETS + 3 * wp.first + 0) * ts];
+  wp.t0y = tb[(int64_t)(FW_TARGETS + 3 * wp.first + 1) * ts];
+  wp.t0z = tb[(int64_t)(FW_TARGETS + 3 * wp.first + 2) * ts];
 }
 
 // compute_state's waypoint part (waypoint_handler.py:120-157): old <- new, new <- |target0 - pos|
@@ -119,7 +121,7 @@ __device__ __forceinline__ float wp_update_distance(const FixedwingRegs& s, WpSt
 
 // fixedwing_base_env.py:226-244 + fixedwing_waypoints_env.py:169-190
 __device__ __forceinline__ void wp_term_trunc_reward(const WaypointParams& w, FixedwingRegs& s, WpState& wp, float old_dist,
-                                                     int step_count, float& reward, float* __restrict__ st, int64_t N, int64_t i) {
+                                                     int step_count, float& reward, const float* __restrict__ tb, int64_t ts) {
   if (step_count > w.max_steps) s.flags |= FLAG_TRUNC;
   if (s.flags & FLAG_CONTACT_ARRAY) { reward = -100.0f; s.flags |= FLAG_COLLISION | FLAG_TERM; }
   float px = (float)s.px, py = (float)s.py, pz = (float)s.pz;
@@ -135,13 +137,13 @@ __device__ __forceinline__ void wp_term_trunc_reward(const WaypointParams& w, Fi
     wp.first += 1;  // advance_targets (waypoint_handler.py:176-185): the list head moves, nothing is copied
     wp.reached_now = true;
     if (wp.first == w.num_targets) s.flags |= FLAG_TRUNC | FLAG_ENV_COMPLETE;
-    else wp_load_target0(st, N, i, wp);
+    else wp_load_target0(tb, ts, wp);
   }
 }
 
 // compute_state (fixedwing_waypoints_env.py:121-167): attitude + action + aux + body-frame target deltas
 __device__ __forceinline__ void wp_observation(const WaypointParams& w, const FixedwingRegs& s, const float* action, int first,
-                                               const float* __restrict__ st, int64_t N, int64_t i, float* obs) {
+                                               const float* __restrict__ tb, int64_t ts, float* obs) {
   const float x = (float)s.qx, y = (float)s.qy, z = (float)s.qz, qw = (float)s.qw;
   float roll, pitch, yaw;
   euler_from_quat(x, y, z, qw, roll, pitch, yaw);
@@ -164,9 +166,9 @@ __device__ __forceinline__ void wp_observation(const WaypointParams& w, const Fi
   for (int k = 0; k < w.num_targets; ++k) {
     float bx = 0.f, by = 0.f, bz = 0.f;
     if (first + k < w.num_targets) {  // remaining targets first, zero padding after
-      float dx = st[(int64_t)(FW_TARGETS + 3 * (first + k) + 0) * N + i] - (float)s.px;
-      float dy = st[(int64_t)(FW_TARGETS + 3 * (first + k) + 1) * N + i] - (float)s.py;
-      float dz = st[(int64_t)(FW_TARGETS + 3 * (first + k) + 2) * N + i] - (float)s.pz;
+      float dx = tb[(int64_t)(FW_TARGETS + 3 * (first + k) + 0) * ts] - (float)s.px;
+      float dy = tb[(int64_t)(FW_TARGETS + 3 * (first + k) + 1) * ts] - (float)s.py;
+      float dz = tb[(int64_t)(FW_TARGETS + 3 * (first + k) + 2) * ts] - (float)s.pz;
       bx = (float)R.m00 * dx + (float)R.m10 * dy + (float)R.m20 * dz;
       by = (float)R.m01 * dx + (float)R.m11 * dy + (float)R.m21 * dz;
       bz = (float)R.m02 * dx + (float)R.m12 * dy + (float)R.m22 * dz;
@@ -175,28 +177,32 @@ __device__ __forceinline__ void wp_observation(const WaypointParams& w, const Fi
   }
 }
 
-// env.reset() for one env (fixedwing_waypoints_env.py:102-119, fixedwing_base_env.py:126-192)
+// env.reset() for one env (fixedwing_waypoints_env.py:102-119, fixedwing_base_env.py:126-192); `pose` = the 6 start-pose
+// words the caller read (and, when building a spare, recorded), targets go to tb / ts
 template <bool INJECT>
-__device__ __forceinline__ void wp_reset_env(const FixedwingParams& p, const WaypointParams& w, const RngParams& rng,
-                                             float* __restrict__ st, int32_t* __restrict__ ist, const float* __restrict__ start_pos,
-                                             const float* __restrict__ start_orn, const float* __restrict__ reset_targets,
-                                             const float* __restrict__ noise, uint32_t seq, int64_t N, int64_t i,
-                                             FixedwingRegs& s, WpState& wp) {
-  fixedwing_reset(p, s, start_pos[3 * i], start_pos[3 * i + 1], start_pos[3 * i + 2], start_orn[3 * i], start_orn[3 * i + 1],
-                  start_orn[3 * i + 2]);
+__device__ __forceinline__ void wp_reset_env(const FixedwingParams& p, const WaypointParams& w, const RngParams& rng, const float* pose,
+                                             const float* __restrict__ reset_targets, const float* __restrict__ noise, uint32_t seq,
+                                             int64_t N, int64_t i, float* __restrict__ tb, int64_t ts, FixedwingRegs& s, WpState& wp) {
+  fixedwing_reset(p, s, pose[0], pose[1], pose[2], pose[3], pose[4], pose[5]);
   if (reset_targets) {
-    for (int k = 0; k < 3 * w.num_targets; ++k) st[(int64_t)(FW_TARGETS + k) * N + i] = reset_targets[(int64_t)i * 3 * w.num_targets + k];
+    for (int k = 0; k < 3 * w.num_targets; ++k) tb[(int64_t)(FW_TARGETS + k) * ts] = reset_targets[(int64_t)i * 3 * w.num_targets + k];
   } else {
-    wp_sample_targets(w, rng, i, seq, st, N);
+    wp_sample_targets(w, rng, i, seq, tb, ts);
   }
   wp.first = 0;
   wp.reached_now = false;
   wp.new_dist = INFINITY;
-  wp_load_target0(st, N, i, wp);
+  wp_load_target0(tb, ts, wp);
   auto nz = make_noise<INJECT>(noise, N, i, rng, seq, TAG_RESET, p.noise_loc, p.ratio);
   for (int k = 0; k < w.warmup_steps; ++k) fixedwing_aviary_step<0>(p, s, nz);
-  (void)wp_update_distance(s, wp);  // end_reset -> compute_state
+  fixedwing_requantize(s);             // exactly what the state tensor / a spare record will hold
+  (void)wp_update_distance(s, wp);     // end_reset -> compute_state
 }
+
+// ---- spare post-reset states: the QuadX-Hover reset pipeline (pfb_lib.cu) for this env.  A spare is an
+// env-major record of 64 floats: the FW_* state words INCLUDING the episode's targets and new_distance, then:
+enum { WSP_POSE = FW_ROWS, WSP_VALID = FW_ROWS + 6, WSP_FLAGS = FW_ROWS + 7, WSP_EPISODE = FW_ROWS + 8, WSP_ROWS = 64 };
+static_assert(FW_ROWS + 9 <= WSP_ROWS, "spare record too small");
 
 template <bool INJECT, bool RANDACT, bool AUTORESET>
 __global__ void __launch_bounds__(kBlock, kMinBlocks)
@@ -206,7 +212,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
                 uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, uint8_t* __restrict__ info,
                 const float* __restrict__ start_pos, const float* __restrict__ start_orn, const int32_t* __restrict__ prev_count,
                 const int32_t* __restrict__ prev_list, int32_t* __restrict__ cur_count, int32_t* __restrict__ cur_list,
-                int32_t* __restrict__ next_count, int tail_blocks, uint32_t step_seq, int64_t N) {
+                int32_t* __restrict__ next_count, float* __restrict__ spare, int spare_copy, int build, int tail_blocks,
+                uint32_t step_seq, int64_t N) {
   __shared__ float smem[kBlock * kWpObsStride];
   __shared__ uint8_t row_skip[kBlock];
   const int O = (w.angle_representation == 0 ? 22 : 23) + 3 * w.num_targets;
@@ -214,9 +221,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   const int64_t block_first = tail ? 0 : (int64_t)((int)blockIdx.x - (AUTORESET ? tail_blocks : 0)) * kBlock;
   int t, t_end, t_stride;
   if (tail) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *next_count = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !build) *next_count = 0;
     t = blockIdx.x * kBlock + threadIdx.x;
-    t_end = *prev_count;
+    t_end = prev_list ? *prev_count : (int)N;  // build mode after a user reset: every env
     t_stride = tail_blocks * kBlock;
   } else {
     t = 0;
@@ -227,14 +234,54 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   float* row = smem + threadIdx.x * kWpObsStride;
 #pragma unroll 1
   for (; t < t_end; t += t_stride) {
-    const int64_t i = tail ? (int64_t)prev_list[t] : block_first + threadIdx.x;
+    const int64_t i = tail ? (prev_list ? (int64_t)prev_list[t] : (int64_t)t) : block_first + threadIdx.x;
     FixedwingRegs s;
     WpState wp;
     float act[4] = {0.f, 0.f, 0.f, 0.f};
     int step_count = 0;
     float rew = 0.0f;
+    float* tb = st + i;  // where this env's targets live (field-major state rows, or the spare record being built)
+    int64_t ts = N;
     if (tail) {
-      wp_reset_env<false>(p, w, rng, st, ist, start_pos, start_orn, nullptr, nullptr, step_seq, N, i, s, wp);
+      // env.reset(): normally a copy of the env's spare (state, targets, new_distance of the NEXT episode); build mode
+      // computes that spare; without a usable spare the warm-up runs inline with the same episode number
+      float* rec = spare ? spare + i * WSP_ROWS : nullptr;
+      uint32_t nseq = step_seq | 0x40000000u;
+      bool hit = false;
+      float pose[6];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { pose[k] = start_pos[3 * i + k]; pose[3 + k] = start_orn[3 * i + k]; }
+      if (rec) {
+        nseq = __float_as_uint(rec[WSP_EPISODE]) + (build ? 1u : 0u);
+        hit = !build && spare_copy && rec[WSP_VALID] != 0.0f;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) hit = hit && (rec[WSP_POSE + k] == pose[k]);
+      }
+      if (hit) {
+        fixedwing_load(rec, ist, N, i, s, 1, 0);
+        s.flags = __float_as_uint(rec[WSP_FLAGS]);
+        for (int k = 0; k < 3 * w.num_targets; ++k) tb[(int64_t)(FW_TARGETS + k) * ts] = rec[FW_TARGETS + k];
+        wp.first = 0;
+        wp.reached_now = false;
+        wp.new_dist = rec[FW_DIST];
+      } else {
+        if (build) {
+          rec[WSP_VALID] = 0.0f;  // invalid until the warm-up below is stored
+#pragma unroll
+          for (int k = 0; k < 6; ++k) rec[WSP_POSE + k] = pose[k];
+          tb = rec;
+          ts = 1;
+        }
+        wp_reset_env<false>(p, w, rng, pose, nullptr, nullptr, nseq, N, i, tb, ts, s, wp);
+      }
+      if (build) {
+        fixedwing_store(rec, ist, N, i, s, false, 1, 0);
+        rec[FW_DIST] = wp.new_dist;
+        rec[WSP_FLAGS] = __uint_as_float(s.flags);
+        rec[WSP_EPISODE] = __uint_as_float(nseq);
+        rec[WSP_VALID] = 1.0f;
+        continue;
+      }
       s.flags |= fresh_tag(step_seq);
     } else {
       fixedwing_load(st, ist, N, i, s);
@@ -256,7 +303,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
       wp.first = ist[(int64_t)FI_NTARGETS * N + i];
       wp.reached_now = false;
       wp.new_dist = st[(int64_t)FW_DIST * N + i];
-      wp_load_target0(st, N, i, wp);
+      wp_load_target0(tb, ts, wp);
       rew = -0.1f;
       auto nz = make_noise<INJECT>(noise, N, i, rng, step_seq, TAG_ENV_STEP, p.noise_loc, p.ratio);
 #pragma unroll 1
@@ -264,13 +311,13 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
         if (s.flags & (FLAG_TERM | FLAG_TRUNC)) break;
         fixedwing_aviary_step<0>(p, s, nz);
         float old = wp_update_distance(s, wp);
-        wp_term_trunc_reward(w, s, wp, old, step_count, rew, st, N, i);
+        wp_term_trunc_reward(w, s, wp, old, step_count, rew, tb, ts);
       }
       step_count += 1;
     }
     // the reference builds the observation in compute_state, BEFORE compute_term_trunc_reward advances the
     // target list: a target reached on the last Aviary step is still the head of the reported list
-    wp_observation(w, s, act, wp.first - (wp.reached_now ? 1 : 0), st, N, i, row);
+    wp_observation(w, s, act, wp.first - (wp.reached_now ? 1 : 0), tb, ts, row);
     fixedwing_store(st, ist, N, i, s);
     st[(int64_t)FW_DIST * N + i] = wp.new_dist;
     ist[(int64_t)FI_STEP * N + i] = step_count;
@@ -329,10 +376,11 @@ __global__ void __launch_bounds__(kBlock)
   const int O = (w.angle_representation == 0 ? 22 : 23) + 3 * w.num_targets;
   FixedwingRegs s;
   WpState wp;
-  wp_reset_env<INJECT>(p, w, rng, st, ist, start_pos, start_orn, reset_targets, noise, seq, N, i, s, wp);
+  const float pose[6] = {start_pos[3 * i], start_pos[3 * i + 1], start_pos[3 * i + 2], start_orn[3 * i], start_orn[3 * i + 1], start_orn[3 * i + 2]};
+  wp_reset_env<INJECT>(p, w, rng, pose, reset_targets, noise, seq, N, i, st + i, N, s, wp);
   const float zero[4] = {0.f, 0.f, 0.f, 0.f};
   float* row = smem + threadIdx.x * kWpObsStride;
-  wp_observation(w, s, zero, wp.first, st, N, i, row);
+  wp_observation(w, s, zero, wp.first, st + i, N, row);
   fixedwing_store(st, ist, N, i, s);
   st[(int64_t)FW_DIST * N + i] = wp.new_dist;
   ist[(int64_t)FI_STEP * N + i] = 0;
@@ -386,6 +434,11 @@ int fw_observe(PfbContext* h, cudaStream_t s) {
 int fw_env_reset(PfbContext* h, const uint8_t* mask, const float* noise, cudaStream_t s) {
   const uint32_t seq = 0x80000000u | (uint32_t)h->reset_seq++;
   const int g = grid_for(h->n);
+  float* spare = h->env.autoreset ? h->d_spare : nullptr;
+  if (spare) {
+    SPARE_BEFORE_RESET(h, s);
+    if (!mask) CUDA_OK(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(int32_t), s));  // a full reset empties the autoreset queues
+  }
   if (noise)
     k_fwwp_reset<true><<<g, kBlock, 0, s>>>(h->fw, h->wp, h->rng, h->buf.state, h->buf.istate, h->buf.start_pos, h->buf.start_orn,
                                             h->buf.reset_targets, mask, noise, h->buf.obs, seq, h->n);
@@ -393,16 +446,25 @@ int fw_env_reset(PfbContext* h, const uint8_t* mask, const float* noise, cudaStr
     k_fwwp_reset<false><<<g, kBlock, 0, s>>>(h->fw, h->wp, h->rng, h->buf.state, h->buf.istate, h->buf.start_pos, h->buf.start_orn,
                                              h->buf.reset_targets, mask, nullptr, h->buf.obs, seq, h->n);
   LAUNCH_CHECK(h);
+  if (spare) {  // every env gets a fresh spare: the step kernel in build mode over all envs, same stream
+    k_fwwp_step<false, false, true><<<g, kBlock, 0, s>>>(h->fw, h->wp, h->rng, h->buf.state, h->buf.istate, h->buf.setpoint, nullptr, h->buf.obs,
+                                                         h->buf.reward, h->buf.term, h->buf.trunc, h->buf.info, h->buf.start_pos, h->buf.start_orn,
+                                                         nullptr, nullptr, nullptr, nullptr, nullptr, spare, 0, 1, g, 0u, h->n);
+    LAUNCH_CHECK(h);
+  }
   h->mode = 0;
   return 0;
 }
 
 int fw_env_step(PfbContext* h, float* actions, const float* noise, bool randact, cudaStream_t s) {
   StepPlan pl = plan_step(h);
+  float* spare = h->env.autoreset ? h->d_spare : nullptr;
+  const int spare_copy = (spare && !h->env.inline_reset) ? 1 : 0;
+  SPARE_BEFORE_STEP(h, s);
   if (pl.prof) CUDA_OK(cudaEventRecord(h->prof_ev[2 * h->prof_n], s));
 #define WP_ARGS h->fw, h->wp, h->rng, h->buf.state, h->buf.istate, actions, noise, h->buf.obs, h->buf.reward, h->buf.term, \
                 h->buf.trunc, h->buf.info, h->buf.start_pos, h->buf.start_orn, pl.cnt_prev, pl.list_prev, pl.cnt_cur, pl.list_cur, \
-                pl.cnt_next, pl.tail, pl.seq, h->n
+                pl.cnt_next, spare, spare_copy, 0, pl.tail, pl.seq, h->n
   if (h->env.autoreset) {
     if (noise) return fail("injected noise (parity mode) is only supported with autoreset = 0");
     if (randact) k_fwwp_step<false, true, true><<<pl.grid, kBlock, 0, s>>>(WP_ARGS);
@@ -417,6 +479,15 @@ int fw_env_step(PfbContext* h, float* actions, const float* noise, bool randact,
   if (pl.prof) {
     CUDA_OK(cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], s));
     h->prof_n += 1;
+  }
+  if (spare) {  // rebuild the spares this launch consumed, on the side stream, while the next launches run
+    SPARE_REBUILD_BEGIN(h, s);
+    k_fwwp_step<false, false, true><<<h->sm_count, kBlock, 0, h->side>>>(h->fw, h->wp, h->rng, h->buf.state, h->buf.istate, actions, nullptr, h->buf.obs,
+                                                                         h->buf.reward, h->buf.term, h->buf.trunc, h->buf.info, h->buf.start_pos,
+                                                                         h->buf.start_orn, pl.cnt_prev, pl.list_prev, pl.cnt_cur, pl.list_cur, pl.cnt_next,
+                                                                         spare, 0, 1, h->sm_count, pl.seq, h->n);
+    LAUNCH_CHECK(h);
+    SPARE_REBUILD_DONE(h);
   }
   h->step_seq += 1;
   return 0;

@@ -352,8 +352,12 @@ PFB_HD void fixedwing_reset(const FixedwingParams& p, FixedwingRegs& s, float sx
   body_update_state(s);
 }
 
-PFB_HD void fixedwing_load(const float* __restrict__ st, const int32_t* __restrict__ ist, int64_t N, int64_t i, FixedwingRegs& s) {
-  auto F = [&](int row) { return st[(int64_t)row * N + i]; };
+// `st` is field-major [F][N] by default; `rs` / `ci` select an env-major record instead (row stride 1, base already at the
+// env's record): the spare post-reset states of the Waypoints env (pfb_fixedwing.cu)
+PFB_HD void fixedwing_load(const float* __restrict__ st, const int32_t* __restrict__ ist, int64_t N, int64_t i, FixedwingRegs& s,
+                           int64_t rs = -1, int64_t ci = -1) {
+  if (rs < 0) { rs = N; ci = i; }
+  auto F = [&](int row) { return st[(int64_t)row * rs + ci]; };
   s.px = join_hi_lo(F(FW_POS + 0), F(FW_POS_LO + 0));
   s.py = join_hi_lo(F(FW_POS + 1), F(FW_POS_LO + 1));
   s.pz = join_hi_lo(F(FW_POS + 2), F(FW_POS_LO + 2));
@@ -372,8 +376,10 @@ PFB_HD void fixedwing_load(const float* __restrict__ st, const int32_t* __restri
   body_update_state(s);
 }
 
-PFB_HD void fixedwing_store(float* __restrict__ st, int32_t* __restrict__ ist, int64_t N, int64_t i, const FixedwingRegs& s) {
-  auto S = [&](int row, float v) { st[(int64_t)row * N + i] = v; };
+PFB_HD void fixedwing_store(float* __restrict__ st, int32_t* __restrict__ ist, int64_t N, int64_t i, const FixedwingRegs& s,
+                            bool with_flags = true, int64_t rs = -1, int64_t ci = -1) {
+  if (rs < 0) { rs = N; ci = i; }
+  auto S = [&](int row, float v) { st[(int64_t)row * rs + ci] = v; };
   float hi, lo;
   split_hi_lo(s.px, hi, lo); S(FW_POS + 0, hi); S(FW_POS_LO + 0, lo);
   split_hi_lo(s.py, hi, lo); S(FW_POS + 1, hi); S(FW_POS_LO + 1, lo);
@@ -389,7 +395,23 @@ PFB_HD void fixedwing_store(float* __restrict__ st, int32_t* __restrict__ ist, i
 #pragma unroll
   for (int k = 0; k < kMaxSurfaces; ++k) S(FW_ACT + k, s.act[k]);
   S(FW_THR, s.thr);
-  ist[(int64_t)FI_FLAGS * N + i] = (int32_t)s.flags;
+  if (with_flags) ist[(int64_t)FI_FLAGS * N + i] = (int32_t)s.flags;
+}
+
+// Round the fp64-carried fields to what the state tensor holds (hi + lo fp32 words) and re-derive the body-frame state
+PFB_HD void fixedwing_requantize(FixedwingRegs& s) {
+  float hi, lo;
+  split_hi_lo(s.px, hi, lo); s.px = join_hi_lo(hi, lo);
+  split_hi_lo(s.py, hi, lo); s.py = join_hi_lo(hi, lo);
+  split_hi_lo(s.pz, hi, lo); s.pz = join_hi_lo(hi, lo);
+  split_hi_lo(s.qx, hi, lo); s.qx = join_hi_lo(hi, lo);
+  split_hi_lo(s.qy, hi, lo); s.qy = join_hi_lo(hi, lo);
+  split_hi_lo(s.qz, hi, lo); s.qz = join_hi_lo(hi, lo);
+  split_hi_lo(s.qw, hi, lo); s.qw = join_hi_lo(hi, lo);
+  split_hi_lo(s.vx, hi, lo); s.vx = join_hi_lo(hi, lo);
+  split_hi_lo(s.vy, hi, lo); s.vy = join_hi_lo(hi, lo);
+  split_hi_lo(s.vz, hi, lo); s.vz = join_hi_lo(hi, lo);
+  body_update_state(s);
 }
 
 // Aviary.state(i) (4,3) + aux_state (5 surface actuations + motor throttle): fixedwing.py:285-291

@@ -43,6 +43,7 @@ class FixedwingWaypointsVecEnv:
         seed: int | None = None,
         device: str | torch.device = "cuda:0",
         env_offset: int = 0,
+        inline_reset: bool = False,
     ):
         if 120 % agent_hz != 0:  # fixedwing_base_env.py:47-52
             lowest = int(120 / (int(120 / agent_hz) + 1))
@@ -70,6 +71,7 @@ class FixedwingWaypointsVecEnv:
         cfg.goal_reach_angle = float("inf")
         cfg.num_targets = self.num_targets
         cfg.use_yaw_targets = 0
+        cfg.inline_reset = int(bool(inline_reset))  # tests: spare-copy resets must equal inline ones bit for bit
         self.config = cfg
         sp = np.tile(np.array([[0.0, 0.0, 10.0]]), (self.num_envs, 1))  # fixedwing_waypoints_env.py:63
         so = np.zeros((self.num_envs, 3))

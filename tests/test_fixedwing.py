@@ -100,3 +100,30 @@ def test_cuda_waypoints_autoreset_and_determinism():
     for x, y in zip(a, b):
         assert torch.equal(x, y)
     assert torch.isfinite(a[0]).all() and ra >= 1 and ra == rb
+
+
+@pytest.mark.gpu
+def test_waypoints_spare_reset_equals_inline_reset():
+    """Fixedwing-Waypoints autoreset copies the env's spare (state + targets of the next episode, rebuilt on a side
+    stream); it must equal integrating every warm-up inside the step launch bit for bit."""
+    import torch
+
+    from pyflyt_b200.gym_envs import FixedwingWaypointsVecEnv
+
+    outs = []
+    for inline in (False, True):
+        env = FixedwingWaypointsVecEnv(num_envs=4096, seed=7, inline_reset=inline, max_duration_seconds=0.5, goal_reach_distance=30.0)
+        env.reset()
+        resets, trace = 0, []
+        for k in range(80):
+            env.rollout(1)
+            resets += int((env.aviary.term | env.aviary.trunc).sum())
+            trace.append(env.aviary.obs.sum().item())
+            if k == 30:
+                env.aviary.start_pos[::2, 2] += 5.0  # stale spares must be ignored
+        torch.cuda.synchronize()
+        outs.append((env.aviary.obs.clone(), env.aviary.reward.clone(), env.aviary.state_tensor.clone(), resets, trace))
+        env.close()
+    a, b = outs
+    assert a[3] > 4096 and a[3] == b[3] and a[4] == b[4]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
