@@ -167,5 +167,6 @@ int df_split_combat(PfbContext* h, const float* table, int64_t first_gid, int64_
 int qwp_state_rows();
 int qwp_istate_rows();
 int qwp_obs_dim(const PfbContext* h);
+int qwp_spare_rows();
 int qwp_env_reset(PfbContext* h, const uint8_t* mask, const float* noise, cudaStream_t s);
 int qwp_env_step(PfbContext* h, float* actions, const float* noise, bool randact, cudaStream_t s);

@@ -45,6 +45,7 @@ class QuadXWaypointsVecEnv:
         seed: int | None = None,
         device: str | torch.device = "cuda:0",
         env_offset: int = 0,
+        inline_reset: bool = False,
     ):
         if 120 % agent_hz != 0:  # quadx_base_env.py:47-52
             lowest = int(120 / (int(120 / agent_hz) + 1))
@@ -74,6 +75,7 @@ class QuadXWaypointsVecEnv:
         cfg.goal_reach_angle = float(goal_reach_angle)
         cfg.num_targets = self.num_targets
         cfg.use_yaw_targets = int(self.use_yaw_targets)
+        cfg.inline_reset = int(bool(inline_reset))  # tests: spare-copy resets must equal inline ones bit for bit
         self.config = cfg
         sp = np.tile(np.array([[0.0, 0.0, 1.0]]), (self.num_envs, 1))  # quadx_waypoints_env.py:71
         so = np.zeros((self.num_envs, 3))

@@ -132,3 +132,31 @@ def test_single_env_adaptors():
     obs2, rew, term, trunc, info = env.step(np.array([0.0, 0.0, 0.0, 1.0, 0.5, 0.0, 0.0]))
     assert obs.shape == obs2.shape and obs.ndim == 1 and set(info) == {"out_of_bounds", "fatal_collision", "env_complete"}
     env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 6])
+def test_spare_reset_equals_inline_reset(mode):
+    """Autoreset copies the env's spare (state + targets + distances of the next episode, rebuilt on a side stream); it
+    must equal integrating every warm-up inside the step launch bit for bit."""
+    import torch
+
+    from pyflyt_b200.gym_envs import QuadXWaypointsVecEnv
+
+    outs = []
+    for inline in (False, True):
+        env = QuadXWaypointsVecEnv(num_envs=8192, seed=7, flight_mode=mode, use_yaw_targets=True, inline_reset=inline, max_duration_seconds=0.3)
+        env.reset()
+        resets, trace = 0, []
+        for k in range(70):
+            env.rollout(1)
+            resets += int((env.aviary.term | env.aviary.trunc).sum())
+            trace.append(env.aviary.obs.sum().item())
+            if k == 30:
+                env.aviary.start_pos[::2, 2] += 0.5  # stale spares must be ignored
+        torch.cuda.synchronize()
+        outs.append((env.aviary.obs.clone(), env.aviary.reward.clone(), env.aviary.state_tensor.clone(), resets, trace))
+        env.close()
+    a, b = outs
+    assert a[3] > 8192 and a[3] == b[3] and a[4] == b[4]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
