@@ -150,13 +150,13 @@ __device__ __forceinline__ void landing_observation(const LandingParams& l, cons
 }
 
 // env.reset() for one env (rocket_landing_env.py:87-127, rocket_base_env.py:166-261)
+// `pose` = the 6 start-pose words the caller read from start_pos / start_orn (ignored with randomize_drop)
 template <bool INJECT>
-__device__ __forceinline__ void landing_reset_env(const RocketParams& p, const LandingParams& l, const RngParams& rng,
-                                                  const float* __restrict__ start_pos, const float* __restrict__ start_orn,
+__device__ __forceinline__ void landing_reset_env(const RocketParams& p, const LandingParams& l, const RngParams& rng, const float* pose,
                                                   const float* __restrict__ noise, uint32_t seq, bool randomize, int64_t N, int64_t i,
                                                   RocketRegs& s) {
-  float sx = start_pos[3 * i], sy = start_pos[3 * i + 1], sz = start_pos[3 * i + 2];
-  float r0 = start_orn[3 * i], r1 = start_orn[3 * i + 1], r2 = start_orn[3 * i + 2];
+  float sx = pose[0], sy = pose[1], sz = pose[2];
+  float r0 = pose[3], r1 = pose[4], r2 = pose[5];
   if (randomize) {  // options["randomize_drop"] (rocket_base_env.py:192-199), drawn from this env's Philox stream
     uint64_t g = ((uint64_t)rng.env_offset_hi << 32 | rng.env_offset_lo) + (uint64_t)i;
     U4 a = philox4x32_10(U4{(uint32_t)g, (uint32_t)(g >> 32), seq, 5u << 24}, rng.k0, rng.k1);
@@ -175,7 +175,13 @@ __device__ __forceinline__ void landing_reset_env(const RocketParams& p, const L
   if (l.accelerate_drop) s.vz += (vreal)(-100.0);
   auto nz = make_noise<INJECT>(noise, N, i, rng, seq, TAG_RESET, p.noise_loc, p.ratio);
   for (int k = 0; k < l.warmup_steps; ++k) rocket_aviary_step(p, s, nz, true);
+  rocket_requantize(s);  // exactly what the state tensor / a spare record will hold
 }
+
+// ---- spare post-reset states: the QuadX-Hover reset pipeline (pfb_lib.cu) for this env.  A spare is an
+// env-major record of 64 floats: the RK_* state words, then:
+enum { LSP_POSE = RK_ROWS, LSP_VALID = RK_ROWS + 6, LSP_FLAGS = RK_ROWS + 7, LSP_EPISODE = RK_ROWS + 8, LSP_ROWS = 64 };
+static_assert(RK_ROWS + 9 <= LSP_ROWS, "spare record too small");
 
 template <bool INJECT, bool RANDACT, bool AUTORESET>
 __global__ void __launch_bounds__(kBlock, kMinBlocks)
@@ -184,7 +190,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
                 float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ term, uint8_t* __restrict__ trunc,
                 uint8_t* __restrict__ info, const float* __restrict__ start_pos, const float* __restrict__ start_orn,
                 const int32_t* __restrict__ prev_count, const int32_t* __restrict__ prev_list, int32_t* __restrict__ cur_count,
-                int32_t* __restrict__ cur_list, int32_t* __restrict__ next_count, int tail_blocks, uint32_t step_seq, int64_t N) {
+                int32_t* __restrict__ cur_list, int32_t* __restrict__ next_count, float* __restrict__ spare, int spare_copy, int build,
+                int tail_blocks, uint32_t step_seq, int64_t N) {
   __shared__ float smem[kBlock * kLandObsStride];
   __shared__ uint8_t row_skip[kBlock];
   const int O = (l.angle_representation == 0 ? 12 : 13) + 17;
@@ -192,9 +199,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   const int64_t block_first = tail ? 0 : (int64_t)((int)blockIdx.x - (AUTORESET ? tail_blocks : 0)) * kBlock;
   int t, t_end, t_stride;
   if (tail) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *next_count = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !build) *next_count = 0;
     t = blockIdx.x * kBlock + threadIdx.x;
-    t_end = *prev_count;
+    t_end = prev_list ? *prev_count : (int)N;  // build mode after a user reset: every env
     t_stride = tail_blocks * kBlock;
   } else {
     t = 0;
@@ -205,14 +212,47 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   float* row = smem + threadIdx.x * kLandObsStride;
 #pragma unroll 1
   for (; t < t_end; t += t_stride) {
-    const int64_t i = tail ? (int64_t)prev_list[t] : block_first + threadIdx.x;
+    const int64_t i = tail ? (prev_list ? (int64_t)prev_list[t] : (int64_t)t) : block_first + threadIdx.x;
     RocketRegs s;
     float act[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     int step_count = 0;
     float rew = 0.0f;
     bool pad_obs = false;
     if (tail) {
-      landing_reset_env<false>(p, l, rng, start_pos, start_orn, nullptr, step_seq, l.randomize_drop != 0, N, i, s);
+      // env.reset(): normally a copy of the env's spare; build mode computes that spare; without a usable spare the
+      // warm-up runs inline with the same episode number (which also keys a randomised drop)
+      float* rec = spare ? spare + i * LSP_ROWS : nullptr;
+      uint32_t nseq = step_seq | 0x40000000u;
+      bool hit = false;
+      float pose[6];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { pose[k] = start_pos[3 * i + k]; pose[3 + k] = start_orn[3 * i + k]; }
+      if (rec) {
+        nseq = __float_as_uint(rec[LSP_EPISODE]) + (build ? 1u : 0u);
+        hit = !build && spare_copy && rec[LSP_VALID] != 0.0f;
+        if (!l.randomize_drop) {  // a randomised drop does not read the start pose
+#pragma unroll
+          for (int k = 0; k < 6; ++k) hit = hit && (rec[LSP_POSE + k] == pose[k]);
+        }
+      }
+      if (hit) {
+        rocket_load(rec, ist, N, i, s, 1, 0);
+        s.flags = __float_as_uint(rec[LSP_FLAGS]);
+      } else {
+        if (build) {
+          rec[LSP_VALID] = 0.0f;  // invalid until the warm-up below is stored
+#pragma unroll
+          for (int k = 0; k < 6; ++k) rec[LSP_POSE + k] = pose[k];
+        }
+        landing_reset_env<false>(p, l, rng, pose, nullptr, nseq, l.randomize_drop != 0, N, i, s);
+      }
+      if (build) {
+        rocket_store(rec, ist, N, i, s, false, 1, 0);
+        rec[LSP_FLAGS] = __uint_as_float(s.flags);
+        rec[LSP_EPISODE] = __uint_as_float(nseq);
+        rec[LSP_VALID] = 1.0f;
+        continue;
+      }
       s.flags |= fresh_tag(step_seq);
     } else {
       rocket_load(st, ist, N, i, s);
@@ -304,7 +344,8 @@ __global__ void __launch_bounds__(kBlock)
   if (mask && !mask[i]) return;
   const int O = (l.angle_representation == 0 ? 12 : 13) + 17;
   RocketRegs s;
-  landing_reset_env<INJECT>(p, l, rng, start_pos, start_orn, noise, seq, randomize != 0, N, i, s);
+  const float pose[6] = {start_pos[3 * i], start_pos[3 * i + 1], start_pos[3 * i + 2], start_orn[3 * i], start_orn[3 * i + 1], start_orn[3 * i + 2]};
+  landing_reset_env<INJECT>(p, l, rng, pose, noise, seq, randomize != 0, N, i, s);
   const float zero[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float* row = smem + threadIdx.x * kLandObsStride;
   landing_observation(l, s, zero, false, row);
@@ -358,6 +399,11 @@ int rk_env_reset(PfbContext* h, const uint8_t* mask, const float* noise, cudaStr
   const int g = grid_for(h->n);
   // an explicit env.reset() honours the bound start_pos / start_orn unless randomize_drop is configured
   const int randomize = h->land.randomize_drop;
+  float* spare = h->env.autoreset ? h->d_spare : nullptr;
+  if (spare) {
+    SPARE_BEFORE_RESET(h, s);
+    if (!mask) CUDA_OK(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(int32_t), s));  // a full reset empties the autoreset queues
+  }
   if (noise)
     k_land_reset<true><<<g, kBlock, 0, s>>>(h->rk, h->land, h->rng, h->buf.state, h->buf.istate, h->buf.start_pos, h->buf.start_orn, mask, noise,
                                             h->buf.obs, seq, randomize, h->n);
@@ -365,16 +411,25 @@ int rk_env_reset(PfbContext* h, const uint8_t* mask, const float* noise, cudaStr
     k_land_reset<false><<<g, kBlock, 0, s>>>(h->rk, h->land, h->rng, h->buf.state, h->buf.istate, h->buf.start_pos, h->buf.start_orn, mask,
                                              nullptr, h->buf.obs, seq, randomize, h->n);
   LAUNCH_CHECK(h);
+  if (spare) {  // every env gets a fresh spare: the step kernel in build mode over all envs, same stream
+    k_land_step<false, false, true><<<g, kBlock, 0, s>>>(h->rk, h->land, h->rng, h->buf.state, h->buf.istate, h->buf.setpoint, nullptr, h->buf.obs,
+                                                         h->buf.reward, h->buf.term, h->buf.trunc, h->buf.info, h->buf.start_pos, h->buf.start_orn,
+                                                         nullptr, nullptr, nullptr, nullptr, nullptr, spare, 0, 1, g, 0u, h->n);
+    LAUNCH_CHECK(h);
+  }
   h->mode = 0;
   return 0;
 }
 
 int rk_env_step(PfbContext* h, float* actions, const float* noise, bool randact, cudaStream_t s) {
   StepPlan pl = plan_step(h);
+  float* spare = h->env.autoreset ? h->d_spare : nullptr;
+  const int spare_copy = (spare && !h->env.inline_reset) ? 1 : 0;
+  SPARE_BEFORE_STEP(h, s);
   if (pl.prof) CUDA_OK(cudaEventRecord(h->prof_ev[2 * h->prof_n], s));
 #define LD_ARGS h->rk, h->land, h->rng, h->buf.state, h->buf.istate, actions, noise, h->buf.obs, h->buf.reward, h->buf.term, h->buf.trunc, \
-                h->buf.info, h->buf.start_pos, h->buf.start_orn, pl.cnt_prev, pl.list_prev, pl.cnt_cur, pl.list_cur, pl.cnt_next, pl.tail, \
-                pl.seq, h->n
+                h->buf.info, h->buf.start_pos, h->buf.start_orn, pl.cnt_prev, pl.list_prev, pl.cnt_cur, pl.list_cur, pl.cnt_next, spare, \
+                spare_copy, 0, pl.tail, pl.seq, h->n
   if (h->env.autoreset) {
     if (noise) return fail("injected noise (parity mode) is only supported with autoreset = 0");
     if (randact) k_land_step<false, true, true><<<pl.grid, kBlock, 0, s>>>(LD_ARGS);
@@ -389,6 +444,15 @@ int rk_env_step(PfbContext* h, float* actions, const float* noise, bool randact,
   if (pl.prof) {
     CUDA_OK(cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], s));
     h->prof_n += 1;
+  }
+  if (spare) {  // rebuild the spares this launch consumed, on the side stream, while the next launches run
+    SPARE_REBUILD_BEGIN(h, s);
+    k_land_step<false, false, true><<<h->sm_count, kBlock, 0, h->side>>>(h->rk, h->land, h->rng, h->buf.state, h->buf.istate, actions, nullptr, h->buf.obs,
+                                                                         h->buf.reward, h->buf.term, h->buf.trunc, h->buf.info, h->buf.start_pos,
+                                                                         h->buf.start_orn, pl.cnt_prev, pl.list_prev, pl.cnt_cur, pl.list_cur, pl.cnt_next,
+                                                                         spare, 0, 1, h->sm_count, pl.seq, h->n);
+    LAUNCH_CHECK(h);
+    SPARE_REBUILD_DONE(h);
   }
   h->step_seq += 1;
   return 0;

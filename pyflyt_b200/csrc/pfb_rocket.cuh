@@ -238,8 +238,12 @@ PFB_HD void rocket_reset(const RocketParams& p, RocketRegs& s, float sx, float s
   body_update_state(s);
 }
 
-PFB_HD void rocket_load(const float* __restrict__ st, const int32_t* __restrict__ ist, int64_t N, int64_t i, RocketRegs& s) {
-  auto F = [&](int row) { return st[(int64_t)row * N + i]; };
+// `st` is field-major [F][N] by default; `rs` / `ci` select an env-major record instead (row stride 1, base already at the
+// env's record): the spare post-reset states of the Landing env (pfb_rocket.cu)
+PFB_HD void rocket_load(const float* __restrict__ st, const int32_t* __restrict__ ist, int64_t N, int64_t i, RocketRegs& s,
+                        int64_t rs = -1, int64_t ci = -1) {
+  if (rs < 0) { rs = N; ci = i; }
+  auto F = [&](int row) { return st[(int64_t)row * rs + ci]; };
   s.px = join_hi_lo(F(RK_POS + 0), F(RK_POS_LO + 0));
   s.py = join_hi_lo(F(RK_POS + 1), F(RK_POS_LO + 1));
   s.pz = join_hi_lo(F(RK_POS + 2), F(RK_POS_LO + 2));
@@ -259,8 +263,10 @@ PFB_HD void rocket_load(const float* __restrict__ st, const int32_t* __restrict_
   body_update_state(s);
 }
 
-PFB_HD void rocket_store(float* __restrict__ st, int32_t* __restrict__ ist, int64_t N, int64_t i, const RocketRegs& s) {
-  auto S = [&](int row, float v) { st[(int64_t)row * N + i] = v; };
+PFB_HD void rocket_store(float* __restrict__ st, int32_t* __restrict__ ist, int64_t N, int64_t i, const RocketRegs& s,
+                         bool with_flags = true, int64_t rs = -1, int64_t ci = -1) {
+  if (rs < 0) { rs = N; ci = i; }
+  auto S = [&](int row, float v) { st[(int64_t)row * rs + ci] = v; };
   float hi, lo;
   split_hi_lo(s.px, hi, lo); S(RK_POS + 0, hi); S(RK_POS_LO + 0, lo);
   split_hi_lo(s.py, hi, lo); S(RK_POS + 1, hi); S(RK_POS_LO + 1, lo);
@@ -277,7 +283,23 @@ PFB_HD void rocket_store(float* __restrict__ st, int32_t* __restrict__ ist, int6
   for (int k = 0; k < 4; ++k) S(RK_ACT + k, s.act[k]);
   S(RK_IGN, s.ign); S(RK_FUEL, s.fuel); S(RK_THR, s.thr);
   S(RK_GIMBAL, s.gim[0]); S(RK_GIMBAL + 1, s.gim[1]);
-  ist[(int64_t)RI_FLAGS * N + i] = (int32_t)s.flags;
+  if (with_flags) ist[(int64_t)RI_FLAGS * N + i] = (int32_t)s.flags;
+}
+
+// Round the fp64-carried fields to what the state tensor holds (hi + lo fp32 words) and re-derive the body-frame state
+PFB_HD void rocket_requantize(RocketRegs& s) {
+  float hi, lo;
+  split_hi_lo(s.px, hi, lo); s.px = join_hi_lo(hi, lo);
+  split_hi_lo(s.py, hi, lo); s.py = join_hi_lo(hi, lo);
+  split_hi_lo(s.pz, hi, lo); s.pz = join_hi_lo(hi, lo);
+  split_hi_lo(s.qx, hi, lo); s.qx = join_hi_lo(hi, lo);
+  split_hi_lo(s.qy, hi, lo); s.qy = join_hi_lo(hi, lo);
+  split_hi_lo(s.qz, hi, lo); s.qz = join_hi_lo(hi, lo);
+  split_hi_lo(s.qw, hi, lo); s.qw = join_hi_lo(hi, lo);
+  split_hi_lo(s.vx, hi, lo); s.vx = join_hi_lo(hi, lo);
+  split_hi_lo(s.vy, hi, lo); s.vy = join_hi_lo(hi, lo);
+  split_hi_lo(s.vz, hi, lo); s.vz = join_hi_lo(hi, lo);
+  body_update_state(s);
 }
 
 // Aviary.state(i) (4,3) + aux_state (rocket.py:324-332): finlets x4, ignition, fuel, throttle, gimbal x2

@@ -42,6 +42,7 @@ class RocketLandingVecEnv:
         seed: int | None = None,
         device: str | torch.device = "cuda:0",
         env_offset: int = 0,
+        inline_reset: bool = False,
     ):
         """``randomize_drop`` / ``accelerate_drop`` are the reference's ``reset(options=...)`` switches
         (rocket_landing_env.py:94-98: both on when ``options=None``)."""
@@ -68,6 +69,7 @@ class RocketLandingVecEnv:
         cfg.randomize_drop = int(bool(randomize_drop))
         cfg.accelerate_drop = int(bool(accelerate_drop))
         cfg.flight_dome_size = float("inf")
+        cfg.inline_reset = int(bool(inline_reset))  # tests: spare-copy resets must equal inline ones bit for bit
         self.config = cfg
         sp = np.tile(np.array([[0.0, 0.0, ceiling * 0.9]]), (self.num_envs, 1))  # rocket_landing_env.py:60
         so = np.zeros((self.num_envs, 3))

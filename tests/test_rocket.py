@@ -104,3 +104,29 @@ def test_cuda_landing_autoreset_and_determinism():
         assert torch.equal(x, y)
     assert torch.isfinite(a[0]).all() and da == db and da > 100  # crashes happen; random throttle slows most drops
     assert float(z0.min()) > 380.0 and float(z0.max()) < 455.0  # randomize_drop: U(0.8, 0.9) * ceiling minus the warm-up fall
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("randomize", [True, False])
+def test_landing_spare_reset_equals_inline_reset(randomize):
+    """Rocket-Landing autoreset copies the env's spare (rebuilt on a side stream; a randomised drop is keyed by the
+    episode number); it must equal integrating every warm-up inside the step launch bit for bit."""
+    import torch
+
+    from pyflyt_b200.gym_envs import RocketLandingVecEnv
+
+    outs = []
+    for inline in (False, True):
+        env = RocketLandingVecEnv(num_envs=4096, seed=7, inline_reset=inline, max_duration_seconds=0.4, randomize_drop=randomize)
+        env.reset()
+        resets, trace = 0, []
+        for k in range(70):
+            env.rollout(1)
+            resets += int((env.aviary.term | env.aviary.trunc).sum())
+            trace.append(env.aviary.obs.sum().item())
+        torch.cuda.synchronize()
+        outs.append((env.aviary.obs.clone(), env.aviary.reward.clone(), env.aviary.state_tensor.clone(), resets, trace))
+        env.close()
+    a, b = outs
+    assert a[3] > 4096 and a[3] == b[3] and a[4] == b[4]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
