@@ -44,6 +44,9 @@ extern "C" {
 #define PFB_ENV_FIXEDWING_WAYPOINTS 3
 #define PFB_ENV_ROCKET_LANDING 4
 #define PFB_ENV_DOGFIGHT 5
+#define PFB_ENV_MA_QUADX_HOVER 6 /* pz_envs/quadx_envs/ma_quadx_hover_env.py: per-AGENT epilogue (observation with past
+                                   * action + start position, rewards summed over the Aviary steps of an env step);
+                                   * the arena bookkeeping (who is still alive, reset when all are done) is host-side */
 
 #define PFB_MAX_MOTORS 4
 #define PFB_MAX_SURFACES 5

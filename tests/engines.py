@@ -601,3 +601,43 @@ def replay_dogfight(make_engine, g):
             err["reward"] = max(err["reward"], float(np.abs(r[alive] - ref_r[alive]).max()))
             err["flag_mismatch"] += int((te[alive].astype(bool) != g[f"ep{k}_term"][i][alive]).sum()) + int((tr[alive].astype(bool) != g[f"ep{k}_trunc"][i][alive]).sum())
     return err
+
+
+def ma_hover_config(flight_mode=0, angle_representation="quaternion", sparse=False, dome=10.0, agent_hz=40, max_duration=30.0):
+    """MAQuadXHoverEnv.__init__ defaults (ma_quadx_hover_env.py:37-60); per-agent env kind 6 (no in-kernel autoreset: the
+    arena bookkeeping is host-side)."""
+    e = PfbEnvConfig()
+    e.env_kind = 6
+    e.flight_mode = int(flight_mode)
+    e.env_step_ratio = int(120 / agent_hz)
+    e.max_steps = int(agent_hz * max_duration)
+    e.angle_representation = 1 if angle_representation == "quaternion" else 0
+    e.sparse_reward = int(bool(sparse))
+    e.autoreset = 0
+    e.warmup_steps = 10
+    e.flight_dome_size = float(dome)
+    return e
+
+
+def replay_ma_hover(make_engine, g):
+    """Replays a ma_quadx_hover fixture: one engine env per agent, noise injected; the agents the reference has culled
+    are stepped with a zero action (their outputs are not compared)."""
+    A = int(g["n_agents"])
+    model = build_model("quadx", "cf2x")
+    env = ma_hover_config(int(g["flight_mode"]), str(g["angle_representation"]), bool(g["sparse"]), float(g["dome"]), 40, float(g["max_duration_seconds"]))
+    eng = make_engine(model, env, A, g["start_pos"], g["start_orn"])
+    err = dict(obs=0.0, pos=0.0, reward=0.0, flag_mismatch=0, episodes=int(g["n_episodes"]))
+    p0 = 10 if str(g["angle_representation"]) == "quaternion" else 9
+    for k in range(int(g["n_episodes"])):
+        obs = eng.env_reset(g[f"ep{k}_reset_noise"].reshape(-1, A))
+        err["obs"] = max(err["obs"], float(np.abs(obs - g[f"ep{k}_reset_obs"]).max()))
+        for i in range(len(g[f"ep{k}_actions"])):
+            alive = g[f"ep{k}_alive"][i]
+            act = g[f"ep{k}_actions"][i] * alive[:, None]  # current_actions *= 0 for the agents not in self.agents
+            ob, r, te, tr, _ = eng.env_step(act, g[f"ep{k}_noise"][i].reshape(-1, A))
+            ref_o, ref_r = g[f"ep{k}_obs"][i], g[f"ep{k}_reward"][i]
+            err["obs"] = max(err["obs"], float(np.abs(ob[alive] - ref_o[alive]).max()))
+            err["pos"] = max(err["pos"], float(np.abs(ob[alive][:, p0 : p0 + 3] - ref_o[alive][:, p0 : p0 + 3]).max()))
+            err["reward"] = max(err["reward"], float(np.abs(r[alive] - ref_r[alive]).max()))
+            err["flag_mismatch"] += int((te[alive].astype(bool) != g[f"ep{k}_term"][i][alive]).sum()) + int((tr[alive].astype(bool) != g[f"ep{k}_trunc"][i][alive]).sum())
+    return err

@@ -330,6 +330,74 @@ def fly_dogfight(name, seed, n_steps, action_seed, team_size=1, sparse=False, ac
     print(name, "episodes", len(episodes), "steps", [len(e["actions"]) for e in episodes], "reward range", min(np.nanmin(e["reward"]) for e in episodes), max(np.nanmax(e["reward"]) for e in episodes))
 
 
+def fly_ma_hover(name, seed, n_steps, action_seed, flight_mode=0, angle_representation="quaternion", sparse=False, dome=10.0,
+                 max_duration_seconds=30.0, action_scale=0.3, start_pos=None):
+    """MAQuadXHoverEnv (pz_envs/quadx_envs/ma_quadx_hover_env.py) with scripted actions; a new episode is started whenever
+    every agent is done.  The Aviary's own generator (seeded by reset(seed)) is wrapped so that its draws are recorded."""
+    from PyFlyt.pz_envs.quadx_envs.ma_quadx_hover_env import MAQuadXHoverEnv
+
+    kw = dict(sparse_reward=sparse, flight_mode=flight_mode, flight_dome_size=dome, max_duration_seconds=max_duration_seconds,
+              angle_representation=angle_representation)
+    if start_pos is not None:
+        kw.update(start_pos=np.asarray(start_pos, dtype=np.float64), start_orn=np.zeros_like(np.asarray(start_pos, dtype=np.float64)))
+    env = MAQuadXHoverEnv(**kw)
+    A = len(env.possible_agents)
+    real_default_rng = np.random.default_rng
+    loggers = []
+
+    def reset(seed_):
+        def patched(s=None):
+            lg = ril.ScriptedNoise.__new__(ril.ScriptedNoise)
+            lg._rng = real_default_rng(s)
+            lg.normal_log = []
+            loggers.append(lg)
+            return lg
+        np.random.default_rng = patched
+        try:
+            obs, _ = env.reset(seed=seed_)
+        finally:
+            np.random.default_rng = real_default_rng
+        return np.stack([obs[f"uav_{i}"] for i in range(A)])
+
+    def drained():
+        lg = loggers[-1]
+        out = np.array(lg.normal_log)
+        lg.normal_log.clear()
+        return out
+
+    arng = real_default_rng(action_seed)
+    lo, hi = np.array([-np.pi, -np.pi, -np.pi, 0.0]), np.array([np.pi, np.pi, np.pi, 0.8])
+    episodes = []
+    ep_seed = seed
+    obs0 = reset(ep_seed)
+    new_ep = lambda o: dict(reset_obs=o, reset_noise=drained(), actions=[], obs=[], reward=[], term=[], trunc=[], noise=[], alive=[])  # noqa: E731
+    ep = new_ep(obs0)
+    for i in range(n_steps):
+        alive = set(env.agents)
+        act = arng.uniform(lo, hi, (A, 4)) * np.array([action_scale] * 3 + [1.0])
+        o, r, te, tr, _ = env.step({f"uav_{k}": act[k] for k in range(A) if f"uav_{k}" in alive})
+        ep["actions"].append(act)
+        ep["noise"].append(drained())
+        row = lambda d, default: np.array([d.get(f"uav_{k}", default) for k in range(A)])  # noqa: E731
+        ep["obs"].append(np.stack([o.get(f"uav_{k}", np.full(obs0.shape[1], np.nan)) for k in range(A)]))
+        ep["reward"].append(row(r, np.nan)); ep["term"].append(row(te, True)); ep["trunc"].append(row(tr, False))
+        ep["alive"].append(np.array([f"uav_{k}" in alive for k in range(A)]))
+        if len(env.agents) == 0:
+            episodes.append(ep)
+            ep_seed += 1
+            ep = new_ep(reset(ep_seed))
+    if ep["actions"]:
+        episodes.append(ep)
+    flat = {}
+    for k, e in enumerate(episodes):
+        for key, v in e.items():
+            flat[f"ep{k}_{key}"] = np.array(v)
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), kind="ma_quadx_hover", n_agents=A, sparse=sparse, n_episodes=len(episodes), flight_mode=flight_mode,
+                        angle_representation=angle_representation, dome=dome, max_duration_seconds=max_duration_seconds,
+                        start_pos=np.asarray(env.start_pos, dtype=np.float64), start_orn=np.asarray(env.start_orn, dtype=np.float64), **flat)
+    print(name, "episodes", len(episodes), "steps", [len(e["actions"]) for e in episodes], "reward range", min(np.nanmin(e["reward"]) for e in episodes), max(np.nanmax(e["reward"]) for e in episodes))
+
+
 def fly_hover(name, seed, n_steps, action_seed, angle_representation, flight_mode=0, sparse=False, dome=3.0, action_scale=1.0):
     from PyFlyt.gym_envs.quadx_envs.quadx_hover_env import QuadXHoverEnv
 
@@ -451,6 +519,14 @@ def quadx_waypoints_fixtures():
     fly_qx_waypoints("qxwp_euler_sparse", seed=104, n_steps=200, action_seed=24, angle_representation="euler", sparse=True, action_scale=0.5)
 
 
+def ma_hover_fixtures():
+    # MAQuadXHover: default 4 agents; crashes end agents one by one (dead agents keep falling)
+    fly_ma_hover("mahover_mode0", seed=201, n_steps=160, action_seed=31)
+    fly_ma_hover("mahover_euler_sparse", seed=203, n_steps=120, action_seed=32, angle_representation="euler", sparse=True, action_scale=0.5)
+    fly_ma_hover("mahover_mode6_trunc", seed=205, n_steps=100, action_seed=33, flight_mode=6, max_duration_seconds=1.0, action_scale=0.1, dome=10.0)
+    fly_ma_hover("mahover_two_agents_small_dome", seed=207, n_steps=140, action_seed=34, dome=2.0, start_pos=[[0.0, 0.0, 1.0], [0.5, 0.5, 1.5]])
+
+
 def dogfight_fixtures():
     # MAFixedwingDogfight (BASELINE configs[4]): 1-vs-1 arenas; a wide lethal cone makes scripted flights score hits
     fly_dogfight("dogfight_1v1", seed=81, n_steps=260, action_seed=12)
@@ -515,5 +591,7 @@ if __name__ == "__main__":
         rocket_fixtures()
     if which in ("all", "dogfight"):
         dogfight_fixtures()
+    if which in ("all", "mahover"):
+        ma_hover_fixtures()
     if which in ("all", "qxwp"):
         quadx_waypoints_fixtures()
