@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kBlock) k_quadx_observe(const float* __restric
 // ---------------------------------------------------------------------------------------------------
 // kernels — QuadX-Hover env
 // ---------------------------------------------------------------------------------------------------
-constexpr int kObsStride = 21;  // floats of shared memory per env for the observation tile (rows are packed at stride O <= 21)
+constexpr int kObsStride = 24;  // floats of shared memory per env for the observation tile (rows are packed at stride O <= 24)
 // 640 threads per SM resident (<= 96 registers): the regular + tail CTAs of a 65 536-env step and the CTAs of the
 // concurrent spare rebuild must all be resident at once, or the stragglers form a second wave
 constexpr int kHoverBlocks = 640 / kBlock;
@@ -145,6 +145,9 @@ __device__ __forceinline__ void spare_store(float* __restrict__ spare, int32_t* 
   c[6] = 1.0f;
 }
 
+// row of element j in a dense [rows][O] tile; O is one of the four observation widths (constant divisors, no idiv)
+__device__ __forceinline__ int obs_row(int j, int O) { return O == 21 ? j / 21 : (O == 20 ? j / 20 : (O == 24 ? j / 24 : j / 23)); }
+
 // env.reset() body for one env: begin_reset + end_reset (quadx_base_env.py:149-212); obs -> `out`
 template <int MODE, bool INJECT>
 __device__ __forceinline__ void hover_reset_env(const QuadXParams& p, const HoverParams& h, const RngParams& rng,
@@ -159,7 +162,13 @@ __device__ __forceinline__ void hover_reset_env(const QuadXParams& p, const Hove
   auto nz = make_noise<INJECT>(noise, N, i, rng, seq, TAG_RESET, p.noise_loc, p.ratio);
   for (int k = 0; k < h.warmup_steps; ++k) quadx_aviary_step<MODE>(p, s, nz);
   const float zero[4] = {0.f, 0.f, 0.f, 0.f};  // self.action = zeros (quadx_base_env.py:165)
-  hover_observation(h, s, zero, out);
+  if (h.ma) {  // past_actions is NOT cleared by a reset in the reference: it still holds the previous episode's value
+    float past[4];
+    for (int k = 0; k < 4; ++k) past[k] = st[(int64_t)(QM_PAST + k) * N + i];
+    ma_hover_observation(h, s, past, start_pos[3 * i], start_pos[3 * i + 1], start_pos[3 * i + 2], out);
+  } else {
+    hover_observation(h, s, zero, out);
+  }
   quadx_store<7>(st, ist, N, i, s);
   ist[(int64_t)QI_STEP * N + i] = 0;
 }
@@ -185,7 +194,7 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
                  float* __restrict__ spare, int spare_copy, int build, int tail_blocks, uint32_t step_seq, int64_t N) {
   __shared__ __align__(16) float smem[kBlock * kObsStride];
   __shared__ uint8_t row_skip[kBlock];
-  const int O = h.angle_representation == 0 ? 20 : 21;
+  const int O = (h.angle_representation == 0 ? 20 : 21) + (h.ma ? 3 : 0);
   const bool tail = AUTORESET && (int)blockIdx.x < tail_blocks;  // CTA-uniform role
   const int64_t block_first = tail ? 0 : (int64_t)((int)blockIdx.x - (AUTORESET ? tail_blocks : 0)) * kBlock;
 
@@ -208,6 +217,7 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
     const int64_t i = tail ? (prev_list ? (int64_t)prev_list[t] : (int64_t)t) : block_first + threadIdx.x;
     QuadXRegs s;
     float act[4] = {0.f, 0.f, 0.f, 0.f};
+    float past[4] = {0.f, 0.f, 0.f, 0.f};
     int n_aviary, step_count;
     float rew;
     uint32_t nseq = step_seq;
@@ -267,13 +277,26 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
       n_aviary = h.env_step_ratio;
       step_count = ist[(int64_t)QI_STEP * N + i];
       rew = -0.1f;
+      if (h.ma) {  // MAQuadXHover: flags are re-evaluated every step, rewards add up from 0, the obs shows the PREVIOUS action
+        s.flags &= ~(uint32_t)(FLAG_TERM | FLAG_TRUNC | FLAG_OOB | FLAG_COLLISION);
+        rew = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          past[k] = st[(int64_t)(QM_CUR + k) * N + i];
+          st[(int64_t)(QM_PAST + k) * N + i] = past[k];
+          st[(int64_t)(QM_CUR + k) * N + i] = act[k];
+        }
+      }
     }
     auto nz = make_noise<INJECT>(noise, N, i, rng, nseq, tail ? TAG_RESET : TAG_ENV_STEP, p.noise_loc, p.ratio);
 #pragma unroll 1
     for (int k = 0; k < n_aviary; ++k) {
-      if (s.flags & (FLAG_TERM | FLAG_TRUNC)) break;  // quadx_base_env.py:289-290 (never set while resetting)
+      if (!h.ma && (s.flags & (FLAG_TERM | FLAG_TRUNC))) break;  // quadx_base_env.py:289-290 (never set while resetting)
       quadx_aviary_step<MODE>(p, s, nz);
-      if (!tail) hover_term_trunc_reward(h, s, step_count, rew);
+      if (!tail) {
+        if (h.ma) ma_hover_term_trunc_reward(h, s, step_count, start_pos[3 * i], start_pos[3 * i + 1], start_pos[3 * i + 2], rew);
+        else hover_term_trunc_reward(h, s, step_count, rew);
+      }
     }
     step_count = tail ? 0 : step_count + 1;
     if (tail && build) {  // build mode: the warm-up result is the env's new spare
@@ -281,7 +304,8 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
       continue;
     }
     if (tail && n_aviary > 0) quadx_requantize(s);  // an inline warm-up must leave exactly what a copied spare holds
-    hover_observation(h, s, act, row);
+    if (h.ma) ma_hover_observation(h, s, past, start_pos[3 * i], start_pos[3 * i + 1], start_pos[3 * i + 2], row);
+    else hover_observation(h, s, act, row);
     quadx_store<MODE>(st, ist, N, i, s);
     ist[(int64_t)QI_STEP * N + i] = step_count;
     reward[i] = rew;
@@ -325,7 +349,7 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
   } else {
     for (int v = threadIdx.x; v < nvec; v += kBlock) {
       const int j = v << 2;
-      const int r0 = (O == 21) ? j / 21 : j / 20, r1 = (O == 21) ? (j + 3) / 21 : (j + 3) / 20;
+      const int r0 = obs_row(j, O), r1 = obs_row(j + 3, O);
       const float4 val = src4[v];
       if (!row_skip[r0] && !row_skip[r1]) {
         dst4[v] = val;
@@ -339,7 +363,7 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
     }
   }
   for (int j = (nvec << 2) + threadIdx.x; j < total; j += kBlock)  // ragged last CTA only
-    if (!row_skip[(O == 21) ? j / 21 : j / 20]) dst[j] = smem[j];
+    if (!row_skip[obs_row(j, O)]) dst[j] = smem[j];
 }
 
 // env.reset() for all / masked envs
@@ -354,7 +378,7 @@ __global__ void __launch_bounds__(kBlock)
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (i >= N) return;
   if (mask && !mask[i]) return;
-  const int O = h.angle_representation == 0 ? 20 : 21;
+  const int O = (h.angle_representation == 0 ? 20 : 21) + (h.ma ? 3 : 0);
   float* row = smem + threadIdx.x * kObsStride;
   hover_reset_env<MODE, INJECT>(p, h, rng, st, ist, start_pos, start_orn, noise, seq, N, i, row);
   if (obs) {
@@ -428,9 +452,15 @@ int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, i
     double dome = env ? env->flight_dome_size : INFINITY;
     c->hover.dome2 = (float)(dome * dome);
   }
+  c->hover.ma = (env && env->env_kind == PFB_ENV_MA_QUADX_HOVER) ? 1 : 0;
+  if (c->hover.ma && env->autoreset) {
+    delete c;
+    return fail("MAQuadXHover is a per-agent epilogue: arenas are reset by the caller (pfb_env_reset with a mask), autoreset must be 0");
+  }
   if (env && env->env_kind != PFB_ENV_NONE) {
     const bool ok = (model->kind == PFB_KIND_QUADX && env->env_kind == PFB_ENV_QUADX_HOVER) ||
                     (model->kind == PFB_KIND_QUADX && env->env_kind == PFB_ENV_QUADX_WAYPOINTS) ||
+                    (model->kind == PFB_KIND_QUADX && env->env_kind == PFB_ENV_MA_QUADX_HOVER) ||
                     (model->kind == PFB_KIND_FIXEDWING && env->env_kind == PFB_ENV_FIXEDWING_WAYPOINTS) ||
                     (model->kind == PFB_KIND_FIXEDWING && env->env_kind == PFB_ENV_DOGFIGHT) ||
                     (model->kind == PFB_KIND_ROCKET && env->env_kind == PFB_ENV_ROCKET_LANDING);
@@ -511,11 +541,12 @@ int pfb_set_env_offset(PfbHandle h, uint64_t first_global_env) {
 static inline bool is_fw(PfbHandle h) { return h->model.kind == PFB_KIND_FIXEDWING; }
 static inline bool is_rk(PfbHandle h) { return h->model.kind == PFB_KIND_ROCKET; }
 static inline bool is_qwp(PfbHandle h) { return h->model.kind == PFB_KIND_QUADX && h->env.env_kind == PFB_ENV_QUADX_WAYPOINTS; }
+static inline bool is_ma(PfbHandle h) { return h->model.kind == PFB_KIND_QUADX && h->env.env_kind == PFB_ENV_MA_QUADX_HOVER; }
 static inline bool is_df(PfbHandle h) { return h->model.kind == PFB_KIND_FIXEDWING && h->env.env_kind == PFB_ENV_DOGFIGHT; }
-int pfb_state_rows(PfbHandle h) { return is_rk(h) ? rk_state_rows() : (is_fw(h) ? fw_state_rows() : (is_qwp(h) ? qwp_state_rows() : QX_ROWS)); }
+int pfb_state_rows(PfbHandle h) { return is_rk(h) ? rk_state_rows() : (is_fw(h) ? fw_state_rows() : (is_qwp(h) ? qwp_state_rows() : (is_ma(h) ? QM_ROWS : QX_ROWS))); }
 int pfb_istate_rows(PfbHandle h) { return is_rk(h) ? rk_istate_rows() : (is_fw(h) ? fw_istate_rows() : (is_qwp(h) ? qwp_istate_rows() : QI_ROWS)); }
 int pfb_setpoint_dim(PfbHandle h) { return is_rk(h) ? 7 : ((is_fw(h) && h->env.env_kind == PFB_ENV_NONE) ? 6 : 4); }
-int pfb_obs_dim(PfbHandle h) { return is_df(h) ? df_obs_dim(h) : is_rk(h) ? rk_obs_dim(h) : (is_fw(h) ? fw_obs_dim(h) : (is_qwp(h) ? qwp_obs_dim(h) : (h->hover.angle_representation == 0 ? 20 : 21))); }
+int pfb_obs_dim(PfbHandle h) { return is_df(h) ? df_obs_dim(h) : is_rk(h) ? rk_obs_dim(h) : (is_fw(h) ? fw_obs_dim(h) : (is_qwp(h) ? qwp_obs_dim(h) : (h->hover.angle_representation == 0 ? 20 : 21) + (is_ma(h) ? 3 : 0))); }
 int pfb_aux_dim(PfbHandle h) { return is_rk(h) ? 9 : (is_fw(h) ? 6 : 4); }
 
 int pfb_bind(PfbHandle h, const PfbBuffers* b) {

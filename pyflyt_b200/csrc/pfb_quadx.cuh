@@ -62,6 +62,7 @@ struct HoverParams {
   int warmup_steps;
   int flight_mode;
   float dome2;  // flight_dome_size squared (inf stays inf)
+  int ma;       // 1: MAQuadXHover per-agent epilogue (pz_envs/quadx_envs/ma_quadx_hover_env.py)
 };
 
 // QuadX-Waypoints constants (gym_envs/quadx_envs/quadx_waypoints_env.py:38-52, utils/waypoint_handler.py)
@@ -616,6 +617,10 @@ PFB_HD void quadx_drone_state(const QuadXRegs& s, float* out12, float* aux4) {
   for (int k = 0; k < 4; ++k) aux4[k] = s.thr[k];
 }
 
+// MAQuadXHover keeps the agent's current and past actions behind the QuadX rows: the observation carries the PAST one, and
+// neither is cleared by a reset (ma_quadx_base_env.py:141-150, 326-332)
+enum { QM_CUR = QX_ROWS, QM_PAST = QX_ROWS + 4, QM_ROWS = QX_ROWS + 8 };
+
 // ---- QuadX-Hover epilogue ------------------------------------------------------------------------
 // quadx_base_env.py:251-266 + quadx_hover_env.py:117-138, evaluated after every Aviary step
 PFB_HD void hover_term_trunc_reward(const HoverParams& h, QuadXRegs& s, int step_count, float& reward) {
@@ -683,6 +688,34 @@ PFB_HD void hover_observation(const HoverParams& h, const QuadXRegs& s, const fl
   for (int k = 0; k < 4; ++k) obs[o++] = action[k];
 #pragma unroll
   for (int k = 0; k < 4; ++k) obs[o++] = s.thr[k];
+}
+
+// ---- MAQuadXHover, one agent (pz_envs/quadx_envs/ma_quadx_hover_env.py) ---------------------------------------------
+// compute_term_trunc_reward_info_by_id (:170-206), evaluated after EVERY Aviary step of an env step: rewards add up,
+// nothing leaves the loop early (ma_quadx_base_env.py:343-362); the hover point is the agent's start position.
+PFB_HD void ma_hover_term_trunc_reward(const HoverParams& h, QuadXRegs& s, int step_count, float sx, float sy, float sz, float& reward) {
+  if (step_count > h.max_steps) s.flags |= FLAG_TRUNC;
+  if (s.flags & FLAG_CONTACT_ARRAY) { reward -= 100.0f; s.flags |= FLAG_COLLISION | FLAG_TERM; }
+  float px = (float)s.px, py = (float)s.py, pz = (float)s.pz;
+  if (px * px + py * py + pz * pz > h.dome2) { reward -= 100.0f; s.flags |= FLAG_OOB | FLAG_TERM; }
+  if (!h.sparse_reward) {
+    float dx = px - sx, dy = py - sy, dz = pz - sz;
+    float linear_distance = fast_sqrt(dx * dx + dy * dy + dz * dz);
+    float roll, pitch;
+    roll_pitch_from_quat((float)s.qx, (float)s.qy, (float)s.qz, (float)s.qw, roll, pitch);
+    float angular_distance = fast_sqrt(roll * roll + pitch * pitch);
+    reward -= linear_distance + 0.1f * angular_distance;
+    reward += 1.0f;
+  }
+}
+
+// compute_observation_by_id (:119-168): attitude, aux_state (throttles), PAST action, start position
+PFB_HD void ma_hover_observation(const HoverParams& h, const QuadXRegs& s, const float* past, float sx, float sy, float sz, float* obs) {
+  hover_observation(h, s, s.thr, obs);  // [.., thr (as "action"), thr]: the attitude block and the throttles are in place
+  int o = (h.angle_representation == 0 ? 12 : 13) + 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) obs[o++] = past[k];
+  obs[o++] = sx; obs[o++] = sy; obs[o++] = sz;
 }
 
 }  // namespace pfb
