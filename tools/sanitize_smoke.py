@@ -5,7 +5,7 @@ import os, sys
 import torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from pyflyt_b200.gym_envs import FixedwingWaypointsVecEnv, QuadXHoverVecEnv, QuadXWaypointsVecEnv, RocketLandingVecEnv
-from pyflyt_b200.pz_envs import MAFixedwingDogfightSplitEnv, MAFixedwingDogfightVecEnv
+from pyflyt_b200.pz_envs import MAFixedwingDogfightSplitEnv, MAFixedwingDogfightVecEnv, MAQuadXHoverVecEnv
 
 def drive(env, n):
     env.reset()
@@ -20,6 +20,12 @@ drive(QuadXWaypointsVecEnv(num_envs=500, seed=1, use_yaw_targets=True, max_durat
 drive(FixedwingWaypointsVecEnv(num_envs=300, seed=1, max_duration_seconds=0.3), 20)
 drive(RocketLandingVecEnv(num_envs=300, seed=1, max_duration_seconds=0.3), 20)
 drive(MAFixedwingDogfightVecEnv(num_arenas=100, team_size=2, seed=1, max_duration_seconds=0.3), 20)
+ma = MAQuadXHoverVecEnv(num_arenas=70, seed=1, flight_dome_size=2.0)
+ma.reset()
+for _ in range(40):
+    ma.step(torch.rand(ma.num_agents, 4, device=ma.device) * 2 - 1)
+torch.cuda.synchronize()
+ma.close()
 env = MAFixedwingDogfightSplitEnv(64, seed=1)
 env.reset()
 for _ in range(5):
