@@ -295,13 +295,12 @@ PFB_HD void fixedwing_command(const FixedwingRegs& s, float* cmd) {
 PFB_HD void fixedwing_substep(const FixedwingParams& p, FixedwingRegs& s, const float* cmd, float xi) {
   Vec3 F = Vec3{0.f, 0.f, 0.f}, T = Vec3{0.f, 0.f, 0.f};
   const Vec3 w = Vec3{s.wx, s.wy, s.wz};
-#pragma unroll 1
-  for (int i = 0; i < p.n_surfaces; ++i) {
-    // registers cannot be indexed dynamically: select the surface's actuation / command by chain
-    float a = i == 0 ? s.act[0] : (i == 1 ? s.act[1] : (i == 2 ? s.act[2] : (i == 3 ? s.act[3] : s.act[4])));
-    float c = i == 0 ? cmd[0] : (i == 1 ? cmd[1] : (i == 2 ? cmd[2] : (i == 3 ? cmd[3] : cmd[4])));
-    surface_force(p.surf[i], a, c, s.vb, w, F, T);
-    if (i == 0) s.act[0] = a; else if (i == 1) s.act[1] = a; else if (i == 2) s.act[2] = a; else if (i == 3) s.act[3] = a; else s.act[4] = a;
+  // fully unrolled: the surfaces are independent until their forces are summed, and with < 1 warp per scheduler at the
+  // batch sizes these vehicles run at (16 384 envs) instruction-level parallelism is the only latency hiding there is;
+  // the surface tables also become immediate constant-bank operands instead of indexed loads
+#pragma unroll
+  for (int i = 0; i < kMaxSurfaces; ++i) {
+    if (i < p.n_surfaces) surface_force(p.surf[i], s.act[i], cmd[i], s.vb, w, F, T);
   }
   // motor (motors.py:130-155): thrust + reaction torque along +x at motor_r
   {

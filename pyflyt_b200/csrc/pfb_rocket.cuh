@@ -100,12 +100,10 @@ PFB_HD void rocket_substep(const RocketParams& p, RocketRegs& s, const float* cm
     T = T + cross(r, Fd);
   }
   // finlets
-#pragma unroll 1
-  for (int i = 0; i < p.n_surfaces; ++i) {
-    float a = i == 0 ? s.act[0] : (i == 1 ? s.act[1] : (i == 2 ? s.act[2] : s.act[3]));
-    float c = i == 0 ? cmd[0] : (i == 1 ? cmd[1] : (i == 2 ? cmd[2] : cmd[3]));
-    surface_force(p.surf[i], a, c, s.vb, w, F, T);
-    if (i == 0) s.act[0] = a; else if (i == 1) s.act[1] = a; else if (i == 2) s.act[2] = a; else s.act[3] = a;
+  // fully unrolled (4 finlets): independent until summed, and ILP is the only latency hiding at 16 384 envs
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i < p.n_surfaces) surface_force(p.surf[i], s.act[i], cmd[i], s.vb, w, F, T);
   }
   // gimbal (gimbals.py:145-176): lag on both axes, thrust axis = R1 (R2 u)
   s.gim[0] = fmaf(p.gimbal_lag, cmd[6] - s.gim[0], s.gim[0]);
