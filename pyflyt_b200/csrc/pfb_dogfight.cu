@@ -48,6 +48,14 @@ int df_build_params(const PfbEnvConfig* env, DogfightParams& d) {
 }
 int df_obs_dim(const PfbContext* h) { return 23 + 14 * (2 * h->df.team_size - 1); }
 
+// spare post-reset states (the QuadX-Hover reset pipeline): one env-major record of 160 floats per AGENT —
+// the FW_* / DF_* state words, received-hits counter, validity, flags, episode number, and the agent's first observation
+// (its past-action slots are patched when the spare is used: the action history survives resets)
+enum { DSP_HITS = FW_ROWS, DSP_VALID = FW_ROWS + 1, DSP_FLAGS = FW_ROWS + 2, DSP_EPISODE = FW_ROWS + 3, DSP_OBS = 64, DSP_ROWS = 160 };
+static_assert(FW_ROWS + 4 <= DSP_OBS && DSP_OBS + 23 + 14 * 3 <= DSP_ROWS, "spare record too small");
+constexpr int kDfObsPast = 19;  // index of past_actions inside the observation (3 + 3 + 3 + 3 + 5 + 1 + 1)
+int df_spare_rows() { return DSP_ROWS; }
+
 struct DfAgent {
   float health, acc_reward;
   float past[4], cur[4];
@@ -205,23 +213,32 @@ __device__ __forceinline__ void df_update_states(const DogfightParams& d, Fixedw
   (void)p_hit_ij;
 }
 
-__device__ __forceinline__ void df_load_agent(const float* __restrict__ st, const int32_t* __restrict__ ist, int64_t N, int64_t i, DfAgent& ag) {
-  auto F = [&](int row) { return st[(int64_t)row * N + i]; };
+// rs / ci: as for fixedwing_load — field-major state rows by default, an env-major spare record with (1, 0); `hits` then
+// comes from the record's own word instead of the int tensor
+__device__ __forceinline__ void df_load_agent(const float* __restrict__ st, const int32_t* __restrict__ ist, int64_t N, int64_t i, DfAgent& ag,
+                                              int64_t rs = -1, int64_t ci = -1) {
+  const bool rec = rs >= 0;
+  if (!rec) { rs = N; ci = i; }
+  auto F = [&](int row) { return st[(int64_t)row * rs + ci]; };
   ag.health = F(DF_HEALTH); ag.acc_reward = F(DF_REWARD);
 #pragma unroll
   for (int k = 0; k < 4; ++k) { ag.past[k] = F(DF_PAST + k); ag.cur[k] = F(DF_CUR + k); }
 #pragma unroll
   for (int k = 0; k < 3; ++k) { ag.dist[k] = F(DF_DIST + k); ag.ang[k] = F(DF_ANG + k); }
-  ag.hits = ist[(int64_t)DI_HITS * N + i];
+  ag.hits = rec ? __float_as_int(st[DSP_HITS]) : ist[(int64_t)DI_HITS * N + i];
 }
-__device__ __forceinline__ void df_store_agent(float* __restrict__ st, int32_t* __restrict__ ist, int64_t N, int64_t i, const DfAgent& ag) {
-  auto S = [&](int row, float v) { st[(int64_t)row * N + i] = v; };
+__device__ __forceinline__ void df_store_agent(float* __restrict__ st, int32_t* __restrict__ ist, int64_t N, int64_t i, const DfAgent& ag,
+                                               int64_t rs = -1, int64_t ci = -1) {
+  const bool rec = rs >= 0;
+  if (!rec) { rs = N; ci = i; }
+  auto S = [&](int row, float v) { st[(int64_t)row * rs + ci] = v; };
   S(DF_HEALTH, ag.health); S(DF_REWARD, ag.acc_reward);
 #pragma unroll
   for (int k = 0; k < 4; ++k) { S(DF_PAST + k, ag.past[k]); S(DF_CUR + k, ag.cur[k]); }
 #pragma unroll
   for (int k = 0; k < 3; ++k) { S(DF_DIST + k, ag.dist[k]); S(DF_ANG + k, ag.ang[k]); }
-  ist[(int64_t)DI_HITS * N + i] = ag.hits;
+  if (rec) st[DSP_HITS] = __int_as_float(ag.hits);
+  else ist[(int64_t)DI_HITS * N + i] = ag.hits;
 }
 
 // reset of the calling agent's arena (:219-344): spawn pose from the bound buffers or drawn on device
@@ -257,6 +274,7 @@ __device__ __forceinline__ void df_reset_agent(const FixedwingParams& p, const D
   // current_actions / past_actions survive a reset in the reference (they are only created in __init__)
   auto nz = make_noise<INJECT>(noise, N, i, rng, seq, TAG_RESET, p.noise_loc, p.ratio);
   for (int k = 0; k < d.warmup_steps; ++k) fixedwing_aviary_step<0>(p, s, nz);
+  fixedwing_requantize(s);  // exactly what the state tensor / a spare record will hold
   df_update_states<A>(d, s, ag, li, base, 0, true, obs, lanes);
 }
 
@@ -267,7 +285,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
               float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ term, uint8_t* __restrict__ trunc,
               uint8_t* __restrict__ info, const float* __restrict__ start_pos, const float* __restrict__ start_orn,
               const int32_t* __restrict__ prev_count, const int32_t* __restrict__ prev_list, int32_t* __restrict__ cur_count,
-              int32_t* __restrict__ cur_list, int32_t* __restrict__ next_count, int tail_blocks, uint32_t step_seq, int64_t N) {
+              int32_t* __restrict__ cur_list, int32_t* __restrict__ next_count, float* __restrict__ spare, int spare_copy, int build,
+              int tail_blocks, uint32_t step_seq, int64_t N) {
   __shared__ float smem[kBlock * kDfObsStride];
   __shared__ uint8_t row_skip[kBlock];
   constexpr int O = 23 + 14 * (A - 1);
@@ -278,9 +297,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   // work items are whole arenas: a regular lane owns one agent; tail lanes stride over the done-arena list
   int t, t_end, t_stride;
   if (tail) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *next_count = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !build) *next_count = 0;
     t = (blockIdx.x * kBlock + threadIdx.x) / A;
-    t_end = *prev_count;
+    t_end = prev_list ? *prev_count : (int)(N / A);  // build mode after a user reset: every arena
     t_stride = tail_blocks * kBlock / A;
   } else {
     t = 0;
@@ -297,14 +316,51 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
     unsigned lanes = __ballot_sync(0xffffffffu, go);
     if (lanes == 0u) break;
     if (!go) continue;
-    const int64_t i = tail ? (int64_t)prev_list[t] + li : block_first + threadIdx.x;
+    const int64_t i = tail ? (prev_list ? (int64_t)prev_list[t] : (int64_t)t * A) + li : block_first + threadIdx.x;
     FixedwingRegs s;
     DfAgent ag;
     float rew_out = 0.0f;
     int step_count = 0;
     if (tail) {
-      df_load_agent(st, ist, N, i, ag);  // keeps current / past actions across the reset, like the reference
-      df_reset_agent<A, false>(p, d, rng, start_pos, start_orn, nullptr, step_seq, true, N, i, li, base, s, ag, row, lanes);
+      // arena reset: normally every agent copies its spare (state, combat bookkeeping, first observation of the next
+      // episode); build mode computes those spares; without usable spares the arena runs its warm-up inline.  The episode
+      // number (arena-uniform: agent 0's) keys the spawn and the warm-up noise in all three cases.
+      float* rec = spare ? spare + i * DSP_ROWS : nullptr;
+      uint32_t nseq = step_seq | 0x40000000u;
+      bool mine = false;
+      if (rec) {
+        nseq = __float_as_uint(rec[DSP_EPISODE]) + (build ? 1u : 0u);
+        mine = !build && spare_copy && rec[DSP_VALID] != 0.0f;
+      }
+      nseq = __shfl_sync(lanes, nseq, base);
+      const unsigned arena_mask = ((1u << A) - 1u) << base;
+      const bool hit = (__ballot_sync(lanes, mine) & arena_mask) == arena_mask;  // all of the arena's spares, or none
+      df_load_agent(st, ist, N, i, ag);  // current / past actions survive the reset, like the reference's arrays
+      if (hit) {
+        const float p0 = ag.past[0], p1 = ag.past[1], p2 = ag.past[2], p3 = ag.past[3];
+        const float c0 = ag.cur[0], c1 = ag.cur[1], c2 = ag.cur[2], c3 = ag.cur[3];
+        fixedwing_load(rec, ist, N, i, s, 1, 0);
+        df_load_agent(rec, ist, N, i, ag, 1, 0);
+        ag.past[0] = p0; ag.past[1] = p1; ag.past[2] = p2; ag.past[3] = p3;
+        ag.cur[0] = c0; ag.cur[1] = c1; ag.cur[2] = c2; ag.cur[3] = c3;
+        s.flags = __float_as_uint(rec[DSP_FLAGS]);
+        for (int k = 0; k < O; ++k) row[k] = rec[DSP_OBS + k];
+        row[kDfObsPast + 0] = p0; row[kDfObsPast + 1] = p1; row[kDfObsPast + 2] = p2; row[kDfObsPast + 3] = p3;
+      }
+      const unsigned inl = __ballot_sync(lanes, !hit);  // the arenas that run their warm-up here exchange among themselves
+      if (!hit) {
+        if (build) rec[DSP_VALID] = 0.0f;  // invalid until the warm-up below is stored
+        df_reset_agent<A, false>(p, d, rng, start_pos, start_orn, nullptr, nseq, true, N, i, li, base, s, ag, row, inl);
+      }
+      if (build) {
+        fixedwing_store(rec, ist, N, i, s, false, 1, 0);
+        df_store_agent(rec, ist, N, i, ag, 1, 0);
+        for (int k = 0; k < O; ++k) rec[DSP_OBS + k] = row[k];
+        rec[DSP_FLAGS] = __uint_as_float(s.flags & ~(uint32_t)FLAG_AGENT_DONE);
+        rec[DSP_EPISODE] = __uint_as_float(nseq);
+        rec[DSP_VALID] = 1.0f;
+        continue;
+      }
       s.flags &= ~(uint32_t)(FLAG_AGENT_DONE);
       s.flags |= fresh_tag(step_seq);
     } else {
@@ -430,11 +486,24 @@ int df_env_reset(PfbContext* h, const uint8_t* mask, const float* noise, cudaStr
   const int A = 2 * h->df.team_size;
   if (h->n % A) return fail("the number of envs (%lld) must be a multiple of the arena size %d", (long long)h->n, A);
   const int rnd = h->env.randomize_drop;  // reused as "draw the spawn on device" for the dogfight
+  float* spare = h->env.autoreset ? h->d_spare : nullptr;
+  if (spare) {
+    SPARE_BEFORE_RESET(h, s);
+    if (!mask) CUDA_OK(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(int32_t), s));  // a full reset empties the autoreset queues
+  }
 #define DR_ARGS h->fw, h->df, h->rng, h->buf.state, h->buf.istate, h->buf.start_pos, h->buf.start_orn, mask, noise, h->buf.obs, seq, rnd, h->n
   if (A == 2) { if (noise) k_df_reset<2, true><<<g, kBlock, 0, s>>>(DR_ARGS); else k_df_reset<2, false><<<g, kBlock, 0, s>>>(DR_ARGS); }
   else { if (noise) k_df_reset<4, true><<<g, kBlock, 0, s>>>(DR_ARGS); else k_df_reset<4, false><<<g, kBlock, 0, s>>>(DR_ARGS); }
 #undef DR_ARGS
   LAUNCH_CHECK(h);
+  if (spare) {  // every arena gets fresh spares: the step kernel in build mode over all arenas, same stream
+#define DB_ARGS h->fw, h->df, h->rng, h->buf.state, h->buf.istate, h->buf.setpoint, nullptr, h->buf.obs, h->buf.reward, h->buf.term, h->buf.trunc, \
+                h->buf.info, h->buf.start_pos, h->buf.start_orn, nullptr, nullptr, nullptr, nullptr, nullptr, spare, 0, 1, g, 0u, h->n
+    if (A == 2) k_df_step<2, false, false, true><<<g, kBlock, 0, s>>>(DB_ARGS);
+    else k_df_step<4, false, false, true><<<g, kBlock, 0, s>>>(DB_ARGS);
+#undef DB_ARGS
+    LAUNCH_CHECK(h);
+  }
   h->mode = 0;
   return 0;
 }
@@ -443,10 +512,13 @@ int df_env_step(PfbContext* h, float* actions, const float* noise, bool randact,
   StepPlan pl = plan_step(h);
   const int A = 2 * h->df.team_size;
   if (h->n % A) return fail("the number of envs (%lld) must be a multiple of the arena size %d", (long long)h->n, A);
+  float* spare = h->env.autoreset ? h->d_spare : nullptr;
+  const int spare_copy = (spare && !h->env.inline_reset) ? 1 : 0;
+  SPARE_BEFORE_STEP(h, s);
   if (pl.prof) CUDA_OK(cudaEventRecord(h->prof_ev[2 * h->prof_n], s));
 #define DF_ARGS h->fw, h->df, h->rng, h->buf.state, h->buf.istate, actions, noise, h->buf.obs, h->buf.reward, h->buf.term, h->buf.trunc, \
-                h->buf.info, h->buf.start_pos, h->buf.start_orn, pl.cnt_prev, pl.list_prev, pl.cnt_cur, pl.list_cur, pl.cnt_next, pl.tail, \
-                pl.seq, h->n
+                h->buf.info, h->buf.start_pos, h->buf.start_orn, pl.cnt_prev, pl.list_prev, pl.cnt_cur, pl.list_cur, pl.cnt_next, spare, \
+                spare_copy, 0, pl.tail, pl.seq, h->n
 #define DF_LAUNCH(AA)                                                                                         \
   if (h->env.autoreset) {                                                                                     \
     if (noise) return fail("injected noise (parity mode) is only supported with autoreset = 0");              \
@@ -464,6 +536,17 @@ int df_env_step(PfbContext* h, float* actions, const float* noise, bool randact,
   if (pl.prof) {
     CUDA_OK(cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], s));
     h->prof_n += 1;
+  }
+  if (spare) {  // rebuild the spares this launch consumed, on the side stream, while the next launches run
+    SPARE_REBUILD_BEGIN(h, s);
+#define DB_ARGS h->fw, h->df, h->rng, h->buf.state, h->buf.istate, actions, nullptr, h->buf.obs, h->buf.reward, h->buf.term, h->buf.trunc, \
+                h->buf.info, h->buf.start_pos, h->buf.start_orn, pl.cnt_prev, pl.list_prev, pl.cnt_cur, pl.list_cur, pl.cnt_next, spare, 0, 1, \
+                h->sm_count, pl.seq, h->n
+    if (A == 2) k_df_step<2, false, false, true><<<h->sm_count, kBlock, 0, h->side>>>(DB_ARGS);
+    else k_df_step<4, false, false, true><<<h->sm_count, kBlock, 0, h->side>>>(DB_ARGS);
+#undef DB_ARGS
+    LAUNCH_CHECK(h);
+    SPARE_REBUILD_DONE(h);
   }
   h->step_seq += 1;
   return 0;

@@ -55,6 +55,7 @@ class MAFixedwingDogfightVecEnv:
         seed: int | None = None,
         device: str | torch.device = "cuda:0",
         env_offset: int = 0,
+        inline_reset: bool = False,
     ):
         if 120 % agent_hz != 0:  # ma_fixedwing_base_env.py:43-48
             lowest = int(120 / (int(120 / agent_hz) + 1))
@@ -86,6 +87,7 @@ class MAFixedwingDogfightVecEnv:
         cfg.spawn_min_radius, cfg.spawn_max_radius = float(spawn_min_radius), float(spawn_max_radius)
         cfg.spawn_min_height, cfg.spawn_max_height = float(spawn_min_height), float(spawn_max_height)
         cfg.randomize_drop = int(bool(random_spawn))  # draw the spawn on device like _get_start_pos_orn
+        cfg.inline_reset = int(bool(inline_reset))  # tests: spare-copy arena resets must equal inline ones bit for bit
         self.config = cfg
         n = self.num_agents
         self.aviary = BatchedAviary(np.zeros((n, 3)), np.zeros((n, 3)), drone_type="fixedwing", drone_options=dict(drone_model="acrowing"),

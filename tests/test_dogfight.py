@@ -96,3 +96,31 @@ def test_cuda_dogfight_autoreset_and_determinism():
     for x, y in zip(a, b):
         assert torch.equal(x, y)
     assert torch.isfinite(a[0]).all() and da == db and da > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("team_size", [1, 2])
+def test_cuda_dogfight_spare_reset_equals_inline_reset(team_size):
+    """Arena autoreset copies every agent's spare (state, combat bookkeeping, first observation; rebuilt on a side
+    stream with the spawn and noise keyed by the arena's episode number); it must equal running the warm-up and the
+    first pairwise update inside the step launch bit for bit."""
+    import torch
+
+    from pyflyt_b200.pz_envs import MAFixedwingDogfightVecEnv
+
+    outs = []
+    for inline in (False, True):
+        env = MAFixedwingDogfightVecEnv(num_arenas=2048, team_size=team_size, seed=11, lethal_distance=100.0, lethal_angle_radians=0.8,
+                                        damage_per_hit=0.05, max_duration_seconds=1.0, inline_reset=inline)
+        env.reset()
+        resets, trace = 0, []
+        for _ in range(90):
+            env.rollout(1)
+            resets += int((env.aviary.istate_tensor[0] == 0).sum())
+            trace.append(env.aviary.obs.sum().item())
+        torch.cuda.synchronize()
+        outs.append((env.aviary.obs.clone(), env.aviary.reward.clone(), env.aviary.state_tensor.clone(), resets, trace))
+        env.close()
+    a, b = outs
+    assert a[3] > 2048 and a[3] == b[3] and a[4] == b[4]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
