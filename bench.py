@@ -50,6 +50,20 @@ def ncu_traffic():
     return None
 
 
+def ncu_flops():
+    """(fp32, fp64) FLOPs per step launch from the committed ncu capture, or (None, None)."""
+    path = os.path.join(ROOT, "profiles", "r01_k_hover_step_ncu_summary.txt")
+    out = {}
+    try:
+        for line in open(path):
+            f = line.split()
+            if len(f) >= 3 and f[0] == "derived:" and f[1] not in out:
+                out[f[1]] = float(f[2])
+    except Exception:
+        pass
+    return out.get("fp32_flops_per_launch"), out.get("fp64_flops_per_launch")
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
 
@@ -304,6 +318,15 @@ def run_ours(args, rank, local_rank, world):
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the step launch in profiles/r01_k_hover_step_ncu_summary.txt (ncu replays with a warm L2: state written by the previous replay is still resident, so traffic < algorithmic bytes)",
             },
         }
+        f32, f64 = ncu_flops()
+        if f32:
+            # SURVEY 8(d) asks for both fractions: the non-tensor fp32 pipe next to HBM (148 SMs x 128 lanes x 2 x 1.965 GHz)
+            peak32 = 148 * 128 * 2 * 1.965e9 / 1e12
+            line["roofline"]["fp32"] = {
+                "flops_per_launch": f32, "fp64_flops_per_launch": f64, "achieved_tflops": f32 / kern_avg_s / 1e12, "peak_tflops": peak32,
+                "frac": f32 / kern_avg_s / 1e12 / peak32,
+                "source": "FFMA/FMUL/FADD thread-instruction counters of the step launch in profiles/r01_k_hover_step_ncu_summary.txt",
+            }
         if world == 1 and not args.no_cpu_baseline:
             rate, cores, steps, dt = cpu_oracle_rate(16384, args.cpu_seconds)
             line["cpu_baseline"] = {

@@ -31,6 +31,16 @@ def main(path, which=0):
         if w in hdr:
             i = hdr.index(w)
             print(f"  {w:76s} {d[i]:>16s} {units[i]}")
+    # FLOPs per launch from the per-op thread-instruction counters (reported per elapsed cycle by this ncu version)
+    try:
+        cyc = float(d[hdr.index("sm__cycles_elapsed.max")].replace(",", ""))
+        cnt = {}
+        for op in ("ffma", "fmul", "fadd", "dfma", "dmul", "dadd"):
+            cnt[op] = float(d[hdr.index(f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed")].replace(",", "")) * cyc
+        print(f"  derived: fp32_flops_per_launch {2 * cnt['ffma'] + cnt['fmul'] + cnt['fadd']:.0f}")
+        print(f"  derived: fp64_flops_per_launch {2 * cnt['dfma'] + cnt['dmul'] + cnt['dadd']:.0f}")
+    except (ValueError, KeyError):
+        pass
     stalls = []
     for i, h in enumerate(hdr):
         if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio") and "not_issued" not in h:
