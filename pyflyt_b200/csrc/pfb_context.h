@@ -43,8 +43,9 @@ struct PfbContext {
   PfbBuffers buf;
   bool bound;
   int mode;               // Aviary-level flight mode
-  int32_t* d_counters;    // [3] rotating done-list counters: step k appends to [k%3], reads [(k-1)%3], zeroes [(k+1)%3]
-  int32_t* d_done_list;   // [2][N] ping-pong lists of envs that finished on a step
+  int32_t* d_counters;    // [4] rotating done-list counters: step k appends to [k%4], reads [(k-1)%4], zeroes [(k+1)%4]
+  int32_t* d_done_list;   // [4][N] rotating lists of envs (arenas) that finished on a step; list (k-1)%4 is also read by the
+                          // side-stream spare rebuild of step k, which step k+2 waits for before list (k+3)%4 is reused
   uint64_t step_seq;      // env.step() calls so far (selects counters/lists, keys the Philox streams)
   uint64_t aviary_seq;    // pfb_aviary_step calls so far
   uint64_t reset_seq;     // pfb_env_reset calls so far
@@ -78,7 +79,7 @@ static inline int grid_for(int64_t n) { return (int)((n + kBlock - 1) / kBlock);
     (h)->launches += 1;                                                     \
   } while (0)
 
-// per-step bookkeeping shared by every env kind (rotating counters, ping-pong lists, tail CTAs)
+// per-step bookkeeping shared by every env kind (rotating counters and lists, tail CTAs)
 struct StepPlan {
   int32_t *cnt_cur, *cnt_prev, *cnt_next, *list_cur, *list_prev;
   uint32_t seq;
