@@ -123,33 +123,6 @@ PFB_HD void split_hi_lo(double d, float& hi, float& lo) {
 }
 PFB_HD double join_hi_lo(float hi, float lo) { return (double)hi + (double)lo; }
 
-// ---- two-float ("double-float") accumulators: a value carried as hi + lo with |lo| <= ulp(hi)/2 — exactly the pair of
-// fp32 words the state tensors hold.  All arithmetic is fp32 FADD/FMUL/FFMA (4-cycle dependent latency, full rate), no
-// fp64 pipe and no fp32<->fp64 conversions.  The error-free transformations below need IEEE adds in source order; nvcc
-// does not reassociate floating point, and none of them is a multiply-add pattern the compiler could contract.
-struct ff {
-  float hi, lo;
-  PFB_HD ff() {}
-  PFB_HD ff(float h) : hi(h), lo(0.0f) {}
-  PFB_HD ff(double d) { split_hi_lo(d, hi, lo); }
-  PFB_HD explicit operator float() const { return hi; }
-  PFB_HD explicit operator double() const { return (double)hi + (double)lo; }
-};
-// s + e == a + b exactly (Knuth); 6 flops
-PFB_HD void two_sum(float a, float b, float& s, float& e) {
-  s = a + b;
-  float bb = s - a;
-  e = (a - (s - bb)) + (b - bb);
-}
-// x += d + de, where d + de is a small increment with its own rounding error de (Dekker-style renormalisation)
-PFB_HD void ff_add(ff& x, float d, float de) {
-  float s, e;
-  two_sum(x.hi, d, s, e);
-  e += x.lo + de;
-  x.hi = s + e;
-  x.lo = e - (x.hi - s);
-}
-
 // -------------------------------------------------------------------------------------------------
 // Philox4x32-10 counter RNG: stateless, keyed by (seed), counter = (env, draw index) — results do
 // not depend on how envs are split over GPUs.

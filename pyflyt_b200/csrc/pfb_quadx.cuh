@@ -110,27 +110,10 @@ typedef double rreal;
 typedef float rreal;
 #endif
 
-// Position, attitude and world velocity are carried as two-float accumulators (pfb_common.cuh): the same hi / lo words the
-// state tensor holds, integrated with fp32 error-free transformations.  The fp64 formulation (PFB_QUADX_TWOFLOAT=0, kept
-// for tools/precision_study.py) put ~25 DFMA/DMUL at ~30 cycles dependent latency and 20 fp32<->fp64 conversions on every
-// substep's critical path; this one is all 4-cycle FFMA/FADD.
-#ifndef PFB_QUADX_TWOFLOAT
-#define PFB_QUADX_TWOFLOAT 1
-#endif
-#if PFB_QUADX_TWOFLOAT
-typedef ff qx_xreal;
-typedef ff qx_qreal;
-typedef ff qx_vreal;
-#else
-typedef xreal qx_xreal;
-typedef qreal qx_qreal;
-typedef vreal qx_vreal;
-#endif
-
 struct QuadXRegs {
-  qx_xreal px, py, pz;
-  qx_qreal qx, qy, qz, qw;
-  qx_vreal vx, vy, vz;   // world
+  xreal px, py, pz;
+  qreal qx, qy, qz, qw;
+  vreal vx, vy, vz;   // world
   float wx, wy, wz;   // body
   float thr[4];
   float pwm[4];
@@ -346,23 +329,16 @@ Vec3 quadx_clamp_world_rates(float vmax, Mat3 R, Vec3 w) {
 // Bullet's +-vmax clamp of the world linear velocity (btMultiBody::applyDeltaVeeMultiDof): only ever taken by a body
 // falling at the 100 m/s limit.  Out of line for the same reason as above: inlined, the compiler if-converts it into
 // ~45 predicated fp64 instructions that occupy issue slots on every substep.
-struct Vel3 { qx_vreal x, y, z; };
+struct Vel3 { vreal x, y, z; };
 #if defined(__CUDACC__)
 static __host__ __device__ __noinline__
 #else
 inline
 #endif
-Vel3 quadx_clamp_world_velocity(float vmax_f, Vel3 v) {
-#if PFB_QUADX_TWOFLOAT
-  if (fabsf(v.x.hi) >= vmax_f) v.x = ff(copysignf(vmax_f, v.x.hi));
-  if (fabsf(v.y.hi) >= vmax_f) v.y = ff(copysignf(vmax_f, v.y.hi));
-  if (fabsf(v.z.hi) >= vmax_f) v.z = ff(copysignf(vmax_f, v.z.hi));
-#else
-  const vreal vmax = (vreal)vmax_f;
+Vel3 quadx_clamp_world_velocity(vreal vmax, Vel3 v) {
   v.x = fmin(fmax(v.x, -vmax), vmax);
   v.y = fmin(fmax(v.y, -vmax), vmax);
   v.z = fmin(fmax(v.z, -vmax), vmax);
-#endif
   return v;
 }
 
@@ -411,25 +387,6 @@ PFB_HD void quadx_substep(const QuadXParams& p, QuadXRegs& s, float xi) {
   rreal ax = R.m00 * fx + R.m01 * fy + R.m02 * fz;
   rreal ay = R.m10 * fx + R.m11 * fy + R.m12 * fz;
   rreal az = R.m20 * fx + R.m21 * fy + R.m22 * fz + (rreal)p.gravity;
-#if PFB_QUADX_TWOFLOAT
-  {
-    // v += a dt and x += v dt on the two-float accumulators: the product's rounding error comes back with one FMA
-    const float dt = p.dt;
-    float d, de;
-    d = (float)ax * dt; de = fmaf((float)ax, dt, -d); ff_add(s.vx, d, de);
-    d = (float)ay * dt; de = fmaf((float)ay, dt, -d); ff_add(s.vy, d, de);
-    d = (float)az * dt; de = fmaf((float)az, dt, -d); ff_add(s.vz, d, de);
-    // +-vmax clamp per world coordinate (btMultiBody::applyDeltaVeeMultiDof): only ever taken by a body falling at the
-    // 100 m/s limit
-    if (fmaxf(fmaxf(fabsf(s.vx.hi), fabsf(s.vy.hi)), fabsf(s.vz.hi)) >= p.vmax) {
-      Vel3 c = quadx_clamp_world_velocity(p.vmax, Vel3{s.vx, s.vy, s.vz});
-      s.vx = c.x; s.vy = c.y; s.vz = c.z;
-    }
-    d = s.vx.hi * dt; de = fmaf(s.vx.hi, dt, -d) + s.vx.lo * dt; ff_add(s.px, d, de);
-    d = s.vy.hi * dt; de = fmaf(s.vy.hi, dt, -d) + s.vy.lo * dt; ff_add(s.py, d, de);
-    d = s.vz.hi * dt; de = fmaf(s.vz.hi, dt, -d) + s.vz.lo * dt; ff_add(s.pz, d, de);
-  }
-#else
   const vreal dt = (vreal)p.dt;
   s.vx += (vreal)ax * dt;
   s.vy += (vreal)ay * dt;
@@ -437,13 +394,12 @@ PFB_HD void quadx_substep(const QuadXParams& p, QuadXRegs& s, float xi) {
   // +-vmax clamp per world coordinate (btMultiBody::applyDeltaVeeMultiDof): tested on the fp32 copy,
   // applied exactly, and only ever taken by a body falling at the 100 m/s limit
   if (fmaxf(fmaxf(fabsf((float)s.vx), fabsf((float)s.vy)), fabsf((float)s.vz)) >= p.vmax) {
-    Vel3 c = quadx_clamp_world_velocity(p.vmax, Vel3{s.vx, s.vy, s.vz});
+    Vel3 c = quadx_clamp_world_velocity((vreal)p.vmax, Vel3{s.vx, s.vy, s.vz});
     s.vx = c.x; s.vy = c.y; s.vz = c.z;
   }
   s.px += (xreal)(s.vx * dt);
   s.py += (xreal)(s.vy * dt);
   s.pz += (xreal)(s.vz * dt);
-#endif
   s.wx = fmaf(wdx, p.dt, s.wx);
   s.wy = fmaf(wdy, p.dt, s.wy);
   s.wz = fmaf(wdz, p.dt, s.wz);
@@ -459,25 +415,6 @@ PFB_HD void quadx_substep(const QuadXParams& p, QuadXRegs& s, float xi) {
   float h2 = (s.wx * s.wx + s.wy * s.wy + s.wz * s.wz) * (0.25f * p.dt * p.dt);
   float sinc = fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, 2.7557319e-6f, -1.9841270e-4f), 8.3333333e-3f), -1.6666667e-1f), 1.0f);
   float scale = 0.5f * p.dt * sinc;
-#if PFB_QUADX_TWOFLOAT
-  {
-    // q <- normalise(q (x) dq) as an INCREMENT on the two-float accumulators: d = q (x) (dq - 1) is O(h), so fp32 products
-    // carry it to ~1e-10 absolute; |q + d|^2 - 1 = 2 q.d + |d|^2 is a sum of small terms (|q| = 1 from the previous
-    // substep), and the first-order renormalisation -e/2 (q + d) is folded into the same increment (e ~ 1e-8, e^2 is
-    // below the accumulators' resolution).  cw1 = cos(h) - 1 comes straight from the series, no cancellation.
-    const float cw1 = h2 * fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, -2.7557319e-7f, 2.4801587e-5f), -1.3888889e-3f), 4.1666667e-2f), -0.5f);
-    const float dx = s.wx * scale, dy = s.wy * scale, dz = s.wz * scale;
-    const float qx = s.qx.hi, qy = s.qy.hi, qz = s.qz.hi, qw = s.qw.hi;
-    float ex = fmaf(qw, dx, fmaf(qx, cw1, fmaf(qy, dz, -qz * dy)));
-    float ey = fmaf(qw, dy, fmaf(qy, cw1, fmaf(qz, dx, -qx * dz)));
-    float ez = fmaf(qw, dz, fmaf(qz, cw1, fmaf(qx, dy, -qy * dx)));
-    float ew = fmaf(qw, cw1, -fmaf(qx, dx, fmaf(qy, dy, qz * dz)));
-    const float e = 2.0f * fmaf(qx, ex, fmaf(qy, ey, fmaf(qz, ez, qw * ew))) + fmaf(ex, ex, fmaf(ey, ey, fmaf(ez, ez, ew * ew)));
-    const float k = -0.5f * e;
-    ex = fmaf(k, qx + ex, ex); ey = fmaf(k, qy + ey, ey); ez = fmaf(k, qz + ez, ez); ew = fmaf(k, qw + ew, ew);
-    ff_add(s.qx, ex, 0.0f); ff_add(s.qy, ey, 0.0f); ff_add(s.qz, ez, 0.0f); ff_add(s.qw, ew, 0.0f);
-  }
-#else
   float cw = fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, -2.7557319e-7f, 2.4801587e-5f), -1.3888889e-3f), 4.1666667e-2f), -0.5f), 1.0f);
   qreal dx = (qreal)(s.wx * scale), dy = (qreal)(s.wy * scale), dz = (qreal)(s.wz * scale), dw = (qreal)cw;
   qreal nx = s.qw * dx + s.qx * dw + s.qy * dz - s.qz * dy;
@@ -493,7 +430,6 @@ PFB_HD void quadx_substep(const QuadXParams& p, QuadXRegs& s, float xi) {
   qreal inv = 1.0f / sqrtf(n2);
 #endif
   s.qx = nx * inv; s.qy = ny * inv; s.qz = nz * inv; s.qw = nw * inv;
-#endif
   // ---- update_state (quadx.py:512-535)
   quadx_update_state(s);
 }
@@ -531,17 +467,16 @@ PFB_HD void quadx_set_mode(QuadXRegs& s) {
 
 // quadx.py:222-231 + aviary.py:310-311: a freshly constructed drone at its start pose
 PFB_HD void quadx_reset(QuadXRegs& s, float sx, float sy, float sz, float roll, float pitch, float yaw) {
-  s.px = (qx_xreal)sx; s.py = (qx_xreal)sy; s.pz = (qx_xreal)sz;
+  s.px = (xreal)sx; s.py = (xreal)sy; s.pz = (xreal)sz;
   {  // getQuaternionFromEuler in the attitude precision
-    // evaluated in double (cold path), then split into the accumulators' hi / lo words
-    double hr = (double)roll * 0.5, hp = (double)pitch * 0.5, hy = (double)yaw * 0.5;
-    double sr = sin(hr), cr = cos(hr), sp = sin(hp), cp = cos(hp), sy_ = sin(hy), cy = cos(hy);
+    qreal hr = (qreal)roll * (qreal)0.5, hp = (qreal)pitch * (qreal)0.5, hy = (qreal)yaw * (qreal)0.5;
+    qreal sr = sin(hr), cr = cos(hr), sp = sin(hp), cp = cos(hp), sy_ = sin(hy), cy = cos(hy);
     s.qx = sr * cp * cy - cr * sp * sy_;
     s.qy = cr * sp * cy + sr * cp * sy_;
     s.qz = cr * cp * sy_ - sr * sp * cy;
     s.qw = cr * cp * cy + sr * sp * sy_;
   }
-  s.vx = s.vy = s.vz = (qx_vreal)0.0f;
+  s.vx = s.vy = s.vz = (vreal)0;
   s.wx = s.wy = s.wz = 0.0f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) { s.thr[i] = 0.0f; s.pwm[i] = 0.0f; s.sp[i] = 0.0f; }
@@ -575,19 +510,6 @@ PFB_HD void quadx_load(const float* __restrict__ st, const int32_t* __restrict__
                        int64_t rs = -1, int64_t ci = -1) {
   if (rs < 0) { rs = N; ci = i; }
   auto F = [&](int row) { return st[(int64_t)row * rs + ci]; };
-#if PFB_QUADX_TWOFLOAT
-  // the accumulators ARE the stored words: no conversion either way
-  s.px.hi = F(QX_POS + 0); s.px.lo = F(QX_POS_LO + 0);
-  s.py.hi = F(QX_POS + 1); s.py.lo = F(QX_POS_LO + 1);
-  s.pz.hi = F(QX_POS + 2); s.pz.lo = F(QX_POS_LO + 2);
-  s.qx.hi = F(QX_QUAT + 0); s.qx.lo = F(QX_QUAT_LO + 0);
-  s.qy.hi = F(QX_QUAT + 1); s.qy.lo = F(QX_QUAT_LO + 1);
-  s.qz.hi = F(QX_QUAT + 2); s.qz.lo = F(QX_QUAT_LO + 2);
-  s.qw.hi = F(QX_QUAT + 3); s.qw.lo = F(QX_QUAT_LO + 3);
-  s.vx.hi = F(QX_VEL + 0); s.vx.lo = F(QX_VEL_LO + 0);
-  s.vy.hi = F(QX_VEL + 1); s.vy.lo = F(QX_VEL_LO + 1);
-  s.vz.hi = F(QX_VEL + 2); s.vz.lo = F(QX_VEL_LO + 2);
-#else
 #if PFB_X_DOUBLE
   s.px = join_hi_lo(F(QX_POS + 0), F(QX_POS_LO + 0));
   s.py = join_hi_lo(F(QX_POS + 1), F(QX_POS_LO + 1));
@@ -610,7 +532,6 @@ PFB_HD void quadx_load(const float* __restrict__ st, const int32_t* __restrict__
 #else
   s.vx = F(QX_VEL + 0); s.vy = F(QX_VEL + 1); s.vz = F(QX_VEL + 2);
 #endif
-#endif
   s.wx = F(QX_ANGVEL + 0); s.wy = F(QX_ANGVEL + 1); s.wz = F(QX_ANGVEL + 2);
 #pragma unroll
   // the pwm rows are write-only: every Aviary step starts with a control tick that recomputes pwm before any
@@ -628,15 +549,6 @@ PFB_HD void quadx_store(float* __restrict__ st, int32_t* __restrict__ ist, int64
   if (rs < 0) { rs = N; ci = i; }
   auto S = [&](int row, float v) { st[(int64_t)row * rs + ci] = v; };
   float hi, lo;
-#if PFB_QUADX_TWOFLOAT
-  hi = lo = 0.0f;
-  S(QX_POS + 0, s.px.hi); S(QX_POS_LO + 0, s.px.lo); S(QX_POS + 1, s.py.hi); S(QX_POS_LO + 1, s.py.lo);
-  S(QX_POS + 2, s.pz.hi); S(QX_POS_LO + 2, s.pz.lo);
-  S(QX_QUAT + 0, s.qx.hi); S(QX_QUAT_LO + 0, s.qx.lo); S(QX_QUAT + 1, s.qy.hi); S(QX_QUAT_LO + 1, s.qy.lo);
-  S(QX_QUAT + 2, s.qz.hi); S(QX_QUAT_LO + 2, s.qz.lo); S(QX_QUAT + 3, s.qw.hi); S(QX_QUAT_LO + 3, s.qw.lo);
-  S(QX_VEL + 0, s.vx.hi); S(QX_VEL_LO + 0, s.vx.lo); S(QX_VEL + 1, s.vy.hi); S(QX_VEL_LO + 1, s.vy.lo);
-  S(QX_VEL + 2, s.vz.hi); S(QX_VEL_LO + 2, s.vz.lo);
-#else
 #if PFB_X_DOUBLE
   split_hi_lo(s.px, hi, lo); S(QX_POS + 0, hi); S(QX_POS_LO + 0, lo);
   split_hi_lo(s.py, hi, lo); S(QX_POS + 1, hi); S(QX_POS_LO + 1, lo);
@@ -659,7 +571,6 @@ PFB_HD void quadx_store(float* __restrict__ st, int32_t* __restrict__ ist, int64
 #else
   S(QX_VEL + 0, s.vx); S(QX_VEL + 1, s.vy); S(QX_VEL + 2, s.vz);
 #endif
-#endif
   (void)hi; (void)lo;
   S(QX_ANGVEL + 0, s.wx); S(QX_ANGVEL + 1, s.wy); S(QX_ANGVEL + 2, s.wz);
 #pragma unroll
@@ -674,7 +585,6 @@ PFB_HD void quadx_store(float* __restrict__ st, int32_t* __restrict__ ist, int64
 // afterwards the registers equal what quadx_store followed by quadx_load would produce.
 PFB_HD void quadx_requantize(QuadXRegs& s) {
   float hi, lo;
-#if !PFB_QUADX_TWOFLOAT  // the two-float accumulators already are the stored words
 #if PFB_X_DOUBLE
   split_hi_lo(s.px, hi, lo); s.px = join_hi_lo(hi, lo);
   split_hi_lo(s.py, hi, lo); s.py = join_hi_lo(hi, lo);
@@ -690,9 +600,6 @@ PFB_HD void quadx_requantize(QuadXRegs& s) {
   split_hi_lo(s.vx, hi, lo); s.vx = join_hi_lo(hi, lo);
   split_hi_lo(s.vy, hi, lo); s.vy = join_hi_lo(hi, lo);
   split_hi_lo(s.vz, hi, lo); s.vz = join_hi_lo(hi, lo);
-#endif
-#else
-  hi = lo = 0.0f;
 #endif
   (void)hi; (void)lo;
   quadx_update_state(s);

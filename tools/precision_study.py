@@ -13,15 +13,13 @@ ROOT = os.path.join(os.path.dirname(os.path.realpath(__file__)), "..")
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from engines import HostSimEngine, OracleEngine, build_model  # noqa: E402
 
-F64 = "-DPFB_QUADX_TWOFLOAT=0 "  # the fp64-register formulation the two-float accumulators replaced
 VARIANTS = {
-    "two-float q x v, R32 (shipped)": "",
-    "q64 x64 v64 R64": F64 + "-DPFB_R_DOUBLE=1",
-    "q64 x64 v64 R32": F64,
-    "q64 x64 v32 R32": F64 + "-DPFB_R_DOUBLE=0 -DPFB_V_DOUBLE=0",
-    "q64 x32 v32 R32": F64 + "-DPFB_R_DOUBLE=0 -DPFB_V_DOUBLE=0 -DPFB_X_DOUBLE=0",
-    "q32 x64 v64 R32": F64 + "-DPFB_R_DOUBLE=0 -DPFB_Q_DOUBLE=0",
-    "all fp32": F64 + "-DPFB_R_DOUBLE=0 -DPFB_V_DOUBLE=0 -DPFB_X_DOUBLE=0 -DPFB_Q_DOUBLE=0",
+    "q64 x64 v64 R64": "-DPFB_R_DOUBLE=1",
+    "q64 x64 v64 R32 (shipped)": "",
+    "q64 x64 v32 R32": "-DPFB_R_DOUBLE=0 -DPFB_V_DOUBLE=0",
+    "q64 x32 v32 R32": "-DPFB_R_DOUBLE=0 -DPFB_V_DOUBLE=0 -DPFB_X_DOUBLE=0",
+    "q32 x64 v64 R32": "-DPFB_R_DOUBLE=0 -DPFB_Q_DOUBLE=0",
+    "all fp32": "-DPFB_R_DOUBLE=0 -DPFB_V_DOUBLE=0 -DPFB_X_DOUBLE=0 -DPFB_Q_DOUBLE=0",
 }
 
 
@@ -60,7 +58,7 @@ def main(n=64, steps=3000, mode=0, seed=0):
             if i % 30 == 29:
                 err[i // 30] = np.abs(hs.state()[:, 3] - ref[i // 30]).max(axis=1)
         worst = err.max(axis=0)
-        print(f"{name:32s} max|dpos| {worst.max():.2e}  median {np.median(worst):.2e}  p90 {np.quantile(worst, 0.9):.2e}   (at 333 env-steps: {err[:33].max():.2e})")
+        print(f"{name:28s} max|dpos| {worst.max():.2e}  median {np.median(worst):.2e}  p90 {np.quantile(worst, 0.9):.2e}   (at 333 env-steps: {err[:33].max():.2e})")
 
 
 if __name__ == "__main__":
