@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kBlock) k_quadx_observe(const float* __restric
 constexpr int kObsStride = 24;  // floats of shared memory per env for the observation tile (rows are packed at stride O <= 24)
 // 640 threads per SM resident (<= 96 registers): the regular + tail CTAs of a 65 536-env step and the CTAs of the
 // concurrent spare rebuild must all be resident at once, or the stragglers form a second wave
-constexpr int kHoverBlocks = 512 / kBlock;
+constexpr int kHoverBlocks = 640 / kBlock;
 
 // ---- spare post-reset states ("reset pipeline") ---------------------------------------
 // env.reset() = start pose + `warmup_steps` Aviary steps (quadx_base_env.py:149-212): 3.3x the work of an env step and a
