@@ -263,6 +263,11 @@ int pfb_env_step_host(PfbHandle h, const float* host_actions, float* host_obs, f
 int pfb_dogfight_payload_dim(void);
 int pfb_dogfight_physics(PfbHandle h, const float* actions, const float* noise, float* payload_out, int first, int do_reset,
                          int aviary_index, void* stream);
+/* Fused exchange: as pfb_dogfight_physics, but every payload is stored straight into the payload table of EVERY rank
+ * (peer_tables_dev: DEVICE array of `world` table base pointers, peer-mapped, e.g. torch symmetric memory) at float offset
+ * slot_offset_floats + 20 * local_agent.  No all-gather: the caller follows with a cross-rank barrier on the stream.    */
+int pfb_dogfight_physics_peer(PfbHandle h, const float* actions, const float* noise, const uint64_t* peer_tables_dev, int world,
+                             int64_t slot_offset_floats, int first, int do_reset, int aviary_index, void* stream);
 int pfb_dogfight_combat(PfbHandle h, const float* payload_table, int64_t first_global_agent, int64_t num_arenas, int last,
                         void* stream);
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches).                  */

@@ -268,6 +268,16 @@ class BatchedAviary:
         _lib.check(_lib.lib().pfb_dogfight_physics(self._h, act, nz, C.c_void_p(payload.data_ptr()), int(first), int(do_reset), int(aviary_index), self._s()))
         self._state_fresh = False
 
+    def dogfight_physics_peer(self, peer_tables: torch.Tensor, world: int, slot_offset_floats: int, actions: torch.Tensor | None = None,
+                              noise: torch.Tensor | None = None, first: bool = False, do_reset: bool = False, aviary_index: int = 0) -> None:
+        """Split dogfight, half 1 with the exchange fused in: every payload is stored straight into all ranks' tables
+        (``peer_tables``: int64 device tensor of ``world`` peer-mapped base pointers)."""
+        act = None if actions is None else C.c_void_p(actions.data_ptr())
+        nz = None if noise is None else C.c_void_p(noise.data_ptr())
+        _lib.check(_lib.lib().pfb_dogfight_physics_peer(self._h, act, nz, C.c_void_p(peer_tables.data_ptr()), int(world), int(slot_offset_floats),
+                                                        int(first), int(do_reset), int(aviary_index), self._s()))
+        self._state_fresh = False
+
     def dogfight_combat(self, table: torch.Tensor, first_global_agent: int, num_arenas: int, last: int) -> None:
         """Split dogfight, half 2: combat state from the all-gathered payload ``table`` [2 * num_arenas, 20]."""
         _lib.check(_lib.lib().pfb_dogfight_combat(self._h, C.c_void_p(table.data_ptr()), int(first_global_agent), int(num_arenas), int(last), self._s()))

@@ -556,7 +556,8 @@ int df_env_step(PfbContext* h, float* actions, const float* noise, bool randact,
 // Split ("agent-major") variant — BASELINE.json configs[4] as written: the agents of one arena live on
 // DIFFERENT ranks, so the combat state needs one exchange per Aviary step.  Per Aviary step:
 //     k_df_split_physics  (integrate my aircraft, publish a 20-float payload per agent)
-//     ncclAllGather       (torch.distributed.all_gather_into_tensor on the payload table, host side)
+//     exchange            either ncclAllGather of the payload table (host side), or NONE: the physics kernel stores every
+//                         payload directly into all ranks' tables over NVLink peer memory, followed by a cross-rank barrier
 //     k_df_split_combat   (pairwise combat state, health, rewards, terminations from the gathered table)
 // Global agent id gid = k * num_arenas + g (member k of arena g); rank r owns gids [r*n_local, (r+1)*n_local).
 // 1-vs-1 arenas (team_size 1).  No in-kernel autoreset: reset() is a collective call.
@@ -582,8 +583,9 @@ template <bool INJECT>
 __global__ void __launch_bounds__(kBlock, kMinBlocks)
     k_df_split_physics(const __grid_constant__ FixedwingParams p, const __grid_constant__ DogfightParams d, const __grid_constant__ RngParams rng,
                        float* __restrict__ st, int32_t* __restrict__ ist, const float* __restrict__ actions, const float* __restrict__ noise,
-                       const float* __restrict__ start_pos, const float* __restrict__ start_orn, float* __restrict__ payload, int first,
-                       int do_reset, uint32_t seq, uint32_t sub, int64_t N) {
+                       const float* __restrict__ start_pos, const float* __restrict__ start_orn, float* __restrict__ payload,
+                       const uint64_t* __restrict__ peers, int world, int64_t slot0, int first, int do_reset, uint32_t seq, uint32_t sub,
+                       int64_t N) {
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (i >= N) return;
   FixedwingRegs s;
@@ -616,7 +618,15 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   }
   fixedwing_store(st, ist, N, i, s);
   df_store_agent(st, ist, N, i, ag);
-  df_publish(s, ag, payload + (int64_t)kPayload * i);
+  if (peers) {
+    // fused exchange: the payload goes straight into the table of EVERY rank (peer stores over NVLink, 80 bytes = 5 float4
+    // per agent per peer) instead of into a local buffer that a separate all-gather would then move; slot0 = float offset
+    // of this rank's first agent inside the (double-buffered) table.  The stores are visible to the peers once this
+    // kernel has completed; the cross-rank barrier that follows on the stream orders the readers behind it.
+    for (int r = 0; r < world; ++r) df_publish(s, ag, reinterpret_cast<float*>(peers[r]) + slot0 + (int64_t)kPayload * i);
+  } else {
+    df_publish(s, ag, payload + (int64_t)kPayload * i);
+  }
 }
 
 // combat state for 1-vs-1 arenas from the gathered payload table [num_agents][kPayload]
@@ -726,17 +736,18 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   df_store_agent(st, ist, N, i, ag);
 }
 
-int df_split_physics(PfbContext* h, const float* actions, const float* noise, float* payload, int first, int do_reset, int sub, cudaStream_t s) {
+int df_split_physics(PfbContext* h, const float* actions, const float* noise, float* payload, const uint64_t* peers, int world,
+                     int64_t slot0, int first, int do_reset, int sub, cudaStream_t s) {
   if (h->df.team_size != 1) return fail("the split (all-gather) dogfight path is built for team_size 1");
   const uint32_t seq = do_reset ? (0x80000000u | (uint32_t)h->reset_seq) : (uint32_t)h->step_seq;
   if (do_reset) h->reset_seq += 1;
   const int g = grid_for(h->n);
   if (noise)
     k_df_split_physics<true><<<g, kBlock, 0, s>>>(h->fw, h->df, h->rng, h->buf.state, h->buf.istate, actions, noise, h->buf.start_pos,
-                                                  h->buf.start_orn, payload, first, do_reset, seq, (uint32_t)sub, h->n);
+                                                  h->buf.start_orn, payload, peers, world, slot0, first, do_reset, seq, (uint32_t)sub, h->n);
   else
     k_df_split_physics<false><<<g, kBlock, 0, s>>>(h->fw, h->df, h->rng, h->buf.state, h->buf.istate, actions, nullptr, h->buf.start_pos,
-                                                   h->buf.start_orn, payload, first, do_reset, seq, (uint32_t)sub, h->n);
+                                                   h->buf.start_orn, payload, peers, world, slot0, first, do_reset, seq, (uint32_t)sub, h->n);
   LAUNCH_CHECK(h);
   return 0;
 }

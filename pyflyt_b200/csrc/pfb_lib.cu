@@ -788,7 +788,16 @@ int pfb_dogfight_physics(PfbHandle h, const float* actions, const float* noise, 
   REQUIRE_BOUND(h);
   if (!is_df(h)) return fail("handle is not a dogfight env");
   if (!payload_out) return fail("pfb_dogfight_physics: null payload buffer");
-  return df_split_physics(h, actions ? actions : h->buf.setpoint, noise, payload_out, first, do_reset, aviary_index, (cudaStream_t)stream);
+  return df_split_physics(h, actions ? actions : h->buf.setpoint, noise, payload_out, nullptr, 0, 0, first, do_reset, aviary_index, (cudaStream_t)stream);
+}
+
+int pfb_dogfight_physics_peer(PfbHandle h, const float* actions, const float* noise, const uint64_t* peer_tables_dev, int world,
+                             int64_t slot_offset_floats, int first, int do_reset, int aviary_index, void* stream) {
+  REQUIRE_BOUND(h);
+  if (!is_df(h)) return fail("handle is not a dogfight env");
+  if (!peer_tables_dev || world < 1) return fail("pfb_dogfight_physics_peer: need the device array of peer table pointers");
+  return df_split_physics(h, actions ? actions : h->buf.setpoint, noise, nullptr, peer_tables_dev, world, slot_offset_floats, first, do_reset,
+                          aviary_index, (cudaStream_t)stream);
 }
 
 int pfb_dogfight_combat(PfbHandle h, const float* payload_table, int64_t first_global_agent, int64_t num_arenas, int last, void* stream) {

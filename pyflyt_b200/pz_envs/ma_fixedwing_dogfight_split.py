@@ -11,6 +11,15 @@ Global agent id ``gid = member * num_arenas + arena``; rank ``r`` of ``world`` o
 (ma_fixedwing_dogfight_env.py:346-465 `_compute_agent_states` is the part that reads other agents).  1-vs-1 arenas,
 no autoreset (``reset`` is a collective call), explicit or host-drawn spawns.  With ``group=None`` and no initialised
 process group it runs single-rank (the "gather" is a copy), which is how the parity tests drive it on one GPU.
+
+``exchange="peer"`` fuses the exchange into the physics kernel: the payload table lives in symmetric (peer-mapped)
+memory, every rank's kernel stores its payloads straight into ALL ranks' tables over NVLink, and the only thing left
+between the two kernels is a cross-rank barrier — no all-gather launch, no staging buffer:
+
+    pfb_dogfight_physics_peer (peer stores)  ->  symmetric-memory barrier  ->  pfb_dogfight_combat
+
+The table is double-buffered by Aviary-step parity: a rank that runs ahead writes the other half while a slower rank
+still reads its own.
 """
 
 from __future__ import annotations
@@ -52,7 +61,8 @@ class MAFixedwingDogfightSplitEnv:
     def __init__(self, num_arenas: int, damage_per_hit: float = 0.003, lethal_distance: float = 20.0, lethal_angle_radians: float = 0.07,
                  aggressiveness: float = 0.5, cooperativeness: float = 0.5, sparse_reward: bool = False, flight_dome_size: float = 800.0,
                  max_duration_seconds: float = 60.0, agent_hz: int = 30, spawn_min_radius: float = 10.0, spawn_max_radius: float = 50.0,
-                 seed: int | None = None, device: str | torch.device = "cuda:0", group=None, single_rank: bool = False):
+                 seed: int | None = None, device: str | torch.device = "cuda:0", group=None, single_rank: bool = False,
+                 exchange: str = "nccl"):
         assert 120 % agent_hz == 0
         self.group = group
         self.distributed = dist.is_available() and dist.is_initialized() and not single_rank
@@ -89,6 +99,23 @@ class MAFixedwingDogfightSplitEnv:
         self.ratio = cfg.env_step_ratio
         self.collectives = 0
         self._resets = 0
+        assert exchange in ("nccl", "peer")
+        self.exchange = exchange
+        self._symm = None
+        if exchange == "peer":
+            na = 2 * self.num_arenas
+            if self.world > 1:
+                import torch.distributed._symmetric_memory as symm_mem
+
+                grp = group if group is not None else dist.group.WORLD
+                self._tables = symm_mem.empty((2, na, PAYLOAD), dtype=torch.float32, device=self.device)
+                self._tables.zero_()
+                self._symm = symm_mem.rendezvous(self._tables, grp)
+                ptrs = [int(p) for p in self._symm.buffer_ptrs]
+            else:
+                self._tables = torch.zeros((2, na, PAYLOAD), dtype=torch.float32, device=self.device)
+                ptrs = [self._tables.data_ptr()]
+            self._peers = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
 
     def _gather(self) -> None:
         if self.world > 1:
@@ -96,6 +123,21 @@ class MAFixedwingDogfightSplitEnv:
         else:
             self.table.copy_(self.payload)
         self.collectives += 1
+
+    def _physics(self, **kw) -> torch.Tensor:
+        """One Aviary step (or the reset) + the exchange; returns the payload table to read."""
+        a = self.aviary
+        if self.exchange == "nccl":
+            a.dogfight_physics(self.payload, **kw)
+            self._gather()
+            return self.table
+        phase = self.collectives & 1
+        na = 2 * self.num_arenas
+        a.dogfight_physics_peer(self._peers, self.world, (phase * na + self.first_gid) * PAYLOAD, **kw)
+        if self._symm is not None:
+            self._symm.barrier(channel=0)  # every rank's peer stores have landed; enqueued on the current stream
+        self.collectives += 1
+        return self._tables[phase]
 
     def reset(self, start_pos=None, start_orn=None, noise=None):
         """Collective.  ``start_pos`` / ``start_orn``: [2 * num_arenas, 3] in global-agent order (all ranks pass the same)."""
@@ -106,9 +148,8 @@ class MAFixedwingDogfightSplitEnv:
         sl = slice(self.first_gid, self.first_gid + self.n_local)
         a.start_pos.copy_(torch.as_tensor(np.asarray(start_pos, dtype=np.float32)[sl], device=self.device))
         a.start_orn.copy_(torch.as_tensor(np.asarray(start_orn, dtype=np.float32)[sl], device=self.device))
-        a.dogfight_physics(self.payload, noise=noise, do_reset=True)
-        self._gather()
-        a.dogfight_combat(self.table, self.first_gid, self.num_arenas, last=2)
+        table = self._physics(noise=noise, do_reset=True)
+        a.dogfight_combat(table, self.first_gid, self.num_arenas, last=2)
         a.info_bits.zero_()
         return a.obs
 
@@ -118,9 +159,8 @@ class MAFixedwingDogfightSplitEnv:
         actions = torch.as_tensor(actions, dtype=torch.float32, device=self.device).contiguous()
         for k in range(self.ratio):
             nz = None if noise is None else noise[2 * k:]
-            a.dogfight_physics(self.payload, actions=actions, noise=nz, first=(k == 0), aviary_index=k)
-            self._gather()
-            a.dogfight_combat(self.table, self.first_gid, self.num_arenas, last=int(k == self.ratio - 1))
+            table = self._physics(actions=actions, noise=nz, first=(k == 0), aviary_index=k)
+            a.dogfight_combat(table, self.first_gid, self.num_arenas, last=int(k == self.ratio - 1))
         return a.obs, a.reward, a.term.bool(), a.trunc.bool()
 
     def close(self) -> None:

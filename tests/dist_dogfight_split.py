@@ -26,10 +26,10 @@ def scenario(num_arenas, steps, seed=5):
     return pos, orn, nz0, acts, nz
 
 
-def run(num_arenas, steps, device, single_rank=False):
+def run(num_arenas, steps, device, single_rank=False, exchange="nccl"):
     pos, orn, nz0, acts, nz = scenario(num_arenas, steps)
     env = MAFixedwingDogfightSplitEnv(num_arenas, seed=3, device=device, lethal_distance=150.0, lethal_angle_radians=1.0, damage_per_hit=0.05,
-                                      single_rank=single_rank)
+                                      single_rank=single_rank, exchange=exchange)
     lo, hi = env.first_gid, env.first_gid + env.n_local
     dev = env.device
     out = [env.reset(pos, orn, noise=torch.as_tensor(nz0[:, lo:hi].copy(), device=dev)).clone()]
@@ -45,7 +45,8 @@ def main():
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
     dist.init_process_group("nccl")
     num_arenas, steps = 4096, 20
-    obs, rew, term, env = run(num_arenas, steps, f"cuda:{torch.cuda.current_device()}")
+    exchange = os.environ.get("PFB_SPLIT_EXCHANGE", "nccl")
+    obs, rew, term, env = run(num_arenas, steps, f"cuda:{torch.cuda.current_device()}", exchange=exchange)
     lo, hi = env.first_gid, env.first_gid + env.n_local
     # gather everything on every rank and compare with a local single-rank run of all agents
     def gather(x):
@@ -58,7 +59,7 @@ def main():
         assert torch.equal(g_obs, s_obs), float((g_obs - s_obs).abs().max())
         assert torch.equal(g_rew, s_rew) and torch.equal(g_term, s_term.to(torch.uint8))
         assert int(s_term.sum()) > 0
-        print(f"SPLIT_OK world={world} collectives={env.collectives} terminations={int(s_term[-1].sum())}")
+        print(f"SPLIT_OK world={world} exchange={exchange} collectives={env.collectives} terminations={int(s_term[-1].sum())}")
     dist.barrier()
     dist.destroy_process_group()
 
