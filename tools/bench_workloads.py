@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--only", default="")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"], help="dogfight-split: NCCL all-gather or peer stores + barrier")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -94,12 +95,12 @@ def main():
         env.close()
     if want("dogfight-split"):
         arenas = 8192 * world
-        env = MAFixedwingDogfightSplitEnv(arenas, seed=1, device=dev)
+        env = MAFixedwingDogfightSplitEnv(arenas, seed=1, device=dev, exchange=args.exchange)
         env.reset()
         act = torch.rand(env.n_local, 4, device=dev) * 2 - 1
         c0 = env.collectives
         ms = time_steps(lambda: env.step(act), K, W, dev, world)
-        report(f"MAFixedwingDogfight split: {arenas} arenas x 2 agents over {world} rank(s), all-gather of the payload table every Aviary step; value counts agent-steps",
+        report(f"MAFixedwingDogfight split: {arenas} arenas x 2 agents over {world} rank(s), exchange={args.exchange} every Aviary step; value counts agent-steps",
                env.n_local, ms, 8, {"collectives_per_step": 4, "payload_bytes_per_rank_per_collective": env.n_local * 80})
         env.close()
     if world > 1:
