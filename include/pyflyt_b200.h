@@ -265,9 +265,16 @@ int pfb_dogfight_physics(PfbHandle h, const float* actions, const float* noise, 
                          int aviary_index, void* stream);
 /* Fused exchange: as pfb_dogfight_physics, but every payload is stored straight into the payload table of EVERY rank
  * (peer_tables_dev: DEVICE array of `world` table base pointers, peer-mapped, e.g. torch symmetric memory) at float offset
- * slot_offset_floats + 20 * local_agent.  No all-gather: the caller follows with a cross-rank barrier on the stream.    */
+ * slot_offset_floats + 20 * local_agent.  No all-gather: the caller follows with a cross-rank barrier on the stream.
+ * With peer_flags_dev (DEVICE array of `world` peer-mapped int32[world] flag arrays, zero-initialised) the kernel also
+ * signals: when all of its peer stores are fenced it writes `epoch` into entry `rank` of every rank's flag array, and
+ * pfb_dogfight_combat_wait spins on its own array until all `world` entries have reached `epoch` — no barrier launch.
+ * `epoch` must increase by one per exchange.  peer_flags_dev = NULL: no signalling (the caller barriers).               */
 int pfb_dogfight_physics_peer(PfbHandle h, const float* actions, const float* noise, const uint64_t* peer_tables_dev, int world,
-                             int64_t slot_offset_floats, int first, int do_reset, int aviary_index, void* stream);
+                             int64_t slot_offset_floats, const uint64_t* peer_flags_dev, int rank, int epoch, int first, int do_reset,
+                             int aviary_index, void* stream);
+int pfb_dogfight_combat_wait(PfbHandle h, const float* payload_table, int64_t first_global_agent, int64_t num_arenas, int last,
+                             const int32_t* flags, int world, int epoch, void* stream);
 int pfb_dogfight_combat(PfbHandle h, const float* payload_table, int64_t first_global_agent, int64_t num_arenas, int last,
                         void* stream);
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches).                  */

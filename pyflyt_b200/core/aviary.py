@@ -269,13 +269,22 @@ class BatchedAviary:
         self._state_fresh = False
 
     def dogfight_physics_peer(self, peer_tables: torch.Tensor, world: int, slot_offset_floats: int, actions: torch.Tensor | None = None,
-                              noise: torch.Tensor | None = None, first: bool = False, do_reset: bool = False, aviary_index: int = 0) -> None:
+                              noise: torch.Tensor | None = None, first: bool = False, do_reset: bool = False, aviary_index: int = 0,
+                              peer_flags: torch.Tensor | None = None, rank: int = 0, epoch: int = 0) -> None:
         """Split dogfight, half 1 with the exchange fused in: every payload is stored straight into all ranks' tables
         (``peer_tables``: int64 device tensor of ``world`` peer-mapped base pointers)."""
         act = None if actions is None else C.c_void_p(actions.data_ptr())
         nz = None if noise is None else C.c_void_p(noise.data_ptr())
+        fl = None if peer_flags is None else C.c_void_p(peer_flags.data_ptr())
         _lib.check(_lib.lib().pfb_dogfight_physics_peer(self._h, act, nz, C.c_void_p(peer_tables.data_ptr()), int(world), int(slot_offset_floats),
-                                                        int(first), int(do_reset), int(aviary_index), self._s()))
+                                                        fl, int(rank), int(epoch), int(first), int(do_reset), int(aviary_index), self._s()))
+        self._state_fresh = False
+
+    def dogfight_combat_wait(self, table: torch.Tensor, first_global_agent: int, num_arenas: int, last: int, flags: torch.Tensor,
+                             world: int, epoch: int) -> None:
+        """Split dogfight, half 2, waiting in-kernel until every rank's physics kernel has raised its flag to ``epoch``."""
+        _lib.check(_lib.lib().pfb_dogfight_combat_wait(self._h, C.c_void_p(table.data_ptr()), int(first_global_agent), int(num_arenas), int(last),
+                                                       C.c_void_p(flags.data_ptr()), int(world), int(epoch), self._s()))
         self._state_fresh = False
 
     def dogfight_combat(self, table: torch.Tensor, first_global_agent: int, num_arenas: int, last: int) -> None:

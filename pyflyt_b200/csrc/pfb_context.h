@@ -163,8 +163,9 @@ int df_env_reset(PfbContext* h, const uint8_t* mask, const float* noise, cudaStr
 int df_env_step(PfbContext* h, float* actions, const float* noise, bool randact, cudaStream_t s);
 int df_spare_rows();
 int df_split_physics(PfbContext* h, const float* actions, const float* noise, float* payload, const uint64_t* peers, int world, int64_t slot0,
-                     int first, int do_reset, int sub, cudaStream_t s);
-int df_split_combat(PfbContext* h, const float* table, int64_t first_gid, int64_t num_arenas, int last, cudaStream_t s);
+                     const uint64_t* peer_flags, int rank, int epoch, int first, int do_reset, int sub, cudaStream_t s);
+int df_split_combat(PfbContext* h, const float* table, int64_t first_gid, int64_t num_arenas, int last, const int* wait_flags, int world, int epoch,
+                    cudaStream_t s);
 
 // QuadX-Waypoints translation unit (pfb_quadx_wp.cu)
 int qwp_state_rows();

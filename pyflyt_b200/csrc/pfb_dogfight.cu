@@ -584,10 +584,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
     k_df_split_physics(const __grid_constant__ FixedwingParams p, const __grid_constant__ DogfightParams d, const __grid_constant__ RngParams rng,
                        float* __restrict__ st, int32_t* __restrict__ ist, const float* __restrict__ actions, const float* __restrict__ noise,
                        const float* __restrict__ start_pos, const float* __restrict__ start_orn, float* __restrict__ payload,
-                       const uint64_t* __restrict__ peers, int world, int64_t slot0, int first, int do_reset, uint32_t seq, uint32_t sub,
-                       int64_t N) {
+                       const uint64_t* __restrict__ peers, int world, int64_t slot0, const uint64_t* __restrict__ peer_flags, int rank,
+                       int epoch, unsigned* __restrict__ ticket, int first, int do_reset, uint32_t seq, uint32_t sub, int64_t N) {
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-  if (i >= N) return;
+  if (i < N) {
   FixedwingRegs s;
   DfAgent ag;
   df_load_agent(st, ist, N, i, ag);
@@ -627,13 +627,41 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   } else {
     df_publish(s, ag, payload + (int64_t)kPayload * i);
   }
+  }  // i < N
+  if (peer_flags) {
+    // in-kernel signalling: once EVERY CTA's peer stores are fenced, the last CTA to finish raises this rank's flag in all
+    // ranks' flag arrays (release, system scope); the combat kernels wait on those flags instead of on a barrier launch
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned t = atomicAdd(ticket, 1u);
+      if (t == gridDim.x - 1) {
+        *ticket = 0u;
+        __threadfence_system();
+        for (int r = 0; r < world; ++r) {
+          int* flag = reinterpret_cast<int*>(peer_flags[r]) + rank;
+          asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+        }
+      }
+    }
+  }
 }
 
 // combat state for 1-vs-1 arenas from the gathered payload table [num_agents][kPayload]
 __global__ void __launch_bounds__(kBlock, kMinBlocks)
     k_df_split_combat(const __grid_constant__ DogfightParams d, float* __restrict__ st, int32_t* __restrict__ ist,
                       const float* __restrict__ table, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ term,
-                      uint8_t* __restrict__ trunc, uint8_t* __restrict__ info, int64_t first_gid, int64_t num_arenas, int last, int64_t N) {
+                      uint8_t* __restrict__ trunc, uint8_t* __restrict__ info, int64_t first_gid, int64_t num_arenas, int last,
+                      const int* __restrict__ wait_flags, int world, int epoch, int64_t N) {
+  if (wait_flags) {  // every rank's physics kernel has raised its flag for this exchange (acquire, system scope)
+    if ((int)threadIdx.x < world) {
+      int v;
+      do {
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(wait_flags + threadIdx.x) : "memory");
+      } while (v < epoch);
+    }
+    __syncthreads();
+  }
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (i >= N) return;
   const int64_t gid = first_gid + i;
@@ -737,25 +765,30 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
 }
 
 int df_split_physics(PfbContext* h, const float* actions, const float* noise, float* payload, const uint64_t* peers, int world,
-                     int64_t slot0, int first, int do_reset, int sub, cudaStream_t s) {
+                     int64_t slot0, const uint64_t* peer_flags, int rank, int epoch, int first, int do_reset, int sub, cudaStream_t s) {
   if (h->df.team_size != 1) return fail("the split (all-gather) dogfight path is built for team_size 1");
   const uint32_t seq = do_reset ? (0x80000000u | (uint32_t)h->reset_seq) : (uint32_t)h->step_seq;
   if (do_reset) h->reset_seq += 1;
   const int g = grid_for(h->n);
+  unsigned* ticket = reinterpret_cast<unsigned*>(h->d_counters) + 4;  // word 4 of the counter block: not part of the rotating queues
   if (noise)
     k_df_split_physics<true><<<g, kBlock, 0, s>>>(h->fw, h->df, h->rng, h->buf.state, h->buf.istate, actions, noise, h->buf.start_pos,
-                                                  h->buf.start_orn, payload, peers, world, slot0, first, do_reset, seq, (uint32_t)sub, h->n);
+                                                  h->buf.start_orn, payload, peers, world, slot0, peer_flags, rank, epoch, ticket, first, do_reset,
+                                                  seq, (uint32_t)sub, h->n);
   else
     k_df_split_physics<false><<<g, kBlock, 0, s>>>(h->fw, h->df, h->rng, h->buf.state, h->buf.istate, actions, nullptr, h->buf.start_pos,
-                                                   h->buf.start_orn, payload, peers, world, slot0, first, do_reset, seq, (uint32_t)sub, h->n);
+                                                   h->buf.start_orn, payload, peers, world, slot0, peer_flags, rank, epoch, ticket, first, do_reset,
+                                                   seq, (uint32_t)sub, h->n);
   LAUNCH_CHECK(h);
   return 0;
 }
 
-int df_split_combat(PfbContext* h, const float* table, int64_t first_gid, int64_t num_arenas, int last, cudaStream_t s) {
+int df_split_combat(PfbContext* h, const float* table, int64_t first_gid, int64_t num_arenas, int last, const int* wait_flags, int world,
+                    int epoch, cudaStream_t s) {
   if (h->df.team_size != 1) return fail("the split (all-gather) dogfight path is built for team_size 1");
+  if (wait_flags && (world < 1 || world > kBlock)) return fail("the in-kernel wait supports 1..%d ranks, got %d", kBlock, world);
   k_df_split_combat<<<grid_for(h->n), kBlock, 0, s>>>(h->df, h->buf.state, h->buf.istate, table, h->buf.obs, h->buf.reward, h->buf.term,
-                                                      h->buf.trunc, h->buf.info, first_gid, num_arenas, last, h->n);
+                                                      h->buf.trunc, h->buf.info, first_gid, num_arenas, last, wait_flags, world, epoch, h->n);
   LAUNCH_CHECK(h);
   if (last) h->step_seq += 1;
   return 0;

@@ -492,8 +492,8 @@ int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, i
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
-  CUDA_OK(cudaMalloc(&c->d_counters, 4 * sizeof(int32_t)));
-  CUDA_OK(cudaMemset(c->d_counters, 0, 4 * sizeof(int32_t)));
+  CUDA_OK(cudaMalloc(&c->d_counters, 8 * sizeof(int32_t)));  // [0..3] rotating autoreset counters, [4] ticket of the split dogfight
+  CUDA_OK(cudaMemset(c->d_counters, 0, 8 * sizeof(int32_t)));
   CUDA_OK(cudaMalloc(&c->d_done_list, 4 * (size_t)n_envs * sizeof(int32_t)));
   if (env && env->autoreset && (env->env_kind == PFB_ENV_QUADX_HOVER || env->env_kind == PFB_ENV_FIXEDWING_WAYPOINTS ||
                                  env->env_kind == PFB_ENV_QUADX_WAYPOINTS || env->env_kind == PFB_ENV_ROCKET_LANDING ||
@@ -788,23 +788,34 @@ int pfb_dogfight_physics(PfbHandle h, const float* actions, const float* noise, 
   REQUIRE_BOUND(h);
   if (!is_df(h)) return fail("handle is not a dogfight env");
   if (!payload_out) return fail("pfb_dogfight_physics: null payload buffer");
-  return df_split_physics(h, actions ? actions : h->buf.setpoint, noise, payload_out, nullptr, 0, 0, first, do_reset, aviary_index, (cudaStream_t)stream);
+  return df_split_physics(h, actions ? actions : h->buf.setpoint, noise, payload_out, nullptr, 0, 0, nullptr, 0, 0, first, do_reset, aviary_index,
+                          (cudaStream_t)stream);
 }
 
 int pfb_dogfight_physics_peer(PfbHandle h, const float* actions, const float* noise, const uint64_t* peer_tables_dev, int world,
-                             int64_t slot_offset_floats, int first, int do_reset, int aviary_index, void* stream) {
+                             int64_t slot_offset_floats, const uint64_t* peer_flags_dev, int rank, int epoch, int first, int do_reset,
+                             int aviary_index, void* stream) {
   REQUIRE_BOUND(h);
   if (!is_df(h)) return fail("handle is not a dogfight env");
   if (!peer_tables_dev || world < 1) return fail("pfb_dogfight_physics_peer: need the device array of peer table pointers");
-  return df_split_physics(h, actions ? actions : h->buf.setpoint, noise, nullptr, peer_tables_dev, world, slot_offset_floats, first, do_reset,
-                          aviary_index, (cudaStream_t)stream);
+  return df_split_physics(h, actions ? actions : h->buf.setpoint, noise, nullptr, peer_tables_dev, world, slot_offset_floats, peer_flags_dev, rank,
+                          epoch, first, do_reset, aviary_index, (cudaStream_t)stream);
 }
 
 int pfb_dogfight_combat(PfbHandle h, const float* payload_table, int64_t first_global_agent, int64_t num_arenas, int last, void* stream) {
   REQUIRE_BOUND(h);
   if (!is_df(h)) return fail("handle is not a dogfight env");
   if (require_env(h)) return -1;
-  return df_split_combat(h, payload_table, first_global_agent, num_arenas, last, (cudaStream_t)stream);
+  return df_split_combat(h, payload_table, first_global_agent, num_arenas, last, nullptr, 0, 0, (cudaStream_t)stream);
+}
+
+int pfb_dogfight_combat_wait(PfbHandle h, const float* payload_table, int64_t first_global_agent, int64_t num_arenas, int last,
+                             const int32_t* flags, int world, int epoch, void* stream) {
+  REQUIRE_BOUND(h);
+  if (!is_df(h)) return fail("handle is not a dogfight env");
+  if (require_env(h)) return -1;
+  if (!flags) return fail("pfb_dogfight_combat_wait: null flag array");
+  return df_split_combat(h, payload_table, first_global_agent, num_arenas, last, flags, world, epoch, (cudaStream_t)stream);
 }
 
 int64_t pfb_launch_count(PfbHandle h) { return h ? h->launches : 0; }

@@ -19,7 +19,8 @@ between the two kernels is a cross-rank barrier — no all-gather launch, no sta
     pfb_dogfight_physics_peer (peer stores)  ->  symmetric-memory barrier  ->  pfb_dogfight_combat
 
 The table is double-buffered by Aviary-step parity: a rank that runs ahead writes the other half while a slower rank
-still reads its own.
+still reads its own.  ``exchange="peer-signal"`` also removes the barrier launch: the last CTA of the physics kernel raises
+this rank's flag in every rank's (symmetric) flag array, and the combat kernel spins on its own array before it reads.
 """
 
 from __future__ import annotations
@@ -99,10 +100,10 @@ class MAFixedwingDogfightSplitEnv:
         self.ratio = cfg.env_step_ratio
         self.collectives = 0
         self._resets = 0
-        assert exchange in ("nccl", "peer")
+        assert exchange in ("nccl", "peer", "peer-signal")
         self.exchange = exchange
         self._symm = None
-        if exchange == "peer":
+        if exchange in ("peer", "peer-signal"):
             na = 2 * self.num_arenas
             if self.world > 1:
                 import torch.distributed._symmetric_memory as symm_mem
@@ -112,10 +113,18 @@ class MAFixedwingDogfightSplitEnv:
                 self._tables.zero_()
                 self._symm = symm_mem.rendezvous(self._tables, grp)
                 ptrs = [int(p) for p in self._symm.buffer_ptrs]
+                self._flags = symm_mem.empty((32,), dtype=torch.int32, device=self.device)
+                self._flags.zero_()
+                self._symm_flags = symm_mem.rendezvous(self._flags, grp)
+                fptrs = [int(p) for p in self._symm_flags.buffer_ptrs]
+                self._symm.barrier(channel=0)  # everybody's tables and flags are zeroed before anyone stores into them
             else:
                 self._tables = torch.zeros((2, na, PAYLOAD), dtype=torch.float32, device=self.device)
                 ptrs = [self._tables.data_ptr()]
+                self._flags = torch.zeros(32, dtype=torch.int32, device=self.device)
+                fptrs = [self._flags.data_ptr()]
             self._peers = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+            self._peer_flags = torch.tensor(fptrs, dtype=torch.int64, device=self.device)
 
     def _gather(self) -> None:
         if self.world > 1:
@@ -133,11 +142,21 @@ class MAFixedwingDogfightSplitEnv:
             return self.table
         phase = self.collectives & 1
         na = 2 * self.num_arenas
+        self.collectives += 1
+        if self.exchange == "peer-signal":
+            a.dogfight_physics_peer(self._peers, self.world, (phase * na + self.first_gid) * PAYLOAD, peer_flags=self._peer_flags, rank=self.rank,
+                                    epoch=self.collectives, **kw)
+            return self._tables[phase]
         a.dogfight_physics_peer(self._peers, self.world, (phase * na + self.first_gid) * PAYLOAD, **kw)
         if self._symm is not None:
             self._symm.barrier(channel=0)  # every rank's peer stores have landed; enqueued on the current stream
-        self.collectives += 1
         return self._tables[phase]
+
+    def _combat(self, table: torch.Tensor, last: int) -> None:
+        if self.exchange == "peer-signal":
+            self.aviary.dogfight_combat_wait(table, self.first_gid, self.num_arenas, last, self._flags, self.world, self.collectives)
+        else:
+            self.aviary.dogfight_combat(table, self.first_gid, self.num_arenas, last)
 
     def reset(self, start_pos=None, start_orn=None, noise=None):
         """Collective.  ``start_pos`` / ``start_orn``: [2 * num_arenas, 3] in global-agent order (all ranks pass the same)."""
@@ -149,7 +168,7 @@ class MAFixedwingDogfightSplitEnv:
         a.start_pos.copy_(torch.as_tensor(np.asarray(start_pos, dtype=np.float32)[sl], device=self.device))
         a.start_orn.copy_(torch.as_tensor(np.asarray(start_orn, dtype=np.float32)[sl], device=self.device))
         table = self._physics(noise=noise, do_reset=True)
-        a.dogfight_combat(table, self.first_gid, self.num_arenas, last=2)
+        self._combat(table, last=2)
         a.info_bits.zero_()
         return a.obs
 
@@ -160,7 +179,7 @@ class MAFixedwingDogfightSplitEnv:
         for k in range(self.ratio):
             nz = None if noise is None else noise[2 * k:]
             table = self._physics(actions=actions, noise=nz, first=(k == 0), aviary_index=k)
-            a.dogfight_combat(table, self.first_gid, self.num_arenas, last=int(k == self.ratio - 1))
+            self._combat(table, last=int(k == self.ratio - 1))
         return a.obs, a.reward, a.term.bool(), a.trunc.bool()
 
     def close(self) -> None:

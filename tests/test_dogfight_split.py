@@ -94,7 +94,7 @@ def test_split_matches_fused_arena_kernel():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+@pytest.mark.parametrize("exchange", ["nccl", "peer", "peer-signal"])
 def test_split_two_ranks(exchange):
     """Two ranks over NVLink: NCCL all-gather between the kernels, or the exchange fused into the physics kernel (peer
     stores into symmetric memory + barrier); both must equal the single-rank run bit for bit."""
@@ -103,7 +103,7 @@ def test_split_two_ranks(exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533" if exchange == "nccl" else "29534", os.path.join(HERE, "dist_dogfight_split.py")]
+           "--master-port", {"nccl": "29533", "peer": "29534", "peer-signal": "29535"}[exchange], os.path.join(HERE, "dist_dogfight_split.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, PFB_SPLIT_EXCHANGE=exchange))
     assert out.returncode == 0 and f"SPLIT_OK world=2 exchange={exchange}" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
@@ -117,5 +117,6 @@ def test_split_peer_exchange_single_rank_equals_nccl_path():
     from dist_dogfight_split import run
 
     a = run(1024, 20, "cuda:0", exchange="nccl")
-    b = run(1024, 20, "cuda:0", exchange="peer")
-    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    for ex in ("peer", "peer-signal"):
+        b = run(1024, 20, "cuda:0", exchange=ex)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]), ex

@@ -42,7 +42,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--only", default="")
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"], help="dogfight-split: NCCL all-gather or peer stores + barrier")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer", "peer-signal"], help="dogfight-split: NCCL all-gather or peer stores + barrier")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
