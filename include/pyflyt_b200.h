@@ -273,6 +273,12 @@ int pfb_dogfight_physics(PfbHandle h, const float* actions, const float* noise, 
 int pfb_dogfight_physics_peer(PfbHandle h, const float* actions, const float* noise, const uint64_t* peer_tables_dev, int world,
                              int64_t slot_offset_floats, const uint64_t* peer_flags_dev, int rank, int epoch, int first, int do_reset,
                              int aviary_index, void* stream);
+/* One whole env step (env_step_ratio x physics_peer + combat_wait) in a single call: with in-kernel signalling nothing
+ * between the kernels needs the host.  local_tables: this rank's [2][2*num_arenas][20] table, local_flags: its int32[world]
+ * flag array; epoch0: number of the step's first exchange (1-based, continuing the count of all earlier exchanges).       */
+int pfb_dogfight_split_step(PfbHandle h, const float* actions, const uint64_t* peer_tables_dev, const uint64_t* peer_flags_dev,
+                            const float* local_tables, const int32_t* local_flags, int world, int rank, int epoch0,
+                            int64_t first_global_agent, int64_t num_arenas, void* stream);
 int pfb_dogfight_combat_wait(PfbHandle h, const float* payload_table, int64_t first_global_agent, int64_t num_arenas, int last,
                              const int32_t* flags, int world, int epoch, void* stream);
 int pfb_dogfight_combat(PfbHandle h, const float* payload_table, int64_t first_global_agent, int64_t num_arenas, int last,

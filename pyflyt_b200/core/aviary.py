@@ -287,6 +287,14 @@ class BatchedAviary:
                                                        C.c_void_p(flags.data_ptr()), int(world), int(epoch), self._s()))
         self._state_fresh = False
 
+    def dogfight_split_step(self, actions: torch.Tensor, peer_tables: torch.Tensor, peer_flags: torch.Tensor, tables: torch.Tensor,
+                            flags: torch.Tensor, world: int, rank: int, epoch0: int, first_global_agent: int, num_arenas: int) -> None:
+        """A whole env step of the split dogfight (fused exchange, in-kernel signalling) in one library call."""
+        _lib.check(_lib.lib().pfb_dogfight_split_step(self._h, C.c_void_p(actions.data_ptr()), C.c_void_p(peer_tables.data_ptr()),
+                                                      C.c_void_p(peer_flags.data_ptr()), C.c_void_p(tables.data_ptr()), C.c_void_p(flags.data_ptr()),
+                                                      int(world), int(rank), int(epoch0), int(first_global_agent), int(num_arenas), self._s()))
+        self._state_fresh = False
+
     def dogfight_combat(self, table: torch.Tensor, first_global_agent: int, num_arenas: int, last: int) -> None:
         """Split dogfight, half 2: combat state from the all-gathered payload ``table`` [2 * num_arenas, 20]."""
         _lib.check(_lib.lib().pfb_dogfight_combat(self._h, C.c_void_p(table.data_ptr()), int(first_global_agent), int(num_arenas), int(last), self._s()))

@@ -818,6 +818,30 @@ int pfb_dogfight_combat_wait(PfbHandle h, const float* payload_table, int64_t fi
   return df_split_combat(h, payload_table, first_global_agent, num_arenas, last, flags, world, epoch, (cudaStream_t)stream);
 }
 
+// One whole env step of the split dogfight with the fused exchange: env_step_ratio x (physics with peer stores + in-kernel
+// signal, combat with in-kernel wait).  Nothing between the kernels needs the host, so the step is ONE call.
+int pfb_dogfight_split_step(PfbHandle h, const float* actions, const uint64_t* peer_tables_dev, const uint64_t* peer_flags_dev,
+                            const float* local_tables, const int32_t* local_flags, int world, int rank, int epoch0,
+                            int64_t first_global_agent, int64_t num_arenas, void* stream) {
+  REQUIRE_BOUND(h);
+  if (!is_df(h)) return fail("handle is not a dogfight env");
+  if (require_env(h)) return -1;
+  if (!peer_tables_dev || !peer_flags_dev || !local_tables || !local_flags) return fail("pfb_dogfight_split_step: null argument");
+  const int64_t na = 2 * num_arenas;
+  const int ratio = h->env.env_step_ratio;
+  for (int k = 0; k < ratio; ++k) {
+    const int epoch = epoch0 + k;          // exchange number, 1-based; its parity selects the half of the double-buffered table
+    const int phase = (epoch - 1) & 1;
+    if (df_split_physics(h, actions ? actions : h->buf.setpoint, nullptr, nullptr, peer_tables_dev, world, (phase * na + first_global_agent) * 20,
+                         peer_flags_dev, rank, epoch, k == 0, 0, k, (cudaStream_t)stream))
+      return -1;
+    if (df_split_combat(h, local_tables + phase * na * 20, first_global_agent, num_arenas, k == ratio - 1, local_flags, world, epoch,
+                        (cudaStream_t)stream))
+      return -1;
+  }
+  return 0;
+}
+
 int64_t pfb_launch_count(PfbHandle h) { return h ? h->launches : 0; }
 
 int pfb_profile_begin(PfbHandle h, int capacity) {

@@ -176,6 +176,11 @@ class MAFixedwingDogfightSplitEnv:
         """``actions`` [n_local, 4] for this rank's agents; ``noise`` (parity tests) [ratio * 2, n_local]."""
         a = self.aviary
         actions = torch.as_tensor(actions, dtype=torch.float32, device=self.device).contiguous()
+        if self.exchange == "peer-signal" and noise is None:  # nothing between the kernels needs the host: one call
+            a.dogfight_split_step(actions, self._peers, self._peer_flags, self._tables, self._flags, self.world, self.rank, self.collectives + 1,
+                                  self.first_gid, self.num_arenas)
+            self.collectives += self.ratio
+            return a.obs, a.reward, a.term.bool(), a.trunc.bool()
         for k in range(self.ratio):
             nz = None if noise is None else noise[2 * k:]
             table = self._physics(actions=actions, noise=nz, first=(k == 0), aviary_index=k)
