@@ -26,10 +26,11 @@ for _ in range(40):
     ma.step(torch.rand(ma.num_agents, 4, device=ma.device) * 2 - 1)
 torch.cuda.synchronize()
 ma.close()
-env = MAFixedwingDogfightSplitEnv(64, seed=1)
-env.reset()
-for _ in range(5):
-    env.step(torch.zeros(env.n_local, 4, device=env.device))
-torch.cuda.synchronize()
-env.close()
+for ex in ("nccl", "peer", "peer-signal"):
+    env = MAFixedwingDogfightSplitEnv(64, seed=1, exchange=ex)
+    env.reset()
+    for _ in range(5):
+        env.step(torch.zeros(env.n_local, 4, device=env.device))
+    torch.cuda.synchronize()
+    env.close()
 print("SANITIZE_SMOKE_DONE")
