@@ -267,6 +267,23 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     warm_ms = e0.elapsed_time(e1)
 
+    # ---- timed region A3 (context): the same flushed measurement with every reset integrated INSIDE the step launch
+    #      (inline_reset=True: no spare states, no side-stream rebuild), i.e. all of a step's work between its event pair
+    env_in = QuadXHoverVecEnv(num_envs=n, seed=args.seed, device=dev, env_offset=rank * n, inline_reset=True)
+    env_in.reset()
+    for k in range(max(W, 30)):  # past the first terminations, so that resets are in the timed steps
+        env_in.aviary.env_step(actions=actions[k % pool])
+    barrier()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for k in range(K):
+        flush.fill_(float(k))
+        ev2[k][0].record()
+        env_in.aviary.env_step(actions=actions[(W + k) % pool])
+        ev2[k][1].record()
+    barrier()
+    inline_ms = float(sum(a.elapsed_time(b) for a, b in ev2))
+    env_in.close()
+
     # ---- timed region B: end to end through the host-buffer entry of the C-ABI (pinned host memory)
     act_h = [actions[k].cpu().pin_memory() for k in range(4)]
     # one pinned slab, obs | reward | term | trunc back to back like the device side: the library returns it in one D2H copy
@@ -284,10 +301,10 @@ def run_ours(args, rank, local_rank, world):
     clocks = sampler.stop()
 
     # ---- reduce: max over ranks
-    t = torch.tensor([total_ms, warm_ms, e2e_s * 1e3, float(sum(kern_ms))], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, warm_ms, e2e_s * 1e3, float(sum(kern_ms)), inline_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, warm_ms, e2e_ms, kern_total_ms = (float(x) for x in t.tolist())
+    total_ms, warm_ms, e2e_ms, kern_total_ms, inline_ms = (float(x) for x in t.tolist())
     if rank == 0:
         peak, peak_src = load_peaks()
         value = world * n * K / (total_ms * 1e-3)
@@ -303,6 +320,8 @@ def run_ours(args, rank, local_rank, world):
                 "l2": "flushed between timed steps (256 MiB write outside the event pairs); per-step CUDA-event pairs summed",
                 "precision": "fp32 forces/control/obs; quaternion, position, velocity carried as fp64 (hi+lo fp32 words in HBM)",
                 "value_l2_warm": world * n * K / (warm_ms * 1e-3), "ms_per_step_l2_warm": warm_ms / K,
+                "value_inline_resets": world * n * K / (inline_ms * 1e-3), "ms_per_step_inline_resets": inline_ms / K,
+                "reset_pipeline": "finished envs take a spare post-reset state inside the step launch; the spares consumed are rebuilt by a second launch of the same kernel on a side stream, concurrently with the next step (here: with the L2 flush). Both launches are counted in gpu_launches; the rebuild is inside the back-to-back measurement (value_l2_warm) and outside the per-step event pairs of `value`; value_inline_resets is the same flushed measurement with every reset integrated inside the step launch",
             },
             "e2e": {
                 "value": world * n * K / (e2e_ms * 1e-3), "unit": "env-steps/s",
