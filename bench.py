@@ -269,7 +269,7 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- timed region A3 (context): the same flushed measurement with every reset integrated INSIDE the step launch
     #      (inline_reset=True: no spare states, no side-stream rebuild), i.e. all of a step's work between its event pair
-    env_in = QuadXHoverVecEnv(num_envs=n, seed=args.seed, device=dev, env_offset=rank * n, inline_reset=True)
+    env_in = QuadXHoverVecEnv(num_envs=n, seed=args.seed, device=dev, env_offset=rank * n, inline_reset=2)
     env_in.reset()
     for k in range(max(W, 30)):  # past the first terminations, so that resets are in the timed steps
         env_in.aviary.env_step(actions=actions[k % pool])

@@ -163,8 +163,10 @@ typedef struct PfbEnvConfig {
   /* MAFixedwingDogfight (pz_envs/fixedwing_envs/ma_fixedwing_dogfight_env.py:42-62): an arena is
    * 2*team_size CONSECUTIVE envs of the batch; the first team_size of them are team 0                 */
   int32_t team_size;
-  int32_t inline_reset;      /* QuadX-Hover autoreset: 1 = integrate every warm-up inside the step launch instead of
-                              * copying the env's spare post-reset state (same results, longer launches; tests)  */
+  int32_t inline_reset;      /* autoreset: 1 = integrate every warm-up inside the step launch instead of copying the env's
+                              * spare post-reset state (same results, longer launches; tests).  QuadX-Hover also takes 2 =
+                              * spares as usual, but rebuilt on the CALLER's stream right behind the step launch (no side
+                              * stream: all of a step's work is in order on one stream)                              */
   double damage_per_hit, lethal_distance, lethal_angle, aggressiveness, cooperativeness;
   double spawn_min_radius, spawn_max_radius, spawn_min_height, spawn_max_height;
 } PfbEnvConfig;
@@ -213,6 +215,15 @@ int pfb_set_env_offset(PfbHandle h, uint64_t first_global_env);
 
 /* Shapes the caller must allocate. */
 int pfb_state_rows(PfbHandle h);     /* F of PfbBuffers.state                                         */
+/* Layout of PfbBuffers.state.  FIELD_MAJOR: [F][N], word (row r, env i) at r*N + i (fixed-wing, rocket, QuadX-Waypoints).
+ * WARP_TILED (every other QuadX handle): env i lives in tile i/32, lane i%32; a tile is F/4 groups of 32 lanes x 4 words:
+ * word (r, i) at (((i/32) * (F/4) + r/4) * 32 + i%32) * 4 + r%4.  A warp moves a group with one 128-bit access per lane,
+ * and the rows an env step touches are one contiguous block per tile.  pfb_state_floats() is the number of floats to
+ * allocate (tiles are padded to 32 envs); step_count and the flag word live in rows 17 / 18 of the tile as int32 bits.  */
+#define PFB_LAYOUT_FIELD_MAJOR 0
+#define PFB_LAYOUT_WARP_TILED 1
+int pfb_state_layout(PfbHandle h);
+int64_t pfb_state_floats(PfbHandle h);
 int pfb_istate_rows(PfbHandle h);    /* I of PfbBuffers.istate                                        */
 int pfb_setpoint_dim(PfbHandle h);   /* S                                                             */
 int pfb_obs_dim(PfbHandle h);        /* O                                                             */
@@ -283,6 +294,10 @@ int pfb_dogfight_combat_wait(PfbHandle h, const float* payload_table, int64_t fi
                              const int32_t* flags, int world, int epoch, void* stream);
 int pfb_dogfight_combat(PfbHandle h, const float* payload_table, int64_t first_global_agent, int64_t num_arenas, int last,
                         void* stream);
+/* Test / audit aid: device buffer [env_step_ratio * updates_per_step][N] (or NULL = off) that receives every motor-noise
+ * draw the QuadX-Hover step kernel hands out on the following pfb_env_step calls (overwritten per call): lets a test replay
+ * the Philox stream of the timed instantiation through the CPU oracle.                                                  */
+int pfb_set_noise_dump(PfbHandle h, float* dump);
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches).                  */
 int64_t pfb_launch_count(PfbHandle h);
 /* Measurement aid: record a CUDA-event pair around the dominant kernel of each of the next

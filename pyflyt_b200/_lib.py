@@ -65,8 +65,11 @@ def lib() -> C.CDLL:
     L.pfb_create.argtypes = [vp, vp, i64, i32, u64, C.POINTER(vp)]
     L.pfb_destroy.argtypes = [vp]
     L.pfb_set_env_offset.argtypes = [vp, u64]
-    for name in ("pfb_state_rows", "pfb_istate_rows", "pfb_setpoint_dim", "pfb_obs_dim", "pfb_aux_dim"):
+    for name in ("pfb_state_rows", "pfb_istate_rows", "pfb_setpoint_dim", "pfb_obs_dim", "pfb_aux_dim", "pfb_state_layout"):
         getattr(L, name).argtypes = [vp]
+    L.pfb_state_floats.restype = i64
+    L.pfb_state_floats.argtypes = [vp]
+    L.pfb_set_noise_dump.argtypes = [vp, vp]
     L.pfb_bind.argtypes = [vp, vp]
     L.pfb_reset.argtypes = [vp, vp, vp]
     L.pfb_set_mode.argtypes = [vp, i32, vp]
@@ -99,7 +102,8 @@ def check(rc: int) -> None:
 
 EXPORTS = [
     "pfb_last_error", "pfb_abi_version", "pfb_sizeof_model", "pfb_sizeof_env_config", "pfb_sizeof_buffers",
-    "pfb_create", "pfb_destroy", "pfb_set_env_offset", "pfb_state_rows", "pfb_istate_rows", "pfb_setpoint_dim",
+    "pfb_create", "pfb_destroy", "pfb_set_env_offset", "pfb_state_rows", "pfb_state_layout", "pfb_state_floats", "pfb_set_noise_dump",
+    "pfb_istate_rows", "pfb_setpoint_dim",
     "pfb_obs_dim", "pfb_aux_dim", "pfb_bind", "pfb_reset", "pfb_set_mode", "pfb_aviary_step", "pfb_observe_state",
     "pfb_set_base_velocity",
     "pfb_env_reset", "pfb_env_step", "pfb_env_rollout", "pfb_env_step_host", "pfb_launch_count",

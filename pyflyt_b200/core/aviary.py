@@ -90,8 +90,13 @@ class BatchedAviary:
         self.obs_dim = L.pfb_obs_dim(self._h)
         self.setpoint_dim = L.pfb_setpoint_dim(self._h)
         self.aux_dim = L.pfb_aux_dim(self._h)
-        # persistent state, SoA [F][N]
-        self.state_tensor = torch.zeros((L.pfb_state_rows(self._h), n), **f32)
+        # persistent state: fp32 SoA, field-major [F][N] or warp-tiled [N/32][F/4][32][4] (include/pyflyt_b200.h)
+        self.state_rows = int(L.pfb_state_rows(self._h))
+        self.tiled = int(L.pfb_state_layout(self._h)) == 1
+        if self.tiled:
+            self.state_tensor = torch.zeros((int(L.pfb_state_floats(self._h)) // (self.state_rows * 32), self.state_rows // 4, 32, 4), **f32)
+        else:
+            self.state_tensor = torch.zeros((self.state_rows, n), **f32)
         self.istate_tensor = torch.zeros((L.pfb_istate_rows(self._h), n), dtype=torch.int32, device=dev)
         self.setpoints = torch.zeros((n, self.setpoint_dim), **f32)
         self.start_pos = torch.from_numpy(start_pos).to(dev).contiguous()
@@ -212,6 +217,34 @@ class BatchedAviary:
         """(N,) bool: ground contact during the last step (aviary.py:322, 523-525, per world)."""
         self._refresh()
         return self._contact.bool()
+
+    # ------------------------------------------------------------------ raw state access (tests, debugging)
+    def state_row(self, row: int) -> torch.Tensor:
+        """[N] fp32 copy-free view (field-major) or gathered copy (warp-tiled) of state row ``row``."""
+        if not self.tiled:
+            return self.state_tensor[row]
+        return self.state_tensor[:, row // 4, :, row % 4].reshape(-1)[: self.num_drones]
+
+    def state_row_int(self, row: int) -> torch.Tensor:
+        """[N] int32: a row that holds integer bits (warp-tiled layout: 17 = step_count, 18 = flags)."""
+        return self.state_row(row).contiguous().view(torch.int32)
+
+    @property
+    def precise_positions(self) -> torch.Tensor:
+        """(N, 3) float64 world positions as the kernels carry them: hi + lo fp32 words of the state tensor."""
+        lo = {"quadx": 25, "fixedwing": 19, "rocket": 22}[self.drone_type]
+        return torch.stack([self.state_row(k).double() + self.state_row(lo + k).double() for k in range(3)], dim=1)
+
+    @property
+    def step_counts(self) -> torch.Tensor:
+        """[N] int32 env step counters."""
+        return self.state_row_int(17) if self.tiled else self.istate_tensor[0]
+
+    def set_noise_dump(self, buf: torch.Tensor | None) -> None:
+        """Test aid: ``buf`` [env_step_ratio * updates_per_step, N] fp32 receives every motor-noise draw of the following
+        QuadX-Hover ``env_step`` calls (None = off)."""
+        self._noise_dump = buf
+        _lib.check(_lib.lib().pfb_set_noise_dump(self._h, None if buf is None else C.c_void_p(buf.data_ptr())))
 
     @property
     def launch_count(self) -> int:

@@ -59,6 +59,7 @@ struct PfbContext {
   cudaEvent_t ev_spare[4]; // ev_spare[k % 4]: spares consumed by step k are rebuilt; step k + 2 waits on it
   int64_t side_launches;
   // optional per-step CUDA-event pairs around the dominant kernel (bench.py's roofline leg)
+  float* noise_dump;      // optional [substeps per env step][N] device buffer: the step kernel writes every noise draw it hands out (tests)
   cudaEvent_t* prof_ev;   // [2 * prof_cap]
   int prof_cap;
   int prof_n;

@@ -33,8 +33,32 @@ int pfb_fail(const char* fmt, ...) {
 // ---------------------------------------------------------------------------------------------------
 // kernels — Aviary surface
 // ---------------------------------------------------------------------------------------------------
+// QuadX handles keep their state WARP-TILED (pfb_quadx.cuh) except QuadX-Waypoints, whose kernels (pfb_quadx_wp.cu) still use
+// the field-major [F][N] rows + istate; TILED selects the addressing of the kernels both layouts share.
+template <int MODE, bool TILED>
+__device__ __forceinline__ void qx_load_any(const float* __restrict__ st, const int32_t* __restrict__ ist, int rows, int64_t N, int64_t i,
+                                            QuadXRegs& s, int& step_count) {
+  if (TILED) {
+    quadx_load_tile<MODE, kTileGroupStride>(st + qx_tile_base(i, rows), s, step_count);
+  } else {
+    quadx_load<MODE>(st, ist, N, i, s);
+    step_count = ist[(int64_t)QI_STEP * N + i];
+  }
+}
+template <int MODE, bool TILED>
+__device__ __forceinline__ void qx_store_any(float* __restrict__ st, int32_t* __restrict__ ist, int rows, int64_t N, int64_t i,
+                                             const QuadXRegs& s, int step_count) {
+  if (TILED) {
+    quadx_store_tile<MODE, kTileGroupStride>(st + qx_tile_base(i, rows), s, step_count);
+  } else {
+    quadx_store<MODE>(st, ist, N, i, s);
+    ist[(int64_t)QI_STEP * N + i] = step_count;
+  }
+}
+
 // Aviary.reset + QuadX.reset + update_state (aviary.py:218-312, quadx.py:222-231)
-__global__ void __launch_bounds__(kBlock) k_quadx_reset(float* __restrict__ st, int32_t* __restrict__ ist,
+template <bool TILED>
+__global__ void __launch_bounds__(kBlock) k_quadx_reset(float* __restrict__ st, int32_t* __restrict__ ist, int rows,
                                                         float* __restrict__ setpoint, const float* __restrict__ start_pos,
                                                         const float* __restrict__ start_orn,
                                                         const uint8_t* __restrict__ mask, int64_t N) {
@@ -44,51 +68,54 @@ __global__ void __launch_bounds__(kBlock) k_quadx_reset(float* __restrict__ st, 
   QuadXRegs s;
   quadx_reset(s, start_pos[3 * i + 0], start_pos[3 * i + 1], start_pos[3 * i + 2], start_orn[3 * i + 0],
               start_orn[3 * i + 1], start_orn[3 * i + 2]);
-  quadx_store<7>(st, ist, N, i, s);  // mode 7 touches every PID row
-  ist[(int64_t)QI_STEP * N + i] = 0;
+  qx_store_any<7, TILED>(st, ist, rows, N, i, s, 0);  // mode 7 touches every PID row
   if (setpoint) reinterpret_cast<float4*>(setpoint)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // Aviary.set_mode -> QuadX.set_mode (quadx.py:233-373): preset the setpoint, fresh attitude/position PIDs
-template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_quadx_set_mode(float* __restrict__ st, int32_t* __restrict__ ist,
+template <int MODE, bool TILED>
+__global__ void __launch_bounds__(kBlock) k_quadx_set_mode(float* __restrict__ st, int32_t* __restrict__ ist, int rows,
                                                            float* __restrict__ setpoint, int64_t N) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   QuadXRegs s;
-  quadx_load<7>(st, ist, N, i, s);
+  int step_count;
+  qx_load_any<7, TILED>(st, ist, rows, N, i, s, step_count);
   float4 sp = reinterpret_cast<const float4*>(setpoint)[i];
   s.sp[0] = sp.x; s.sp[1] = sp.y; s.sp[2] = sp.z; s.sp[3] = sp.w;
   quadx_set_mode<MODE>(s);
-  quadx_store<7>(st, ist, N, i, s);
+  qx_store_any<7, TILED>(st, ist, rows, N, i, s, step_count);
   reinterpret_cast<float4*>(setpoint)[i] = make_float4(s.sp[0], s.sp[1], s.sp[2], s.sp[3]);
 }
 
 // n_steps x Aviary.step() (aviary.py:480-531)
-template <int MODE, bool INJECT>
+template <int MODE, bool INJECT, bool TILED>
 __global__ void __launch_bounds__(kBlock, kMinBlocks)
     k_quadx_aviary_step(const __grid_constant__ QuadXParams p, const __grid_constant__ RngParams rng,
-                        float* __restrict__ st, int32_t* __restrict__ ist, const float* __restrict__ setpoint,
+                        float* __restrict__ st, int32_t* __restrict__ ist, int rows, const float* __restrict__ setpoint,
                         const float* __restrict__ noise, int n_steps, uint32_t seq, int64_t N) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   QuadXRegs s;
-  quadx_load<MODE>(st, ist, N, i, s);
+  int step_count;
+  qx_load_any<MODE, TILED>(st, ist, rows, N, i, s, step_count);
   float4 sp = __ldg(reinterpret_cast<const float4*>(setpoint) + i);
   s.sp[0] = sp.x; s.sp[1] = sp.y; s.sp[2] = sp.z; s.sp[3] = sp.w;
   auto nz = make_noise<INJECT>(noise, N, i, rng, seq, TAG_AVIARY, p.noise_loc, p.ratio);
   for (int k = 0; k < n_steps; ++k) quadx_aviary_step<MODE>(p, s, nz);
-  quadx_store<MODE>(st, ist, N, i, s);
+  qx_store_any<MODE, TILED>(st, ist, rows, N, i, s, step_count);
 }
 
 // Aviary.state(i) / aux_state(i) / contact_array  -> row-major API buffers
-__global__ void __launch_bounds__(kBlock) k_quadx_observe(const float* __restrict__ st, const int32_t* __restrict__ ist,
+template <bool TILED>
+__global__ void __launch_bounds__(kBlock) k_quadx_observe(const float* __restrict__ st, const int32_t* __restrict__ ist, int rows,
                                                           float* __restrict__ drone_state, float* __restrict__ aux,
                                                           uint8_t* __restrict__ contact, int64_t N) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   QuadXRegs s;
-  quadx_load<-1>(st, ist, N, i, s);
+  int step_count;
+  qx_load_any<-1, TILED>(st, ist, rows, N, i, s, step_count);
   float o[12], a[4];
   quadx_drone_state(s, o, a);
   if (drone_state) {
@@ -102,287 +129,253 @@ __global__ void __launch_bounds__(kBlock) k_quadx_observe(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------
-// kernels — QuadX-Hover env
+// kernels — QuadX-Hover env (warp-tiled state)
 // ---------------------------------------------------------------------------------------------------
-constexpr int kObsStride = 24;  // floats of shared memory per env for the observation tile (rows are packed at stride O <= 24)
-// 640 threads per SM resident (<= 96 registers): the regular + tail CTAs of a 65 536-env step and the CTAs of the
-// concurrent spare rebuild must all be resident at once, or the stragglers form a second wave
-constexpr int kHoverBlocks = 640 / kBlock;
+// 512 threads per SM resident (<= 128 registers): the 2048 CTAs of a 65 536-env step and the 148 of the concurrent spare rebuild
+// must all be resident at once, or the stragglers form a second wave
+constexpr int kHoverBlocks = 512 / kBlock;
+constexpr int kObsMax = 24;  // floats per observation row (20 / 21, + 3 for MAQuadXHover)
 
 // ---- spare post-reset states ("reset pipeline") ---------------------------------------
 // env.reset() = start pose + `warmup_steps` Aviary steps (quadx_base_env.py:149-212): 3.3x the work of an env step and a
-// strictly serial chain; reset inline, even one finished env stretches the launch to the length of that chain.  So each
-// env owns a SPARE, the post-warm-up state of its NEXT episode, with noise keyed by (env id, episode number, Aviary
-// step) so that it does not matter when it is computed.  The step kernel's tail CTAs only COPY the spare of a finished
-// env; a second launch of the SAME kernel in build mode (all CTAs are tail CTAs, same compiled warm-up loop, hence
-// bit-identical results) rebuilds the spares just consumed on a side stream, concurrently with the following step
-// launches (the step two launches later waits for it: an env cannot finish again sooner).  If the start pose was
-// edited since a spare was built it is ignored and the warm-up runs inline (same episode number, same result).
-// Library-owned buffer [N][SP_ROWS], ENV-MAJOR (a 256-byte record per env: a tail thread touches 2-3 lines of DRAM instead of
-// one 32-byte sector per field; measured 9 MB -> ~1 MB of DRAM reads per launch with ~2200 resets): words [0, QX_ROWS) the
-// spare's state, then:
-enum { SP_POSE = QX_ROWS, SP_VALID = QX_ROWS + 6, SP_FLAGS = QX_ROWS + 7, SP_EPISODE = QX_ROWS + 8, SP_ROWS = 64 };
-static_assert(QX_ROWS + 9 <= SP_ROWS, "spare record too small");
+// strictly serial chain; run inline, even one finished env stretches the launch to the length of that chain.  So each env
+// owns a SPARE, the post-warm-up state of its NEXT episode, with the warm-up noise keyed by (env id, episode number,
+// Aviary step) so that it does not matter when it is computed.  An env that finished on call k is reset on call k + 1 BY ITS
+// OWN THREAD: the thread skips the physics loop and, at the end of the launch, swaps the env's spare record in (prefetched
+// into L2 at the top of the launch) — no separate reset CTAs, no queue on the step's critical path, every observation row of
+// a warp's tile is written by that warp.  The envs that finish are appended to a list; k_hover_spare_build rebuilds the
+// spares that were consumed, on a side stream, concurrently with the following step launches (the step two launches later
+// waits for it: an env cannot finish again sooner).  If the start pose was edited since a spare was built, or with
+// inline_reset = 1, the spare is ignored and the warm-up runs inline in the owning thread (same episode number, same result).
+// Library-owned buffer [N][SP_ROWS], ENV-MAJOR records: the QX_* state rows in record layout (group stride 4), then:
+enum { SP_POSE = QX_ROWS, SP_VALID = QX_ROWS + 6, SP_FLAGS = QX_ROWS + 7, SP_EPISODE = QX_ROWS + 8, SP_ROWS = 80 };
+static_assert(QX_ROWS % 4 == 0 && QX_ROWS + 12 <= SP_ROWS && SP_ROWS % 4 == 0, "spare record layout");
 
-__device__ __forceinline__ bool spare_usable(const float* __restrict__ spare, const float* __restrict__ start_pos,
-                                             const float* __restrict__ start_orn, int64_t N, int64_t i) {
-  const float* c = spare + i * SP_ROWS + SP_POSE;
-  bool ok = c[6] != 0.0f;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) ok = ok && (c[k] == start_pos[3 * i + k]) && (c[3 + k] == start_orn[3 * i + k]);
-  return ok;
+// cp.async.bulk (TMA, 1-D) shared -> global: one instruction moves a warp's whole observation tile
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+  const uint32_t sa = (uint32_t)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// the pose rows are written by the caller at reset time, from the very values the warm-up started from (the user may
-// edit start_pos / start_orn while a rebuild is in flight on the side stream)
-template <int MODE>
-__device__ __forceinline__ void spare_store(float* __restrict__ spare, int32_t* __restrict__ ist, int64_t N, int64_t i,
-                                            const QuadXRegs& s, uint32_t episode) {
-  quadx_store<MODE>(spare + i * SP_ROWS, ist, N, i, s, false, 1, 0);
-  float* c = spare + i * SP_ROWS + SP_POSE;
-  c[7] = __uint_as_float(s.flags);
-  c[8] = __uint_as_float(episode);
-  c[6] = 1.0f;
-}
-
-// row of element j in a dense [rows][O] tile; O is one of the four observation widths (constant divisors, no idiv)
-__device__ __forceinline__ int obs_row(int j, int O) { return O == 21 ? j / 21 : (O == 20 ? j / 20 : (O == 24 ? j / 24 : j / 23)); }
-
-// env.reset() body for one env: begin_reset + end_reset (quadx_base_env.py:149-212); obs -> `out`
+// env.reset() integrated inline: start pose, set_mode, warm-up Aviary steps (quadx_base_env.py:149-212).  Everything by
+// value: the caller's register-resident state never has its address taken (this is the COLD path of the step kernel and
+// the body of the reset / spare-build kernels).
 template <int MODE, bool INJECT>
-__device__ __forceinline__ void hover_reset_env(const QuadXParams& p, const HoverParams& h, const RngParams& rng,
-                                                float* __restrict__ st, int32_t* __restrict__ ist,
-                                                const float* __restrict__ start_pos, const float* __restrict__ start_orn,
-                                                const float* __restrict__ noise, uint32_t seq, int64_t N, int64_t i,
-                                                float* out) {
+__device__ __noinline__ QuadXRegs hover_warmup(const QuadXParams p, int warmup_steps, const RngParams rng, const float* __restrict__ noise,
+                                               int64_t N, int64_t i, uint32_t seq, float px, float py, float pz, float ox, float oy, float oz) {
   QuadXRegs s;
-  quadx_reset(s, start_pos[3 * i + 0], start_pos[3 * i + 1], start_pos[3 * i + 2], start_orn[3 * i + 0],
-              start_orn[3 * i + 1], start_orn[3 * i + 2]);
+  quadx_reset(s, px, py, pz, ox, oy, oz);
   quadx_set_mode<MODE>(s);
   auto nz = make_noise<INJECT>(noise, N, i, rng, seq, TAG_RESET, p.noise_loc, p.ratio);
-  for (int k = 0; k < h.warmup_steps; ++k) quadx_aviary_step<MODE>(p, s, nz);
-  const float zero[4] = {0.f, 0.f, 0.f, 0.f};  // self.action = zeros (quadx_base_env.py:165)
-  if (h.ma) {  // past_actions is NOT cleared by a reset in the reference: it still holds the previous episode's value
-    float past[4];
-    for (int k = 0; k < 4; ++k) past[k] = st[(int64_t)(QM_PAST + k) * N + i];
-    ma_hover_observation(h, s, past, start_pos[3 * i], start_pos[3 * i + 1], start_pos[3 * i + 2], out);
-  } else {
-    hover_observation(h, s, zero, out);
-  }
-  quadx_store<7>(st, ist, N, i, s);
-  ist[(int64_t)QI_STEP * N + i] = 0;
+#pragma unroll 1
+  for (int k = 0; k < warmup_steps; ++k) quadx_aviary_step<MODE>(p, s, nz);
+  return s;
 }
 
-// env.step(action) for every env (quadx_base_env.py:269-301 + quadx_hover_env.py), ONE launch.
+// env.step(action) for every env (quadx_base_env.py:269-301 + quadx_hover_env.py), ONE launch, one warp per CTA, one tile
+// of 32 envs per warp.
 //   RANDACT   actions are drawn on device, uniform in the env's action box (quadx_base_env.py:79-102)
-//   AUTORESET gymnasium NEXT_STEP autoreset: an env that finished on the previous call is reset on this
-//             one (its action is ignored; obs = first observation, reward 0, flags cleared).  Those envs
-//             were queued by the previous launch and are handled by dense "tail" CTAs placed at the
-//             front of the grid, so the 10 warm-up Aviary steps run in full warps concurrently with the
-//             regular CTAs instead of diverging inside them.
-// Both roles run the SAME code (role-dependent scalars only): the kernel is instruction-fetch bound, so one
-// compact hot loop shared by every warp on the SM matters more than anything else.
-template <int MODE, bool INJECT, bool RANDACT, bool AUTORESET>
+//   AUTORESET gymnasium NEXT_STEP autoreset: an env that finished on the previous call is reset on this one (its action
+//             is ignored; obs = first observation of the new episode, reward 0, flags cleared)
+template <int MODE, bool INJECT, bool RANDACT, bool AUTORESET, bool MA>
 __global__ void __launch_bounds__(kBlock, kHoverBlocks)
     k_hover_step(const __grid_constant__ QuadXParams p, const __grid_constant__ HoverParams h,
-                 const __grid_constant__ RngParams rng, float* __restrict__ st, int32_t* __restrict__ ist,
-                 float* __restrict__ actions, const float* __restrict__ noise, float* __restrict__ obs,
-                 float* __restrict__ reward, uint8_t* __restrict__ term, uint8_t* __restrict__ trunc,
-                 uint8_t* __restrict__ info, const float* __restrict__ start_pos, const float* __restrict__ start_orn,
-                 const int32_t* __restrict__ prev_count, const int32_t* __restrict__ prev_list,
-                 int32_t* __restrict__ cur_count, int32_t* __restrict__ cur_list, int32_t* __restrict__ next_count,
-                 float* __restrict__ spare, int spare_copy, int build, int tail_blocks, uint32_t step_seq, int64_t N) {
-  __shared__ __align__(16) float smem[kBlock * kObsStride];
-  __shared__ uint8_t row_skip[kBlock];
-  const int O = (h.angle_representation == 0 ? 20 : 21) + (h.ma ? 3 : 0);
-  const bool tail = AUTORESET && (int)blockIdx.x < tail_blocks;  // CTA-uniform role
-  const int64_t block_first = tail ? 0 : (int64_t)((int)blockIdx.x - (AUTORESET ? tail_blocks : 0)) * kBlock;
+                 const __grid_constant__ RngParams rng, float* __restrict__ st, int rows, float* __restrict__ actions,
+                 const float* __restrict__ noise, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ term,
+                 uint8_t* __restrict__ trunc, uint8_t* __restrict__ info, const float* __restrict__ start_pos,
+                 const float* __restrict__ start_orn, int32_t* __restrict__ cur_count, int32_t* __restrict__ cur_list,
+                 int32_t* __restrict__ next_count, const float* __restrict__ spare, int spare_copy, float* __restrict__ noise_dump,
+                 uint32_t step_seq, int64_t N) {
+  __shared__ __align__(128) float smem[kBlock * kObsMax];
+  const int O = (h.angle_representation == 0 ? 20 : 21) + (MA ? 3 : 0);
+  const int lane = threadIdx.x;
+  const int64_t tile_first = (int64_t)blockIdx.x * kBlock;
+  const int64_t i = tile_first + lane;
+  const bool active = i < N;
+  if (AUTORESET && blockIdx.x == 0 && lane == 0) *next_count = 0;  // arm the counter the NEXT launch appends to
+  float* rec = st + qx_tile_base(i, rows);  // the state tensor is padded to whole tiles: every lane may load
 
-  // work items: a regular thread owns exactly one env; a tail thread strides over the done list
-  int t, t_end, t_stride;
-  if (tail) {
-    if (blockIdx.x == 0 && threadIdx.x == 0 && !build) *next_count = 0;  // arm the counter the NEXT launch appends to
-    t = blockIdx.x * kBlock + threadIdx.x;
-    t_end = prev_list ? *prev_count : (int)N;  // build mode after a user reset: every env
-    t_stride = tail_blocks * kBlock;
-  } else {
-    t = 0;
-    t_end = (block_first + threadIdx.x < N) ? 1 : 0;
-    t_stride = 1;
+  QuadXRegs s;
+  int step_count;
+  quadx_load_tile<MODE, kTileGroupStride>(rec, s, step_count);
+  float act[4] = {0.f, 0.f, 0.f, 0.f};
+  float past[4] = {0.f, 0.f, 0.f, 0.f};
+  // noise of this env step: issued right behind the state loads, consumed inside the loop
+  auto nz = make_noise<INJECT>(noise, N, active ? i : 0, rng, step_seq, TAG_ENV_STEP, p.noise_loc, p.ratio);
+  nz.prefetch4();
+  if (!INJECT && noise_dump && active) nz.set_dump(noise_dump + i, N);
+  if (RANDACT) {
+    uint64_t g = ((uint64_t)rng.env_offset_hi << 32 | rng.env_offset_lo) + (uint64_t)i;
+    U4 r = philox4x32_10(U4{(uint32_t)g, (uint32_t)(g >> 32), step_seq, (uint32_t)TAG_ACTION << 24}, rng.k0, rng.k1);
+    const float pi = 3.14159265358979323846f;
+    if (MODE == -1) {
+      act[0] = 0.8f * u32_to_unit_open(r.x); act[1] = 0.8f * u32_to_unit_open(r.y);
+      act[2] = 0.8f * u32_to_unit_open(r.z); act[3] = 0.8f * u32_to_unit_open(r.w);
+    } else {
+      act[0] = pi * (2.0f * u32_to_unit_open(r.x) - 1.0f); act[1] = pi * (2.0f * u32_to_unit_open(r.y) - 1.0f);
+      act[2] = pi * (2.0f * u32_to_unit_open(r.z) - 1.0f); act[3] = 0.8f * u32_to_unit_open(r.w);
+    }
+    if (active) reinterpret_cast<float4*>(actions)[i] = make_float4(act[0], act[1], act[2], act[3]);
+  } else if (active) {
+    float4 a4 = __ldg(reinterpret_cast<const float4*>(actions) + i);
+    act[0] = a4.x; act[1] = a4.y; act[2] = a4.z; act[3] = a4.w;
   }
-  bool skip = true;
-  float* row = smem + threadIdx.x * O;  // dense [kBlock][O] tile: copied out below as float4
-#pragma unroll 1
-  for (; t < t_end; t += t_stride) {
-    const int64_t i = tail ? (prev_list ? (int64_t)prev_list[t] : (int64_t)t) : block_first + threadIdx.x;
-    QuadXRegs s;
-    float act[4] = {0.f, 0.f, 0.f, 0.f};
-    float past[4] = {0.f, 0.f, 0.f, 0.f};
-    int n_aviary, step_count;
-    float rew;
-    uint32_t nseq = step_seq;
-    // ONE load site for every role: a regular thread reads its env's state, a tail thread the env's spare.  The loads are
-    // issued before the spare's pose / validity words are examined, so a cold tail thread pays one round trip, not two.
-    const bool from_spare = tail && spare;  // env-major record vs field-major state rows: same loads, different strides
-    quadx_load<MODE>(from_spare ? spare + i * SP_ROWS : st, ist, N, i, s, from_spare ? 1 : N, from_spare ? 0 : i);
-    if (tail) {
-      // env.reset(): begin_reset + end_reset (quadx_base_env.py:149-212) — normally a copy of the env's spare
-      nseq = step_seq | 0x40000000u;
-      bool hit = false;
-      if (spare) {
-        nseq = __float_as_uint(spare[i * SP_ROWS + SP_EPISODE]) + (build ? 1u : 0u);  // episode number: keys the warm-up noise
-        hit = !build && spare_copy && spare_usable(spare, start_pos, start_orn, N, i);
-      }
-      if (hit) {
-        s.flags = __float_as_uint(spare[i * SP_ROWS + SP_FLAGS]);
+  // an env that finished on the previous call: this call is its reset (NEXT_STEP)
+  const bool resetting = AUTORESET && active && (s.flags & (FLAG_TERM | FLAG_TRUNC)) != 0;
+  const float* srec = spare ? spare + i * SP_ROWS : nullptr;
+  if (AUTORESET && resetting && srec) {  // pull the spare record into L2 while the other lanes integrate
+    prefetch_l2(srec);
+    prefetch_l2(srec + 32);
+    prefetch_l2(srec + 64);
+  }
+  int n_aviary = (active && !resetting) ? h.env_step_ratio : 0;
+  float rew = -0.1f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { s.sp[k] = 0.0f; s.pwm[k] = spare[i * SP_ROWS + QX_PWM + k]; }  // quadx_load skips the pwm words
-        n_aviary = 0;
-      } else {
-        const float px = start_pos[3 * i + 0], py = start_pos[3 * i + 1], pz = start_pos[3 * i + 2];
-        const float ox = start_orn[3 * i + 0], oy = start_orn[3 * i + 1], oz = start_orn[3 * i + 2];
-        if (build) {
-          float* c = spare + i * SP_ROWS + SP_POSE;
-          c[6] = 0.0f;  // invalid until the warm-up below is stored
-          c[0] = px; c[1] = py; c[2] = pz; c[3] = ox; c[4] = oy; c[5] = oz;
+  for (int k = 0; k < 4; ++k) s.sp[k] = act[k];
+  if (MA) {  // MAQuadXHover: flags are re-evaluated every step, rewards add up from 0, the obs shows the PREVIOUS action
+    s.flags &= ~(uint32_t)(FLAG_TERM | FLAG_TRUNC | FLAG_OOB | FLAG_COLLISION);
+    rew = 0.0f;
+    const F4 cur = ld_f4(rec + (QM_CUR / 4) * kTileGroupStride);
+    past[0] = cur.x; past[1] = cur.y; past[2] = cur.z; past[3] = cur.w;
+    if (active) {
+      st_f4(rec + (QM_PAST / 4) * kTileGroupStride, past[0], past[1], past[2], past[3]);
+      st_f4(rec + (QM_CUR / 4) * kTileGroupStride, act[0], act[1], act[2], act[3]);
+    }
+  }
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  if (MA && active) { sx = start_pos[3 * i]; sy = start_pos[3 * i + 1]; sz = start_pos[3 * i + 2]; }
+#pragma unroll 1
+  for (int k = 0; k < n_aviary; ++k) {
+    if (!MA && (s.flags & (FLAG_TERM | FLAG_TRUNC))) break;  // quadx_base_env.py:289-290
+    quadx_aviary_step<MODE>(p, s, nz);
+    if (MA) ma_hover_term_trunc_reward(h, s, step_count, sx, sy, sz, rew);
+    else hover_term_trunc_reward(h, s, step_count, rew);
+  }
+  step_count += 1;
+  if (AUTORESET && __any_sync(0xffffffffu, resetting)) {
+    if (resetting) {
+      // env.reset(): begin_reset + end_reset (quadx_base_env.py:149-212) — normally a copy of the env's spare
+      const float px = start_pos[3 * i + 0], py = start_pos[3 * i + 1], pz = start_pos[3 * i + 2];
+      const float ox = start_orn[3 * i + 0], oy = start_orn[3 * i + 1], oz = start_orn[3 * i + 2];
+      bool hit = false;
+      uint32_t nseq = step_seq | 0x40000000u;
+      if (srec) {
+        const F4 m0 = ld_f4(srec + SP_POSE), m1 = ld_f4(srec + SP_POSE + 4), m2 = ld_f4(srec + SP_POSE + 8);
+        nseq = bits_from_f(m2.x);  // episode number: keys the warm-up noise
+        hit = spare_copy && m1.z != 0.0f && m0.x == px && m0.y == py && m0.z == pz && m0.w == ox && m1.x == oy && m1.y == oz;
+        if (hit) {
+          int dummy;
+          quadx_load_tile<MODE, 4>(srec, s, dummy);
+          const F4 pw = ld_f4(srec + QX_PWM);
+          s.pwm[0] = pw.x; s.pwm[1] = pw.y; s.pwm[2] = pw.z; s.pwm[3] = pw.w;
+          s.flags = bits_from_f(m1.w);
         }
-        quadx_reset(s, px, py, pz, ox, oy, oz);
-        quadx_set_mode<MODE>(s);
-        n_aviary = h.warmup_steps;
       }
+      if (!hit) {
+        s = hover_warmup<MODE, false>(p, h.warmup_steps, rng, nullptr, N, i, nseq, px, py, pz, ox, oy, oz);
+        quadx_requantize(s);  // an inline warm-up must leave exactly what a copied spare holds
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { s.sp[k] = 0.0f; act[k] = 0.0f; }  // self.action = zeros (quadx_base_env.py:165)
       step_count = 0;
       rew = 0.0f;
-      if (!build) s.flags |= fresh_tag(step_seq);
-    } else {
-      if (AUTORESET && (s.flags & (FLAG_TERM | FLAG_TRUNC | fresh_tag(step_seq)))) continue;  // a tail CTA owns this env on this call
-      s.flags &= ~(uint32_t)FLAG_FRESH_ANY;
-      if (RANDACT) {
-        uint64_t g = ((uint64_t)rng.env_offset_hi << 32 | rng.env_offset_lo) + (uint64_t)i;
-        U4 r = philox4x32_10(U4{(uint32_t)g, (uint32_t)(g >> 32), step_seq, (uint32_t)TAG_ACTION << 24}, rng.k0, rng.k1);
-        const float pi = 3.14159265358979323846f;
-        if (MODE == -1) {
-          act[0] = 0.8f * u32_to_unit_open(r.x); act[1] = 0.8f * u32_to_unit_open(r.y);
-          act[2] = 0.8f * u32_to_unit_open(r.z); act[3] = 0.8f * u32_to_unit_open(r.w);
-        } else {
-          act[0] = pi * (2.0f * u32_to_unit_open(r.x) - 1.0f); act[1] = pi * (2.0f * u32_to_unit_open(r.y) - 1.0f);
-          act[2] = pi * (2.0f * u32_to_unit_open(r.z) - 1.0f); act[3] = 0.8f * u32_to_unit_open(r.w);
-        }
-        reinterpret_cast<float4*>(actions)[i] = make_float4(act[0], act[1], act[2], act[3]);
-      } else {
-        float4 a4 = __ldg(reinterpret_cast<const float4*>(actions) + i);
-        act[0] = a4.x; act[1] = a4.y; act[2] = a4.z; act[3] = a4.w;
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) s.sp[k] = act[k];
-      n_aviary = h.env_step_ratio;
-      step_count = ist[(int64_t)QI_STEP * N + i];
-      rew = -0.1f;
-      if (h.ma) {  // MAQuadXHover: flags are re-evaluated every step, rewards add up from 0, the obs shows the PREVIOUS action
-        s.flags &= ~(uint32_t)(FLAG_TERM | FLAG_TRUNC | FLAG_OOB | FLAG_COLLISION);
-        rew = 0.0f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          past[k] = st[(int64_t)(QM_CUR + k) * N + i];
-          st[(int64_t)(QM_PAST + k) * N + i] = past[k];
-          st[(int64_t)(QM_CUR + k) * N + i] = act[k];
-        }
-      }
     }
-    auto nz = make_noise<INJECT>(noise, N, i, rng, nseq, tail ? TAG_RESET : TAG_ENV_STEP, p.noise_loc, p.ratio);
-#pragma unroll 1
-    for (int k = 0; k < n_aviary; ++k) {
-      if (!h.ma && (s.flags & (FLAG_TERM | FLAG_TRUNC))) break;  // quadx_base_env.py:289-290 (never set while resetting)
-      quadx_aviary_step<MODE>(p, s, nz);
-      if (!tail) {
-        if (h.ma) ma_hover_term_trunc_reward(h, s, step_count, start_pos[3 * i], start_pos[3 * i + 1], start_pos[3 * i + 2], rew);
-        else hover_term_trunc_reward(h, s, step_count, rew);
-      }
-    }
-    step_count = tail ? 0 : step_count + 1;
-    if (tail && build) {  // build mode: the warm-up result is the env's new spare
-      spare_store<MODE>(spare, ist, N, i, s, nseq);
-      continue;
-    }
-    if (tail && n_aviary > 0) quadx_requantize(s);  // an inline warm-up must leave exactly what a copied spare holds
-    if (h.ma) ma_hover_observation(h, s, past, start_pos[3 * i], start_pos[3 * i + 1], start_pos[3 * i + 2], row);
-    else hover_observation(h, s, act, row);
-    quadx_store<MODE>(st, ist, N, i, s);
-    ist[(int64_t)QI_STEP * N + i] = step_count;
+  }
+  float* row = smem + lane * O;  // dense [32][O] tile, written out below by one bulk copy
+  if (MA) ma_hover_observation(h, s, past, sx, sy, sz, row);
+  else hover_observation(h, s, act, row);
+  fence_async_smem();  // generic-proxy writes of this lane -> visible to the bulk-copy (async) proxy
+  if (active) {
+    quadx_store_tile<MODE, kTileGroupStride>(rec, s, step_count);
     reward[i] = rew;
     term[i] = (s.flags & FLAG_TERM) ? 1 : 0;
     trunc[i] = (s.flags & FLAG_TRUNC) ? 1 : 0;
     if (info) info[i] = (uint8_t)(((s.flags & FLAG_OOB) ? 1 : 0) | ((s.flags & FLAG_COLLISION) ? 2 : 0));
-    if (tail) {
-      float* dst = obs + i * O;  // scattered rows: the tail handles ~1-3 % of the envs
-      for (int k = 0; k < O; ++k) dst[k] = row[k];
-    } else {
-      skip = false;
-      if (AUTORESET) {  // queue finished episodes for the next launch's tail CTAs (warp-aggregated append)
-        bool done = (s.flags & (FLAG_TERM | FLAG_TRUNC)) != 0;
-        unsigned m = __ballot_sync(__activemask(), done);
-        if (done) {
-          int lane = threadIdx.x & 31;
-          int leader = __ffs(m) - 1;
-          int base = 0;
-          if (lane == leader) base = atomicAdd(cur_count, __popc(m));
-          base = __shfl_sync(m, base, leader);
-          cur_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
-        }
-      }
+  }
+  if (AUTORESET) {  // queue finished episodes: their spares are consumed by the next launch and rebuilt after it
+    const bool done = active && (s.flags & (FLAG_TERM | FLAG_TRUNC)) != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, done);
+    if (done) {
+      const int leader = __ffs(m) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(cur_count, __popc(m));
+      base = __shfl_sync(m, base, leader);
+      cur_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
     }
   }
-  if (tail) return;
-  // ---- block-cooperative write of this CTA's observation tile obs[block_first .. +rows][O]: the tile is contiguous in
-  //      global memory and 16-byte aligned (kBlock * O * 4 bytes per CTA), so it goes out as float4; rows of envs that a
-  //      tail CTA owns on this launch are left alone
-  row_skip[threadIdx.x] = skip ? 1 : 0;
-  const int any_skip = __syncthreads_or(skip ? 1 : 0);
-  int64_t rows = N - block_first;
-  if (rows > kBlock) rows = kBlock;
-  const int total = (int)rows * O;
-  const int nvec = total >> 2;
-  float* dst = obs + block_first * O;
-  const float4* src4 = reinterpret_cast<const float4*>(smem);
-  float4* dst4 = reinterpret_cast<float4*>(dst);
-  if (!any_skip) {
-    for (int v = threadIdx.x; v < nvec; v += kBlock) dst4[v] = src4[v];
-  } else {
-    for (int v = threadIdx.x; v < nvec; v += kBlock) {
-      const int j = v << 2;
-      const int r0 = obs_row(j, O), r1 = obs_row(j + 3, O);
-      const float4 val = src4[v];
-      if (!row_skip[r0] && !row_skip[r1]) {
-        dst4[v] = val;
-      } else {  // the vector straddles a skipped row: element-wise
-        const int split = r1 * O - j;  // elements [0, split) belong to row r0
-        const float e[4] = {val.x, val.y, val.z, val.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (!row_skip[q < split ? r0 : r1]) dst[j + q] = e[q];
-      }
+  __syncwarp();
+  // ---- this warp's observation tile obs[tile_first .. +rows][O] is contiguous in global memory and 16-byte aligned
+  int64_t nrows = N - tile_first;
+  if (nrows > kBlock) nrows = kBlock;
+  const uint32_t bytes = (uint32_t)nrows * (uint32_t)O * 4u;
+  float* dst = obs + tile_first * O;
+  if ((bytes & 15u) == 0u) {
+    if (lane == 0) {
+      bulk_store_s2g(dst, smem, bytes);
+      bulk_store_wait_read();  // the CTA's shared memory must outlive the engine's reads
     }
+  } else {  // ragged last tile whose byte count is not a multiple of 16
+    for (int j = lane; j < (int)nrows * O; j += kBlock) dst[j] = smem[j];
   }
-  for (int j = (nvec << 2) + threadIdx.x; j < total; j += kBlock)  // ragged last CTA only
-    if (!row_skip[obs_row(j, O)]) dst[j] = smem[j];
+}
+
+// Rebuilds spare post-reset states: the envs of `list` (those that finished on step k - 1 and consumed their spare on step
+// k), or every env (list == nullptr: after a user reset).  Dense warps over the list; the same compiled warm-up as the
+// step kernel's inline path and the reset kernel, hence bit-identical results.
+template <int MODE>
+__global__ void __launch_bounds__(kBlock, kHoverBlocks)
+    k_hover_spare_build(const __grid_constant__ QuadXParams p, const __grid_constant__ HoverParams h, const __grid_constant__ RngParams rng,
+                        const float* __restrict__ start_pos, const float* __restrict__ start_orn, const int32_t* __restrict__ count,
+                        const int32_t* __restrict__ list, float* __restrict__ spare, int64_t N) {
+  const int t_end = list ? *count : (int)N;
+  for (int t = blockIdx.x * kBlock + threadIdx.x; t < t_end; t += gridDim.x * kBlock) {
+    const int64_t i = list ? (int64_t)list[t] : (int64_t)t;
+    float* srec = spare + i * SP_ROWS;
+    const uint32_t episode = bits_from_f(srec[SP_EPISODE]) + 1u;
+    const float px = start_pos[3 * i + 0], py = start_pos[3 * i + 1], pz = start_pos[3 * i + 2];
+    const float ox = start_orn[3 * i + 0], oy = start_orn[3 * i + 1], oz = start_orn[3 * i + 2];
+    srec[SP_VALID] = 0.0f;  // invalid until the warm-up below is stored
+    QuadXRegs s = hover_warmup<MODE, false>(p, h.warmup_steps, rng, nullptr, N, i, episode, px, py, pz, ox, oy, oz);
+    quadx_store_tile<7, 4>(srec, s, 0);
+    st_f4(srec + SP_POSE, px, py, pz, ox);
+    st_f4(srec + SP_POSE + 4, oy, oz, 1.0f, f_from_bits(s.flags));
+    st_f4(srec + SP_POSE + 8, f_from_bits(episode), 0.0f, 0.0f, 0.0f);
+  }
 }
 
 // env.reset() for all / masked envs
 template <int MODE, bool INJECT>
 __global__ void __launch_bounds__(kBlock)
     k_hover_reset(const __grid_constant__ QuadXParams p, const __grid_constant__ HoverParams h,
-                  const __grid_constant__ RngParams rng, float* __restrict__ st, int32_t* __restrict__ ist,
+                  const __grid_constant__ RngParams rng, float* __restrict__ st, int rows,
                   const float* __restrict__ start_pos, const float* __restrict__ start_orn,
                   const uint8_t* __restrict__ mask, const float* __restrict__ noise, float* __restrict__ obs,
                   uint32_t seq, int64_t N) {
-  __shared__ float smem[kBlock * kObsStride];
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (i >= N) return;
   if (mask && !mask[i]) return;
   const int O = (h.angle_representation == 0 ? 20 : 21) + (h.ma ? 3 : 0);
-  float* row = smem + threadIdx.x * kObsStride;
-  hover_reset_env<MODE, INJECT>(p, h, rng, st, ist, start_pos, start_orn, noise, seq, N, i, row);
+  float row[kObsMax];
+  QuadXRegs s = hover_warmup<MODE, INJECT>(p, h.warmup_steps, rng, noise, N, i, seq, start_pos[3 * i + 0], start_pos[3 * i + 1],
+                                           start_pos[3 * i + 2], start_orn[3 * i + 0], start_orn[3 * i + 1], start_orn[3 * i + 2]);
+  float* rec = st + qx_tile_base(i, rows);
+  const float zero[4] = {0.f, 0.f, 0.f, 0.f};  // self.action = zeros (quadx_base_env.py:165)
+  if (h.ma) {  // past_actions is NOT cleared by a reset in the reference: it still holds the previous episode's value
+    const F4 pa = ld_f4(rec + (QM_PAST / 4) * kTileGroupStride);
+    const float past[4] = {pa.x, pa.y, pa.z, pa.w};
+    ma_hover_observation(h, s, past, start_pos[3 * i], start_pos[3 * i + 1], start_pos[3 * i + 2], row);
+  } else {
+    hover_observation(h, s, zero, row);
+  }
+  quadx_store_tile<7, kTileGroupStride>(rec, s, 0);
   if (obs) {
-    for (int k = 0; k < O; ++k) obs[i * O + k] = row[k];
+#pragma unroll
+    for (int k = 0; k < kObsMax; ++k)
+      if (k < O) obs[i * O + k] = row[k];
   }
 }
 
@@ -545,7 +538,15 @@ static inline bool is_rk(PfbHandle h) { return h->model.kind == PFB_KIND_ROCKET;
 static inline bool is_qwp(PfbHandle h) { return h->model.kind == PFB_KIND_QUADX && h->env.env_kind == PFB_ENV_QUADX_WAYPOINTS; }
 static inline bool is_ma(PfbHandle h) { return h->model.kind == PFB_KIND_QUADX && h->env.env_kind == PFB_ENV_MA_QUADX_HOVER; }
 static inline bool is_df(PfbHandle h) { return h->model.kind == PFB_KIND_FIXEDWING && h->env.env_kind == PFB_ENV_DOGFIGHT; }
-int pfb_state_rows(PfbHandle h) { return is_rk(h) ? rk_state_rows() : (is_fw(h) ? fw_state_rows() : (is_qwp(h) ? qwp_state_rows() : (is_ma(h) ? QM_ROWS : QX_ROWS))); }
+static inline bool is_tiled(PfbHandle h) { return h->model.kind == PFB_KIND_QUADX && h->env.env_kind != PFB_ENV_QUADX_WAYPOINTS; }
+static inline int qx_rows(PfbHandle h) { return h->env.env_kind == PFB_ENV_MA_QUADX_HOVER ? QM_ROWS : QX_ROWS; }
+int pfb_state_rows(PfbHandle h) { return is_rk(h) ? rk_state_rows() : (is_fw(h) ? fw_state_rows() : (is_qwp(h) ? qwp_state_rows() : qx_rows(h))); }
+int pfb_state_layout(PfbHandle h) { return h && is_tiled(h) ? PFB_LAYOUT_WARP_TILED : PFB_LAYOUT_FIELD_MAJOR; }
+int64_t pfb_state_floats(PfbHandle h) {
+  if (!h) return 0;
+  if (is_tiled(h)) return ((h->n + kTileLanes - 1) / kTileLanes) * qx_tile_floats(qx_rows(h));  // padded to whole tiles
+  return (int64_t)pfb_state_rows(h) * h->n;
+}
 int pfb_istate_rows(PfbHandle h) { return is_rk(h) ? rk_istate_rows() : (is_fw(h) ? fw_istate_rows() : (is_qwp(h) ? qwp_istate_rows() : QI_ROWS)); }
 int pfb_setpoint_dim(PfbHandle h) { return is_rk(h) ? 7 : ((is_fw(h) && h->env.env_kind == PFB_ENV_NONE) ? 6 : 4); }
 int pfb_obs_dim(PfbHandle h) { return is_df(h) ? df_obs_dim(h) : is_rk(h) ? rk_obs_dim(h) : (is_fw(h) ? fw_obs_dim(h) : (is_qwp(h) ? qwp_obs_dim(h) : (h->hover.angle_representation == 0 ? 20 : 21) + (is_ma(h) ? 3 : 0))); }
@@ -572,8 +573,8 @@ int pfb_reset(PfbHandle h, const uint8_t* mask, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (is_fw(h)) return fw_reset(h, mask, s);
   if (is_rk(h)) return rk_reset(h, mask, s);
-  k_quadx_reset<<<grid_for(h->n), kBlock, 0, s>>>(h->buf.state, h->buf.istate, h->buf.setpoint, h->buf.start_pos,
-                                                  h->buf.start_orn, mask, h->n);
+  if (is_tiled(h)) k_quadx_reset<true><<<grid_for(h->n), kBlock, 0, s>>>(h->buf.state, h->buf.istate, qx_rows(h), h->buf.setpoint, h->buf.start_pos, h->buf.start_orn, mask, h->n);
+  else k_quadx_reset<false><<<grid_for(h->n), kBlock, 0, s>>>(h->buf.state, h->buf.istate, qx_rows(h), h->buf.setpoint, h->buf.start_pos, h->buf.start_orn, mask, h->n);
   LAUNCH_CHECK(h);
   if (!mask) h->mode = 0;  // QuadX.reset() calls set_mode(0) (quadx.py:224)
   return 0;
@@ -584,8 +585,8 @@ int pfb_set_mode(PfbHandle h, int mode, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (is_fw(h)) return fw_set_mode(h, mode, s);
   if (is_rk(h)) return rk_set_mode(h, mode, s);
-  PFB_MODE_SWITCH(mode, (k_quadx_set_mode<MODE><<<grid_for(h->n), kBlock, 0, s>>>(h->buf.state, h->buf.istate,
-                                                                                  h->buf.setpoint, h->n)));
+  if (is_tiled(h)) { PFB_MODE_SWITCH(mode, (k_quadx_set_mode<MODE, true><<<grid_for(h->n), kBlock, 0, s>>>(h->buf.state, h->buf.istate, qx_rows(h), h->buf.setpoint, h->n))); }
+  else { PFB_MODE_SWITCH(mode, (k_quadx_set_mode<MODE, false><<<grid_for(h->n), kBlock, 0, s>>>(h->buf.state, h->buf.istate, qx_rows(h), h->buf.setpoint, h->n))); }
   LAUNCH_CHECK(h);
   h->mode = mode;
   return 0;
@@ -599,13 +600,16 @@ int pfb_aviary_step(PfbHandle h, int n_steps, const float* noise, void* stream) 
   if (is_rk(h)) return rk_aviary_step(h, n_steps, noise, s);
   const int mode = h->mode;
   const uint32_t seq = (uint32_t)h->aviary_seq++;
-  if (noise) {
-    PFB_MODE_SWITCH(mode, (k_quadx_aviary_step<MODE, true><<<grid_for(h->n), kBlock, 0, s>>>(
-                              h->qx, h->rng, h->buf.state, h->buf.istate, h->buf.setpoint, noise, n_steps, seq, h->n)));
+#define AV_ARGS h->qx, h->rng, h->buf.state, h->buf.istate, qx_rows(h), h->buf.setpoint, noise, n_steps, seq, h->n
+  const int g = grid_for(h->n);
+  if (is_tiled(h)) {
+    if (noise) { PFB_MODE_SWITCH(mode, (k_quadx_aviary_step<MODE, true, true><<<g, kBlock, 0, s>>>(AV_ARGS))); }
+    else { PFB_MODE_SWITCH(mode, (k_quadx_aviary_step<MODE, false, true><<<g, kBlock, 0, s>>>(AV_ARGS))); }
   } else {
-    PFB_MODE_SWITCH(mode, (k_quadx_aviary_step<MODE, false><<<grid_for(h->n), kBlock, 0, s>>>(
-                              h->qx, h->rng, h->buf.state, h->buf.istate, h->buf.setpoint, nullptr, n_steps, seq, h->n)));
+    if (noise) { PFB_MODE_SWITCH(mode, (k_quadx_aviary_step<MODE, true, false><<<g, kBlock, 0, s>>>(AV_ARGS))); }
+    else { PFB_MODE_SWITCH(mode, (k_quadx_aviary_step<MODE, false, false><<<g, kBlock, 0, s>>>(AV_ARGS))); }
   }
+#undef AV_ARGS
   LAUNCH_CHECK(h);
   return 0;
 }
@@ -621,8 +625,8 @@ int pfb_observe_state(PfbHandle h, void* stream) {
   REQUIRE_BOUND(h);
   if (is_fw(h)) return fw_observe(h, (cudaStream_t)stream);
   if (is_rk(h)) return rk_observe(h, (cudaStream_t)stream);
-  k_quadx_observe<<<grid_for(h->n), kBlock, 0, (cudaStream_t)stream>>>(h->buf.state, h->buf.istate, h->buf.drone_state,
-                                                                      h->buf.aux_state, h->buf.contact, h->n);
+  if (is_tiled(h)) k_quadx_observe<true><<<grid_for(h->n), kBlock, 0, (cudaStream_t)stream>>>(h->buf.state, h->buf.istate, qx_rows(h), h->buf.drone_state, h->buf.aux_state, h->buf.contact, h->n);
+  else k_quadx_observe<false><<<grid_for(h->n), kBlock, 0, (cudaStream_t)stream>>>(h->buf.state, h->buf.istate, qx_rows(h), h->buf.drone_state, h->buf.aux_state, h->buf.contact, h->n);
   LAUNCH_CHECK(h);
   return 0;
 }
@@ -644,26 +648,19 @@ int pfb_env_reset(PfbHandle h, const uint8_t* mask, const float* noise, void* st
   const int mode = h->hover.flight_mode;
   // resets draw from their own Philox stream; the high bit keeps them apart from in-step autoresets
   const uint32_t seq = 0x80000000u | (uint32_t)h->reset_seq++;
-  if (h->d_spare) {  // the reset kernel rewrites spares: let the side stream's last rebuild finish first
+  if (h->d_spare) {  // the build below rewrites spares: let the side stream's last rebuild finish first
     if (h->step_seq > 0) CUDA_OK(cudaStreamWaitEvent(s, h->ev_spare[(h->step_seq - 1) % 4], 0));
-    if (!mask) CUDA_OK(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(int32_t), s));  // a full reset empties the autoreset queues
+    if (!mask) CUDA_OK(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(int32_t), s));  // a full reset empties the rebuild queues
   }
-  if (noise) {
-    PFB_MODE_SWITCH(mode, (k_hover_reset<MODE, true><<<grid_for(h->n), kBlock, 0, s>>>(
-                              h->qx, h->hover, h->rng, h->buf.state, h->buf.istate, h->buf.start_pos, h->buf.start_orn, mask,
-                              noise, h->buf.obs, seq, h->n)));
-  } else {
-    PFB_MODE_SWITCH(mode, (k_hover_reset<MODE, false><<<grid_for(h->n), kBlock, 0, s>>>(
-                              h->qx, h->hover, h->rng, h->buf.state, h->buf.istate, h->buf.start_pos, h->buf.start_orn, mask,
-                              nullptr, h->buf.obs, seq, h->n)));
-  }
+#define HR_ARGS h->qx, h->hover, h->rng, h->buf.state, qx_rows(h), h->buf.start_pos, h->buf.start_orn, mask, noise, h->buf.obs, seq, h->n
+  if (noise) { PFB_MODE_SWITCH(mode, (k_hover_reset<MODE, true><<<grid_for(h->n), kBlock, 0, s>>>(HR_ARGS))); }
+  else { PFB_MODE_SWITCH(mode, (k_hover_reset<MODE, false><<<grid_for(h->n), kBlock, 0, s>>>(HR_ARGS))); }
+#undef HR_ARGS
   LAUNCH_CHECK(h);
-  if (h->d_spare) {  // every env gets a fresh spare (build mode of the step kernel over all envs, same stream)
-    const int g = grid_for(h->n);
-    PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, false, true><<<g, kBlock, 0, s>>>(
-                              h->qx, h->hover, h->rng, h->buf.state, h->buf.istate, h->buf.setpoint, nullptr, h->buf.obs, h->buf.reward,
-                              h->buf.term, h->buf.trunc, h->buf.info, h->buf.start_pos, h->buf.start_orn, nullptr, nullptr, nullptr, nullptr,
-                              nullptr, h->d_spare, 0, 1, g, 0u, h->n)));
+  if (h->d_spare && !mask) {  // every env gets a fresh spare (same stream).  A masked reset keeps the spares: they are keyed by
+                              // (env, episode number) and stay valid; a masked env simply is not `done` on the next step
+    PFB_MODE_SWITCH(mode, (k_hover_spare_build<MODE><<<grid_for(h->n), kBlock, 0, s>>>(h->qx, h->hover, h->rng, h->buf.start_pos, h->buf.start_orn,
+                                                                                      nullptr, nullptr, h->d_spare, h->n)));
     LAUNCH_CHECK(h);
   }
   h->mode = mode;
@@ -678,8 +675,9 @@ static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool r
   const int mode = h->hover.flight_mode;
   const bool autoreset = h->env.autoreset != 0;
   const uint64_t k = h->step_seq;
-  // four rotating done lists / counters: step k appends to [k % 4], its tail CTAs and the side-stream spare rebuild read
-  // [(k - 1) % 4], and it zeroes counter [(k + 1) % 4] (last read by the rebuild of step k - 2, which step k waits for)
+  // four rotating done lists / counters: step k appends to [k % 4]; the spare rebuild launched after step k reads
+  // [(k - 1) % 4] (the envs that finished on step k - 1 and took their spare on step k); step k zeroes counter [(k + 1) % 4]
+  // (last read by the rebuild of step k - 2, which step k waits for)
   int32_t* cnt_cur = h->d_counters + (k % 4);
   int32_t* cnt_prev = h->d_counters + ((k + 3) % 4);
   int32_t* cnt_next = h->d_counters + ((k + 1) % 4);
@@ -687,36 +685,32 @@ static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool r
   int32_t* list_prev = h->d_done_list + ((k + 3) % 4) * h->n;
   const uint32_t seq = (uint32_t)k;
   const bool spares = autoreset && h->d_spare != nullptr;
-  const int spare_copy = (spares && !h->env.inline_reset) ? 1 : 0;
-  if (spares && k >= 2) CUDA_OK(cudaStreamWaitEvent(s, h->ev_spare[(k - 2) % 4], 0));
-  // tail CTAs (front of the grid) reset the envs that finished on the previous call; one per SM is
-  // plenty for the ~1-3 % of envs that finish per step, and the loop is grid-strided anyway
-  int tail = 0;
-  if (autoreset) {
-    tail = h->sm_count;
-    int need = grid_for(h->n);
-    if (tail > need) tail = need;
-  }
-  const int grid = grid_for(h->n) + tail;
+  const int spare_copy = (spares && h->env.inline_reset != 1) ? 1 : 0;
+  const bool same_stream = h->env.inline_reset == 2;  // rebuild on the caller's stream: all of a step's work in order on one stream
+  if (spares && !same_stream && k >= 2) CUDA_OK(cudaStreamWaitEvent(s, h->ev_spare[(k - 2) % 4], 0));
+  const int grid = grid_for(h->n);
   const bool prof = h->prof_ev && h->prof_n < h->prof_cap;
   if (prof) CUDA_OK(cudaEventRecord(h->prof_ev[2 * h->prof_n], s));
-#define STEP_ARGS h->qx, h->hover, h->rng, h->buf.state, h->buf.istate, actions, noise, h->buf.obs, h->buf.reward,     \
-                  h->buf.term, h->buf.trunc, h->buf.info, h->buf.start_pos, h->buf.start_orn, cnt_prev, list_prev, \
-                  cnt_cur, list_cur, cnt_next, h->d_spare, spare_copy, 0, tail, seq, h->n
+#define STEP_ARGS h->qx, h->hover, h->rng, h->buf.state, qx_rows(h), actions, noise, h->buf.obs, h->buf.reward, h->buf.term, h->buf.trunc,    \
+                  h->buf.info, h->buf.start_pos, h->buf.start_orn, cnt_cur, list_cur, cnt_next, h->d_spare, spare_copy, h->noise_dump, seq, h->n
   if (autoreset) {
     if (noise) return fail("injected noise (parity mode) is only supported with autoreset = 0");
     if (randact) {
-      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, true, true><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
+      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, true, true, false><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
     } else {
-      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, false, true><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
+      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, false, true, false><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
     }
+  } else if (h->hover.ma) {
+    if (randact) return fail("MAQuadXHover has no on-device action generator");
+    if (noise) { PFB_MODE_SWITCH(mode, (k_hover_step<MODE, true, false, false, true><<<grid, kBlock, 0, s>>>(STEP_ARGS))); }
+    else { PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, false, false, true><<<grid, kBlock, 0, s>>>(STEP_ARGS))); }
   } else {
     if (noise) {
-      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, true, false, false><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
+      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, true, false, false, false><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
     } else if (randact) {
-      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, true, false><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
+      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, true, false, false><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
     } else {
-      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, false, false><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
+      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, false, false, false><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
     }
   }
 #undef STEP_ARGS
@@ -725,17 +719,27 @@ static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool r
     CUDA_OK(cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], s));
     h->prof_n += 1;
   }
-  if (spares) {  // rebuild the spares this launch consumed, on the side stream, while the next launches run
-    CUDA_OK(cudaEventRecord(h->ev_step, s));
-    CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_step, 0));
-    PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, false, true><<<h->sm_count, kBlock, 0, h->side>>>(
-                              h->qx, h->hover, h->rng, h->buf.state, h->buf.istate, actions, nullptr, h->buf.obs, h->buf.reward, h->buf.term,
-                              h->buf.trunc, h->buf.info, h->buf.start_pos, h->buf.start_orn, cnt_prev, list_prev, cnt_cur, list_cur, cnt_next,
-                              h->d_spare, 0, 1, h->sm_count, seq, h->n)));
+  if (spares && k >= 1) {  // rebuild the spares this launch consumed (the envs that finished on step k - 1)
+    cudaStream_t bs = s;
+    if (!same_stream) {
+      CUDA_OK(cudaEventRecord(h->ev_step, s));
+      CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_step, 0));
+      bs = h->side;
+    }
+    PFB_MODE_SWITCH(mode, (k_hover_spare_build<MODE><<<h->sm_count, kBlock, 0, bs>>>(h->qx, h->hover, h->rng, h->buf.start_pos, h->buf.start_orn,
+                                                                                    cnt_prev, list_prev, h->d_spare, h->n)));
     LAUNCH_CHECK(h);
-    CUDA_OK(cudaEventRecord(h->ev_spare[k % 4], h->side));
+    if (!same_stream) CUDA_OK(cudaEventRecord(h->ev_spare[k % 4], h->side));
+  } else if (spares && !same_stream) {
+    CUDA_OK(cudaEventRecord(h->ev_spare[k % 4], s));  // nothing to rebuild after the first step: keep the event chain uniform
   }
   h->step_seq += 1;
+  return 0;
+}
+
+int pfb_set_noise_dump(PfbHandle h, float* dump) {
+  if (!h) return fail("null handle");
+  h->noise_dump = dump;
   return 0;
 }
 

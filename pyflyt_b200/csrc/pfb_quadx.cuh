@@ -18,6 +18,8 @@
 //    NEW velocities (semi-implicit), exactly like the reference.
 #pragma once
 
+#include <string.h>
+
 #include "pfb_common.cuh"
 
 namespace pfb {
@@ -75,20 +77,43 @@ struct QxWaypointParams {
 // PID memory rows inside the state tensor (24 words)
 enum { PID_P0 = 0, PID_P1 = 6, PID_P2 = 12, PID_P3 = 16, PID_ZV = 20, PID_ZP = 22, PID_WORDS = 24 };
 
-// state tensor rows [F][N] for QuadX
+// QuadX state rows.  Row r is one fp32 word per env.  The row order groups the words a mode-0 env step touches into the
+// first 36 rows so that, in the warp-tiled layout (below), they are 9 consecutive 16-byte groups per env.
 enum {
   QX_POS = 0,       // 3  position (hi)
   QX_QUAT = 3,      // 4  quaternion x,y,z,w (hi)
   QX_VEL = 7,       // 3  world linear velocity (hi)
   QX_ANGVEL = 10,   // 3  BODY angular velocity
   QX_THR = 13,      // 4  motor throttle (aux_state)
-  QX_PWM = 17,      // 4  last motor command
-  QX_POS_LO = 21,   // 3
-  QX_QUAT_LO = 24,  // 4
-  QX_VEL_LO = 28,   // 3
-  QX_PID = 31,      // 24 PID integrals / previous errors
-  QX_ROWS = 55
+  QX_STEP = 17,     // 1  env step_count, int32 bits   (warp-tiled layout only; the field-major layout keeps it in istate)
+  QX_FLAGS = 18,    // 1  flag word, uint32 bits       (same)
+  QX_PID0 = 19,     // 6  ang_vel PID: integrals, previous errors
+  QX_POS_LO = 25,   // 3
+  QX_QUAT_LO = 28,  // 4
+  QX_VEL_LO = 32,   // 3  (+ 1 pad word)
+  QX_PWM = 36,      // 4  last motor command
+  QX_PID1 = 40,     // 18 remaining PID words (ang_pos 6, lin_vel 4, lin_pos 4, z_vel 2, z_pos 2) (+ 2 pad words)
+  QX_ROWS = 60
 };
+// PID word k (0..23, the PID_* offsets above) -> state row
+PFB_HD constexpr int qx_pid_row(int k) { return k < 6 ? QX_PID0 + k : QX_PID1 + (k - 6); }
+
+// ---- warp-tiled layout (QuadX-Hover, MAQuadXHover and Aviary-level QuadX handles) ---------------------------------------
+// Env i lives in tile i >> 5, lane i & 31.  A tile is G = rows / 4 groups; group g holds rows 4g .. 4g+3 of the tile's 32
+// envs as 32 consecutive 16-byte vectors:  word(row r, env i) = st[(((i >> 5) * G + (r >> 2)) * 32 + (i & 31)) * 4 + (r & 3)].
+// A warp therefore moves a group with ONE 128-bit access per lane (512 contiguous bytes), every address is the lane's
+// record pointer plus an immediate, and the rows a mode touches are one contiguous block of the tile.
+// An env-major record (the spare post-reset states) is the same row order with the groups back to back (group stride 4).
+constexpr int kTileLanes = 32;
+constexpr int kTileGroupStride = kTileLanes * 4;  // floats between consecutive groups of one lane inside a tile
+struct alignas(16) F4 { float x, y, z, w; };
+PFB_HD F4 ld_f4(const float* p) { return *reinterpret_cast<const F4*>(p); }
+PFB_HD void st_f4(float* p, float x, float y, float z, float w) { *reinterpret_cast<F4*>(p) = F4{x, y, z, w}; }
+PFB_HD int64_t qx_tile_floats(int rows) { return (int64_t)(rows / 4) * kTileGroupStride; }
+// pointer to the first group word of env i (lane record base)
+PFB_HD int64_t qx_tile_base(int64_t i, int rows) { return (i >> 5) * qx_tile_floats(rows) + (i & 31) * 4; }
+// address of a single word (slow path: accessors, extra rows)
+PFB_HD int64_t qx_tile_word(int64_t i, int rows, int r) { return qx_tile_base(i, rows) + (int64_t)(r >> 2) * kTileGroupStride + (r & 3); }
 // istate rows [I][N]
 enum { QI_STEP = 0, QI_FLAGS = 1, QI_ROWS = 2 };
 enum { FLAG_TERM = 1, FLAG_TRUNC = 2, FLAG_OOB = 4, FLAG_COLLISION = 8, FLAG_CONTACT_PREV = 16, FLAG_CONTACT_ARRAY = 32 };
@@ -489,7 +514,7 @@ PFB_HD void quadx_reset(QuadXRegs& s, float sx, float sy, float sz, float roll, 
 // ---- state tensor <-> registers ----------------------------------------------------------------
 // MODE-dependent PID rows: only the controllers a mode instantiates are moved.
 template <int MODE>
-PFB_HD bool pid_row_used(int k) {
+PFB_HD constexpr bool pid_row_used(int k) {
   if (MODE == -1) return false;
   if (k < PID_P1) return true;                                                   // ang_vel
   if (k < PID_P2) {                                                              // ang_pos
@@ -538,7 +563,7 @@ PFB_HD void quadx_load(const float* __restrict__ st, const int32_t* __restrict__
   // substep reads it (aviary.py:506-531 with physics_control_ratio == updates_per_step), so they are not loaded
   for (int k = 0; k < 4; ++k) { s.thr[k] = F(QX_THR + k); s.pwm[k] = 0.0f; }
 #pragma unroll
-  for (int k = 0; k < PID_WORDS; ++k) s.pid[k] = pid_row_used<MODE>(k) ? F(QX_PID + k) : 0.0f;
+  for (int k = 0; k < PID_WORDS; ++k) s.pid[k] = pid_row_used<MODE>(k) ? F(qx_pid_row(k)) : 0.0f;
   s.flags = (uint32_t)ist[(int64_t)QI_FLAGS * N + i];
   quadx_update_state(s);
 }
@@ -577,8 +602,129 @@ PFB_HD void quadx_store(float* __restrict__ st, int32_t* __restrict__ ist, int64
   for (int k = 0; k < 4; ++k) { S(QX_THR + k, s.thr[k]); S(QX_PWM + k, s.pwm[k]); }
 #pragma unroll
   for (int k = 0; k < PID_WORDS; ++k)
-    if (pid_row_used<MODE>(k)) S(QX_PID + k, s.pid[k]);
+    if (pid_row_used<MODE>(k)) S(qx_pid_row(k), s.pid[k]);
   if (with_flags) ist[(int64_t)QI_FLAGS * N + i] = (int32_t)s.flags;
+}
+
+// ---- warp-tiled / record layout: 16-byte groups -------------------------------------------------------------------------
+PFB_HD float f_from_bits(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+PFB_HD uint32_t bits_from_f(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(f);
+#else
+  uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+// does MODE move group g (rows 4g .. 4g+3)?  Groups 0-8: pose, velocities, throttles, step / flags, ang_vel PID, lo words;
+// 9: pwm (written, never read: every Aviary step starts with a control tick); 10-14: the other controllers' memories
+template <int MODE>
+PFB_HD constexpr bool qx_group_used(int g) {
+  if (g <= 9) return true;
+  for (int c = 0; c < 4; ++c) {
+    const int k = 6 + 4 * (g - 10) + c;
+    if (k < PID_WORDS && pid_row_used<MODE>(k)) return true;
+  }
+  return false;
+}
+template <int MODE>
+PFB_HD constexpr int qx_groups_moved() {  // groups 0 .. n-1 cover every row MODE touches
+  int n = 10;
+  for (int g = 10; g < QX_ROWS / 4; ++g)
+    if (qx_group_used<MODE>(g)) n = g + 1;
+  return n;
+}
+
+// `rec` = the env's record base (tile: st + qx_tile_base(i), GS = kTileGroupStride; env-major record: GS = 4)
+template <int MODE, int GS>
+PFB_HD void quadx_load_tile(const float* __restrict__ rec, QuadXRegs& s, int& step_count) {
+  const F4 g0 = ld_f4(rec + 0 * GS), g1 = ld_f4(rec + 1 * GS), g2 = ld_f4(rec + 2 * GS), g3 = ld_f4(rec + 3 * GS), g4 = ld_f4(rec + 4 * GS),
+           g5 = ld_f4(rec + 5 * GS), g6 = ld_f4(rec + 6 * GS), g7 = ld_f4(rec + 7 * GS), g8 = ld_f4(rec + 8 * GS);
+#if PFB_X_DOUBLE
+  s.px = join_hi_lo(g0.x, g6.y); s.py = join_hi_lo(g0.y, g6.z); s.pz = join_hi_lo(g0.z, g6.w);
+#else
+  s.px = g0.x; s.py = g0.y; s.pz = g0.z;
+#endif
+#if PFB_Q_DOUBLE
+  s.qx = join_hi_lo(g0.w, g7.x); s.qy = join_hi_lo(g1.x, g7.y); s.qz = join_hi_lo(g1.y, g7.z); s.qw = join_hi_lo(g1.z, g7.w);
+#else
+  s.qx = g0.w; s.qy = g1.x; s.qz = g1.y; s.qw = g1.z;
+#endif
+#if PFB_V_DOUBLE
+  s.vx = join_hi_lo(g1.w, g8.x); s.vy = join_hi_lo(g2.x, g8.y); s.vz = join_hi_lo(g2.y, g8.z);
+#else
+  s.vx = g1.w; s.vy = g2.x; s.vz = g2.y;
+#endif
+  s.wx = g2.z; s.wy = g2.w; s.wz = g3.x;
+  s.thr[0] = g3.y; s.thr[1] = g3.z; s.thr[2] = g3.w; s.thr[3] = g4.x;
+  step_count = (int)bits_from_f(g4.y);
+  s.flags = bits_from_f(g4.z);
+  const float p0[6] = {g4.w, g5.x, g5.y, g5.z, g5.w, g6.x};
+#pragma unroll
+  for (int k = 0; k < 6; ++k) s.pid[k] = pid_row_used<MODE>(k) ? p0[k] : 0.0f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) s.pwm[k] = 0.0f;
+#pragma unroll
+  for (int g = 10; g < QX_ROWS / 4; ++g) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (qx_group_used<MODE>(g)) {
+      const F4 q = ld_f4(rec + g * GS);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int k = 6 + 4 * (g - 10) + c;
+      if (k < PID_WORDS) s.pid[k] = pid_row_used<MODE>(k) ? v[c] : 0.0f;
+    }
+  }
+  quadx_update_state(s);
+}
+
+template <int MODE, int GS>
+PFB_HD void quadx_store_tile(float* __restrict__ rec, const QuadXRegs& s, int step_count) {
+  float pxh, pxl, pyh, pyl, pzh, pzl, qxh, qxl, qyh, qyl, qzh, qzl, qwh, qwl, vxh, vxl, vyh, vyl, vzh, vzl;
+#if PFB_X_DOUBLE
+  split_hi_lo(s.px, pxh, pxl); split_hi_lo(s.py, pyh, pyl); split_hi_lo(s.pz, pzh, pzl);
+#else
+  pxh = s.px; pyh = s.py; pzh = s.pz; pxl = pyl = pzl = 0.0f;
+#endif
+#if PFB_Q_DOUBLE
+  split_hi_lo(s.qx, qxh, qxl); split_hi_lo(s.qy, qyh, qyl); split_hi_lo(s.qz, qzh, qzl); split_hi_lo(s.qw, qwh, qwl);
+#else
+  qxh = s.qx; qyh = s.qy; qzh = s.qz; qwh = s.qw; qxl = qyl = qzl = qwl = 0.0f;
+#endif
+#if PFB_V_DOUBLE
+  split_hi_lo(s.vx, vxh, vxl); split_hi_lo(s.vy, vyh, vyl); split_hi_lo(s.vz, vzh, vzl);
+#else
+  vxh = s.vx; vyh = s.vy; vzh = s.vz; vxl = vyl = vzl = 0.0f;
+#endif
+  st_f4(rec + 0 * GS, pxh, pyh, pzh, qxh);
+  st_f4(rec + 1 * GS, qyh, qzh, qwh, vxh);
+  st_f4(rec + 2 * GS, vyh, vzh, s.wx, s.wy);
+  st_f4(rec + 3 * GS, s.wz, s.thr[0], s.thr[1], s.thr[2]);
+  st_f4(rec + 4 * GS, s.thr[3], f_from_bits((uint32_t)step_count), f_from_bits(s.flags), s.pid[0]);
+  st_f4(rec + 5 * GS, s.pid[1], s.pid[2], s.pid[3], s.pid[4]);
+  st_f4(rec + 6 * GS, s.pid[5], pxl, pyl, pzl);
+  st_f4(rec + 7 * GS, qxl, qyl, qzl, qwl);
+  st_f4(rec + 8 * GS, vxl, vyl, vzl, 0.0f);
+  st_f4(rec + 9 * GS, s.pwm[0], s.pwm[1], s.pwm[2], s.pwm[3]);
+#pragma unroll
+  for (int g = 10; g < QX_ROWS / 4; ++g) {
+    if (qx_group_used<MODE>(g)) {
+      float v[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int k = 6 + 4 * (g - 10) + c;
+        v[c] = k < PID_WORDS ? s.pid[k] : 0.0f;
+      }
+      st_f4(rec + g * GS, v[0], v[1], v[2], v[3]);
+    }
+  }
 }
 
 // Round the fp64-carried fields to what the state tensor holds (hi + lo fp32 words) and re-derive R / body velocity:
@@ -619,7 +765,7 @@ PFB_HD void quadx_drone_state(const QuadXRegs& s, float* out12, float* aux4) {
 
 // MAQuadXHover keeps the agent's current and past actions behind the QuadX rows: the observation carries the PAST one, and
 // neither is cleared by a reset (ma_quadx_base_env.py:141-150, 326-332)
-enum { QM_CUR = QX_ROWS, QM_PAST = QX_ROWS + 4, QM_ROWS = QX_ROWS + 8 };
+enum { QM_CUR = QX_ROWS, QM_PAST = QX_ROWS + 4, QM_ROWS = QX_ROWS + 8 };  // groups 15 and 16 of the tile
 
 // ---- QuadX-Hover epilogue ------------------------------------------------------------------------
 // quadx_base_env.py:251-266 + quadx_hover_env.py:117-138, evaluated after every Aviary step

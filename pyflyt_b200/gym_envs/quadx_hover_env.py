@@ -43,7 +43,7 @@ class QuadXHoverVecEnv:
         seed: int | None = None,
         device: str | torch.device = "cuda:0",
         env_offset: int = 0,
-        inline_reset: bool = False,
+        inline_reset: bool | int = False,
     ):
         if 120 % agent_hz != 0:  # quadx_base_env.py:47-52
             lowest = int(120 / (int(120 / agent_hz) + 1))
@@ -74,7 +74,9 @@ class QuadXHoverVecEnv:
         cfg.autoreset = int(self.autoreset)
         cfg.warmup_steps = 10  # quadx_base_env.py:209-210
         cfg.flight_dome_size = self.flight_dome_size
-        cfg.inline_reset = int(bool(inline_reset))  # tests: the spare-copy reset must equal the inline one bit for bit
+        # 0: finished envs take their spare post-reset state, spares rebuilt on the library's side stream; 1: every warm-up is
+        # integrated inside the step launch (tests: must equal the spare path bit for bit); 2: spares, rebuilt on the caller's stream
+        cfg.inline_reset = int(inline_reset)
         self.config = cfg
 
         sp = np.array([[0.0, 0.0, 1.0]]) if start_pos is None else np.asarray(start_pos, dtype=np.float64)

@@ -200,7 +200,7 @@ class HostSimEngine:
 
     def precise_pos(self):
         """hi + lo position words (the fp64 value the kernel carries)."""
-        return (self.st[0:3].astype(np.float64) + self.st[21:24].astype(np.float64)).T
+        return (self.st[0:3].astype(np.float64) + self.st[25:28].astype(np.float64)).T  # QX_POS + QX_POS_LO rows
 
     def env_reset(self, noise, targets=None):
         nz = np.ascontiguousarray(noise, dtype=np.float32)

@@ -129,11 +129,11 @@ def test_full_size_determinism_and_shard_independence():
     lo, hi = run(n // 2, 0), run(n // 2, n // 2)
     assert torch.equal(torch.cat([lo[0], hi[0]]), a[0])
     assert torch.equal(torch.cat([lo[1], hi[1]]), a[1])
-    assert torch.equal(torch.cat([lo[2], hi[2]], dim=1), a[2])
+    assert torch.equal(torch.cat([lo[2], hi[2]], dim=0), a[2])  # warp tiles: [N/32][F/4][32][4]
     assert torch.isfinite(a[0]).all() and torch.isfinite(a[2]).all()
 
 
-@pytest.mark.parametrize("n_envs", [65536, 393216])  # the second is several waves of CTAs: late regular CTAs start after tail CTAs finished
+@pytest.mark.parametrize("n_envs", [65536, 393216])  # the second is several waves of CTAs
 def test_full_size_autoreset_invariants(n_envs):
     """NEXT_STEP autoreset at 65 536 envs: an env that finished on call k returns, on call k+1, the first
     observation of a new episode (z just under the 1 m start after the 10 warm-up steps), reward 0 and
@@ -156,7 +156,7 @@ def test_full_size_autoreset_invariants(n_envs):
             z = a.obs[prev_done][:, 12]
             assert bool(((z > 0.9) & (z < 1.0)).all())
             assert bool((a.reward[prev_done] == 0).all())
-            assert bool((a.istate_tensor[0][prev_done] == 0).all())
+            assert bool((a.step_counts[prev_done] == 0).all())
             # same start pose, same warm-up dynamics: only the motor-noise draws differ
             assert float((a.obs[prev_done][:, :13] - first[prev_done][:, :13]).abs().max()) < 1e-2
         assert bool((a.reward[done & a.term.bool()] < -50).all())  # -100 overwrite on collision / out of bounds
@@ -268,7 +268,7 @@ def test_spare_reset_equals_inline_reset(mode, max_seconds):
     for _ in range(12):
         env.rollout(1)
     torch.cuda.synchronize()
-    assert float(env.aviary.state_tensor[2].min()) > 1.5
+    assert float(env.aviary.state_row(2).min()) > 1.5
     env.close()
 
 
@@ -300,8 +300,7 @@ def test_north_star_parity_4096_envs_1000_env_steps(drone_model):
             e.set_setpoints(sp)
             e.aviary_step(noise, per)
         p0 = orc.state()[:, 3, :]
-        st = cud.av.state_tensor.double().cpu().numpy()
-        p1 = (st[0:3] + st[21:24]).T  # position rows: hi + lo
+        p1 = cud.av.precise_positions.cpu().numpy()  # position rows: hi + lo
         assert p0[:, 2].min() > 10.0  # nobody near the floor
         err = np.maximum(err, np.abs(p0 - p1).max(axis=1))
         travelled += np.linalg.norm(p0 - prev, axis=1)

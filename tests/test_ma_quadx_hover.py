@@ -82,7 +82,7 @@ def test_arena_env_autoreset_and_determinism():
             # an arena is either running (someone alive) or was just reset (everyone alive again, step counter 0)
             per = info["alive"].view(2048, 4)
             assert bool(per.any(dim=1).all())
-            episodes += int((env.aviary.istate_tensor[0].view(2048, 4)[:, 0] == 0).sum())
+            episodes += int((env.aviary.step_counts.view(2048, 4)[:, 0] == 0).sum())
         torch.cuda.synchronize()
         out = (obs.clone(), rew.clone(), env.aviary.state_tensor.clone(), episodes)
         env.close()

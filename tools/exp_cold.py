@@ -25,7 +25,7 @@ def run(env, K, flush):
     q = lambda f: ms[int(f * (len(ms) - 1))] * 1e3
     return f"min {q(0):5.1f}  p10 {q(.1):5.1f}  p50 {q(.5):5.1f}  p90 {q(.9):5.1f}  max {q(1):5.1f} us"
 
-for inline in (False, True):
+for inline in (0, 2, 1):
     env = QuadXHoverVecEnv(num_envs=n, seed=0, device=dev, inline_reset=inline)
     env.reset()
     for flush in ("write", "read", "none"):
