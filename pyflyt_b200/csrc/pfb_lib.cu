@@ -133,7 +133,10 @@ __global__ void __launch_bounds__(kBlock) k_quadx_observe(const float* __restric
 // ---------------------------------------------------------------------------------------------------
 // 512 threads per SM resident (<= 128 registers): the 2048 CTAs of a 65 536-env step and the 148 of the concurrent spare rebuild
 // must all be resident at once, or the stragglers form a second wave
-constexpr int kHoverBlocks = 512 / kBlock;
+#ifndef PFB_HOVER_THREADS
+#define PFB_HOVER_THREADS 512
+#endif
+constexpr int kHoverBlocks = PFB_HOVER_THREADS / kBlock;
 constexpr int kObsMax = 24;  // floats per observation row (20 / 21, + 3 for MAQuadXHover)
 
 // ---- spare post-reset states ("reset pipeline") ---------------------------------------
@@ -156,6 +159,30 @@ __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uin
   const uint32_t sa = (uint32_t)__cvta_generic_to_shared(ssrc);
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// cp.async.bulk (TMA, 1-D) global -> shared with mbarrier completion: the warp's state tile lands asynchronously while
+// the warp runs its noise generator; try_wait is the point the loaded data is first needed
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(sdst), b = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b)
+               : "memory");
+}
+// `dep`: values that must have been COMPUTED before the wait starts (the asm consumes them, no instruction is emitted for
+// them): keeps work that does not need the tile — the noise generator — in front of the wait instead of behind it
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, float d0 = 0.f, float d1 = 0.f, float d2 = 0.f, float d3 = 0.f,
+                                          float d4 = 0.f, float d5 = 0.f, float d6 = 0.f, float d7 = 0.f) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(a),
+      "r"(parity), "f"(d0), "f"(d1), "f"(d2), "f"(d3), "f"(d4), "f"(d5), "f"(d6), "f"(d7)
+      : "memory");
 }
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -199,12 +226,18 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
   if (AUTORESET && blockIdx.x == 0 && lane == 0) *next_count = 0;  // arm the counter the NEXT launch appends to
   float* rec = st + qx_tile_base(i, rows);  // the state tensor is padded to whole tiles: every lane may load
 
-  QuadXRegs s;
-  int step_count;
-  quadx_load_tile<MODE, kTileGroupStride>(rec, s, step_count);
+  // ---- the warp's state tile (groups 0 .. n-1: everything MODE reads) comes in with ONE cp.async.bulk (TMA) into shared
+  //      memory; the noise generator and the action fetch run while it is in flight
+  constexpr int kInGroups = qx_groups_moved<MODE>();
+  __shared__ __align__(128) float stile[kInGroups * kTileGroupStride];
+  __shared__ __align__(8) uint64_t mbar;
+  if (lane == 0) {
+    mbar_init(&mbar, 1);
+    bulk_load_g2s(stile, st + qx_tile_base(tile_first, rows), (uint32_t)(kInGroups * kTileGroupStride * sizeof(float)), &mbar);
+  }
+  __syncwarp();
   float act[4] = {0.f, 0.f, 0.f, 0.f};
   float past[4] = {0.f, 0.f, 0.f, 0.f};
-  // noise of this env step: issued right behind the state loads, consumed inside the loop
   auto nz = make_noise<INJECT>(noise, N, active ? i : 0, rng, step_seq, TAG_ENV_STEP, p.noise_loc, p.ratio);
   nz.prefetch4();
   if (!INJECT && noise_dump && active) nz.set_dump(noise_dump + i, N);
@@ -224,6 +257,10 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
     float4 a4 = __ldg(reinterpret_cast<const float4*>(actions) + i);
     act[0] = a4.x; act[1] = a4.y; act[2] = a4.z; act[3] = a4.w;
   }
+  QuadXRegs s;
+  int step_count;
+  mbar_wait(&mbar, 0, nz.dep(0), nz.dep(1), nz.dep(2), nz.dep(3), nz.dep(4), nz.dep(5), nz.dep(6), nz.dep(7));  // the tile has landed
+  quadx_load_tile<MODE, kTileGroupStride>(stile + lane * 4, s, step_count);  // LDS.128, conflict-free (lane-contiguous vectors)
   // an env that finished on the previous call: this call is its reset (NEXT_STEP)
   const bool resetting = AUTORESET && active && (s.flags & (FLAG_TERM | FLAG_TRUNC)) != 0;
   const float* srec = spare ? spare + i * SP_ROWS : nullptr;
@@ -289,6 +326,19 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
   if (MA) ma_hover_observation(h, s, past, sx, sy, sz, row);
   else hover_observation(h, s, act, row);
   fence_async_smem();  // generic-proxy writes of this lane -> visible to the bulk-copy (async) proxy
+  __syncwarp();
+  // ---- this warp's observation tile obs[tile_first .. +rows][O] is contiguous in global memory and 16-byte aligned: ONE
+  //      cp.async.bulk (TMA) moves it, issued before the state stores so that the engine's reads of shared memory overlap them
+  int64_t nrows = N - tile_first;
+  if (nrows > kBlock) nrows = kBlock;
+  const uint32_t bytes = (uint32_t)nrows * (uint32_t)O * 4u;
+  float* dst = obs + tile_first * O;
+  const bool bulk = (bytes & 15u) == 0u;
+  if (bulk) {
+    if (lane == 0) bulk_store_s2g(dst, smem, bytes);
+  } else {  // ragged last tile whose byte count is not a multiple of 16
+    for (int j = lane; j < (int)nrows * O; j += kBlock) dst[j] = smem[j];
+  }
   if (active) {
     quadx_store_tile<MODE, kTileGroupStride>(rec, s, step_count);
     reward[i] = rew;
@@ -307,20 +357,7 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
       cur_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
     }
   }
-  __syncwarp();
-  // ---- this warp's observation tile obs[tile_first .. +rows][O] is contiguous in global memory and 16-byte aligned
-  int64_t nrows = N - tile_first;
-  if (nrows > kBlock) nrows = kBlock;
-  const uint32_t bytes = (uint32_t)nrows * (uint32_t)O * 4u;
-  float* dst = obs + tile_first * O;
-  if ((bytes & 15u) == 0u) {
-    if (lane == 0) {
-      bulk_store_s2g(dst, smem, bytes);
-      bulk_store_wait_read();  // the CTA's shared memory must outlive the engine's reads
-    }
-  } else {  // ragged last tile whose byte count is not a multiple of 16
-    for (int j = lane; j < (int)nrows * O; j += kBlock) dst[j] = smem[j];
-  }
+  if (bulk && lane == 0) bulk_store_wait_read();  // the CTA's shared memory must outlive the engine's reads
 }
 
 // Rebuilds spare post-reset states: the envs of `list` (those that finished on step k - 1 and consumed their spare on step

@@ -18,6 +18,7 @@ struct InjectedNoise {  // parity tests: the CPU-drawn sequence, [substep][N]
   __device__ __forceinline__ void seek(uint32_t) {}  // the caller passes the pointer already positioned
   __device__ __forceinline__ void prefetch4() {}
   __device__ __forceinline__ void set_dump(float*, int64_t) {}
+  __device__ __forceinline__ float dep(int) const { return 0.0f; }
   __device__ __forceinline__ float get(int) {
     float v = __ldg(ptr);
     ptr += N;
@@ -69,15 +70,30 @@ struct PhiloxNoise {
       pre = step + 4u;
     }
   }
+  __device__ __forceinline__ float dep(int k) const {  // the prefetched draws, for ordering constraints (mbar_wait)
+    return k == 0 ? n0 : k == 1 ? n1 : k == 2 ? n2 : k == 3 ? n3 : k == 4 ? m0 : k == 5 ? m1 : k == 6 ? m2 : m3;
+  }
+  // out-of-line generator for the draws that were not prefetched (long warm-ups, ratio > 2): keeps the physics loop compact
+  struct Four { float a, b, c, d; };
+  static __device__ __noinline__ Four draw_cold(uint32_t env_lo_, uint32_t env_hi_, uint32_t seq_, uint32_t ctr3, uint32_t k0_, uint32_t k1_) {
+    U4 r = philox4x32_10(U4{env_lo_, env_hi_, seq_, ctr3}, k0_, k1_);
+    Four f;
+    box_muller(r.x, r.y, f.a, f.b);
+    box_muller(r.z, r.w, f.c, f.d);
+    return f;
+  }
   __device__ __forceinline__ void begin_step() {
-    if (ratio > 2) {
-      draw(step, n0, n1, n2, n3);
-    } else if ((step & 1u) == 0u) {
+    bool need = ratio > 2;
+    if (!need && (step & 1u) == 0u) {
       if (step < pre) {
         if (step + 2u == pre) { n0 = m0; n1 = m1; n2 = m2; n3 = m3; }  // second prefetched pair moves into place
       } else {
-        draw(step, n0, n1, n2, n3);
+        need = true;
       }
+    }
+    if (need) {
+      const Four f = draw_cold(env_lo, env_hi, seq, tag | step, k0, k1);
+      n0 = f.a; n1 = f.b; n2 = f.c; n3 = f.d;
     }
     ++step;
   }

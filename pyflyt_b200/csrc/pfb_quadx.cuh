@@ -640,11 +640,27 @@ PFB_HD constexpr int qx_groups_moved() {  // groups 0 .. n-1 cover every row MOD
   return n;
 }
 
-// `rec` = the env's record base (tile: st + qx_tile_base(i), GS = kTileGroupStride; env-major record: GS = 4)
+// `rec` = the env's record base (tile: st + qx_tile_base(i), GS = kTileGroupStride; env-major record: GS = 4).
+// Two halves: quadx_fetch_tile issues the 128-bit loads of the groups every mode needs; quadx_unpack_tile turns them into
+// registers.  The step kernel runs its noise generator BETWEEN the two so that it executes in the shadow of the loads.
+struct QxRaw {
+  F4 g0, g1, g2, g3, g4, g5, g6, g7, g8;
+};
+template <int GS>
+PFB_HD QxRaw quadx_fetch_tile(const float* __restrict__ rec) {
+  QxRaw r;
+  r.g0 = ld_f4(rec + 0 * GS); r.g1 = ld_f4(rec + 1 * GS); r.g2 = ld_f4(rec + 2 * GS); r.g3 = ld_f4(rec + 3 * GS); r.g4 = ld_f4(rec + 4 * GS);
+  r.g5 = ld_f4(rec + 5 * GS); r.g6 = ld_f4(rec + 6 * GS); r.g7 = ld_f4(rec + 7 * GS);
+#if PFB_V_DOUBLE
+  r.g8 = ld_f4(rec + 8 * GS);
+#else
+  r.g8 = F4{0.f, 0.f, 0.f, 0.f};
+#endif
+  return r;
+}
 template <int MODE, int GS>
-PFB_HD void quadx_load_tile(const float* __restrict__ rec, QuadXRegs& s, int& step_count) {
-  const F4 g0 = ld_f4(rec + 0 * GS), g1 = ld_f4(rec + 1 * GS), g2 = ld_f4(rec + 2 * GS), g3 = ld_f4(rec + 3 * GS), g4 = ld_f4(rec + 4 * GS),
-           g5 = ld_f4(rec + 5 * GS), g6 = ld_f4(rec + 6 * GS), g7 = ld_f4(rec + 7 * GS), g8 = ld_f4(rec + 8 * GS);
+PFB_HD void quadx_unpack_tile(const QxRaw& r, const float* __restrict__ rec, QuadXRegs& s, int& step_count) {
+  const F4 &g0 = r.g0, &g1 = r.g1, &g2 = r.g2, &g3 = r.g3, &g4 = r.g4, &g5 = r.g5, &g6 = r.g6, &g7 = r.g7, &g8 = r.g8;
 #if PFB_X_DOUBLE
   s.px = join_hi_lo(g0.x, g6.y); s.py = join_hi_lo(g0.y, g6.z); s.pz = join_hi_lo(g0.z, g6.w);
 #else
@@ -684,6 +700,11 @@ PFB_HD void quadx_load_tile(const float* __restrict__ rec, QuadXRegs& s, int& st
   }
   quadx_update_state(s);
 }
+template <int MODE, int GS>
+PFB_HD void quadx_load_tile(const float* __restrict__ rec, QuadXRegs& s, int& step_count) {
+  const QxRaw r = quadx_fetch_tile<GS>(rec);
+  quadx_unpack_tile<MODE, GS>(r, rec, s, step_count);
+}
 
 template <int MODE, int GS>
 PFB_HD void quadx_store_tile(float* __restrict__ rec, const QuadXRegs& s, int step_count) {
@@ -711,7 +732,9 @@ PFB_HD void quadx_store_tile(float* __restrict__ rec, const QuadXRegs& s, int st
   st_f4(rec + 5 * GS, s.pid[1], s.pid[2], s.pid[3], s.pid[4]);
   st_f4(rec + 6 * GS, s.pid[5], pxl, pyl, pzl);
   st_f4(rec + 7 * GS, qxl, qyl, qzl, qwl);
+#if PFB_V_DOUBLE
   st_f4(rec + 8 * GS, vxl, vyl, vzl, 0.0f);
+#endif
   st_f4(rec + 9 * GS, s.pwm[0], s.pwm[1], s.pwm[2], s.pwm[3]);
 #pragma unroll
   for (int g = 10; g < QX_ROWS / 4; ++g) {
