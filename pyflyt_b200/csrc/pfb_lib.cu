@@ -143,16 +143,22 @@ constexpr int kObsMax = 24;  // floats per observation row (20 / 21, + 3 for MAQ
 // env.reset() = start pose + `warmup_steps` Aviary steps (quadx_base_env.py:149-212): 3.3x the work of an env step and a
 // strictly serial chain; run inline, even one finished env stretches the launch to the length of that chain.  So each env
 // owns a SPARE, the post-warm-up state of its NEXT episode, with the warm-up noise keyed by (env id, episode number,
-// Aviary step) so that it does not matter when it is computed.  An env that finished on call k is reset on call k + 1 BY ITS
-// OWN THREAD: the thread skips the physics loop and, at the end of the launch, swaps the env's spare record in (prefetched
-// into L2 at the top of the launch) — no separate reset CTAs, no queue on the step's critical path, every observation row of
-// a warp's tile is written by that warp.  The envs that finish are appended to a list; k_hover_spare_build rebuilds the
-// spares that were consumed, on a side stream, concurrently with the following step launches (the step two launches later
-// waits for it: an env cannot finish again sooner).  If the start pose was edited since a spare was built, or with
-// inline_reset = 1, the spare is ignored and the warm-up runs inline in the owning thread (same episode number, same result).
-// Library-owned buffer [N][SP_ROWS], ENV-MAJOR records: the QX_* state rows in record layout (group stride 4), then:
+// Aviary step) so that it does not matter when it is computed.
+//  * An env that finished on call k is reset on call k + 1 BY ITS OWN THREAD: the thread skips the physics loop and, at the
+//    end of the launch, swaps the env's spare record in (prefetched into L2 at the top of the launch) — every observation
+//    row of a warp's tile is written by that warp.
+//  * The spare it consumed is rebuilt INSIDE the following two step launches by a few BUILDER CTAs appended to the grid:
+//    launch k + 1 (the one that consumes) integrates the first half of the next spare's warm-up, launch k + 2 the second
+//    half — each half is shorter than an env step, so the builders never stretch a launch — and the spare is valid again
+//    before launch k + 3, the earliest the env can be reset again.  Spares are double-buffered by episode parity, so the
+//    builders never write the record a resetting thread is reading.  One launch per env step: no side stream, no events.
+//  * If the start pose was edited since a spare was built, or with inline_reset = 1, the spare is ignored and the warm-up
+//    runs inline in the owning thread (same episode number, hence the same result).
+// Library-owned: spare[2][N][SP_ROWS] ENV-MAJOR records (the QX_* state rows in record layout, group stride 4, then the
+// words below) and episode[N], the episode number of each env's current valid spare (its buffer is episode & 1).
 enum { SP_POSE = QX_ROWS, SP_VALID = QX_ROWS + 6, SP_FLAGS = QX_ROWS + 7, SP_EPISODE = QX_ROWS + 8, SP_ROWS = 80 };
 static_assert(QX_ROWS % 4 == 0 && QX_ROWS + 12 <= SP_ROWS && SP_ROWS % 4 == 0, "spare record layout");
+constexpr int kWarmSplit = 5;  // Aviary steps integrated by the first builder phase; every warm-up requantizes its state there
 
 // cp.async.bulk (TMA, 1-D) shared -> global: one instruction moves a warp's whole observation tile
 __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
@@ -188,19 +194,64 @@ __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// env.reset() integrated inline: start pose, set_mode, warm-up Aviary steps (quadx_base_env.py:149-212).  Everything by
+// env.reset() integrated inline (quadx_base_env.py:149-212): Aviary steps [from, to) of the warm-up that follows the start
+// pose + set_mode.  The state is rounded to what a record holds (hi + lo words) before step kWarmSplit in EVERY path, so a
+// warm-up integrated in two launches through a spare record equals one integrated in one go, bit for bit.  Everything by
 // value: the caller's register-resident state never has its address taken (this is the COLD path of the step kernel and
-// the body of the reset / spare-build kernels).
+// the body of the reset / builder code).
 template <int MODE, bool INJECT>
-__device__ __noinline__ QuadXRegs hover_warmup(const QuadXParams p, int warmup_steps, const RngParams rng, const float* __restrict__ noise,
-                                               int64_t N, int64_t i, uint32_t seq, float px, float py, float pz, float ox, float oy, float oz) {
+__device__ __noinline__ QuadXRegs hover_warmup(const QuadXParams p, QuadXRegs s, int from, int to, const RngParams rng,
+                                               const float* __restrict__ noise, int64_t N, int64_t i, uint32_t seq) {
+  auto nz = make_noise<INJECT>(noise, N, i, rng, seq, TAG_RESET, p.noise_loc, p.ratio);
+  nz.seek((uint32_t)from);
+#pragma unroll 1
+  for (int k = from; k < to; ++k) {
+    if (k == kWarmSplit) quadx_requantize(s);
+    quadx_aviary_step<MODE>(p, s, nz);
+  }
+  return s;
+}
+// a freshly constructed drone in flight mode MODE at its start pose (quadx.py:222-231, quadx_base_env.py:186-207)
+template <int MODE>
+__device__ __forceinline__ QuadXRegs hover_fresh(float px, float py, float pz, float ox, float oy, float oz) {
   QuadXRegs s;
   quadx_reset(s, px, py, pz, ox, oy, oz);
   quadx_set_mode<MODE>(s);
-  auto nz = make_noise<INJECT>(noise, N, i, rng, seq, TAG_RESET, p.noise_loc, p.ratio);
-#pragma unroll 1
-  for (int k = 0; k < warmup_steps; ++k) quadx_aviary_step<MODE>(p, s, nz);
   return s;
+}
+
+// Builder CTAs of the step launch (blockIdx.x >= number of tiles): phase 0 starts the next spare of the envs that are being
+// reset by this launch (list of the previous launch), phase 1 finishes the spares started by the previous launch.
+template <int MODE>
+__device__ __forceinline__ void hover_build_phase(const QuadXParams& p, const HoverParams& h, const RngParams& rng, int phase, int slot, int slots,
+                                                  const int32_t* __restrict__ count, const int32_t* __restrict__ list,
+                                                  const float* __restrict__ start_pos, const float* __restrict__ start_orn,
+                                                  float* __restrict__ spare, uint32_t* __restrict__ episode, int64_t N) {
+  const int t_end = *count;
+  const int split = h.warmup_steps < kWarmSplit ? h.warmup_steps : kWarmSplit;
+  for (int t = slot * kBlock + threadIdx.x; t < t_end; t += slots * kBlock) {
+    const int64_t i = list[t];
+    const uint32_t e = episode[i] + 1u;  // the spare being built; the one being consumed (episode[i]) lives in the other buffer
+    float* rec = spare + ((int64_t)(e & 1u) * N + i) * SP_ROWS;
+    QuadXRegs s;
+    if (phase == 0) {
+      const float px = start_pos[3 * i + 0], py = start_pos[3 * i + 1], pz = start_pos[3 * i + 2];
+      const float ox = start_orn[3 * i + 0], oy = start_orn[3 * i + 1], oz = start_orn[3 * i + 2];
+      s = hover_warmup<MODE, false>(p, hover_fresh<MODE>(px, py, pz, ox, oy, oz), 0, split, rng, nullptr, N, i, e);
+      st_f4(rec + SP_POSE, px, py, pz, ox);
+      st_f4(rec + SP_POSE + 4, oy, oz, 0.0f, 0.0f);  // not valid yet
+      st_f4(rec + SP_POSE + 8, f_from_bits(e), 0.0f, 0.0f, 0.0f);
+      quadx_store_tile<7, 4>(rec, s, 0);
+    } else {
+      int dummy;
+      quadx_load_tile<7, 4>(rec, s, dummy);
+      s = hover_warmup<MODE, false>(p, s, split, h.warmup_steps, rng, nullptr, N, i, e);
+      quadx_store_tile<7, 4>(rec, s, 0);
+      rec[SP_FLAGS] = f_from_bits(s.flags);
+      rec[SP_VALID] = 1.0f;
+      episode[i] = e;
+    }
+  }
 }
 
 // env.step(action) for every env (quadx_base_env.py:269-301 + quadx_hover_env.py), ONE launch, one warp per CTA, one tile
@@ -215,8 +266,17 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
                  const float* __restrict__ noise, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ term,
                  uint8_t* __restrict__ trunc, uint8_t* __restrict__ info, const float* __restrict__ start_pos,
                  const float* __restrict__ start_orn, int32_t* __restrict__ cur_count, int32_t* __restrict__ cur_list,
-                 int32_t* __restrict__ next_count, const float* __restrict__ spare, int spare_copy, float* __restrict__ noise_dump,
-                 uint32_t step_seq, int64_t N) {
+                 int32_t* __restrict__ next_count, const int32_t* __restrict__ b0_count, const int32_t* __restrict__ b0_list,
+                 const int32_t* __restrict__ b1_count, const int32_t* __restrict__ b1_list, float* __restrict__ spare,
+                 uint32_t* __restrict__ episode, int spare_copy, int builders, float* __restrict__ noise_dump, uint32_t step_seq,
+                 int64_t N) {
+  const int n_tiles = (int)((N + kBlock - 1) / kBlock);
+  if (AUTORESET && (int)blockIdx.x >= n_tiles) {  // builder CTA (CTA-uniform role)
+    const int b = (int)blockIdx.x - n_tiles;
+    if (b < builders) hover_build_phase<MODE>(p, h, rng, 0, b, builders, b0_count, b0_list, start_pos, start_orn, spare, episode, N);
+    else hover_build_phase<MODE>(p, h, rng, 1, b - builders, builders, b1_count, b1_list, start_pos, start_orn, spare, episode, N);
+    return;
+  }
   __shared__ __align__(128) float smem[kBlock * kObsMax];
   const int O = (h.angle_representation == 0 ? 20 : 21) + (MA ? 3 : 0);
   const int lane = threadIdx.x;
@@ -263,11 +323,14 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
   quadx_load_tile<MODE, kTileGroupStride>(stile + lane * 4, s, step_count);  // LDS.128, conflict-free (lane-contiguous vectors)
   // an env that finished on the previous call: this call is its reset (NEXT_STEP)
   const bool resetting = AUTORESET && active && (s.flags & (FLAG_TERM | FLAG_TRUNC)) != 0;
-  const float* srec = spare ? spare + i * SP_ROWS : nullptr;
-  if (AUTORESET && resetting && srec) {  // pull the spare record into L2 while the other lanes integrate
-    prefetch_l2(srec);
-    prefetch_l2(srec + 32);
-    prefetch_l2(srec + 64);
+  uint32_t e_next = 0u;
+  if (AUTORESET && resetting && spare) {  // pull both of the env's spare records towards L2 while the other lanes integrate
+    e_next = episode[i];                  // (loaded now, first used at the end of the launch)
+#pragma unroll
+    for (int bsel = 0; bsel < 2; ++bsel) {
+      const float* r = spare + ((int64_t)bsel * N + i) * SP_ROWS;
+      prefetch_l2(r); prefetch_l2(r + 32); prefetch_l2(r + 64); prefetch_l2(r + SP_ROWS - 1);
+    }
   }
   int n_aviary = (active && !resetting) ? h.env_step_ratio : 0;
   float rew = -0.1f;
@@ -300,10 +363,12 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
       const float ox = start_orn[3 * i + 0], oy = start_orn[3 * i + 1], oz = start_orn[3 * i + 2];
       bool hit = false;
       uint32_t nseq = step_seq | 0x40000000u;
-      if (srec) {
+      if (spare) {
+        nseq = e_next;  // episode number: keys the warm-up noise
+        const float* srec = spare + ((int64_t)(e_next & 1u) * N + i) * SP_ROWS;
         const F4 m0 = ld_f4(srec + SP_POSE), m1 = ld_f4(srec + SP_POSE + 4), m2 = ld_f4(srec + SP_POSE + 8);
-        nseq = bits_from_f(m2.x);  // episode number: keys the warm-up noise
-        hit = spare_copy && m1.z != 0.0f && m0.x == px && m0.y == py && m0.z == pz && m0.w == ox && m1.x == oy && m1.y == oz;
+        hit = spare_copy && m1.z != 0.0f && bits_from_f(m2.x) == e_next && m0.x == px && m0.y == py && m0.z == pz && m0.w == ox && m1.x == oy &&
+              m1.y == oz;
         if (hit) {
           int dummy;
           quadx_load_tile<MODE, 4>(srec, s, dummy);
@@ -313,7 +378,7 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
         }
       }
       if (!hit) {
-        s = hover_warmup<MODE, false>(p, h.warmup_steps, rng, nullptr, N, i, nseq, px, py, pz, ox, oy, oz);
+        s = hover_warmup<MODE, false>(p, hover_fresh<MODE>(px, py, pz, ox, oy, oz), 0, h.warmup_steps, rng, nullptr, N, i, nseq);
         quadx_requantize(s);  // an inline warm-up must leave exactly what a copied spare holds
       }
 #pragma unroll
@@ -360,28 +425,24 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
   if (bulk && lane == 0) bulk_store_wait_read();  // the CTA's shared memory must outlive the engine's reads
 }
 
-// Rebuilds spare post-reset states: the envs of `list` (those that finished on step k - 1 and consumed their spare on step
-// k), or every env (list == nullptr: after a user reset).  Dense warps over the list; the same compiled warm-up as the
-// step kernel's inline path and the reset kernel, hence bit-identical results.
+// After a user reset of every env: each env gets a complete fresh spare (dense warps, all envs).
 template <int MODE>
 __global__ void __launch_bounds__(kBlock, kHoverBlocks)
     k_hover_spare_build(const __grid_constant__ QuadXParams p, const __grid_constant__ HoverParams h, const __grid_constant__ RngParams rng,
-                        const float* __restrict__ start_pos, const float* __restrict__ start_orn, const int32_t* __restrict__ count,
-                        const int32_t* __restrict__ list, float* __restrict__ spare, int64_t N) {
-  const int t_end = list ? *count : (int)N;
-  for (int t = blockIdx.x * kBlock + threadIdx.x; t < t_end; t += gridDim.x * kBlock) {
-    const int64_t i = list ? (int64_t)list[t] : (int64_t)t;
-    float* srec = spare + i * SP_ROWS;
-    const uint32_t episode = bits_from_f(srec[SP_EPISODE]) + 1u;
-    const float px = start_pos[3 * i + 0], py = start_pos[3 * i + 1], pz = start_pos[3 * i + 2];
-    const float ox = start_orn[3 * i + 0], oy = start_orn[3 * i + 1], oz = start_orn[3 * i + 2];
-    srec[SP_VALID] = 0.0f;  // invalid until the warm-up below is stored
-    QuadXRegs s = hover_warmup<MODE, false>(p, h.warmup_steps, rng, nullptr, N, i, episode, px, py, pz, ox, oy, oz);
-    quadx_store_tile<7, 4>(srec, s, 0);
-    st_f4(srec + SP_POSE, px, py, pz, ox);
-    st_f4(srec + SP_POSE + 4, oy, oz, 1.0f, f_from_bits(s.flags));
-    st_f4(srec + SP_POSE + 8, f_from_bits(episode), 0.0f, 0.0f, 0.0f);
-  }
+                        const float* __restrict__ start_pos, const float* __restrict__ start_orn, float* __restrict__ spare,
+                        uint32_t* __restrict__ episode, int64_t N) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= N) return;
+  const uint32_t e = episode[i] + 1u;
+  float* rec = spare + ((int64_t)(e & 1u) * N + i) * SP_ROWS;
+  const float px = start_pos[3 * i + 0], py = start_pos[3 * i + 1], pz = start_pos[3 * i + 2];
+  const float ox = start_orn[3 * i + 0], oy = start_orn[3 * i + 1], oz = start_orn[3 * i + 2];
+  QuadXRegs s = hover_warmup<MODE, false>(p, hover_fresh<MODE>(px, py, pz, ox, oy, oz), 0, h.warmup_steps, rng, nullptr, N, i, e);
+  quadx_store_tile<7, 4>(rec, s, 0);
+  st_f4(rec + SP_POSE, px, py, pz, ox);
+  st_f4(rec + SP_POSE + 4, oy, oz, 1.0f, f_from_bits(s.flags));
+  st_f4(rec + SP_POSE + 8, f_from_bits(e), 0.0f, 0.0f, 0.0f);
+  episode[i] = e;
 }
 
 // env.reset() for all / masked envs
@@ -397,8 +458,9 @@ __global__ void __launch_bounds__(kBlock)
   if (mask && !mask[i]) return;
   const int O = (h.angle_representation == 0 ? 20 : 21) + (h.ma ? 3 : 0);
   float row[kObsMax];
-  QuadXRegs s = hover_warmup<MODE, INJECT>(p, h.warmup_steps, rng, noise, N, i, seq, start_pos[3 * i + 0], start_pos[3 * i + 1],
-                                           start_pos[3 * i + 2], start_orn[3 * i + 0], start_orn[3 * i + 1], start_orn[3 * i + 2]);
+  QuadXRegs s = hover_warmup<MODE, INJECT>(p, hover_fresh<MODE>(start_pos[3 * i + 0], start_pos[3 * i + 1], start_pos[3 * i + 2], start_orn[3 * i + 0],
+                                                                start_orn[3 * i + 1], start_orn[3 * i + 2]),
+                                           0, h.warmup_steps, rng, noise, N, i, seq);
   float* rec = st + qx_tile_base(i, rows);
   const float zero[4] = {0.f, 0.f, 0.f, 0.f};  // self.action = zeros (quadx_base_env.py:165)
   if (h.ma) {  // past_actions is NOT cleared by a reset in the reference: it still holds the previous episode's value
@@ -528,16 +590,23 @@ int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, i
   if (env && env->autoreset && (env->env_kind == PFB_ENV_QUADX_HOVER || env->env_kind == PFB_ENV_FIXEDWING_WAYPOINTS ||
                                  env->env_kind == PFB_ENV_QUADX_WAYPOINTS || env->env_kind == PFB_ENV_ROCKET_LANDING ||
                                  env->env_kind == PFB_ENV_DOGFIGHT)) {
-    // spare post-reset states: one env-major record per env (64 floats; 128 for QuadX-Waypoints, whose record holds 8 x 4 targets)
+    // spare post-reset states: env-major records (QuadX-Hover: two per env, double-buffered by episode parity, rebuilt by
+    // builder CTAs inside the step launches; the other env kinds: one per env, rebuilt on a library-owned side stream)
+    const bool hover = env->env_kind == PFB_ENV_QUADX_HOVER;
     const size_t rec = env->env_kind == PFB_ENV_QUADX_WAYPOINTS ? (size_t)qwp_spare_rows()
-                       : (env->env_kind == PFB_ENV_DOGFIGHT ? (size_t)df_spare_rows() : (size_t)SP_ROWS);
+                       : (env->env_kind == PFB_ENV_DOGFIGHT ? (size_t)df_spare_rows() : (size_t)SP_ROWS * (hover ? 2 : 1));
     CUDA_OK(cudaMalloc(&c->d_spare, rec * (size_t)n_envs * sizeof(float)));
     CUDA_OK(cudaMemset(c->d_spare, 0, rec * (size_t)n_envs * sizeof(float)));
-    int prio_lo = 0, prio_hi = 0;  // the rebuild is small and latency-critical: let its CTAs go first when slots free up
-    CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    CUDA_OK(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_hi));
-    CUDA_OK(cudaEventCreateWithFlags(&c->ev_step, cudaEventDisableTiming));
-    for (int k = 0; k < 4; ++k) CUDA_OK(cudaEventCreateWithFlags(&c->ev_spare[k], cudaEventDisableTiming));
+    if (hover) {
+      CUDA_OK(cudaMalloc(&c->d_episode, (size_t)n_envs * sizeof(uint32_t)));
+      CUDA_OK(cudaMemset(c->d_episode, 0, (size_t)n_envs * sizeof(uint32_t)));
+    } else {
+      int prio_lo = 0, prio_hi = 0;  // the rebuild is small and latency-critical: let its CTAs go first when slots free up
+      CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      CUDA_OK(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_hi));
+      CUDA_OK(cudaEventCreateWithFlags(&c->ev_step, cudaEventDisableTiming));
+      for (int k = 0; k < 4; ++k) CUDA_OK(cudaEventCreateWithFlags(&c->ev_spare[k], cudaEventDisableTiming));
+    }
   }
   *out = c;
   return 0;
@@ -547,11 +616,14 @@ int pfb_destroy(PfbHandle h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   if (h->d_spare) {
-    cudaStreamSynchronize(h->side);
-    cudaStreamDestroy(h->side);
-    cudaEventDestroy(h->ev_step);
-    for (int k = 0; k < 4; ++k) cudaEventDestroy(h->ev_spare[k]);
+    if (h->side) {
+      cudaStreamSynchronize(h->side);
+      cudaStreamDestroy(h->side);
+      cudaEventDestroy(h->ev_step);
+      for (int k = 0; k < 4; ++k) cudaEventDestroy(h->ev_spare[k]);
+    }
     cudaFree(h->d_spare);
+    if (h->d_episode) cudaFree(h->d_episode);
   }
   cudaFree(h->d_counters);
   cudaFree(h->d_done_list);
@@ -685,19 +757,16 @@ int pfb_env_reset(PfbHandle h, const uint8_t* mask, const float* noise, void* st
   const int mode = h->hover.flight_mode;
   // resets draw from their own Philox stream; the high bit keeps them apart from in-step autoresets
   const uint32_t seq = 0x80000000u | (uint32_t)h->reset_seq++;
-  if (h->d_spare) {  // the build below rewrites spares: let the side stream's last rebuild finish first
-    if (h->step_seq > 0) CUDA_OK(cudaStreamWaitEvent(s, h->ev_spare[(h->step_seq - 1) % 4], 0));
-    if (!mask) CUDA_OK(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(int32_t), s));  // a full reset empties the rebuild queues
-  }
+  if (h->d_spare && !mask) CUDA_OK(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(int32_t), s));  // a full reset empties the rebuild queues
 #define HR_ARGS h->qx, h->hover, h->rng, h->buf.state, qx_rows(h), h->buf.start_pos, h->buf.start_orn, mask, noise, h->buf.obs, seq, h->n
   if (noise) { PFB_MODE_SWITCH(mode, (k_hover_reset<MODE, true><<<grid_for(h->n), kBlock, 0, s>>>(HR_ARGS))); }
   else { PFB_MODE_SWITCH(mode, (k_hover_reset<MODE, false><<<grid_for(h->n), kBlock, 0, s>>>(HR_ARGS))); }
 #undef HR_ARGS
   LAUNCH_CHECK(h);
-  if (h->d_spare && !mask) {  // every env gets a fresh spare (same stream).  A masked reset keeps the spares: they are keyed by
-                              // (env, episode number) and stay valid; a masked env simply is not `done` on the next step
+  if (h->d_spare && !mask) {  // every env gets a fresh spare.  A masked reset keeps the spares: they are keyed by (env, episode
+                              // number) and stay valid; a masked env simply is not `done` on the next step
     PFB_MODE_SWITCH(mode, (k_hover_spare_build<MODE><<<grid_for(h->n), kBlock, 0, s>>>(h->qx, h->hover, h->rng, h->buf.start_pos, h->buf.start_orn,
-                                                                                      nullptr, nullptr, h->d_spare, h->n)));
+                                                                                      h->d_spare, h->d_episode, h->n)));
     LAUNCH_CHECK(h);
   }
   h->mode = mode;
@@ -712,24 +781,26 @@ static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool r
   const int mode = h->hover.flight_mode;
   const bool autoreset = h->env.autoreset != 0;
   const uint64_t k = h->step_seq;
-  // four rotating done lists / counters: step k appends to [k % 4]; the spare rebuild launched after step k reads
-  // [(k - 1) % 4] (the envs that finished on step k - 1 and took their spare on step k); step k zeroes counter [(k + 1) % 4]
-  // (last read by the rebuild of step k - 2, which step k waits for)
+  // four rotating done lists / counters: step k appends the envs that finish to [k % 4]; its builder CTAs start the next
+  // spares of [(k - 1) % 4] (the envs this launch resets) and finish those of [(k - 2) % 4]; it zeroes counter [(k + 1) % 4]
   int32_t* cnt_cur = h->d_counters + (k % 4);
-  int32_t* cnt_prev = h->d_counters + ((k + 3) % 4);
+  int32_t* cnt_b0 = h->d_counters + ((k + 3) % 4);
+  int32_t* cnt_b1 = h->d_counters + ((k + 2) % 4);
   int32_t* cnt_next = h->d_counters + ((k + 1) % 4);
   int32_t* list_cur = h->d_done_list + (k % 4) * h->n;
-  int32_t* list_prev = h->d_done_list + ((k + 3) % 4) * h->n;
+  int32_t* list_b0 = h->d_done_list + ((k + 3) % 4) * h->n;
+  int32_t* list_b1 = h->d_done_list + ((k + 2) % 4) * h->n;
   const uint32_t seq = (uint32_t)k;
   const bool spares = autoreset && h->d_spare != nullptr;
   const int spare_copy = (spares && h->env.inline_reset != 1) ? 1 : 0;
-  const bool same_stream = h->env.inline_reset == 2;  // rebuild on the caller's stream: all of a step's work in order on one stream
-  if (spares && !same_stream && k >= 2) CUDA_OK(cudaStreamWaitEvent(s, h->ev_spare[(k - 2) % 4], 0));
-  const int grid = grid_for(h->n);
+  const int tiles = grid_for(h->n);
+  const int builders = spares ? (h->sm_count < tiles ? h->sm_count : tiles) : 0;
+  const int grid = tiles + 2 * builders;
   const bool prof = h->prof_ev && h->prof_n < h->prof_cap;
   if (prof) CUDA_OK(cudaEventRecord(h->prof_ev[2 * h->prof_n], s));
 #define STEP_ARGS h->qx, h->hover, h->rng, h->buf.state, qx_rows(h), actions, noise, h->buf.obs, h->buf.reward, h->buf.term, h->buf.trunc,    \
-                  h->buf.info, h->buf.start_pos, h->buf.start_orn, cnt_cur, list_cur, cnt_next, h->d_spare, spare_copy, h->noise_dump, seq, h->n
+                  h->buf.info, h->buf.start_pos, h->buf.start_orn, cnt_cur, list_cur, cnt_next, cnt_b0, list_b0, cnt_b1, list_b1, h->d_spare,  \
+                  h->d_episode, spare_copy, builders, h->noise_dump, seq, h->n
   if (autoreset) {
     if (noise) return fail("injected noise (parity mode) is only supported with autoreset = 0");
     if (randact) {
@@ -755,20 +826,6 @@ static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool r
   if (prof) {
     CUDA_OK(cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], s));
     h->prof_n += 1;
-  }
-  if (spares && k >= 1) {  // rebuild the spares this launch consumed (the envs that finished on step k - 1)
-    cudaStream_t bs = s;
-    if (!same_stream) {
-      CUDA_OK(cudaEventRecord(h->ev_step, s));
-      CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_step, 0));
-      bs = h->side;
-    }
-    PFB_MODE_SWITCH(mode, (k_hover_spare_build<MODE><<<h->sm_count, kBlock, 0, bs>>>(h->qx, h->hover, h->rng, h->buf.start_pos, h->buf.start_orn,
-                                                                                    cnt_prev, list_prev, h->d_spare, h->n)));
-    LAUNCH_CHECK(h);
-    if (!same_stream) CUDA_OK(cudaEventRecord(h->ev_spare[k % 4], h->side));
-  } else if (spares && !same_stream) {
-    CUDA_OK(cudaEventRecord(h->ev_spare[k % 4], s));  // nothing to rebuild after the first step: keep the event chain uniform
   }
   h->step_seq += 1;
   return 0;

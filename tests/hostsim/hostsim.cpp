@@ -60,6 +60,15 @@ static void hover_params(const PfbEnvConfig* env, HoverParams& h) {
 
 #define HS_API extern "C"
 HS_API const char* hs_last_error() { return g_err; }
+// the counter RNG of the kernels (pfb_common.cuh), for tests/test_philox_replay.py
+HS_API void hs_philox(const uint32_t* ctr, uint32_t k0, uint32_t k1, uint32_t* out, float* normals, int64_t n) {
+  for (int64_t i = 0; i < n; ++i) {
+    U4 r = philox4x32_10(U4{ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3]}, k0, k1);
+    out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+    box_muller(r.x, r.y, normals[4 * i], normals[4 * i + 1]);
+    box_muller(r.z, r.w, normals[4 * i + 2], normals[4 * i + 3]);
+  }
+}
 HS_API int hs_state_rows() { return QX_ROWS; }
 HS_API int hs_istate_rows() { return QI_ROWS; }
 HS_API int hs_precision_flags() { return PFB_Q_DOUBLE | (PFB_X_DOUBLE << 1) | (PFB_V_DOUBLE << 2) | (PFB_R_DOUBLE << 3); }
