@@ -156,8 +156,9 @@ constexpr int kObsMax = 24;  // floats per observation row (20 / 21, + 3 for MAQ
 //    runs inline in the owning thread (same episode number, hence the same result).
 // Library-owned: spare[2][N][SP_ROWS] ENV-MAJOR records (the QX_* state rows in record layout, group stride 4, then the
 // words below) and episode[N], the episode number of each env's current valid spare (its buffer is episode & 1).
-enum { SP_POSE = QX_ROWS, SP_VALID = QX_ROWS + 6, SP_FLAGS = QX_ROWS + 7, SP_EPISODE = QX_ROWS + 8, SP_ROWS = 80 };
-static_assert(QX_ROWS % 4 == 0 && QX_ROWS + 12 <= SP_ROWS && SP_ROWS % 4 == 0, "spare record layout");
+enum { SP_POSE = QX_ROWS, SP_VALID = QX_ROWS + 6, SP_FLAGS = QX_ROWS + 7, SP_EPISODE = QX_ROWS + 8,
+       SP_SETPOINT = QX_ROWS + 12 /* 4: the flight mode's preset setpoint, carried between the two halves of a warm-up */, SP_ROWS = 80 };
+static_assert(QX_ROWS % 4 == 0 && QX_ROWS + 16 <= SP_ROWS && SP_ROWS % 4 == 0, "spare record layout");
 constexpr int kWarmSplit = 5;  // Aviary steps integrated by the first builder phase; every warm-up requantizes its state there
 
 // cp.async.bulk (TMA, 1-D) shared -> global: one instruction moves a warp's whole observation tile
@@ -196,12 +197,12 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 
 // env.reset() integrated inline (quadx_base_env.py:149-212): Aviary steps [from, to) of the warm-up that follows the start
 // pose + set_mode.  The state is rounded to what a record holds (hi + lo words) before step kWarmSplit in EVERY path, so a
-// warm-up integrated in two launches through a spare record equals one integrated in one go, bit for bit.  Everything by
-// value: the caller's register-resident state never has its address taken (this is the COLD path of the step kernel and
-// the body of the reset / builder code).
+// warm-up integrated in two launches through a spare record equals one integrated in one go, bit for bit.
+// The INLINE form is what the builder CTAs and the reset / build kernels run: `p` must be the kernel's __grid_constant__
+// parameter so that the coefficients stay constant-bank operands.
 template <int MODE, bool INJECT>
-__device__ __noinline__ QuadXRegs hover_warmup(const QuadXParams p, QuadXRegs s, int from, int to, const RngParams rng,
-                                               const float* __restrict__ noise, int64_t N, int64_t i, uint32_t seq) {
+__device__ __forceinline__ void hover_warmup_inline(const QuadXParams& p, QuadXRegs& s, int from, int to, const RngParams& rng,
+                                                    const float* __restrict__ noise, int64_t N, int64_t i, uint32_t seq) {
   auto nz = make_noise<INJECT>(noise, N, i, rng, seq, TAG_RESET, p.noise_loc, p.ratio);
   nz.seek((uint32_t)from);
 #pragma unroll 1
@@ -209,6 +210,14 @@ __device__ __noinline__ QuadXRegs hover_warmup(const QuadXParams p, QuadXRegs s,
     if (k == kWarmSplit) quadx_requantize(s);
     quadx_aviary_step<MODE>(p, s, nz);
   }
+}
+// Out-of-line form for the COLD fallback inside the step role (a spare that cannot be used): everything by value, so the
+// caller's register-resident state never has its address taken.  Slow (the coefficient table is read from the stack copy),
+// and rare.
+template <int MODE>
+__device__ __noinline__ QuadXRegs hover_warmup_cold(const QuadXParams p, QuadXRegs s, int to, const RngParams rng, int64_t N, int64_t i,
+                                                    uint32_t seq) {
+  hover_warmup_inline<MODE, false>(p, s, 0, to, rng, nullptr, N, i, seq);
   return s;
 }
 // a freshly constructed drone in flight mode MODE at its start pose (quadx.py:222-231, quadx_base_env.py:186-207)
@@ -220,33 +229,45 @@ __device__ __forceinline__ QuadXRegs hover_fresh(float px, float py, float pz, f
   return s;
 }
 
-// Builder CTAs of the step launch (blockIdx.x >= number of tiles): phase 0 starts the next spare of the envs that are being
-// reset by this launch (list of the previous launch), phase 1 finishes the spares started by the previous launch.
+// Builder CTAs of the step launch (blockIdx.x >= number of tiles): the first `builders` of them (phase 0) start the next
+// spare of the envs that are being reset by this launch (done list of the previous launch), the others (phase 1) finish the
+// spares started by the previous launch.  ONE copy of the warm-up loop serves both phases.
 template <int MODE>
-__device__ __forceinline__ void hover_build_phase(const QuadXParams& p, const HoverParams& h, const RngParams& rng, int phase, int slot, int slots,
-                                                  const int32_t* __restrict__ count, const int32_t* __restrict__ list,
-                                                  const float* __restrict__ start_pos, const float* __restrict__ start_orn,
-                                                  float* __restrict__ spare, uint32_t* __restrict__ episode, int64_t N) {
-  const int t_end = *count;
+__device__ __forceinline__ void hover_build(const QuadXParams& p, const HoverParams& h, const RngParams& rng, int b, int builders,
+                                            const int32_t* __restrict__ b0_count, const int32_t* __restrict__ b0_list,
+                                            const int32_t* __restrict__ b1_count, const int32_t* __restrict__ b1_list,
+                                            const float* __restrict__ start_pos, const float* __restrict__ start_orn,
+                                            float* __restrict__ spare, uint32_t* __restrict__ episode, int64_t N) {
+  const int phase = b >= builders ? 1 : 0;
+  const int slot = b - phase * builders;
+  const int32_t* __restrict__ list = phase ? b1_list : b0_list;
+  const int t_end = phase ? *b1_count : *b0_count;
   const int split = h.warmup_steps < kWarmSplit ? h.warmup_steps : kWarmSplit;
-  for (int t = slot * kBlock + threadIdx.x; t < t_end; t += slots * kBlock) {
+#pragma unroll 1
+  for (int t = slot * kBlock + threadIdx.x; t < t_end; t += builders * kBlock) {
     const int64_t i = list[t];
     const uint32_t e = episode[i] + 1u;  // the spare being built; the one being consumed (episode[i]) lives in the other buffer
     float* rec = spare + ((int64_t)(e & 1u) * N + i) * SP_ROWS;
     QuadXRegs s;
+    float px = 0.f, py = 0.f, pz = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
     if (phase == 0) {
-      const float px = start_pos[3 * i + 0], py = start_pos[3 * i + 1], pz = start_pos[3 * i + 2];
-      const float ox = start_orn[3 * i + 0], oy = start_orn[3 * i + 1], oz = start_orn[3 * i + 2];
-      s = hover_warmup<MODE, false>(p, hover_fresh<MODE>(px, py, pz, ox, oy, oz), 0, split, rng, nullptr, N, i, e);
-      st_f4(rec + SP_POSE, px, py, pz, ox);
-      st_f4(rec + SP_POSE + 4, oy, oz, 0.0f, 0.0f);  // not valid yet
-      st_f4(rec + SP_POSE + 8, f_from_bits(e), 0.0f, 0.0f, 0.0f);
-      quadx_store_tile<7, 4>(rec, s, 0);
+      px = start_pos[3 * i + 0]; py = start_pos[3 * i + 1]; pz = start_pos[3 * i + 2];
+      ox = start_orn[3 * i + 0]; oy = start_orn[3 * i + 1]; oz = start_orn[3 * i + 2];
+      s = hover_fresh<MODE>(px, py, pz, ox, oy, oz);
     } else {
       int dummy;
       quadx_load_tile<7, 4>(rec, s, dummy);
-      s = hover_warmup<MODE, false>(p, s, split, h.warmup_steps, rng, nullptr, N, i, e);
-      quadx_store_tile<7, 4>(rec, s, 0);
+      const F4 sp = ld_f4(rec + SP_SETPOINT);
+      s.sp[0] = sp.x; s.sp[1] = sp.y; s.sp[2] = sp.z; s.sp[3] = sp.w;
+    }
+    hover_warmup_inline<MODE, false>(p, s, phase ? split : 0, phase ? h.warmup_steps : split, rng, nullptr, N, i, e);
+    quadx_store_tile<7, 4>(rec, s, 0);
+    if (phase == 0) {
+      st_f4(rec + SP_POSE, px, py, pz, ox);
+      st_f4(rec + SP_POSE + 4, oy, oz, 0.0f, 0.0f);  // not valid yet
+      st_f4(rec + SP_POSE + 8, f_from_bits(e), 0.0f, 0.0f, 0.0f);
+      st_f4(rec + SP_SETPOINT, s.sp[0], s.sp[1], s.sp[2], s.sp[3]);
+    } else {
       rec[SP_FLAGS] = f_from_bits(s.flags);
       rec[SP_VALID] = 1.0f;
       episode[i] = e;
@@ -272,9 +293,7 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
                  int64_t N) {
   const int n_tiles = (int)((N + kBlock - 1) / kBlock);
   if (AUTORESET && (int)blockIdx.x >= n_tiles) {  // builder CTA (CTA-uniform role)
-    const int b = (int)blockIdx.x - n_tiles;
-    if (b < builders) hover_build_phase<MODE>(p, h, rng, 0, b, builders, b0_count, b0_list, start_pos, start_orn, spare, episode, N);
-    else hover_build_phase<MODE>(p, h, rng, 1, b - builders, builders, b1_count, b1_list, start_pos, start_orn, spare, episode, N);
+    hover_build<MODE>(p, h, rng, (int)blockIdx.x - n_tiles, builders, b0_count, b0_list, b1_count, b1_list, start_pos, start_orn, spare, episode, N);
     return;
   }
   __shared__ __align__(128) float smem[kBlock * kObsMax];
@@ -378,7 +397,7 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
         }
       }
       if (!hit) {
-        s = hover_warmup<MODE, false>(p, hover_fresh<MODE>(px, py, pz, ox, oy, oz), 0, h.warmup_steps, rng, nullptr, N, i, nseq);
+        s = hover_warmup_cold<MODE>(p, hover_fresh<MODE>(px, py, pz, ox, oy, oz), h.warmup_steps, rng, N, i, nseq);
         quadx_requantize(s);  // an inline warm-up must leave exactly what a copied spare holds
       }
 #pragma unroll
@@ -437,7 +456,8 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
   float* rec = spare + ((int64_t)(e & 1u) * N + i) * SP_ROWS;
   const float px = start_pos[3 * i + 0], py = start_pos[3 * i + 1], pz = start_pos[3 * i + 2];
   const float ox = start_orn[3 * i + 0], oy = start_orn[3 * i + 1], oz = start_orn[3 * i + 2];
-  QuadXRegs s = hover_warmup<MODE, false>(p, hover_fresh<MODE>(px, py, pz, ox, oy, oz), 0, h.warmup_steps, rng, nullptr, N, i, e);
+  QuadXRegs s = hover_fresh<MODE>(px, py, pz, ox, oy, oz);
+  hover_warmup_inline<MODE, false>(p, s, 0, h.warmup_steps, rng, nullptr, N, i, e);
   quadx_store_tile<7, 4>(rec, s, 0);
   st_f4(rec + SP_POSE, px, py, pz, ox);
   st_f4(rec + SP_POSE + 4, oy, oz, 1.0f, f_from_bits(s.flags));
@@ -458,9 +478,9 @@ __global__ void __launch_bounds__(kBlock)
   if (mask && !mask[i]) return;
   const int O = (h.angle_representation == 0 ? 20 : 21) + (h.ma ? 3 : 0);
   float row[kObsMax];
-  QuadXRegs s = hover_warmup<MODE, INJECT>(p, hover_fresh<MODE>(start_pos[3 * i + 0], start_pos[3 * i + 1], start_pos[3 * i + 2], start_orn[3 * i + 0],
-                                                                start_orn[3 * i + 1], start_orn[3 * i + 2]),
-                                           0, h.warmup_steps, rng, noise, N, i, seq);
+  QuadXRegs s = hover_fresh<MODE>(start_pos[3 * i + 0], start_pos[3 * i + 1], start_pos[3 * i + 2], start_orn[3 * i + 0], start_orn[3 * i + 1],
+                                  start_orn[3 * i + 2]);
+  hover_warmup_inline<MODE, INJECT>(p, s, 0, h.warmup_steps, rng, noise, N, i, seq);
   float* rec = st + qx_tile_base(i, rows);
   const float zero[4] = {0.f, 0.f, 0.f, 0.f};  // self.action = zeros (quadx_base_env.py:165)
   if (h.ma) {  // past_actions is NOT cleared by a reset in the reference: it still holds the previous episode's value

