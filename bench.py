@@ -4,10 +4,14 @@
     python bench.py --gpus N --steps K --warmup W            (ours; torchrun for N > 1)
     python bench.py --impl reference --gpus N --steps K ...  (CPU arm: the oracle port, all host threads)
 
-One "step" = one env.step() of every env of this rank's shard = one k_hover_step launch (6 physics
-substeps, 3 control ticks, reward/termination/observation fused) + one k_hover_autoreset launch.
-Workload (config.workload): QuadX-Hover-v4, mode 0, 65 536 envs per GPU, uniform random actions in the
-env's action box, NEXT_STEP autoreset — BASELINE.json configs[1].  Prints ONE JSON line on rank 0.
+One "step" = one env.step() of every env of this rank's shard = ONE k_hover_step launch (6 physics substeps,
+3 control ticks, reward / termination / observation fused; finished envs are reset by their own thread on the next
+call, and builder CTAs appended to the same grid rebuild the spare post-reset states that were consumed).
+Workload (config.workload): QuadX-Hover-v4, mode 0, 65 536 envs per GPU, uniform random actions in the env's action
+box, NEXT_STEP autoreset — BASELINE.json configs[1].  Prints ONE JSON line on rank 0.  R blocks of exactly K steps
+are timed (L2 flushed between steps, per-step CUDA-event pairs); `value` is the median block.  Under torchrun the line
+also carries config.value_strong_65536_total (BASELINE's 65 536 envs in total, split over the ranks) and
+config.dogfight_split (configs[4] with an arena's aircraft on different ranks: exchange every Aviary step).
 """
 import argparse
 import json
@@ -32,9 +36,17 @@ def load_peaks():
     return 6650.0, "fallback"
 
 
+def _ncu_summary_path():
+    """newest committed `ncu --set full` summary of the step kernel (profiles/rNN_k_hover_step_ncu_summary.txt), or None"""
+    import glob
+
+    found = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_hover_step_ncu_summary.txt")))
+    return found[-1] if found else None
+
+
 def ncu_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
-    path = os.path.join(ROOT, "profiles", "r01_k_hover_step_ncu_summary.txt")
+    path = _ncu_summary_path()
     try:
         total, seen = 0.0, 0
         for line in open(path):
@@ -52,7 +64,7 @@ def ncu_traffic():
 
 def ncu_flops():
     """(fp32, fp64) FLOPs per step launch from the committed ncu capture, or (None, None)."""
-    path = os.path.join(ROOT, "profiles", "r01_k_hover_step_ncu_summary.txt")
+    path = _ncu_summary_path()
     out = {}
     try:
         for line in open(path):
@@ -166,12 +178,21 @@ def cpu_oracle_rate(envs: int, target_seconds: float, threads: int | None = None
     return done / dt, cores, steps, dt
 
 
+WORKLOAD = ("QuadX-Hover-v4 (BASELINE configs[1]): flight mode 0, 65536 envs per GPU, uniform random actions, NEXT_STEP autoreset, "
+            "6 physics substeps + 3 control ticks per env-step")
+
+
+def base_config(world: int, n: int) -> dict:
+    """keys shared by both arms (the driver compares them)"""
+    return {"workload": WORKLOAD, "envs_per_gpu": n, "global_envs": world * n, "parallelism": f"env-shard x{world} (no data-path collective)"}
+
+
 def run_reference(args, rank, world):
     """CPU arm: the reference's algorithm (oracle port; PyBullet itself is not installable here) timed
-    on the box's host cores, same metric and config; rank 0 only."""
+    on the box's host cores, same metric and config (the same GLOBAL number of envs as our arm steps); rank 0 only."""
     if rank != 0:
         return
-    envs = ENVS_PER_GPU
+    envs = args.envs * world
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import numpy as np
 
@@ -197,12 +218,83 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "QuadX-Hover-v4 mode 0, 65536 envs, uniform random actions, NEXT_STEP autoreset", "envs": envs},
+        "config": base_config(world, args.envs),
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x {envs} envs of the full workload (oracle/pfb_oracle.c, OpenMP)"},
+                         "sample": f"{args.steps} steps x {envs} envs of the full workload (oracle/pfb_oracle.c, fp64, OpenMP; thread count tuned by a short probe)"},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def _median(x):
+    x = sorted(x)
+    return x[len(x) // 2]
+
+
+def dogfight_split_block(rank, world, dev, steps=40, arenas=8192):
+    """BASELINE configs[4] as written: 8192 arenas x 2 agents with an arena's two aircraft on DIFFERENT ranks, one exchange per
+    Aviary step (4 per env step).  Times every exchange flavour and checks bit-equality with a single-rank run."""
+    import torch
+    import torch.distributed as dist
+
+    from pyflyt_b200.pz_envs import MAFixedwingDogfightSplitEnv
+
+    out = {"arenas": arenas, "agents": 2 * arenas, "ranks": world, "collectives_per_step": 4, "payload_bytes_per_agent_per_exchange": 80}
+    # ---- parity: every rank steps its slice (Philox noise keyed by global agent id), rank 0 repeats all of it alone
+    pa, ps = 1024, 6
+    g = torch.Generator().manual_seed(7)
+    acts = (torch.rand((ps, 2 * pa, 4), generator=g) * 2 - 1) * 0.4
+    kw = dict(seed=3, lethal_distance=150.0, lethal_angle_radians=1.0, damage_per_hit=0.05)
+
+    def run(env):
+        lo, hi = env.first_gid, env.first_gid + env.n_local
+        obs = [env.reset().clone()]
+        rew = []
+        for k in range(ps):
+            o, r, _, _ = env.step(acts[k, lo:hi].to(dev))
+            obs.append(o.clone())
+            rew.append(r.clone())
+        env.close()
+        return torch.stack(obs), torch.stack(rew)
+
+    ok = True
+    for ex in ("nccl", "peer-signal"):
+        o, r = run(MAFixedwingDogfightSplitEnv(pa, device=dev, exchange=ex, **kw))
+        parts_o = [torch.empty_like(o) for _ in range(world)]
+        parts_r = [torch.empty_like(r) for _ in range(world)]
+        dist.all_gather(parts_o, o.contiguous())
+        dist.all_gather(parts_r, r.contiguous())
+        if rank == 0:
+            so, sr = run(MAFixedwingDogfightSplitEnv(pa, device=dev, single_rank=True, exchange="nccl", **kw))
+            ok = ok and bool(torch.equal(torch.cat(parts_o, dim=1), so)) and bool(torch.equal(torch.cat(parts_r, dim=1), sr))
+        dist.barrier()
+    out["parity_ok"] = ok
+    # ---- timing (L2 flushed between steps, per-step event pairs, max over ranks)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    for ex in ("nccl", "peer", "peer-signal"):
+        env = MAFixedwingDogfightSplitEnv(arenas, seed=1, device=dev, exchange=ex)
+        env.reset()
+        act = torch.rand(env.n_local, 4, device=dev) * 2 - 1
+        for _ in range(5):
+            env.step(act)
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for k in range(steps):
+            flush.fill_(float(k))
+            ev[k][0].record()
+            env.step(act)
+            ev[k][1].record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        us = float(t[0]) * 1e3 / steps
+        out[ex] = {"us_per_step": us, "agent_steps_per_s": 2 * arenas / (us * 1e-6)}
+        env.close()
+        dist.barrier()
+    best = min(("nccl", "peer", "peer-signal"), key=lambda e: out[e]["us_per_step"])
+    out.update({"exchange": best, "us_per_step": out[best]["us_per_step"], "agent_steps_per_s": out[best]["agent_steps_per_s"], "steps": steps})
+    return out
 
 
 def run_ours(args, rank, local_rank, world):
@@ -219,7 +311,7 @@ def run_ours(args, rank, local_rank, world):
     env = QuadXHoverVecEnv(num_envs=n, seed=args.seed, device=dev, env_offset=rank * n)
     av = env.aviary
     env.reset()
-    K, W = args.steps, args.warmup
+    K, W, R = args.steps, args.warmup, args.repeats
     # action pool resident in HBM before the timed region (uniform in the action box, quadx_base_env.py:79-102)
     pool = 32
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -233,31 +325,37 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for k in range(W):
+    def flushed_block(aviary, steps, acts, off=0):
+        """`steps` env steps, L2 flushed before each (outside the event pair), one CUDA-event pair per step; returns ms summed"""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for k in range(steps):
+            flush.fill_(float(k))
+            ev[k][0].record()
+            aviary.env_step(actions=acts[(off + k) % pool])
+            ev[k][1].record()
+        barrier()
+        return float(sum(a.elapsed_time(b) for a, b in ev))
+
+    for k in range(max(W, 30)):  # past the first terminations: resets and spare rebuilds are inside every timed step
         av.env_step(actions=actions[k % pool])
     barrier()
 
-    # ---- timed region A: device-resident inputs, L2 flushed between steps, per-step CUDA-event pairs
+    # ---- timed region A: device-resident inputs, L2 flushed between steps, per-step CUDA-event pairs; R blocks of exactly K
+    #      steps, the MEDIAN block is reported (one scheduling hiccup inside a 5 ms block no longer moves the number)
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
     launches0 = av.launch_count
+    block_ms = [flushed_block(av, K, actions, off=W + r * K) for r in range(R)]
+    launches = (av.launch_count - launches0) // R
+
+    # ---- region K: the same flushed steps with the library's event pair tightly around the step launch (roofline leg)
     av.profile_begin(K)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    barrier()
-    for k in range(K):
-        flush.fill_(float(k))
-        ev[k][0].record()
-        av.env_step(actions=actions[(W + k) % pool])
-        ev[k][1].record()
-    barrier()
-    launches = av.launch_count - launches0
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(sum(step_ms))
+    flushed_block(av, K, actions)
     kern_ms = av.profile_read(K)
     av.profile_begin(0)
 
-    # ---- timed region A2 (context): back-to-back, L2-warm
+    # ---- region A2 (context): back-to-back, L2-warm, one event pair around K steps
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -267,24 +365,7 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     warm_ms = e0.elapsed_time(e1)
 
-    # ---- timed region A3 (context): the same flushed measurement with every reset integrated INSIDE the step launch
-    #      (inline_reset=True: no spare states, no side-stream rebuild), i.e. all of a step's work between its event pair
-    env_in = QuadXHoverVecEnv(num_envs=n, seed=args.seed, device=dev, env_offset=rank * n, inline_reset=2)
-    env_in.reset()
-    for k in range(max(W, 30)):  # past the first terminations, so that resets are in the timed steps
-        env_in.aviary.env_step(actions=actions[k % pool])
-    barrier()
-    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    for k in range(K):
-        flush.fill_(float(k))
-        ev2[k][0].record()
-        env_in.aviary.env_step(actions=actions[(W + k) % pool])
-        ev2[k][1].record()
-    barrier()
-    inline_ms = float(sum(a.elapsed_time(b) for a, b in ev2))
-    env_in.close()
-
-    # ---- timed region B: end to end through the host-buffer entry of the C-ABI (pinned host memory)
+    # ---- region B: end to end through the host-buffer entry of the C-ABI (pinned host memory)
     act_h = [actions[k].cpu().pin_memory() for k in range(4)]
     # one pinned slab, obs | reward | term | trunc back to back like the device side: the library returns it in one D2H copy
     slab_h = torch.empty(av.out_slab_bytes(n, env.obs_dim), dtype=torch.uint8).pin_memory()
@@ -299,30 +380,54 @@ def run_ours(args, rank, local_rank, world):
     e2e_s = time.perf_counter() - t0
     barrier()
     clocks = sampler.stop()
+    env.close()
+
+    # ---- region S (context, world > 1): STRONG scaling — BASELINE's 65 536 envs in total, split over the ranks
+    strong_ms = 0.0
+    if world > 1:
+        ns = ENVS_PER_GPU // world
+        env_s = QuadXHoverVecEnv(num_envs=ns, seed=args.seed, device=dev, env_offset=rank * ns)
+        env_s.reset()
+        acts_s = actions[:, :ns].contiguous()
+        for k in range(30):
+            env_s.aviary.env_step(actions=acts_s[k % pool])
+        barrier()
+        strong_ms = _median([flushed_block(env_s.aviary, K, acts_s) for _ in range(3)])
+        env_s.close()
 
     # ---- reduce: max over ranks
-    t = torch.tensor([total_ms, warm_ms, e2e_s * 1e3, float(sum(kern_ms)), inline_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor(block_ms + [warm_ms, e2e_s * 1e3, float(sum(kern_ms)), strong_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, warm_ms, e2e_ms, kern_total_ms, inline_ms = (float(x) for x in t.tolist())
+    vals = [float(x) for x in t.tolist()]
+    block_ms, (warm_ms, e2e_ms, kern_total_ms, strong_ms) = vals[:R], vals[R:]
+    split = dogfight_split_block(rank, world, dev) if (world > 1 and not args.no_dogfight_split) else None
     if rank == 0:
         peak, peak_src = load_peaks()
+        total_ms = _median(block_ms)
         value = world * n * K / (total_ms * 1e-3)
         kern_avg_s = kern_total_ms * 1e-3 / max(len(kern_ms), 1)
         achieved = ALGO_BYTES_PER_ENV_STEP * n / kern_avg_s / 1e9
+        cfg = base_config(world, n)
+        cfg.update({
+            "l2": "flushed between timed steps (256 MiB write outside the event pairs); per-step CUDA-event pairs summed over a block of K steps",
+            "repeats": R, "block_ms": block_ms, "statistic": "median block",
+            "precision": "fp32 forces/control/obs; quaternion, position, velocity carried as fp64 (hi+lo fp32 words in HBM)",
+            "value_l2_warm": world * n * K / (warm_ms * 1e-3), "ms_per_step_l2_warm": warm_ms / K,
+            "value_inline_resets": value, "ms_per_step_inline_resets": total_ms / K,
+            "reset_pipeline": "ONE launch per env step: finished envs take their spare post-reset state in the launch after they finish, and the spares consumed are rebuilt in two halves by builder CTAs appended to the grids of that launch and the next. All of it is inside the event pairs (value_inline_resets == value; no side stream, no second launch)",
+        })
+        if world > 1:
+            cfg["value_strong_65536_total"] = ENVS_PER_GPU * K / (strong_ms * 1e-3)
+            cfg["ms_per_step_strong"] = strong_ms / K
+            cfg["strong_note"] = f"BASELINE's 65536 envs in total = {ENVS_PER_GPU // world} per GPU: the launch is latency-bound (one tile per SM or less), so strong scaling is flat"
+        if split is not None:
+            cfg["dogfight_split"] = split
         line = {
             "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {
-                "workload": "QuadX-Hover-v4 (BASELINE configs[1]): flight mode 0, 65536 envs per GPU, uniform random actions, NEXT_STEP autoreset, 6 physics substeps + 3 control ticks per env-step",
-                "envs_per_gpu": n, "global_envs": world * n, "parallelism": f"env-shard x{world} (no data-path collective)",
-                "l2": "flushed between timed steps (256 MiB write outside the event pairs); per-step CUDA-event pairs summed",
-                "precision": "fp32 forces/control/obs; quaternion, position, velocity carried as fp64 (hi+lo fp32 words in HBM)",
-                "value_l2_warm": world * n * K / (warm_ms * 1e-3), "ms_per_step_l2_warm": warm_ms / K,
-                "value_inline_resets": world * n * K / (inline_ms * 1e-3), "ms_per_step_inline_resets": inline_ms / K,
-                "reset_pipeline": "finished envs take a spare post-reset state inside the step launch; the spares consumed are rebuilt by a second launch of the same kernel on a side stream, concurrently with the next step (here: with the L2 flush). Both launches are counted in gpu_launches; the rebuild is inside the back-to-back measurement (value_l2_warm) and outside the per-step event pairs of `value`; value_inline_resets is the same flushed measurement with every reset integrated inside the step launch",
-            },
+            "config": cfg,
             "e2e": {
                 "value": world * n * K / (e2e_ms * 1e-3), "unit": "env-steps/s",
                 "h2d_bytes_per_step": n * 4 * 4, "d2h_bytes_per_step": n * (env.obs_dim * 4 + 4 + 1 + 1),
@@ -331,10 +436,10 @@ def run_ours(args, rank, local_rank, world):
             "clocks": clocks,
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
-                "kernel": "k_hover_step<0,false,false>", "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
+                "kernel": "k_hover_step<0,false,false,true,false>", "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
                 "kernel_avg_us": kern_avg_s * 1e6, "peak_source": peak_src,
-                "note": "issue/FMA-bound kernel: the HBM fraction is reported because BASELINE.json asks for it; see DESIGN.md",
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the step launch in profiles/r01_k_hover_step_ncu_summary.txt (ncu replays with a warm L2: state written by the previous replay is still resident, so traffic < algorithmic bytes)",
+                "note": "issue/latency-bound kernel: the HBM fraction is reported because BASELINE.json asks for it; see DESIGN.md",
+                "traffic_source": f"dram__bytes_read.sum + dram__bytes_write.sum of the step launch in {os.path.relpath(_ncu_summary_path() or 'profiles/', ROOT)} (one ncu --set full capture, cold caches: the state written by the launch is still L2-resident when it ends, so traffic < algorithmic bytes)",
             },
         }
         f32, f64 = ncu_flops()
@@ -344,7 +449,7 @@ def run_ours(args, rank, local_rank, world):
             line["roofline"]["fp32"] = {
                 "flops_per_launch": f32, "fp64_flops_per_launch": f64, "achieved_tflops": f32 / kern_avg_s / 1e12, "peak_tflops": peak32,
                 "frac": f32 / kern_avg_s / 1e12 / peak32,
-                "source": "FFMA/FMUL/FADD thread-instruction counters of the step launch in profiles/r01_k_hover_step_ncu_summary.txt",
+                "source": "FFMA/FMUL/FADD thread-instruction counters of the step launch in the same ncu capture",
             }
         if world == 1 and not args.no_cpu_baseline:
             rate, cores, steps, dt = cpu_oracle_rate(16384, args.cpu_seconds)
@@ -367,6 +472,8 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--repeats", type=int, default=5, help="blocks of --steps timed steps; the median block is reported")
+    ap.add_argument("--no-dogfight-split", action="store_true", help="skip the configs[4] split-dogfight block under torchrun")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

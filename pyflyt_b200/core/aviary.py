@@ -240,6 +240,12 @@ class BatchedAviary:
         """[N] int32 env step counters."""
         return self.state_row_int(17) if self.tiled else self.istate_tensor[0]
 
+    def reseed(self, seed: int) -> None:
+        """``env.reset(seed=s)``: re-key the random streams and rewind every call counter, so that the same seed replays the same
+        episodes (the reference re-creates ``np_random``, aviary.py:108-117)."""
+        self.seed = int(seed)
+        _lib.check(_lib.lib().pfb_reseed(self._h, self.seed, self._s()))
+
     def set_noise_dump(self, buf: torch.Tensor | None) -> None:
         """Test aid: ``buf`` [env_step_ratio * updates_per_step, N] fp32 receives every motor-noise draw of the following
         QuadX-Hover ``env_step`` calls (None = off)."""

@@ -229,7 +229,7 @@ __device__ __forceinline__ QuadXRegs hover_fresh(float px, float py, float pz, f
   return s;
 }
 
-// Builder CTAs of the step launch (blockIdx.x >= number of tiles): the first `builders` of them (phase 0) start the next
+// Builder CTAs of the step launch (the first 2 * builders CTAs of the grid): the first `builders` of them (phase 0) start the next
 // spare of the envs that are being reset by this launch (done list of the previous launch), the others (phase 1) finish the
 // spares started by the previous launch.  ONE copy of the warm-up loop serves both phases.
 template <int MODE>
@@ -291,18 +291,21 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
                  const int32_t* __restrict__ b1_count, const int32_t* __restrict__ b1_list, float* __restrict__ spare,
                  uint32_t* __restrict__ episode, int spare_copy, int builders, float* __restrict__ noise_dump, uint32_t step_seq,
                  int64_t N) {
-  const int n_tiles = (int)((N + kBlock - 1) / kBlock);
-  if (AUTORESET && (int)blockIdx.x >= n_tiles) {  // builder CTA (CTA-uniform role)
-    hover_build<MODE>(p, h, rng, (int)blockIdx.x - n_tiles, builders, b0_count, b0_list, b1_count, b1_list, start_pos, start_orn, spare, episode, N);
+  // builder CTAs come FIRST in the grid: their serial warm-up chain is the longest thing in the launch, so they must be
+  // dispatched at t = 0, not behind the ~2000 step CTAs
+  const int n_build = AUTORESET ? 2 * builders : 0;
+  if (AUTORESET && (int)blockIdx.x < n_build) {  // builder CTA (CTA-uniform role)
+    hover_build<MODE>(p, h, rng, (int)blockIdx.x, builders, b0_count, b0_list, b1_count, b1_list, start_pos, start_orn, spare, episode, N);
     return;
   }
+  const int tile = (int)blockIdx.x - n_build;
   __shared__ __align__(128) float smem[kBlock * kObsMax];
   const int O = (h.angle_representation == 0 ? 20 : 21) + (MA ? 3 : 0);
   const int lane = threadIdx.x;
-  const int64_t tile_first = (int64_t)blockIdx.x * kBlock;
+  const int64_t tile_first = (int64_t)tile * kBlock;
   const int64_t i = tile_first + lane;
   const bool active = i < N;
-  if (AUTORESET && blockIdx.x == 0 && lane == 0) *next_count = 0;  // arm the counter the NEXT launch appends to
+  if (AUTORESET && tile == 0 && lane == 0) *next_count = 0;  // arm the counter the NEXT launch appends to
   float* rec = st + qx_tile_base(i, rows);  // the state tensor is padded to whole tiles: every lane may load
 
   // ---- the warp's state tile (groups 0 .. n-1: everything MODE reads) comes in with ONE cp.async.bulk (TMA) into shared
@@ -848,6 +851,21 @@ static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool r
     h->prof_n += 1;
   }
   h->step_seq += 1;
+  return 0;
+}
+
+int pfb_reseed(PfbHandle h, uint64_t seed, void* stream) {
+  if (!h) return fail("null handle");
+  CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->side) CUDA_OK(cudaStreamSynchronize(h->side));  // no spare rebuild of the old streams may still be in flight
+  h->rng.k0 = (uint32_t)seed;
+  h->rng.k1 = (uint32_t)(seed >> 32);
+  h->step_seq = 0;
+  h->aviary_seq = 0;
+  h->reset_seq = 0;
+  CUDA_OK(cudaMemsetAsync(h->d_counters, 0, 8 * sizeof(int32_t), s));
+  if (h->d_episode) CUDA_OK(cudaMemsetAsync(h->d_episode, 0, (size_t)h->n * sizeof(uint32_t), s));
   return 0;
 }
 

@@ -145,24 +145,19 @@ class QuadXHoverEnv:
         self._seed = kwargs.pop("seed", None)
         self._kwargs = kwargs
         self._vec = QuadXHoverVecEnv(num_envs=1, seed=self._seed, **kwargs)
-        try:  # pragma: no cover
-            from gymnasium import spaces
+        from . import spaces
 
-            n = self._vec.obs_dim
-            self.observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=(n,), dtype=np.float64)
-            self.action_space = spaces.Box(low=self._vec.action_low, high=self._vec.action_high, dtype=np.float64)
-        except Exception:
-            self.observation_space = None
-            self.action_space = None
+        n = self._vec.obs_dim
+        self.observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=(n,), dtype=np.float64)
+        self.action_space = spaces.Box(low=self._vec.action_low, high=self._vec.action_high, dtype=np.float64)
 
     def _np_info(self, info):
         return {k: bool(v[0].item()) for k, v in info.items()}
 
     def reset(self, *, seed: None | int = None, options: None | dict[str, Any] = dict()):
-        if seed is not None and seed != self._seed:
-            self._vec.close()
-            self._seed = seed
-            self._vec = QuadXHoverVecEnv(num_envs=1, seed=seed, **self._kwargs)
+        if seed is not None:  # the same seed must replay the same episode (gymnasium contract; tests/test_gym_envs.py:92-112)
+            self._seed = int(seed)
+            self._vec.aviary.reseed(self._seed)
         obs, info = self._vec.reset()
         return obs[0].double().cpu().numpy(), self._np_info(info)
 

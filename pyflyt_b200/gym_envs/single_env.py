@@ -15,6 +15,8 @@ from typing import Any
 import numpy as np
 import torch
 
+from . import spaces
+
 
 class _SingleEnv:
     _vec_cls = None
@@ -25,8 +27,11 @@ class _SingleEnv:
         self._seed = kwargs.pop("seed", None)
         self._kwargs = kwargs
         self._vec = self._vec_cls(num_envs=1, seed=self._seed, **kwargs)
-        self.observation_space = None  # gymnasium is not a dependency of the batched stepper
-        self.action_space = None
+        self.action_space = spaces.Box(low=self._vec.action_low, high=self._vec.action_high, dtype=np.float64)
+        self.observation_space = self._make_observation_space()
+
+    def _make_observation_space(self):
+        return spaces.Box(low=-np.inf, high=np.inf, shape=(self._vec.obs_dim,), dtype=np.float64)
 
     def _info(self, info) -> dict:
         out = {}
@@ -39,10 +44,9 @@ class _SingleEnv:
         return obs[0].double().cpu().numpy()
 
     def reset(self, *, seed: None | int = None, options: None | dict[str, Any] = dict()):
-        if seed is not None and seed != self._seed:
-            self._vec.close()
-            self._seed = seed
-            self._vec = self._vec_cls(num_envs=1, seed=seed, **self._kwargs)
+        if seed is not None:  # the same seed must replay the same episode (gymnasium contract; tests/test_gym_envs.py:92-112)
+            self._seed = int(seed)
+            self._vec.aviary.reseed(self._seed)
         obs, info = self._vec.reset()
         info = self._info(info)
         return self._obs(obs, info), info
@@ -59,6 +63,15 @@ class _SingleEnv:
 
 class _WaypointsMixin:
     _attitude_dim = {"quadx": (20, 21), "fixedwing": (22, 23)}
+
+    def _make_observation_space(self):  # quadx_waypoints_env.py:95-110, fixedwing_waypoints_env.py:88-101
+        v = self._vec
+        a = self._attitude_dim[self._vehicle][1 if v.config.angle_representation == 1 else 0]
+        t = 4 if getattr(v, "use_yaw_targets", False) else 3
+        return spaces.Dict({
+            "attitude": spaces.Box(low=-np.inf, high=np.inf, shape=(a,), dtype=np.float64),
+            "target_deltas": spaces.Sequence(spaces.Box(low=-np.inf, high=np.inf, shape=(t,), dtype=np.float64), stack=True),
+        })
 
     def _obs(self, obs: torch.Tensor, info: dict):
         v = self._vec
