@@ -171,6 +171,31 @@ typedef struct PfbEnvConfig {
   double spawn_min_radius, spawn_max_radius, spawn_min_height, spawn_max_height;
 } PfbEnvConfig;
 
+/* Analytic, time-invariant wind field evaluated IN-KERNEL at every drag body / lifting surface.
+ * Replaces the Python callback of Aviary.register_wind_field_function (aviary.py:324-334, "for less complicated wind
+ * field models (time invariant models)"), which the reference evaluates at each link COM in BoringBodies.state_update
+ * (boring_bodies.py:93-96) and LiftingSurfaces.state_update (lifting_surfaces.py:88-93):
+ *      wind(x, y, z) = base * f(z)
+ *   PFB_WIND_CONSTANT  f = 1
+ *   PFB_WIND_POWER     f = (max(z, 0) / z_ref) ^ alpha            (atmospheric power law)
+ *   PFB_WIND_LOG       f = ln(max(z, z0) / z0) / ln(z_ref / z0)   (logarithmic boundary layer, 0 below z0)
+ *   PFB_WIND_EXP       f = exp(z / z_ref)                          (the field of the reference's tests/test_core.py:275-278)
+ * pyflyt_b200.core.wind.AnalyticWind is the same function as a Python callable: hand it to the reference's
+ * register_wind_field_function and to BatchedAviary.register_wind_field to fly both in the same air.              */
+#define PFB_WIND_NONE 0
+#define PFB_WIND_CONSTANT 1
+#define PFB_WIND_POWER 2
+#define PFB_WIND_LOG 3
+#define PFB_WIND_EXP 4
+typedef struct PfbWind {
+  int32_t kind;
+  int32_t _pad;
+  double base[3];  /* m/s, world frame */
+  double z_ref;
+  double alpha;
+  double z0;
+} PfbWind;
+
 /* Caller-owned DEVICE buffers.  Any pointer may be NULL if the env kind does not use it. */
 typedef struct PfbBuffers {
   /* persistent state, fp32 SoA [F][N]; row map is fixed per vehicle kind: see pfb_state_rows()      */
@@ -216,6 +241,11 @@ int pfb_reseed(PfbHandle h, uint64_t seed, void* stream);
 /* Global index of this handle's env 0 (rank * n_envs when the batch is sharded over GPUs): keeps
  * the Philox streams, and therefore every trajectory, independent of the number of ranks.          */
 int pfb_set_env_offset(PfbHandle h, uint64_t first_global_env);
+
+/* Aviary.register_wind_field_function for an analytic field (NULL or kind PFB_WIND_NONE: still air).  Takes effect from the
+ * next call on; every vehicle kind.                                                                                  */
+int pfb_set_wind(PfbHandle h, const PfbWind* wind);
+int pfb_sizeof_wind(void);
 
 /* Shapes the caller must allocate. */
 int pfb_state_rows(PfbHandle h);     /* F of PfbBuffers.state                                         */

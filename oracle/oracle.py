@@ -40,6 +40,7 @@ def lib() -> C.CDLL:
         L.orc_create.argtypes = [vp, vp, i64, u64]
         L.orc_destroy.argtypes = [vp]
         L.orc_set_start.argtypes = [vp, dp, dp]
+        L.orc_set_wind.argtypes = [vp, vp]
         L.orc_reset.argtypes = [vp, u8p]
         L.orc_set_mode.argtypes = [vp, C.c_int]
         L.orc_set_setpoints.argtypes = [vp, dp, C.c_int]
@@ -101,6 +102,14 @@ class Oracle:
 
     def set_mode(self, mode: int):
         lib().orc_set_mode(self._h, int(mode))
+
+    def set_wind(self, wind):
+        """wind: pyflyt_b200.core.wind.AnalyticWind or None"""
+        if wind is None:
+            lib().orc_set_wind(self._h, None)
+        else:
+            w = wind.as_struct()
+            lib().orc_set_wind(self._h, C.byref(w))
 
     def set_setpoints(self, sp):
         sp = np.ascontiguousarray(sp, dtype=np.float64)

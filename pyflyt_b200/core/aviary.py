@@ -240,6 +240,26 @@ class BatchedAviary:
         """[N] int32 env step counters."""
         return self.state_row_int(17) if self.tiled else self.istate_tensor[0]
 
+    def register_wind_field(self, wind) -> None:
+        """``Aviary.register_wind_field_function`` (aviary.py:324-334) for an analytic field: ``wind`` is a
+        :class:`pyflyt_b200.core.wind.AnalyticWind` (the same object is a valid wind-field function for the reference) or ``None``
+        for still air.  Arbitrary Python callbacks cannot run inside the step kernel (out of scope)."""
+        from .wind import AnalyticWind, PfbWind
+
+        if wind is None:
+            _lib.check(_lib.lib().pfb_set_wind(self._h, None))
+            self.wind_field = None
+            return
+        if not isinstance(wind, AnalyticWind):
+            raise TypeError("the batched stepper evaluates the wind inside the CUDA kernels: pass a pyflyt_b200.core.wind.AnalyticWind")
+        L = _lib.lib()
+        assert L.pfb_sizeof_wind() == C.sizeof(PfbWind)
+        w = wind.as_struct()
+        _lib.check(L.pfb_set_wind(self._h, C.byref(w)))
+        self.wind_field = wind
+
+    register_wind_field_function = register_wind_field
+
     def reseed(self, seed: int) -> None:
         """``env.reset(seed=s)``: re-key the random streams and rewind every call counter, so that the same seed replays the same
         episodes (the reference re-creates ``np_random``, aviary.py:108-117)."""

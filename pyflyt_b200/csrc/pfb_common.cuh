@@ -116,6 +116,47 @@ PFB_HD float fast_sqrt(float x) {
 // -sign(v) * k * v^2  ==  -k * v * |v|   (boring_bodies.py:115-119, quadx.py:502-506)
 PFB_HD float signed_square(float v) { return v * fabsf(v); }
 
+// -------------------------------------------------------------------------------------------------
+// Analytic wind field (include/pyflyt_b200.h, PfbWind): wind = base * f(z), evaluated per drag body / lifting surface at
+// the link COM like Aviary.wind_field in boring_bodies.py:93-96 and lifting_surfaces.py:88-93.  A member of every vehicle's
+// parameter block; kind 0 (still air) costs one uniform branch.
+// -------------------------------------------------------------------------------------------------
+struct WindParams {
+  int kind;  // PFB_WIND_*
+  float bx, by, bz;
+  float inv_zref, alpha, z0, inv_z0, inv_log;  // inv_log = 1 / ln(z_ref / z0)
+};
+PFB_HD float wind_profile(const WindParams& w, float z) {
+#if defined(__CUDA_ARCH__)
+  if (w.kind == 1) return 1.0f;
+  if (w.kind == 2) return exp2f(w.alpha * __log2f(fmaxf(z, 0.0f) * w.inv_zref));  // 0 ^ alpha = exp2(-inf) = 0
+  if (w.kind == 3) return __logf(fmaxf(z, w.z0) * w.inv_z0) * w.inv_log;
+  return __expf(z * w.inv_zref);
+#else
+  if (w.kind == 1) return 1.0f;
+  if (w.kind == 2) return powf(fmaxf(z, 0.0f) * w.inv_zref, w.alpha);
+  if (w.kind == 3) return logf(fmaxf(z, w.z0) * w.inv_z0) * w.inv_log;
+  return expf(z * w.inv_zref);
+#endif
+}
+// per-substep context: the base wind rotated into the body frame (R^T base) and what is needed for a link's altitude
+struct WindCtx {
+  Vec3 wb;
+  float pz, r20, r21, r22;
+};
+PFB_HD WindCtx wind_ctx(const WindParams& w, float pz, float m00, float m01, float m02, float m10, float m11, float m12, float m20, float m21,
+                        float m22) {
+  WindCtx c;
+  c.wb = Vec3{m00 * w.bx + m10 * w.by + m20 * w.bz, m01 * w.bx + m11 * w.by + m21 * w.bz, m02 * w.bx + m12 * w.by + m22 * w.bz};
+  c.pz = pz; c.r20 = m20; c.r21 = m21; c.r22 = m22;
+  return c;
+}
+// body-frame wind at the link COM r (base frame)
+PFB_HD Vec3 wind_body_at(const WindParams& w, const WindCtx& c, float rx, float ry, float rz) {
+  const float z = c.pz + c.r20 * rx + c.r21 * ry + c.r22 * rz;
+  return wind_profile(w, z) * c.wb;
+}
+
 // hi/lo split of an fp64 value into two fp32 words and back
 PFB_HD void split_hi_lo(double d, float& hi, float& lo) {
   hi = (float)d;

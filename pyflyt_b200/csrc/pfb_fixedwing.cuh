@@ -68,6 +68,7 @@ struct FixedwingParams {
   float thrust_k, torque_k, motor_lag, noise_ratio, noise_loc;
   float start_vel[3];
   ContactParams contact;
+  WindParams wind;  // analytic wind field; kind 0 = still air
 };
 
 struct WaypointParams {
@@ -120,11 +121,14 @@ PFB_HD void sincos_f(float x, float& s, float& c) {
 
 // LiftingSurface.physics_update (lifting_surfaces.py:266-324): actuation lag, AoA, (Cl, Cd, CM) with the
 // pre-/post-stall branches evaluated as selects, force + torque in the base frame.
-PFB_HD void surface_force(const SurfaceParams& sf, float& act, float cmd, Vec3 vb, Vec3 w, Vec3& F, Vec3& T) {
+// `wind` / `wc`: optional analytic wind (lifting_surfaces.py:88-93): the surface sees the velocity through the air
+PFB_HD void surface_force(const SurfaceParams& sf, float& act, float cmd, Vec3 vb, Vec3 w, Vec3& F, Vec3& T, const WindParams* wind = nullptr,
+                          const WindCtx* wc = nullptr) {
   act = fmaf(sf.lag, cmd - act, act);
   // link COM velocity in the body frame: v_b + w_b x r
   Vec3 r = Vec3{sf.r[0], sf.r[1], sf.r[2]};
   Vec3 v = vb + cross(w, r);
+  if (wind) v = v - wind_body_at(*wind, *wc, sf.r[0], sf.r[1], sf.r[2]);
   float lifting = v.x * sf.lift[0] + v.y * sf.lift[1] + v.z * sf.lift[2];
   float forward = v.x * sf.fwd[0] + v.y * sf.fwd[1] + v.z * sf.fwd[2];
   float speed2 = v.x * v.x + v.y * v.y + v.z * v.z;
@@ -298,9 +302,13 @@ PFB_HD void fixedwing_substep(const FixedwingParams& p, FixedwingRegs& s, const 
   // fully unrolled: the surfaces are independent until their forces are summed, and with < 1 warp per scheduler at the
   // batch sizes these vehicles run at (16 384 envs) instruction-level parallelism is the only latency hiding there is;
   // the surface tables also become immediate constant-bank operands instead of indexed loads
+  const bool windy = p.wind.kind != 0;  // uniform: the parameter block is launch-constant
+  WindCtx wc = WindCtx{Vec3{0.f, 0.f, 0.f}, 0.f, 0.f, 0.f, 0.f};
+  if (windy) wc = wind_ctx(p.wind, (float)s.pz, (float)s.R.m00, (float)s.R.m01, (float)s.R.m02, (float)s.R.m10, (float)s.R.m11, (float)s.R.m12,
+                           (float)s.R.m20, (float)s.R.m21, (float)s.R.m22);
 #pragma unroll
   for (int i = 0; i < kMaxSurfaces; ++i) {
-    if (i < p.n_surfaces) surface_force(p.surf[i], s.act[i], cmd[i], s.vb, w, F, T);
+    if (i < p.n_surfaces) surface_force(p.surf[i], s.act[i], cmd[i], s.vb, w, F, T, windy ? &p.wind : nullptr, &wc);
   }
   // motor (motors.py:130-155): thrust + reaction torque along +x at motor_r
   {

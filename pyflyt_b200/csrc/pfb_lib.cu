@@ -6,6 +6,7 @@
 // and a shared-memory transpose so that global traffic stays fully coalesced.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -851,6 +852,32 @@ static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool r
     h->prof_n += 1;
   }
   h->step_seq += 1;
+  return 0;
+}
+
+int pfb_sizeof_wind(void) { return (int)sizeof(PfbWind); }
+
+int pfb_set_wind(PfbHandle h, const PfbWind* wind) {
+  if (!h) return fail("null handle");
+  WindParams w;
+  memset(&w, 0, sizeof(w));
+  if (wind && wind->kind != PFB_WIND_NONE) {
+    if (wind->kind < PFB_WIND_CONSTANT || wind->kind > PFB_WIND_EXP) return fail("unknown wind kind %d", wind->kind);
+    if (!(wind->z_ref > 0.0)) return fail("wind z_ref must be positive");
+    if (wind->kind == PFB_WIND_LOG && !(wind->z0 > 0.0 && wind->z0 < wind->z_ref)) return fail("log wind profile needs 0 < z0 < z_ref");
+    w.kind = wind->kind;
+    w.bx = (float)wind->base[0]; w.by = (float)wind->base[1]; w.bz = (float)wind->base[2];
+    w.inv_zref = (float)(1.0 / wind->z_ref);
+    w.alpha = (float)wind->alpha;
+    if (wind->kind == PFB_WIND_LOG) {
+      w.z0 = (float)wind->z0;
+      w.inv_z0 = (float)(1.0 / wind->z0);
+      w.inv_log = (float)(1.0 / log(wind->z_ref / wind->z0));
+    }
+  }
+  h->qx.wind = w;
+  h->fw.wind = w;
+  h->rk.wind = w;
   return 0;
 }
 

@@ -54,6 +54,7 @@ struct QuadXParams {
   float shape_thr[5];
   float contact_zmax;  // base altitude above which no primitive can be within its contact threshold
   int ratio;           // physics substeps per control tick (physics_hz / control_hz)
+  WindParams wind;     // analytic wind field; kind 0 = still air
 };
 
 struct HoverParams {
@@ -388,10 +389,16 @@ PFB_HD void quadx_substep(const QuadXParams& p, QuadXRegs& s, float xi) {
     ty = fmaf(-p.motor_x[i], Ti, ty);
     tz = fmaf(p.torque_k[i], a, tz);
   }
-  // ---- body drag (boring_bodies.py:113-127), body link at the base origin
-  float Fx = -p.drag_k[0] * signed_square(s.vb.x);
-  float Fy = -p.drag_k[1] * signed_square(s.vb.y);
-  Fz = fmaf(-p.drag_k[2], signed_square(s.vb.z), Fz);
+  // ---- body drag (boring_bodies.py:113-127), body link at the base origin, on the velocity through the AIR
+  Vec3 va = s.vb;
+  if (p.wind.kind != 0) {  // boring_bodies.py:93-96 (uniform branch: the parameter block is launch-constant)
+    const WindCtx wc = wind_ctx(p.wind, (float)s.pz, (float)s.R.m00, (float)s.R.m01, (float)s.R.m02, (float)s.R.m10, (float)s.R.m11,
+                                (float)s.R.m12, (float)s.R.m20, (float)s.R.m21, (float)s.R.m22);
+    va = va - wind_body_at(p.wind, wc, 0.0f, 0.0f, 0.0f);
+  }
+  float Fx = -p.drag_k[0] * signed_square(va.x);
+  float Fy = -p.drag_k[1] * signed_square(va.y);
+  Fz = fmaf(-p.drag_k[2], signed_square(va.z), Fz);
   // ---- rotational drag unless something touched the floor last step (quadx.py:502-510)
   const float kpqr = (s.flags & FLAG_CONTACT_PREV) ? 0.0f : -p.drag_pqr;
   tx = fmaf(kpqr, signed_square(s.wx), tx);

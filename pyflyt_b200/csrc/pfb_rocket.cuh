@@ -30,6 +30,7 @@ struct RocketParams {
   float start_fuel;
   float noise_loc;
   ContactParams contact;
+  WindParams wind;  // analytic wind field; kind 0 = still air
 };
 
 struct LandingParams {
@@ -91,10 +92,15 @@ PFB_HD void rocket_command(const RocketRegs& s, float* cmd) {
 PFB_HD void rocket_substep(const RocketParams& p, RocketRegs& s, const float* cmd, float xi, bool with_pad) {
   Vec3 F = Vec3{0.f, 0.f, 0.f}, T = Vec3{0.f, 0.f, 0.f};
   const Vec3 w = Vec3{s.wx, s.wy, s.wz};
-  // body drag (boring_bodies.py:113-127) on the body link
+  const bool windy = p.wind.kind != 0;  // uniform: the parameter block is launch-constant
+  WindCtx wc = WindCtx{Vec3{0.f, 0.f, 0.f}, 0.f, 0.f, 0.f, 0.f};
+  if (windy) wc = wind_ctx(p.wind, (float)s.pz, (float)s.R.m00, (float)s.R.m01, (float)s.R.m02, (float)s.R.m10, (float)s.R.m11, (float)s.R.m12,
+                           (float)s.R.m20, (float)s.R.m21, (float)s.R.m22);
+  // body drag (boring_bodies.py:113-127) on the body link, on the velocity through the air (boring_bodies.py:93-96)
   {
     Vec3 r = Vec3{p.body_r[0], p.body_r[1], p.body_r[2]};
     Vec3 v = s.vb + cross(w, r);
+    if (windy) v = v - wind_body_at(p.wind, wc, p.body_r[0], p.body_r[1], p.body_r[2]);
     Vec3 Fd = Vec3{-p.drag_k[0] * signed_square(v.x), -p.drag_k[1] * signed_square(v.y), -p.drag_k[2] * signed_square(v.z)};
     F = F + Fd;
     T = T + cross(r, Fd);
@@ -103,7 +109,7 @@ PFB_HD void rocket_substep(const RocketParams& p, RocketRegs& s, const float* cm
   // fully unrolled (4 finlets): independent until summed, and ILP is the only latency hiding at 16 384 envs
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    if (i < p.n_surfaces) surface_force(p.surf[i], s.act[i], cmd[i], s.vb, w, F, T);
+    if (i < p.n_surfaces) surface_force(p.surf[i], s.act[i], cmd[i], s.vb, w, F, T, windy ? &p.wind : nullptr, &wc);
   }
   // gimbal (gimbals.py:145-176): lag on both axes, thrust axis = R1 (R2 u)
   s.gim[0] = fmaf(p.gimbal_lag, cmd[6] - s.gim[0], s.gim[0]);

@@ -60,6 +60,10 @@ class OracleEngine:
     def get_setpoints(self):
         return self.o.get_setpoints()
 
+    def set_wind(self, wind):
+        self.o.set_wind(wind)
+        self.o.update_state()  # the fixtures call drone.update_state() after registering the field
+
     def set_base_velocity(self, lin, ang):
         self.o.set_base_velocity(lin, ang)
         self.o.update_state()  # the fixtures call drone.update_state() after resetBaseVelocity
@@ -228,12 +232,23 @@ def load_golden(name):
     return np.load(os.path.join(GOLDEN, name if name.endswith(".npz") else name + ".npz"))
 
 
+def fixture_wind(g):
+    """the AnalyticWind a fixture was flown in (None = still air)"""
+    if "wind_kind" not in g.files:
+        return None
+    from pyflyt_b200.core.wind import AnalyticWind
+
+    return AnalyticWind(str(g["wind_kind"]), base=g["wind_base"], z_ref=float(g["wind_z_ref"]), alpha=float(g["wind_alpha"]), z0=float(g["wind_z0"]))
+
+
 def replay_aviary(make_engine, g, every=1):
     """Replays a quadx_aviary fixture; returns dict of max abs errors vs the reference's outputs."""
     model = build_model("quadx", str(g["drone_model"]))
     eng = make_engine(model, None, 1, g["start_pos"][None], g["start_orn"][None])
     eng.reset()
     eng.set_mode(int(g["mode"]))
+    if fixture_wind(g) is not None:
+        eng.set_wind(fixture_wind(g))
     T = len(g["state"])
     noise = g["noise"].reshape(T, eng.ups)
     err = dict(setpoint=float(np.abs(eng.get_setpoints()[0] - g["setpoint_after_set_mode"]).max()), pos=0.0, euler=0.0, angvel=0.0, linvel=0.0, aux=0.0, contact_mismatch=0)
@@ -274,6 +289,8 @@ def replay_hover(make_engine, g):
 
     per_step = env.env_step_ratio * eng.ups
     obs = eng.env_reset(take()[:, None])
+    if fixture_wind(g) is not None:  # attached to the env's Aviary after reset()
+        eng.set_wind(fixture_wind(g))
     err = dict(obs=float(np.abs(obs[0] - g["reset_obs"]).max()), reward=0.0, flag_mismatch=0, episodes=0)
     ep_starts = set(g["episode_start"].tolist())
     k = 0
@@ -329,6 +346,9 @@ class CudaEngine:
 
     def get_setpoints(self):
         return self.av.setpoints.double().cpu().numpy()
+
+    def set_wind(self, wind):
+        self.av.register_wind_field(wind)
 
     def set_base_velocity(self, lin, ang):
         lin = self._dev(np.broadcast_to(lin, (self.n, 3)))
@@ -388,6 +408,8 @@ def replay_vehicle(make_engine, g, every=1):
     eng = make_engine(model, None, 1, g["start_pos"][None], g["start_orn"][None])
     eng.reset()
     eng.set_mode(int(g["mode"]))
+    if fixture_wind(g) is not None:
+        eng.set_wind(fixture_wind(g))
     if "has_pre_hook" in g.files and bool(g["has_pre_hook"]):
         eng.set_base_velocity(g["start_lin_vel"][None], g["start_ang_vel"][None])  # p.resetBaseVelocity + drone.update_state()
     T = len(g["state"])
@@ -531,6 +553,8 @@ def replay_landing(make_engine, g, max_steps=None):
 
     per_step = env.env_step_ratio * eng.ups
     obs = eng.env_reset(take()[:, None])
+    if fixture_wind(g) is not None:  # attached to the env's Aviary after reset()
+        eng.set_wind(fixture_wind(g))
     err = dict(obs=float(np.abs(obs[0] - g["reset_obs"]).max()), reward=0.0, flag_mismatch=0, episodes=0)
     ep_starts = set(g["episode_start"].tolist())
     k = 0

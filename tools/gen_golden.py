@@ -26,7 +26,7 @@ from PyFlyt.core import Aviary  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def fly_quadx(name, mode, drone_model, start_pos, start_orn, setpoint_schedule, n_steps, seed):
+def fly_quadx(name, mode, drone_model, start_pos, start_orn, setpoint_schedule, n_steps, seed, wind=None):
     """Aviary-level QuadX flight; setpoint_schedule: {step_index: setpoint(4)} applied before step."""
     rng = ril.ScriptedNoise(seed)
     env = Aviary(
@@ -37,6 +37,9 @@ def fly_quadx(name, mode, drone_model, start_pos, start_orn, setpoint_schedule, 
         np_random=rng,
     )
     env.set_mode(mode)
+    if wind is not None:
+        env.register_wind_field_function(wind)  # the UNMODIFIED reference evaluates our AnalyticWind as a plain wind-field function
+        env.drones[0].update_state()  # the cached body velocity now sees the wind (update_state runs after every step anyway)
     sp_after_mode = np.array(env.drones[0].setpoint, dtype=np.float64)
     states, auxs, pwms, contacts, raws, sps = [], [], [], [], [], []
     for i in range(n_steps):
@@ -67,11 +70,19 @@ def fly_quadx(name, mode, drone_model, start_pos, start_orn, setpoint_schedule, 
         pwm=np.array(pwms),
         contact=np.array(contacts),
         raw=np.array(raws),
+        **wind_fields(wind),
     )
     print(name, "final pos", states[-1][3], "draws", len(rng.normal_log))
 
 
-def fly_vehicle(name, drone_type, drone_model, mode, start_pos, start_orn, setpoint_schedule, n_steps, seed, drone_options=None, pre_hook=None):
+def wind_fields(wind):
+    """npz entries describing an AnalyticWind (absent = still air)"""
+    if wind is None:
+        return {}
+    return dict(wind_kind=wind.kind, wind_base=wind.base, wind_z_ref=wind.z_ref, wind_alpha=wind.alpha, wind_z0=wind.z0)
+
+
+def fly_vehicle(name, drone_type, drone_model, mode, start_pos, start_orn, setpoint_schedule, n_steps, seed, drone_options=None, pre_hook=None, wind=None):
     """Aviary-level flight of a fixedwing / rocket; setpoint_schedule: {step: setpoint} applied before the step."""
     rng = ril.ScriptedNoise(seed)
     opts = dict(drone_model=drone_model, **(drone_options or {}))
@@ -83,6 +94,9 @@ def fly_vehicle(name, drone_type, drone_model, mode, start_pos, start_orn, setpo
         np_random=rng,
     )
     env.set_mode(mode)
+    if wind is not None:
+        env.register_wind_field_function(wind)
+        env.drones[0].update_state()  # the cached surface / body velocities now see the wind (update_state runs after every step)
     if pre_hook is not None:
         pre_hook(env)
         env.drones[0].update_state()  # resetBaseVelocity alone leaves the drone's cached velocities stale
@@ -120,6 +134,7 @@ def fly_vehicle(name, drone_type, drone_model, mode, start_pos, start_orn, setpo
         aux=np.array(auxs),
         contact=np.array(contacts),
         raw=np.array(raws),
+        **wind_fields(wind),
     )
     print(name, "final pos", states[-1][3], "draws", len(rng.normal_log))
 
@@ -261,6 +276,7 @@ def fly_landing(name, seed, n_steps, action_seed, options, angle_representation=
         actions=np.array(acts), obs=np.array(obs), reward=np.array(rew), term=np.array(term), trunc=np.array(trunc), info=np.array(info),
         noise=np.array(rng.normal_log), noise_splits=np.array(noise_splits), episode_start=np.array(episode_start, dtype=np.int64),
         after_reset_obs=np.array(resets_obs) if resets_obs else np.zeros((0, len(obs0))),
+        **wind_fields(wind),
     )
     print(name, "steps", n_steps, "episodes", len(episode_start) + 1, "infos", sorted(set(info)), "draws", len(rng.normal_log))
 
@@ -398,7 +414,7 @@ def fly_ma_hover(name, seed, n_steps, action_seed, flight_mode=0, angle_represen
     print(name, "episodes", len(episodes), "steps", [len(e["actions"]) for e in episodes], "reward range", min(np.nanmin(e["reward"]) for e in episodes), max(np.nanmax(e["reward"]) for e in episodes))
 
 
-def fly_hover(name, seed, n_steps, action_seed, angle_representation, flight_mode=0, sparse=False, dome=3.0, action_scale=1.0):
+def fly_hover(name, seed, n_steps, action_seed, angle_representation, flight_mode=0, sparse=False, dome=3.0, action_scale=1.0, wind=None):
     from PyFlyt.gym_envs.quadx_envs.quadx_hover_env import QuadXHoverEnv
 
     env = QuadXHoverEnv(
@@ -407,6 +423,9 @@ def fly_hover(name, seed, n_steps, action_seed, angle_representation, flight_mod
     rng = ril.ScriptedNoise(seed)
     env._np_random = rng  # the env hands its generator to the Aviary (quadx_base_env.py:192)
     obs0, _ = env.reset()
+    if wind is not None:  # the reference envs have no wind argument: a user attaches the field to the env's Aviary after reset()
+        env.env.register_wind_field_function(wind)
+        env.env.drones[0].update_state()
     arng = np.random.default_rng(action_seed)
     lo, hi = env.action_space.low, env.action_space.high
     obs, rew, term, trunc, info, acts, episode_start = [], [], [], [], [], [], []
@@ -423,6 +442,7 @@ def fly_hover(name, seed, n_steps, action_seed, angle_representation, flight_mod
         info.append(int(inf["out_of_bounds"]) | (int(inf["collision"]) << 1) | (int(inf["env_complete"]) << 2))
         noise_splits.append(len(rng.normal_log))
         if te or tr:
+            assert wind is None, "wind fixtures are single-episode (a reset re-creates the Aviary without the field)"
             # next-episode reset exactly as a user loop would do it
             o2, _ = env.reset()
             resets_obs.append(o2)
@@ -446,6 +466,7 @@ def fly_hover(name, seed, n_steps, action_seed, angle_representation, flight_mod
         noise_splits=np.array(noise_splits),
         episode_start=np.array(episode_start, dtype=np.int64),
         after_reset_obs=np.array(resets_obs) if resets_obs else np.zeros((0, len(obs0))),
+        **wind_fields(wind),
     )
     print(name, "steps", n_steps, "episodes", len(episode_start) + 1, "draws", len(rng.normal_log))
 
@@ -580,6 +601,32 @@ def main():
     fly_hover("hover_mode6", seed=7, n_steps=300, action_seed=4, angle_representation="quaternion", flight_mode=6, action_scale=0.3)
 
 
+def wind_fixtures():
+    """SURVEY 8f item 4: the UNMODIFIED reference flown in an analytic wind (register_wind_field_function, aviary.py:324-334;
+    tests/test_core.py:262-290 of the reference does the same with exp(z))."""
+    from pyflyt_b200.core.wind import AnalyticWind
+
+    # QuadX, position hold in a power-law boundary layer; the drag body feels it, the controller leans into it
+    fly_quadx("wind_quadx_power", 7, "cf2x", [0, 0, 2.0], [0, 0, 0.3], {0: [0.5, -0.5, 0.3, 3.0]}, 400, seed=71,
+              wind=AnalyticWind("power", base=(3.0, -1.5, 0.2), z_ref=10.0, alpha=1.0 / 7.0))
+    # Fixedwing in a logarithmic profile: every lifting surface sees the wind at its own altitude
+    r = np.random.default_rng(72)
+    sched = {k: np.concatenate([r.uniform(-0.4, 0.4, 3), r.uniform(0.4, 1.0, 1)]) for k in range(0, 500, 50)}
+    fly_vehicle("wind_fixedwing_log", "fixedwing", "fixedwing", 0, [0, 0, 50.0], [0.05, -0.05, 0.4], sched, 500, seed=72,
+                wind=AnalyticWind("log", base=(-4.0, 2.0, 0.0), z_ref=10.0, z0=0.03))
+    # Rocket: the reference test's own field shape, wind_z = exp(z / z_ref), plus a constant cross wind on a second fixture
+    def sched_r(n, every, thr):
+        rr = np.random.default_rng(73)
+        return {k: np.concatenate([rr.uniform(-0.5, 0.5, 3), [1.0, thr], rr.uniform(-0.5, 0.5, 2)]) for k in range(0, n, every)}
+    fly_vehicle("wind_rocket_exp", "rocket", "rocket", 0, [0, 0, 100.0], [0.05, -0.04, 0.3], sched_r(400, 40, 0.8), 400, seed=73,
+                wind=AnalyticWind("exp", base=(0.0, 0.0, 1.0), z_ref=60.0))
+    fly_vehicle("wind_rocket_constant", "rocket", "rocket", 0, [0, 0, 200.0], [0.1, 0.0, 0.0], sched_r(300, 30, 0.5), 300, seed=74,
+                wind=AnalyticWind("constant", base=(6.0, -3.0, 0.5)))
+    # one env: QuadX-Hover, a single episode with the field attached to the env's Aviary after reset()
+    fly_hover("wind_hover_quat", seed=75, n_steps=80, action_seed=6, angle_representation="quaternion", flight_mode=6, action_scale=0.2, dome=50.0,
+              wind=AnalyticWind("constant", base=(2.0, 1.0, 0.0)))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -595,3 +642,5 @@ if __name__ == "__main__":
         ma_hover_fixtures()
     if which in ("all", "qxwp"):
         quadx_waypoints_fixtures()
+    if which in ("all", "wind"):
+        wind_fixtures()
