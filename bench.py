@@ -307,8 +307,12 @@ def run_ours(args, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    from pyflyt_b200.sharding import shard_range
+
     n = args.envs
-    env = QuadXHoverVecEnv(num_envs=n, seed=args.seed, device=dev, env_offset=rank * n)
+    first, last = shard_range(world * n, rank, world)  # contiguous global env ids per rank; Philox is keyed by them
+    assert last - first == n
+    env = QuadXHoverVecEnv(num_envs=n, seed=args.seed, device=dev, env_offset=first)
     av = env.aviary
     env.reset()
     K, W, R = args.steps, args.warmup, args.repeats
@@ -385,8 +389,9 @@ def run_ours(args, rank, local_rank, world):
     # ---- region S (context, world > 1): STRONG scaling — BASELINE's 65 536 envs in total, split over the ranks
     strong_ms = 0.0
     if world > 1:
-        ns = ENVS_PER_GPU // world
-        env_s = QuadXHoverVecEnv(num_envs=ns, seed=args.seed, device=dev, env_offset=rank * ns)
+        s0, s1 = shard_range(ENVS_PER_GPU, rank, world)
+        ns = s1 - s0
+        env_s = QuadXHoverVecEnv(num_envs=ns, seed=args.seed, device=dev, env_offset=s0)
         env_s.reset()
         acts_s = actions[:, :ns].contiguous()
         for k in range(30):
