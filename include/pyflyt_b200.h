@@ -169,6 +169,10 @@ typedef struct PfbEnvConfig {
                               * stream: all of a step's work is in order on one stream)                              */
   double damage_per_hit, lethal_distance, lethal_angle, aggressiveness, cooperativeness;
   double spawn_min_radius, spawn_max_radius, spawn_min_height, spawn_max_height;
+  int32_t contact_response;  /* Rocket-Landing: 1 = ground / pad contact RESPONSE (sequential-impulse normal + Coulomb friction
+                              * on the collision primitives' corner / rim points; a restatement): a gentle touchdown
+                              * rests on the pad and reaches env_complete (rocket_landing_env.py:231-263).  0 = contact FLAG only  */
+  int32_t _pad_cr;
 } PfbEnvConfig;
 
 /* Analytic, time-invariant wind field evaluated IN-KERNEL at every drag body / lifting surface.

@@ -583,6 +583,94 @@ class World:
             out = [c for c in out if c[1] == bodyB or c[2] == bodyB]
         return tuple(out)
 
+    # ---- contact RESPONSE (opt-in) ------------------------------------------------
+    # A restatement of a Bullet-like sequential-impulse contact for a free body landing on a horizontal surface (ground
+    # plane z = 0, or the top of the landing pad under the base).  **Unpinned**: Bullet's btMultiBodyConstraintSolver is
+    # not reproduced (no manifold reduction, no warm starting, no split impulse); what is kept is its structure — velocities
+    # are predicted from the applied forces, contacts are found on the pose at the START of the step, impulses act on the
+    # predicted velocities, then the pose is integrated — with: candidate points = the 8 corners of every box and 4 + 4 rim
+    # points of every cylinder; per point, in order, CONTACT_ITERATIONS sweeps of a non-accumulated normal impulse that
+    # removes the approach velocity and pushes out with Baumgarte bias ERP * depth / dt (restitution 0), then Coulomb
+    # friction (mu = CONTACT_FRICTION) against the tangential velocity.  Same arithmetic in oracle/pfb_oracle.c and in the
+    # CUDA rocket kernel.  Off by default: the fixtures recorded before it existed only carry the contact FLAG.
+    CONTACT_ITERATIONS = 8
+    CONTACT_ERP = 0.2
+    CONTACT_SLOP = 0.001
+    CONTACT_FRICTION = 0.5
+    contact_response = False
+
+    @staticmethod
+    def contact_points(links):
+        """candidate contact points in the base inertial frame, fixed order: shapes in link order, 8 points each"""
+        pts = []
+        for lk in links:
+            for kind, dims, cr, cR in lk.shapes:
+                if kind == "box":
+                    h = 0.5 * np.asarray(dims)
+                    loc = [(sx * h[0], sy * h[1], sz * h[2]) for sz in (-1, 1) for sy in (-1, 1) for sx in (-1, 1)]
+                elif kind == "cylinder":
+                    rad, half = dims[0], 0.5 * dims[1]
+                    loc = [(rad * cx, rad * cy, sz * half) for sz in (-1, 1) for cx, cy in ((1, 0), (0, 1), (-1, 0), (0, -1))]
+                else:
+                    continue
+                for q in loc:
+                    pts.append(cr + cR @ np.asarray(q, dtype=np.float64))
+        return pts
+
+    def _surface_height(self, b):
+        """height of the horizontal surface under the body: the top of a static cylinder (landing pad) if the base is over it"""
+        top = 0.0
+        for s in self.bodies.values():
+            if not s.fixed_base or s.is_plane:
+                continue
+            for lk in s.links:
+                for kind, dims, cr, cR in lk.shapes:
+                    if kind == "cylinder":
+                        centre = s.pos + s.R() @ cr
+                        if math.hypot(b.pos[0] - centre[0], b.pos[1] - centre[1]) <= dims[0]:
+                            top = max(top, centre[2] + 0.5 * dims[1])
+        return top
+
+    def _solve_contacts(self, b, Rb, M, c, I_O):
+        dt = self.dt
+        top = self._surface_height(b)
+        cw = Rb @ c
+        Ic = I_O - M * (np.dot(c, c) * np.eye(3) - np.outer(c, c))
+        Iinv = Rb @ np.linalg.inv(Ic) @ Rb.T  # world-frame inverse inertia about the COM
+        vc = b.v + np.cross(b.w, cw)          # COM velocity
+        w = b.w.copy()
+        pts = [Rb @ p for p in self.contact_points(b.links)]
+        n = np.array([0.0, 0.0, 1.0])
+        touched = False
+        for _ in range(self.CONTACT_ITERATIONS):
+            for pw in pts:
+                depth = top - (b.pos[2] + pw[2])
+                if depth <= 0.0:
+                    continue
+                touched = True
+                r = pw - cw
+                u = vc + np.cross(w, r)
+                rn = np.cross(r, n)
+                kn = 1.0 / M + np.dot(rn, Iinv @ rn)
+                bias = self.CONTACT_ERP * max(depth - self.CONTACT_SLOP, 0.0) / dt
+                jn = max(0.0, (bias - u[2]) / kn)
+                if jn > 0.0:
+                    vc = vc + (jn / M) * n
+                    w = w + Iinv @ (jn * rn)
+                    u = vc + np.cross(w, r)
+                    ut = np.array([u[0], u[1], 0.0])
+                    sp = math.sqrt(ut[0] * ut[0] + ut[1] * ut[1])
+                    if sp > 1e-12:
+                        t = ut / sp
+                        rt = np.cross(r, t)
+                        kt = 1.0 / M + np.dot(rt, Iinv @ rt)
+                        jt = min(sp / kt, self.CONTACT_FRICTION * jn)
+                        vc = vc - (jt / M) * t
+                        w = w - Iinv @ (jt * rt)
+        if touched:
+            b.w = w
+            b.v = vc - np.cross(w, cw)
+
     def stepSimulation(self, *a, **k):
         dt = self.dt
         self._detect_contacts()
@@ -616,6 +704,8 @@ class World:
             a_O, wdot = sol[:3], sol[3:]
             b.w = np.clip(b.w + (Rb @ wdot) * dt, -MAX_COORDINATE_VELOCITY, MAX_COORDINATE_VELOCITY)
             b.v = np.clip(b.v + (Rb @ a_O) * dt, -MAX_COORDINATE_VELOCITY, MAX_COORDINATE_VELOCITY)
+            if self.contact_response:
+                self._solve_contacts(b, Rb, M, c, I_O)
             # semi-implicit Euler with the NEW velocities
             b.pos = b.pos + b.v * dt
             ang = float(np.linalg.norm(b.w))

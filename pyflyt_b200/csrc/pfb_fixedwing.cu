@@ -422,10 +422,15 @@ __global__ void __launch_bounds__(kBlock)
 // ---------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------
+// Lanes per aircraft in the Fixedwing-Waypoints step.  MEASURED on B200 (16 384 envs, L2 flushed, us per env step): L = 1: 37.5,
+// L = 2: 39.3, L = 4: 41.8, L = 8: 58.6 — splitting the five lifting surfaces over lanes does NOT pay: the surfaces are only
+// ~55 % of a substep's instructions; the Newton-Euler solve, the integrator and update_state are replicated in every lane of a
+// group, so 4x more warps carry 0.7x the instructions each (2.8x the issue work) for a 3x better issue rate.  Default 1; the
+// multi-lane path stays compiled behind -DPFB_FW_LANES=n as the record of the experiment.
 #ifndef PFB_FW_LANES
-#define PFB_FW_LANES 4
+#define PFB_FW_LANES 1
 #endif
-constexpr int kFwLanes = PFB_FW_LANES;  // lanes per aircraft in the Fixedwing-Waypoints step (1, 2, 4 or 8)
+constexpr int kFwLanes = PFB_FW_LANES;
 static_assert(kFwLanes == 1 || kFwLanes == 2 || kFwLanes == 4 || kFwLanes == 8, "lanes per aircraft");
 
 int fw_reset(PfbContext* h, const uint8_t* mask, cudaStream_t s) {

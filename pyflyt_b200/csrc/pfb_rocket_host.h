@@ -47,6 +47,7 @@ static int rk_build_params_impl(const PfbModel& m, const PfbEnvConfig* env, pfb:
   p.start_fuel = (float)m.starting_fuel_ratio;
   p.noise_loc = 1.0f;  // one booster: normal(*throttle.shape) == normal(loc=1) (boosters.py:241-245)
   if (pfb_build_contact(m, p.contact)) return -1;
+  p.contact_response = (env && env->contact_response) ? 1 : 0;
   if (env) {
     l.env_step_ratio = env->env_step_ratio;
     l.max_steps = env->max_steps;

@@ -43,9 +43,12 @@ class RocketLandingVecEnv:
         device: str | torch.device = "cuda:0",
         env_offset: int = 0,
         inline_reset: bool = False,
+        contact_response: bool = True,
     ):
         """``randomize_drop`` / ``accelerate_drop`` are the reference's ``reset(options=...)`` switches
-        (rocket_landing_env.py:94-98: both on when ``options=None``)."""
+        (rocket_landing_env.py:94-98: both on when ``options=None``).  ``contact_response`` (default on): the legs / body push back
+        against the pad and the ground (sequential-impulse contact with friction, a restatement of Bullet's), so a
+        gentle touchdown RESTS on the pad and the env can report ``env_complete`` like the reference; off = contact flag only."""
         if 120 % agent_hz != 0:
             lowest = int(120 / (int(120 / agent_hz) + 1))
             highest = int(120 / int(120 / agent_hz))
@@ -70,6 +73,7 @@ class RocketLandingVecEnv:
         cfg.accelerate_drop = int(bool(accelerate_drop))
         cfg.flight_dome_size = float("inf")
         cfg.inline_reset = int(bool(inline_reset))  # tests: spare-copy resets must equal inline ones bit for bit
+        cfg.contact_response = int(bool(contact_response))
         self.config = cfg
         sp = np.tile(np.array([[0.0, 0.0, ceiling * 0.9]]), (self.num_envs, 1))  # rocket_landing_env.py:60
         so = np.zeros((self.num_envs, 3))

@@ -143,6 +143,8 @@ class PfbEnvConfig(C.Structure):
         ("spawn_max_radius", C.c_double),
         ("spawn_min_height", C.c_double),
         ("spawn_max_height", C.c_double),
+        ("contact_response", C.c_int32),
+        ("_pad_cr", C.c_int32),
     ]
 
 

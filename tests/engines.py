@@ -518,7 +518,7 @@ def replay_waypoints(make_engine, g):
 
 
 def landing_config(angle_representation="quaternion", sparse=False, randomize_drop=False, accelerate_drop=False, ceiling=500.0,
-                   max_displacement=200.0, agent_hz=40, max_duration=30.0, autoreset=False):
+                   max_displacement=200.0, agent_hz=40, max_duration=30.0, autoreset=False, contact_response=False):
     e = PfbEnvConfig()
     e.env_kind = 4
     e.flight_mode = 0
@@ -533,13 +533,15 @@ def landing_config(angle_representation="quaternion", sparse=False, randomize_dr
     e.randomize_drop = int(bool(randomize_drop))
     e.accelerate_drop = int(bool(accelerate_drop))
     e.flight_dome_size = float("inf")
+    e.contact_response = int(bool(contact_response))
     return e
 
 
 def replay_landing(make_engine, g, max_steps=None):
     """Replays a rocket_landing fixture: every episode's spawn pose is installed explicitly."""
     model = build_model("rocket", "rocket", starting_fuel_ratio=0.05)  # rocket_landing_env.py:104
-    env = landing_config(str(g["angle_representation"]), bool(g["sparse"]), False, bool(g["accelerate_drop"]))
+    extra = {k: (float(g[k]) if k != "contact_response" else bool(g[k])) for k in ("ceiling", "max_displacement", "contact_response") if k in g.files}
+    env = landing_config(str(g["angle_representation"]), bool(g["sparse"]), False, bool(g["accelerate_drop"]), **extra)
     sp = g["spawns"]
     eng = make_engine(model, env, 1, sp[0][None, :3], sp[0][None, 3:])
     noise, splits = g["noise"], g["noise_splits"]

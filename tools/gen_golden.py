@@ -276,9 +276,59 @@ def fly_landing(name, seed, n_steps, action_seed, options, angle_representation=
         actions=np.array(acts), obs=np.array(obs), reward=np.array(rew), term=np.array(term), trunc=np.array(trunc), info=np.array(info),
         noise=np.array(rng.normal_log), noise_splits=np.array(noise_splits), episode_start=np.array(episode_start, dtype=np.int64),
         after_reset_obs=np.array(resets_obs) if resets_obs else np.zeros((0, len(obs0))),
-        **wind_fields(wind),
     )
     print(name, "steps", n_steps, "episodes", len(episode_start) + 1, "infos", sorted(set(info)), "draws", len(rng.normal_log))
+
+
+def fly_touchdown(name, seed, n_steps, descent_rate, ceiling=4.0, max_displacement=20.0, angle_representation="quaternion", lateral=(0.0, 0.0)):
+    """RocketLandingEnv brought down onto the pad by a scripted bang-bang ignition law, with the engine's contact RESPONSE
+    switched on (oracle/fakebullet World.contact_response): the rocket touches down at `descent_rate`-ish m/s, rests on its
+    legs and the UNMODIFIED env reports env_complete (rocket_landing_env.py:231-263).  Same file format as fly_landing."""
+    import pybullet as fb  # oracle/fakebullet
+    from PyFlyt.gym_envs.rocket_envs.rocket_landing_env import RocketLandingEnv
+
+    fb.World.contact_response = True
+    try:
+        env = RocketLandingEnv(ceiling=ceiling, max_displacement=max_displacement, angle_representation=angle_representation)
+        rng = ril.ScriptedNoise(seed)
+        env._np_random = rng
+        obs0, _ = env.reset(options=dict(randomize_drop=False, accelerate_drop=False))
+        if lateral != (0.0, 0.0):  # a small sideways push: friction has to stop the slide
+            env.env.resetBaseVelocity(env.env.drones[0].Id, [lateral[0], lateral[1], 0.0], [0.0, 0.0, 0.0])
+        spawns = [np.concatenate([env.start_pos[0], env.start_orn[0]])]
+        att = 4 if angle_representation == "quaternion" else 3
+        obs_k, acts, obs, rew, term, trunc, info = np.array(obs0), [], [], [], [], [], []
+        noise_splits = [len(rng.normal_log)]
+        for i in range(n_steps):
+            vz, z = obs_k[3 + att + 2], obs_k[3 + att + 3 + 2]
+            h = z - 2.425 - 0.15  # leg soles above the pad
+            ign = 1.0 if (vz < -(descent_rate + 1.0 * max(h, 0.0)) and h > 0.02) else 0.0
+            a = np.array([0.0, 0.0, 0.0, ign, 0.0, 0.0, 0.0])
+            o, r, te, tr, inf = env.step(a)
+            obs_k = np.array(o)
+            acts.append(a); obs.append(obs_k); rew.append(r); term.append(te); trunc.append(tr)
+            info.append(int(inf["out_of_bounds"]) | (int(inf["fatal_collision"]) << 1) | (int(inf["env_complete"]) << 2))
+            noise_splits.append(len(rng.normal_log))
+            if te or tr:
+                break
+    finally:
+        fb.World.contact_response = False
+    np.savez_compressed(
+        os.path.join(OUT, f"{name}.npz"), kind="rocket_landing", sparse=False, angle_representation=angle_representation,
+        randomize_drop=False, accelerate_drop=False, spawns=np.array(spawns), reset_obs=np.array(obs0),
+        actions=np.array(acts), obs=np.array(obs), reward=np.array(rew), term=np.array(term), trunc=np.array(trunc), info=np.array(info),
+        noise=np.array(rng.normal_log), noise_splits=np.array(noise_splits), episode_start=np.zeros(0, dtype=np.int64),
+        after_reset_obs=np.zeros((0, len(obs0))), ceiling=ceiling, max_displacement=max_displacement, contact_response=True,
+        start_lin_vel=np.array([lateral[0], lateral[1], 0.0]),
+    )
+    print(name, "steps", len(acts), "last info", info[-1], "pad contact steps", int(sum(o[-1] for o in obs)), "draws", len(rng.normal_log))
+
+
+def touchdown_fixtures():
+    # SURVEY 8f item 3: gentle touchdowns that must end in env_complete, a hard one that must be a fatal collision
+    fly_touchdown("landing_touchdown", seed=81, n_steps=300, descent_rate=0.6)
+    fly_touchdown("landing_touchdown_soft_euler", seed=82, n_steps=300, descent_rate=0.3, angle_representation="euler")
+    fly_touchdown("landing_touchdown_hard", seed=83, n_steps=300, descent_rate=2.5)
 
 
 def fly_dogfight(name, seed, n_steps, action_seed, team_size=1, sparse=False, action_scale=0.6, lethal_distance=20.0, lethal_angle=0.07,
@@ -644,3 +694,5 @@ if __name__ == "__main__":
         quadx_waypoints_fixtures()
     if which in ("all", "wind"):
         wind_fixtures()
+    if which in ("all", "touchdown"):
+        touchdown_fixtures()
