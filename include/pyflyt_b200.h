@@ -301,6 +301,12 @@ int pfb_env_rollout(PfbHandle h, int n_steps, void* stream);
 int pfb_env_step_host(PfbHandle h, const float* host_actions, float* host_obs, float* host_reward,
                       uint8_t* host_term, uint8_t* host_trunc, void* stream);
 
+/* Zero-copy flavour of the same call: the step kernel reads the actions from and writes obs / reward / term / trunc straight
+ * into the caller's PINNED host buffers (device-mapped under UVA), so the PCIe traffic overlaps the launch instead of
+ * bracketing it with two copies.  Same results, same bytes over the bus.                                              */
+int pfb_env_step_mapped(PfbHandle h, const float* host_actions, float* host_obs, float* host_reward,
+                        uint8_t* host_term, uint8_t* host_trunc, void* stream);
+
 /* ---- MAFixedwingDogfight with an arena's agents on DIFFERENT ranks (ma_fixedwing_dogfight_env.py:346-465):
  * global agent id = member * num_arenas + arena; this handle owns ids [first_global_agent, +n_envs).  Per Aviary
  * step the caller runs  pfb_dogfight_physics -> all-gather of the payload table (NCCL) -> pfb_dogfight_combat.

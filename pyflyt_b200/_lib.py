@@ -83,6 +83,7 @@ def lib() -> C.CDLL:
     L.pfb_env_step.argtypes = [vp, vp, vp, vp]
     L.pfb_env_rollout.argtypes = [vp, i32, vp]
     L.pfb_env_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.pfb_env_step_mapped.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.pfb_dogfight_physics.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
     L.pfb_dogfight_combat.argtypes = [vp, vp, i64, i64, i32, vp]
     L.pfb_dogfight_physics_peer.argtypes = [vp, vp, vp, vp, i32, i64, vp, i32, i32, i32, i32, i32, vp]
@@ -109,6 +110,6 @@ EXPORTS = [
     "pfb_istate_rows", "pfb_setpoint_dim",
     "pfb_obs_dim", "pfb_aux_dim", "pfb_bind", "pfb_reset", "pfb_set_mode", "pfb_aviary_step", "pfb_observe_state",
     "pfb_set_base_velocity",
-    "pfb_env_reset", "pfb_env_step", "pfb_env_rollout", "pfb_env_step_host", "pfb_launch_count",
+    "pfb_env_reset", "pfb_env_step", "pfb_env_rollout", "pfb_env_step_host", "pfb_env_step_mapped", "pfb_launch_count",
     "pfb_profile_begin", "pfb_profile_read", "pfb_dogfight_payload_dim", "pfb_dogfight_physics", "pfb_dogfight_physics_peer", "pfb_dogfight_combat", "pfb_dogfight_combat_wait", "pfb_dogfight_split_step",
 ]  # every symbol include/pyflyt_b200.h declares

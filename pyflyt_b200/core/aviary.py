@@ -373,6 +373,13 @@ class BatchedAviary:
         _lib.check(_lib.lib().pfb_env_rollout(self._h, int(n_steps), self._s()))
         self._state_fresh = False
 
+    def env_step_mapped(self, actions: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor, term: torch.Tensor, trunc: torch.Tensor) -> None:
+        """Zero-copy end-to-end step: the kernel reads ``actions`` from and writes the results into PINNED host tensors."""
+        for t in (actions, obs, reward, term, trunc):
+            assert not t.is_cuda and t.is_contiguous() and t.is_pinned()
+        _lib.check(_lib.lib().pfb_env_step_mapped(self._h, C.c_void_p(actions.data_ptr()), C.c_void_p(obs.data_ptr()), C.c_void_p(reward.data_ptr()), C.c_void_p(term.data_ptr()), C.c_void_p(trunc.data_ptr()), self._s()))
+        self._state_fresh = False
+
     def env_step_host(self, actions: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor, term: torch.Tensor, trunc: torch.Tensor) -> None:
         """Pinned-host in, pinned-host out (the end-to-end path bench.py times)."""
         for t in (actions, obs, reward, term, trunc):

@@ -943,6 +943,29 @@ int pfb_env_step_host(PfbHandle h, const float* host_actions, float* host_obs, f
   return 0;
 }
 
+// Zero-copy variant of pfb_env_step_host: the step kernel reads the actions from, and writes obs / reward / term / trunc
+// straight into, PINNED (device-mapped) host memory.  The PCIe transfers then overlap the launch tile by tile instead of
+// bracketing it as two copies; no staging through the bound device buffers.
+int pfb_env_step_mapped(PfbHandle h, const float* host_actions, float* host_obs, float* host_reward, uint8_t* host_term,
+                        uint8_t* host_trunc, void* stream) {
+  REQUIRE_BOUND(h);
+  if (require_env(h)) return -1;
+  if (!host_actions || !host_obs || !host_reward || !host_term || !host_trunc) return fail("pfb_env_step_mapped: null argument");
+  void *da = nullptr, *dob = nullptr, *dr = nullptr, *dte = nullptr, *dtr = nullptr;
+  if (cudaHostGetDevicePointer(&da, (void*)host_actions, 0) != cudaSuccess || cudaHostGetDevicePointer(&dob, host_obs, 0) != cudaSuccess ||
+      cudaHostGetDevicePointer(&dr, host_reward, 0) != cudaSuccess || cudaHostGetDevicePointer(&dte, host_term, 0) != cudaSuccess ||
+      cudaHostGetDevicePointer(&dtr, host_trunc, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return fail("pfb_env_step_mapped: the host buffers must be pinned (cudaHostAlloc / cudaHostRegister) memory");
+  }
+  if (((uintptr_t)da & 15) || ((uintptr_t)dob & 15)) return fail("pfb_env_step_mapped: actions and obs must be 16-byte aligned");
+  const PfbBuffers saved = h->buf;
+  h->buf.obs = (float*)dob; h->buf.reward = (float*)dr; h->buf.term = (uint8_t*)dte; h->buf.trunc = (uint8_t*)dtr;
+  const int rc = env_step_impl(h, (float*)da, nullptr, false, (cudaStream_t)stream);
+  h->buf = saved;
+  return rc;
+}
+
 // ---- MAFixedwingDogfight, split variant: an arena's agents on different ranks
 int pfb_dogfight_payload_dim(void) { return 20; }
 
