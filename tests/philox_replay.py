@@ -85,6 +85,29 @@ class Streams:
         """spare post-reset states: seq = the env's episode number (1 for the first autoreset after a user reset)"""
         return self.noise(episode, TAG_RESET, warmup, envs)
 
+    def waypoint_targets(self, seq, num_targets: int, dome: float, min_height: float = 0.1, envs=None) -> np.ndarray:
+        """WaypointHandler.reset (gym_envs/utils/waypoint_handler.py:65-83) as the kernels draw it (pfb_fixedwing.cu wp_sample_targets,
+        pfb_quadx_wp.cu qw_sample_targets): stream tag 4, counter word 3 = (4 << 24) | target index; [len(envs)][num_targets][3]"""
+        lo = self.env_lo if envs is None else self.env_lo[envs]
+        hi = self.env_hi if envs is None else self.env_hi[envs]
+        seq = np.broadcast_to(np.asarray(seq, dtype=np.uint32), lo.shape)
+        out = np.zeros((len(lo), num_targets, 3), dtype=np.float32)
+        two_pi = np.float32(6.28318530717958647692)
+        for k in range(num_targets):
+            r = philox4x32_10(lo, hi, seq, np.uint32((4 << 24) | k), self.k0, self.k1)
+            theta, phi = two_pi * unit_open(r[0]), two_pi * unit_open(r[1])
+            dist = np.float32(1.0) + np.float32(dome * 0.9 - 1.0) * unit_open(r[2])
+            out[:, k, 0] = dist * np.sin(phi) * np.cos(theta)
+            out[:, k, 1] = dist * np.sin(phi) * np.sin(theta)
+            z = np.abs(dist * np.cos(phi))
+            out[:, k, 2] = np.where(z > min_height, z, np.float32(min_height))
+        return out
+
+    def uniform_actions(self, step_seq: int) -> np.ndarray:
+        """RANDACT of the fixed-wing envs: U(-1, 1)^4"""
+        r = philox4x32_10(self.env_lo, self.env_hi, np.uint32(step_seq), np.uint32(TAG_ACTION << 24), self.k0, self.k1)
+        return np.stack([np.float32(2.0) * unit_open(x) - np.float32(1.0) for x in r], axis=1)
+
     def actions(self, step_seq: int, mode: int = 0) -> np.ndarray:
         """RANDACT: uniform in the env's action box (quadx_base_env.py:79-102)"""
         r = philox4x32_10(self.env_lo, self.env_hi, np.uint32(step_seq), np.uint32(TAG_ACTION << 24), self.k0, self.k1)
