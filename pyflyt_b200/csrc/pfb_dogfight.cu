@@ -650,7 +650,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
 // combat state for 1-vs-1 arenas from the gathered payload table [num_agents][kPayload]
 __global__ void __launch_bounds__(kBlock, kMinBlocks)
     k_df_split_combat(const __grid_constant__ DogfightParams d, float* __restrict__ st, int32_t* __restrict__ ist,
-                      const float* __restrict__ table, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ term,
+                      const float* table /* NOT __restrict__: other GPUs store into it while this kernel waits (peer-signal) */,
+                      float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ term,
                       uint8_t* __restrict__ trunc, uint8_t* __restrict__ info, int64_t first_gid, int64_t num_arenas, int last,
                       const int* __restrict__ wait_flags, int world, int epoch, int64_t N) {
   if (wait_flags) {  // every rank's physics kernel has raised its flag for this exchange (acquire, system scope)
@@ -668,8 +669,14 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   const int li = (int)(gid / num_arenas);
   const int64_t g = gid - (int64_t)li * num_arenas;
   const int64_t pid = (int64_t)(1 - li) * num_arenas + g;  // my opponent
-  const float* me = table + kPayload * gid;
-  const float* ot = table + kPayload * pid;
+  // the payload rows are copied into registers with ld.global.cg (L2, never the read-only / L1 path): with in-kernel
+  // signalling the table was written by other GPUs during this kernel's lifetime, after the acquire above
+  float me[kPayload], ot[kPayload];
+#pragma unroll
+  for (int k = 0; k < kPayload; ++k) {
+    me[k] = __ldcg(table + kPayload * gid + k);
+    ot[k] = __ldcg(table + kPayload * pid + k);
+  }
   FixedwingRegs s;
   DfAgent ag;
   fixedwing_load(st, ist, N, i, s);

@@ -112,9 +112,16 @@ class MAQuadXHoverVecEnv:
             A = self.agents_per_arena
             done = ~self.alive.view(self.num_arenas, A).any(dim=1)
             self._mask.copy_(done.repeat_interleave(A))
+            # SAME_STEP autoreset overwrites the rows of a finished arena with the first observation of its next episode: keep the
+            # terminal observation (gymnasium's info["final_obs"]; bootstrapping on truncation needs it)
+            torch.where(self._mask.bool()[:, None], a.obs, a.final_obs, out=a.final_obs)
             a.env_reset(mask=self._mask)  # no-op for the arenas that are still running; writes their first observation otherwise
             self.alive |= self._mask.bool()
-        return a.obs, reward, term, trunc, self._info()
+        info = self._info()
+        if self.autoreset:
+            info["final_obs"] = a.final_obs      # valid in the rows where info["reset"] is set
+            info["reset"] = self._mask.bool()
+        return a.obs, reward, term, trunc, info
 
     def close(self) -> None:
         self.aviary.disconnect()
