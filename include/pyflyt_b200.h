@@ -234,6 +234,13 @@ int pfb_sizeof_model(void);
 int pfb_sizeof_env_config(void);
 int pfb_sizeof_buffers(void);
 
+/* Vehicle table from the reference's model files: `<model>.urdf` (fixed joints only; what p.loadURDF(...,
+ * URDF_USE_INERTIA_FROM_FILE) reads, base_drone.py:104-122) + `<model>.yaml` (the parameter file the drone constructors read:
+ * quadx.py:84-197, fixedwing.py:70-166, rocket.py:82-208, lifting_surfaces.py:180-264).  kind = PFB_KIND_*; physics_hz /
+ * control_hz <= 0 select the reference defaults (240 / 120).  Host-only, no CUDA device needed.  Constructor options of the
+ * reference (`starting_velocity`, `starting_fuel_ratio`) are left at their defaults: overwrite the fields afterwards.     */
+int pfb_model_from_files(int kind, const char* urdf_path, const char* yaml_path, double physics_hz, double control_hz, PfbModel* out);
+
 /* Replaces Aviary.__init__ (aviary.py:69-216) for n_envs independent single-drone worlds. */
 int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, int device, uint64_t seed,
                PfbHandle* out);

@@ -152,7 +152,7 @@ __device__ __forceinline__ void landing_observation(const LandingParams& l, cons
 // env.reset() for one env (rocket_landing_env.py:87-127, rocket_base_env.py:166-261)
 // `pose` = the 6 start-pose words the caller read from start_pos / start_orn (ignored with randomize_drop)
 template <bool INJECT>
-__device__ __forceinline__ void landing_reset_env(const RocketParams& p, const LandingParams& l, const RngParams& rng, const float* pose,
+__device__ __forceinline__ void landing_reset_env_inline(const RocketParams& p, const LandingParams& l, const RngParams& rng, const float* pose,
                                                   const float* __restrict__ noise, uint32_t seq, bool randomize, int64_t N, int64_t i,
                                                   RocketRegs& s) {
   float sx = pose[0], sy = pose[1], sz = pose[2];
@@ -178,13 +178,31 @@ __device__ __forceinline__ void landing_reset_env(const RocketParams& p, const L
   rocket_requantize(s);  // exactly what the state tensor / a spare record will hold
 }
 
+// The warm-up of the AUTORESET paths (spare build, inline fallback) is ONE out-of-line copy shared by every instantiation of
+// k_land_step: a spare built by the <RANDACT = false> build launch must equal the warm-up a <RANDACT = true> step launch runs
+// inline BIT FOR BIT, and two inlined copies of the same source are free to contract their multiply-adds differently.  State in
+// and out by value (the caller's registers never have their address taken); the parameter blocks are the kernel's
+// __grid_constant__ parameters, read through their address.
+static __device__ __noinline__ RocketRegs landing_reset_env_shared(const RocketParams* p, const LandingParams* l, const RngParams* rng, float p0,
+                                                                   float p1, float p2, float p3, float p4, float p5, uint32_t seq, int randomize,
+                                                                   int64_t N, int64_t i) {
+  RocketRegs s;
+  const float pose[6] = {p0, p1, p2, p3, p4, p5};
+  landing_reset_env_inline<false>(*p, *l, *rng, pose, nullptr, seq, randomize != 0, N, i, s);
+  return s;
+}
+
+// 8 CTAs of one warp per SM are plenty at the batch sizes this env runs at (16 384 envs = 4.5 CTAs per SM): give the step the
+// whole register file instead of spilling (contact response + wind + variable-mass composite: ~170 live registers)
+constexpr int kLandBlocks = 8;
+
 // ---- spare post-reset states: the QuadX-Hover reset pipeline (pfb_lib.cu) for this env.  A spare is an
 // env-major record of 64 floats: the RK_* state words, then:
 enum { LSP_POSE = RK_ROWS, LSP_VALID = RK_ROWS + 6, LSP_FLAGS = RK_ROWS + 7, LSP_EPISODE = RK_ROWS + 8, LSP_ROWS = 64 };
 static_assert(RK_ROWS + 9 <= LSP_ROWS, "spare record too small");
 
 template <bool INJECT, bool RANDACT, bool AUTORESET>
-__global__ void __launch_bounds__(kBlock, kMinBlocks)
+__global__ void __launch_bounds__(kBlock, kLandBlocks)
     k_land_step(const __grid_constant__ RocketParams p, const __grid_constant__ LandingParams l, const __grid_constant__ RngParams rng,
                 float* __restrict__ st, int32_t* __restrict__ ist, float* __restrict__ actions, const float* __restrict__ noise,
                 float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ term, uint8_t* __restrict__ trunc,
@@ -244,7 +262,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
 #pragma unroll
           for (int k = 0; k < 6; ++k) rec[LSP_POSE + k] = pose[k];
         }
-        landing_reset_env<false>(p, l, rng, pose, nullptr, nseq, l.randomize_drop != 0, N, i, s);
+        s = landing_reset_env_shared(&p, &l, &rng, pose[0], pose[1], pose[2], pose[3], pose[4], pose[5], nseq, l.randomize_drop, N, i);
       }
       if (build) {
         rocket_store(rec, ist, N, i, s, false, 1, 0);
@@ -345,7 +363,7 @@ __global__ void __launch_bounds__(kBlock)
   const int O = (l.angle_representation == 0 ? 12 : 13) + 17;
   RocketRegs s;
   const float pose[6] = {start_pos[3 * i], start_pos[3 * i + 1], start_pos[3 * i + 2], start_orn[3 * i], start_orn[3 * i + 1], start_orn[3 * i + 2]};
-  landing_reset_env<INJECT>(p, l, rng, pose, noise, seq, randomize != 0, N, i, s);
+  landing_reset_env_inline<INJECT>(p, l, rng, pose, noise, seq, randomize != 0, N, i, s);
   const float zero[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float* row = smem + threadIdx.x * kLandObsStride;
   landing_observation(l, s, zero, false, row);

@@ -354,6 +354,24 @@ def build_model(
     return m
 
 
+def model_from_files(kind: str, urdf_path: str, yaml_path: str, physics_hz: int = 240, control_hz: int = 120, **options) -> PfbModel:
+    """The same table built INSIDE the C-ABI (``pfb_model_from_files``, pyflyt_b200/csrc/pfb_model_files.cu) from a
+    ``<model>.urdf`` + ``<model>.yaml`` pair in the reference's layout (base_drone.py:104-110): what a non-Python caller uses.
+    ``options`` are the reference's constructor options (``starting_velocity``, ``starting_fuel_ratio``)."""
+    from .._lib import check, lib
+
+    kinds = {"quadx": KIND_QUADX, "fixedwing": KIND_FIXEDWING, "rocket": KIND_ROCKET}
+    if kind not in kinds:
+        raise ValueError(f"unknown drone_type {kind!r}; known: {list(kinds)}")
+    m = PfbModel()
+    check(lib().pfb_model_from_files(kinds[kind], os.fsencode(urdf_path), os.fsencode(yaml_path), float(physics_hz), float(control_hz), C.addressof(m)))
+    if "starting_velocity" in options and kind == "fixedwing":
+        m.starting_velocity[:] = [float(v) for v in options["starting_velocity"]]
+    if "starting_fuel_ratio" in options and kind == "rocket":
+        m.starting_fuel_ratio = float(options["starting_fuel_ratio"])
+    return m
+
+
 def model_to_dict(m: PfbModel) -> dict:
     """Plain-python view (for tests and debugging)."""
 

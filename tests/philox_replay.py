@@ -85,13 +85,14 @@ class Streams:
         """spare post-reset states: seq = the env's episode number (1 for the first autoreset after a user reset)"""
         return self.noise(episode, TAG_RESET, warmup, envs)
 
-    def waypoint_targets(self, seq, num_targets: int, dome: float, min_height: float = 0.1, envs=None) -> np.ndarray:
-        """WaypointHandler.reset (gym_envs/utils/waypoint_handler.py:65-83) as the kernels draw it (pfb_fixedwing.cu wp_sample_targets,
-        pfb_quadx_wp.cu qw_sample_targets): stream tag 4, counter word 3 = (4 << 24) | target index; [len(envs)][num_targets][3]"""
+    def waypoint_targets(self, seq, num_targets: int, dome: float, min_height: float = 0.1, envs=None, yaw: bool = False) -> np.ndarray:
+        """WaypointHandler.reset (gym_envs/utils/waypoint_handler.py:65-90) as the kernels draw it (pfb_fixedwing.cu wp_sample_targets,
+        pfb_quadx_wp.cu qw_sample_targets): stream tag 4, counter word 3 = (4 << 24) | target index; [len(envs)][num_targets][3]
+        (or [..][4] with `yaw`: the yaw target U(-pi, pi) from the fourth word of the same Philox call)"""
         lo = self.env_lo if envs is None else self.env_lo[envs]
         hi = self.env_hi if envs is None else self.env_hi[envs]
         seq = np.broadcast_to(np.asarray(seq, dtype=np.uint32), lo.shape)
-        out = np.zeros((len(lo), num_targets, 3), dtype=np.float32)
+        out = np.zeros((len(lo), num_targets, 4 if yaw else 3), dtype=np.float32)
         two_pi = np.float32(6.28318530717958647692)
         for k in range(num_targets):
             r = philox4x32_10(lo, hi, seq, np.uint32((4 << 24) | k), self.k0, self.k1)
@@ -101,7 +102,24 @@ class Streams:
             out[:, k, 1] = dist * np.sin(phi) * np.sin(theta)
             z = np.abs(dist * np.cos(phi))
             out[:, k, 2] = np.where(z > min_height, z, np.float32(min_height))
+            if yaw:
+                out[:, k, 3] = np.float32(-3.14159265358979323846) + two_pi * unit_open(r[3])
         return out
+
+    def drop_poses(self, seq, ceiling: float, max_displacement: float, envs=None):
+        """options["randomize_drop"] (rocket_base_env.py:192-199) as k_land_step / k_land_reset draw it (pfb_rocket.cu
+        landing_reset_env_inline): stream tag 5, two Philox calls; returns (start_pos [m][3], start_orn [m][3]) float32"""
+        lo = self.env_lo if envs is None else self.env_lo[envs]
+        hi = self.env_hi if envs is None else self.env_hi[envs]
+        seq = np.broadcast_to(np.asarray(seq, dtype=np.uint32), lo.shape)
+        a = philox4x32_10(lo, hi, seq, np.uint32(5 << 24), self.k0, self.k1)
+        b = philox4x32_10(lo, hi, seq, np.uint32((5 << 24) | 1), self.k0, self.k1)
+        one, two = np.float32(1.0), np.float32(2.0)
+        rng_ = np.float32(max_displacement) * np.float32(0.1)
+        pos = np.stack([rng_ * (two * unit_open(a[0]) - one), rng_ * (two * unit_open(a[1]) - one),
+                        np.float32(ceiling) * (np.float32(0.8) + np.float32(0.1) * unit_open(a[2]))], axis=1)
+        orn = np.stack([np.float32(0.3) * (two * unit_open(b[k]) - one) for k in range(3)], axis=1)
+        return pos.astype(np.float32), orn.astype(np.float32)
 
     def uniform_actions(self, step_seq: int) -> np.ndarray:
         """RANDACT of the fixed-wing envs: U(-1, 1)^4"""

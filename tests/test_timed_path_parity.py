@@ -105,7 +105,7 @@ def test_fixedwing_waypoints_philox_autoreset_matches_oracle():
     orc = OracleEngine(model, cfg, n, np.tile([[0.0, 0.0, 10.0]], (n, 1)), np.zeros((n, 3)))
 
     obs_g, _ = env.reset()
-    tg = streams.waypoint_targets(0x80000000, T, dome)
+    tg = streams.waypoint_targets(0x80000000, T, dome, min_height=0.5)  # fixedwing_waypoints_env.py:81
     obs_o = orc.o.env_reset(noise=streams.user_reset_noise(0).astype(np.float64), targets=tg.astype(np.float64).reshape(n, -1))
     assert np.abs(obs_g.double().cpu().numpy() - obs_o).max() < 2e-3
 
@@ -127,7 +127,7 @@ def test_fixedwing_waypoints_philox_autoreset_matches_oracle():
             rz = np.zeros((20, n))
             rz[:, idx] = streams.autoreset_noise(episode[idx], envs=idx)
             tgr = np.zeros((n, T, 3))
-            tgr[idx] = streams.waypoint_targets(episode[idx], T, dome, envs=idx)
+            tgr[idx] = streams.waypoint_targets(episode[idx], T, dome, min_height=0.5, envs=idx)
             obs_r = orc.o.env_reset(mask=done_prev.astype(np.uint8), noise=rz, targets=tgr.reshape(n, -1))
             oo[done_prev], ro[done_prev], teo[done_prev], tro[done_prev], io[done_prev] = obs_r[done_prev], 0.0, False, False, 0
             episode[idx] += 1
@@ -144,4 +144,142 @@ def test_fixedwing_waypoints_philox_autoreset_matches_oracle():
     assert n_resets > n and reached >= 1
     assert n_flip <= n // 1000
     assert worst_obs < 5e-3 and worst_rew < 5e-3  # target deltas are O(100 m) fp32 numbers
+    env.close()
+
+
+@pytest.mark.parametrize("ceiling,max_duration", [(500.0, 2.0), (120.0, 30.0)])
+def test_rocket_landing_philox_autoreset_matches_oracle(ceiling, max_duration):
+    """The same pin for BASELINE configs[3]: k_land_step with Philox booster noise (N(1, 1)), device-drawn randomised drops
+    (rocket_base_env.py:192-199), accelerated drop, contact response on, NEXT_STEP autoreset through spare post-reset states;
+    16 384 rockets x 200 env steps against the oracle driven with the replayed noise and the replayed drop poses.
+    ceiling 500 / 2 s episodes: every episode ends by truncation in flight; ceiling 120: every rocket reaches the ground (or
+    the pad) within a second, so the crash / pad-contact terminations and the contact response are in the comparison."""
+    import torch
+
+    from engines import landing_config
+    from pyflyt_b200.gym_envs.rocket_landing_env import RocketLandingVecEnv
+
+    n, steps, seed = 16384, 200, 4242
+    env = RocketLandingVecEnv(num_envs=n, seed=seed, ceiling=ceiling, max_duration_seconds=max_duration)
+    av = env.aviary
+    streams = Streams(seed, n, noise_loc=1.0)
+    model = build_model("rocket", "rocket", starting_fuel_ratio=0.05)
+    cfg = landing_config("quaternion", False, False, True, ceiling=ceiling, max_duration=max_duration, contact_response=True)
+    sp, so = streams.drop_poses(0x80000000, ceiling, 200.0)
+    sp, so = sp.astype(np.float64), so.astype(np.float64)
+    orc = OracleEngine(model, cfg, n, sp, so)
+
+    obs_g, _ = env.reset()
+    obs_o = orc.o.env_reset(noise=streams.user_reset_noise(0).astype(np.float64))
+    assert np.abs(obs_g.double().cpu().numpy() - obs_o).max() < 5e-3
+
+    rng = np.random.default_rng(3)
+    episode = np.ones(n, dtype=np.int64)
+    done_prev = np.zeros(n, dtype=bool)
+    live = np.ones(n, dtype=bool)
+    worst_obs = worst_rew = 0.0
+    n_resets = n_flip = n_coll = n_pad = 0
+    for k in range(steps):
+        act = _f(rng.uniform([-1, -1, -1, 0, 0, -1, -1], [1, 1, 1, 1, 1, 1, 1], (n, 7)))
+        env.step(torch.as_tensor(act, dtype=torch.float32, device=av.device))
+        og, rg = av.obs.double().cpu().numpy(), av.reward.double().cpu().numpy()
+        teg, trg, ig = av.term.cpu().numpy().astype(bool), av.trunc.cpu().numpy().astype(bool), av.info_bits.cpu().numpy()
+        oo, ro, teo, tro, io = orc.o.env_step(act, streams.step_noise(k, 3).astype(np.float64))
+        teo, tro = teo.astype(bool), tro.astype(bool)
+        if done_prev.any():
+            idx = np.nonzero(done_prev)[0]
+            rz = np.zeros((20, n))
+            rz[:, idx] = streams.autoreset_noise(episode[idx], envs=idx)
+            p_, o_ = streams.drop_poses(episode[idx], ceiling, 200.0, envs=idx)
+            sp[idx], so[idx] = p_, o_
+            orc.o.set_start(sp, so)
+            obs_r = orc.o.env_reset(mask=done_prev.astype(np.uint8), noise=rz)
+            oo[done_prev], ro[done_prev], teo[done_prev], tro[done_prev], io[done_prev] = obs_r[done_prev], 0.0, False, False, 0
+            episode[idx] += 1
+            n_resets += len(idx)
+        flip = live & ((teg != teo) | (trg != tro) | ((ig & 7) != (io & 7)))
+        n_flip += int(flip.sum())
+        live &= ~flip
+        worst_obs = max(worst_obs, float(np.abs(og[live] - oo[live]).max()))
+        worst_rew = max(worst_rew, float(np.abs(rg[live] - ro[live]).max()))
+        n_coll += int(((ig & 2) != 0).sum())
+        n_pad += int((og[:, -1] != 0).sum())
+        done_prev = teg | trg
+    print(f"\n[timed-path parity, rocket-landing ceiling {ceiling:g}] {n} envs x {steps} steps: {n_resets} autoresets, {n_coll} collisions, "
+          f"{n_pad} pad-contact observations, flips {n_flip}; max |obs| {worst_obs:.2e}, max |reward| {worst_rew:.2e}")
+    assert n_resets > n
+    if ceiling < 200.0:
+        assert n_coll > n  # every episode ends on the ground
+    assert n_flip <= n // 500
+    assert worst_obs < 5e-3 and worst_rew < 2e-2  # positions are O(400 m) fp32 numbers; the reward multiplies velocity differences by 4
+    env.close()
+
+
+@pytest.mark.parametrize("mode,yaw", [(0, False), (7, True)])
+def test_quadx_waypoints_philox_autoreset_matches_oracle(mode, yaw):
+    """The same pin for QuadX-Waypoints: k_qxwp_step with Philox motor noise, device-drawn waypoints (and yaw
+    targets), NEXT_STEP autoreset through spare post-reset states; 16 384 envs x 150 env steps."""
+    import torch
+
+    from engines import quadx_waypoints_config
+    from pyflyt_b200.gym_envs.quadx_waypoints_env import QuadXWaypointsVecEnv
+
+    n, steps, seed, T, dome = 16384, 150, 99, 4, 5.0
+    env = QuadXWaypointsVecEnv(num_envs=n, seed=seed, flight_mode=mode, use_yaw_targets=yaw, goal_reach_distance=1.0, goal_reach_angle=3.0,
+                               max_duration_seconds=2.0)  # episodes of <= 60 steps
+    av = env.aviary
+    streams = Streams(seed, n, noise_loc=4.0)
+    model = build_model("quadx", "cf2x")
+    cfg = quadx_waypoints_config(flight_mode=mode, num_targets=T, use_yaw_targets=yaw, goal_reach_distance=1.0, goal_reach_angle=3.0, dome=dome,
+                                 max_duration=2.0)
+    orc = OracleEngine(model, cfg, n, np.tile([[0.0, 0.0, 1.0]], (n, 1)), np.zeros((n, 3)))
+
+    obs_g, _ = env.reset()
+    tg = streams.waypoint_targets(0x80000000, T, dome, min_height=0.1, yaw=yaw)
+    obs_o = orc.o.env_reset(noise=streams.user_reset_noise(0).astype(np.float64), targets=tg.astype(np.float64).reshape(n, -1))
+    assert np.abs(obs_g.double().cpu().numpy() - obs_o).max() < 1e-4
+
+    rng = np.random.default_rng(5)
+    episode = np.ones(n, dtype=np.int64)
+    done_prev = np.zeros(n, dtype=bool)
+    live = np.ones(n, dtype=bool)
+    worst_obs = worst_rew = 0.0
+    n_resets = n_flip = reached = 0
+    for k in range(steps):
+        if mode == 7:  # position setpoints inside the dome: the drone chases them, reaches targets, sometimes leaves the dome
+            act = _f(rng.uniform([-2.0, -2.0, -1.0, 0.5], [2.0, 2.0, 1.0, 3.0], (n, 4)))
+        else:
+            act = _f(rng.uniform([-1.0, -1.0, -1.0, 0.0], [1.0, 1.0, 1.0, 0.8], (n, 4)))
+        env.step(torch.as_tensor(act, dtype=torch.float32, device=av.device))
+        og, rg = av.obs.double().cpu().numpy(), av.reward.double().cpu().numpy()
+        teg, trg, ig = av.term.cpu().numpy().astype(bool), av.trunc.cpu().numpy().astype(bool), av.info_bits.cpu().numpy()
+        oo, ro, teo, tro, io = orc.o.env_step(act, streams.step_noise(k, 4).astype(np.float64))
+        teo, tro = teo.astype(bool), tro.astype(bool)
+        if done_prev.any():
+            idx = np.nonzero(done_prev)[0]
+            rz = np.zeros((20, n))
+            rz[:, idx] = streams.autoreset_noise(episode[idx], envs=idx)
+            tgr = np.zeros((n, T, 4 if yaw else 3))
+            tgr[idx] = streams.waypoint_targets(episode[idx], T, dome, min_height=0.1, envs=idx, yaw=yaw)
+            obs_r = orc.o.env_reset(mask=done_prev.astype(np.uint8), noise=rz, targets=tgr.reshape(n, -1))
+            oo[done_prev], ro[done_prev], teo[done_prev], tro[done_prev], io[done_prev] = obs_r[done_prev], 0.0, False, False, 0
+            episode[idx] += 1
+            n_resets += len(idx)
+        flip = live & ((teg != teo) | (trg != tro) | ((ig >> 3) != (io >> 3)))
+        n_flip += int(flip.sum())
+        live &= ~flip
+        cols = slice(10, 13) if mode == 7 else slice(None)  # mode 7: the reference's z-velocity PID limit-cycles (DESIGN 5): position envelope
+        worst_obs = max(worst_obs, float(np.abs(og[live][:, cols] - oo[live][:, cols]).max()))
+        worst_rew = max(worst_rew, float(np.abs(rg[live] - ro[live]).max()))
+        reached = max(reached, int((ig >> 3).max()))
+        done_prev = teg | trg
+    print(f"\n[timed-path parity, quadx-waypoints mode {mode}] {n} envs x {steps} steps: {n_resets} autoresets, flips {n_flip}, max targets reached "
+          f"{reached}; max |obs| {worst_obs:.2e}, max |reward| {worst_rew:.2e}")
+    assert n_resets > n
+    assert n_flip <= n // 500
+    if mode == 7:
+        assert reached >= 1
+        assert worst_obs < 1e-3 and worst_rew < 5e-2
+    else:
+        assert worst_obs < 5e-4 and worst_rew < 5e-3  # 1 / distance terms amplify a 1e-6 m difference near a target
     env.close()
