@@ -60,6 +60,8 @@ struct PfbContext {
   cudaEvent_t ev_spare[4]; // ev_spare[k % 4]: spares consumed by step k are rebuilt; step k + 2 waits on it
   int64_t side_launches;
   // optional per-step CUDA-event pairs around the dominant kernel (bench.py's roofline leg)
+  int mapped_dyn_smem;    // dynamic shared memory requested by the step launch of pfb_env_step_mapped (bounds the CTAs resident per SM: several waves)
+  int step_dyn_smem;      // what the next QuadX-Hover step launch requests (0 = everything resident in one wave)
   float* noise_dump;      // optional [substeps per env step][N] device buffer: the step kernel writes every noise draw it hands out (tests)
   cudaEvent_t* prof_ev;   // [2 * prof_cap]
   int prof_cap;
@@ -132,6 +134,9 @@ static inline StepPlan plan_step(PfbContext* h) {
   do {                                                                                                   \
     if ((h)->d_spare && (h)->step_seq > 0) CUDA_OK(cudaStreamWaitEvent((s), (h)->ev_spare[((h)->step_seq - 1) % 4], 0)); \
   } while (0)
+
+// pfb_lib.cu: a masked user reset on an autoreset handle removes the masked envs / arenas from the pending done list
+int pfb_drop_masked_done(PfbContext* h, const uint8_t* mask, cudaStream_t s);
 
 // fixedwing translation unit (pfb_fixedwing.cu)
 int fw_build_params(const PfbModel& m, const PfbEnvConfig* env, pfb::FixedwingParams& p, pfb::WaypointParams& w);

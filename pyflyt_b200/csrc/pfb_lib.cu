@@ -502,6 +502,33 @@ __global__ void __launch_bounds__(kBlock)
   }
 }
 
+// A masked pfb_env_reset on an autoreset handle of the tail-CTA env kinds: an env that finished on the previous step sits in
+// the done list the NEXT step's tail CTAs consume; reset by hand, it must not be reset again by them while its regular thread
+// steps it (two writers for one env).  Drop the masked entries from that list: in-place compaction by ONE CTA, chunk by chunk
+// (a chunk is read completely before anything is written, and the write cursor never passes the read cursor).
+__global__ void __launch_bounds__(1024) k_drop_masked_done(int32_t* __restrict__ list, int32_t* __restrict__ count, const uint8_t* __restrict__ mask) {
+  __shared__ int kept;
+  const int n = *count;
+  if (threadIdx.x == 0) kept = 0;
+  __syncthreads();
+  for (int first = 0; first < n; first += blockDim.x) {
+    const int t = first + (int)threadIdx.x;
+    const int32_t e = t < n ? list[t] : -1;
+    const bool keep = t < n && !mask[e];
+    __syncthreads();  // the whole chunk is in registers
+    if (keep) list[atomicAdd(&kept, 1)] = e;  // order inside the list does not matter: every entry is an independent env / arena
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = kept;
+}
+int pfb_drop_masked_done(PfbContext* h, const uint8_t* mask, cudaStream_t s) {
+  if (!mask || !h->env.autoreset || !h->d_done_list) return 0;
+  const uint64_t k = h->step_seq;  // the next step: its tail CTAs read list [(k - 1) % 4]
+  k_drop_masked_done<<<1, 1024, 0, s>>>(h->d_done_list + ((k + 3) % 4) * h->n, h->d_counters + ((k + 3) % 4), mask);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
@@ -608,6 +635,15 @@ int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, i
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
+  // pfb_env_step_mapped: the kernel reads / writes host memory over PCIe, which is the bottleneck by 10x; with every CTA resident
+  // in one wave the bus idles while all warps compute and then takes the whole output at once.  Requesting dynamic shared
+  // memory the kernel never touches caps the CTAs resident per SM, so the step runs as several waves and the output of a wave
+  // crosses the bus while the next one computes.  PFB_MAPPED_DYN_SMEM overrides (bytes, <= 48 KB; 0 = one wave).
+  c->mapped_dyn_smem = 0;
+  if (const char* e = getenv("PFB_MAPPED_DYN_SMEM")) {
+    const int v = atoi(e);
+    if (v >= 0 && v <= 40 * 1024) c->mapped_dyn_smem = v;
+  }
   CUDA_OK(cudaMalloc(&c->d_counters, 8 * sizeof(int32_t)));  // [0..3] rotating autoreset counters, [4] ticket of the split dogfight
   CUDA_OK(cudaMemset(c->d_counters, 0, 8 * sizeof(int32_t)));
   CUDA_OK(cudaMalloc(&c->d_done_list, 4 * (size_t)n_envs * sizeof(int32_t)));
@@ -821,6 +857,7 @@ static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool r
   const int builders = spares ? (h->sm_count < tiles ? h->sm_count : tiles) : 0;
   const int grid = tiles + 2 * builders;
   const bool prof = h->prof_ev && h->prof_n < h->prof_cap;
+  const size_t dyn_smem = (size_t)h->step_dyn_smem;
   if (prof) CUDA_OK(cudaEventRecord(h->prof_ev[2 * h->prof_n], s));
 #define STEP_ARGS h->qx, h->hover, h->rng, h->buf.state, qx_rows(h), actions, noise, h->buf.obs, h->buf.reward, h->buf.term, h->buf.trunc,    \
                   h->buf.info, h->buf.start_pos, h->buf.start_orn, cnt_cur, list_cur, cnt_next, cnt_b0, list_b0, cnt_b1, list_b1, h->d_spare,  \
@@ -828,21 +865,21 @@ static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool r
   if (autoreset) {
     if (noise) return fail("injected noise (parity mode) is only supported with autoreset = 0");
     if (randact) {
-      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, true, true, false><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
+      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, true, true, false><<<grid, kBlock, dyn_smem, s>>>(STEP_ARGS)));
     } else {
-      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, false, true, false><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
+      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, false, true, false><<<grid, kBlock, dyn_smem, s>>>(STEP_ARGS)));
     }
   } else if (h->hover.ma) {
     if (randact) return fail("MAQuadXHover has no on-device action generator");
-    if (noise) { PFB_MODE_SWITCH(mode, (k_hover_step<MODE, true, false, false, true><<<grid, kBlock, 0, s>>>(STEP_ARGS))); }
-    else { PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, false, false, true><<<grid, kBlock, 0, s>>>(STEP_ARGS))); }
+    if (noise) { PFB_MODE_SWITCH(mode, (k_hover_step<MODE, true, false, false, true><<<grid, kBlock, dyn_smem, s>>>(STEP_ARGS))); }
+    else { PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, false, false, true><<<grid, kBlock, dyn_smem, s>>>(STEP_ARGS))); }
   } else {
     if (noise) {
-      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, true, false, false, false><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
+      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, true, false, false, false><<<grid, kBlock, dyn_smem, s>>>(STEP_ARGS)));
     } else if (randact) {
-      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, true, false, false><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
+      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, true, false, false><<<grid, kBlock, dyn_smem, s>>>(STEP_ARGS)));
     } else {
-      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, false, false, false><<<grid, kBlock, 0, s>>>(STEP_ARGS)));
+      PFB_MODE_SWITCH(mode, (k_hover_step<MODE, false, false, false, false><<<grid, kBlock, dyn_smem, s>>>(STEP_ARGS)));
     }
   }
 #undef STEP_ARGS
@@ -961,7 +998,9 @@ int pfb_env_step_mapped(PfbHandle h, const float* host_actions, float* host_obs,
   if (((uintptr_t)da & 15) || ((uintptr_t)dob & 15)) return fail("pfb_env_step_mapped: actions and obs must be 16-byte aligned");
   const PfbBuffers saved = h->buf;
   h->buf.obs = (float*)dob; h->buf.reward = (float*)dr; h->buf.term = (uint8_t*)dte; h->buf.trunc = (uint8_t*)dtr;
+  h->step_dyn_smem = h->mapped_dyn_smem;
   const int rc = env_step_impl(h, (float*)da, nullptr, false, (cudaStream_t)stream);
+  h->step_dyn_smem = 0;
   h->buf = saved;
   return rc;
 }

@@ -384,6 +384,7 @@ int qwp_env_reset(PfbContext* h, const uint8_t* mask, const float* noise, cudaSt
   if (spare) {
     SPARE_BEFORE_RESET(h, s);
     if (!mask) CUDA_OK(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(int32_t), s));  // a full reset empties the autoreset queues
+    else if (pfb_drop_masked_done(h, mask, s)) return -1;  // a masked one takes its envs out of the pending done list
   }
 #define QR_ARGS h->qx, h->hover, h->qwp, h->rng, h->buf.state, h->buf.istate, h->buf.start_pos, h->buf.start_orn, h->buf.reset_targets, mask, noise, \
                 h->buf.obs, seq, h->n

@@ -421,6 +421,7 @@ int rk_env_reset(PfbContext* h, const uint8_t* mask, const float* noise, cudaStr
   if (spare) {
     SPARE_BEFORE_RESET(h, s);
     if (!mask) CUDA_OK(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(int32_t), s));  // a full reset empties the autoreset queues
+    else if (pfb_drop_masked_done(h, mask, s)) return -1;  // a masked one takes its envs out of the pending done list
   }
   if (noise)
     k_land_reset<true><<<g, kBlock, 0, s>>>(h->rk, h->land, h->rng, h->buf.state, h->buf.istate, h->buf.start_pos, h->buf.start_orn, mask, noise,

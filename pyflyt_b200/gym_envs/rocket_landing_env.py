@@ -6,9 +6,11 @@ one fused launch per ``step`` runs 3 Aviary steps (6 physics substeps of body dr
 booster with fuel burn + variable-mass composite body), the landing reward, termination rules and the
 30-float observation.
 
-Scope note: there is no contact RESPONSE.  Ground contact and hard pad contact end the
-episode exactly as in the reference; a gentle touchdown (which the reference lets rest on the pad) keeps
-falling through it here, so the +3 "landed" bonus is only reachable on the step of first contact.
+Contact: with ``contact_response`` (default) the legs and the body push back against the pad and the
+ground — sequential-impulse normal + Coulomb friction on the collision primitives' corner / rim points, a restatement of a
+Bullet-like solver — so a touchdown below 1 m/s RESTS on the pad and the env reports ``env_complete`` like the
+reference's (tests/test_contact_response.py flies three touchdown episodes of the unmodified reference env through it).
+``contact_response=False`` keeps the round-1 behaviour: contact is a flag only.
 """
 
 from __future__ import annotations

@@ -124,3 +124,26 @@ def test_cuda_dogfight_spare_reset_equals_inline_reset(team_size):
     a, b = outs
     assert a[3] > 2048 and a[3] == b[3] and a[4] == b[4]
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+
+
+@pytest.mark.gpu
+def test_device_spawn_draws_equal_host_replay():
+    """Pins tests/test_draw_distributions.py::dogfight_spawns (the host replay whose DISTRIBUTION is compared with the reference's
+    _get_start_pos_orn) to the kernel: the first observation after a device-drawn spawn is the replayed pose advanced by the 10
+    warm-up Aviary steps (1/12 s at 20 m/s along the heading; the reported position is shifted back 0.35 m, :390)."""
+    from test_draw_distributions import dogfight_spawns
+
+    from pyflyt_b200.pz_envs import MAFixedwingDogfightVecEnv
+
+    num_arenas, seed = 4096, 11
+    env = MAFixedwingDogfightVecEnv(num_arenas=num_arenas, seed=seed)
+    obs, _ = env.reset()
+    o = obs.double().cpu().numpy()
+    pos, yaw = dogfight_spawns(seed, num_arenas, 0x80000000)  # the first pfb_env_reset of the handle
+    pos, yaw = pos.reshape(-1, 3), yaw.reshape(-1)
+    d = 20.0 * 10.0 / 120.0 - 0.35
+    exp_xy = pos[:, :2] + d * np.stack([np.cos(yaw), np.sin(yaw)], axis=1)
+    assert np.abs(o[:, 9:11] - exp_xy).max() < 0.3
+    assert np.abs(o[:, 11] - pos[:, 2]).max() < 0.5
+    assert np.abs(np.angle(np.exp(1j * (o[:, 5] - yaw)))).max() < 0.05
+    env.close()

@@ -308,3 +308,46 @@ def test_north_star_parity_4096_envs_1000_env_steps(drone_model):
     assert np.isfinite(err).all() and err.max() < 1e-3, (err.max(), np.percentile(err, 99))
     assert np.percentile(err, 99) < 4e-4
     assert np.median(travelled) > 50.0  # these are real flights, not hovering drones
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["fixedwing-waypoints", "rocket-landing", "quadx-waypoints"])
+def test_masked_reset_on_autoreset_handle_is_not_reset_twice(kind):
+    """a finished env that the user resets by hand (masked pfb_env_reset) while autoreset is on must leave the
+    pending done list — otherwise the next launch's tail CTA resets it again while its regular thread steps it.  After the
+    masked reset + one step every masked env must have been STEPPED (step_count 1, a non-zero reward), deterministically."""
+    import torch
+
+    from pyflyt_b200.gym_envs import FixedwingWaypointsVecEnv, QuadXWaypointsVecEnv, RocketLandingVecEnv
+
+    def run():
+        if kind == "fixedwing-waypoints":
+            env, row = FixedwingWaypointsVecEnv(num_envs=8192, seed=5, max_duration_seconds=0.5), 0
+        elif kind == "rocket-landing":
+            env, row = RocketLandingVecEnv(num_envs=8192, seed=5, max_duration_seconds=0.4), 0
+        else:
+            env, row = QuadXWaypointsVecEnv(num_envs=8192, seed=5, max_duration_seconds=0.5), 0
+        av = env.aviary
+        env.reset()
+        checked = 0
+        for k in range(40):
+            env.rollout(1)
+            done = av.term.bool() | av.trunc.bool()
+            if k % 3 == 2 and bool(done.any()):
+                mask = done.clone()
+                mask[::7] = True  # plus some envs that were not done
+                env.reset(mask=mask.to(torch.uint8))
+                env.rollout(1)
+                steps = av.istate_tensor[row]
+                assert bool((steps[mask] == 1).all()), (k, steps[mask].unique())
+                assert bool((av.reward[mask] != 0).all()), k
+                checked += int(mask.sum())
+        torch.cuda.synchronize()
+        out = (av.obs.clone(), av.reward.clone(), av.state_tensor.clone())
+        env.close()
+        return out, checked
+
+    (a, ca), (b, cb) = run(), run()
+    assert ca == cb and ca > 1000
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
