@@ -40,6 +40,8 @@ def lib() -> C.CDLL:
         L.orc_create.argtypes = [vp, vp, i64, u64]
         L.orc_destroy.argtypes = [vp]
         L.orc_set_start.argtypes = [vp, dp, dp]
+        L.orc_df_get_actions.argtypes = [vp, dp]
+        L.orc_df_set_actions.argtypes = [vp, C.POINTER(C.c_uint8), dp]
         L.orc_set_wind.argtypes = [vp, vp]
         L.orc_reset.argtypes = [vp, u8p]
         L.orc_set_mode.argtypes = [vp, C.c_int]
@@ -176,6 +178,17 @@ class Oracle:
         sp = np.ascontiguousarray(np.broadcast_to(start_pos, (self.n, 3)), dtype=np.float64)
         so = np.ascontiguousarray(np.broadcast_to(start_orn, (self.n, 3)), dtype=np.float64)
         lib().orc_set_start(self._h, _dp(sp), _dp(so))
+
+    def df_get_actions(self):
+        """MAFixedwingDogfight: [N][8] past_action | current_action of every agent"""
+        out = np.zeros((self.n, 8))
+        lib().orc_df_get_actions(self._h, _dp(out))
+        return out
+
+    def df_set_actions(self, mask, values):
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        v = np.ascontiguousarray(values, dtype=np.float64).reshape(self.n, 8)
+        lib().orc_df_set_actions(self._h, _u8(m), _dp(v))
 
     def env_step(self, actions, noise=None):
         a = np.ascontiguousarray(actions, dtype=np.float64)

@@ -54,6 +54,7 @@ struct PfbContext {
   int sm_count;
   // QuadX-Hover reset pipeline (pfb_lib.cu, "spare post-reset states"): library-owned spares + the side stream that rebuilds them
   float* d_spare;          // spare post-reset states (env-major records), zero-initialised; nullptr = warm-ups run inline
+  uint32_t* d_elist;       // QuadX-Hover: [4][N] episode number being built for each done-list entry (builder phase 0 -> phase 1)
   uint32_t* d_episode;     // QuadX-Hover: [N] episode number of each env's current valid spare (its buffer = episode & 1)
   cudaStream_t side;       // k_hover_spare runs here, concurrently with the following step launches
   cudaEvent_t ev_step;     // recorded on the caller's stream after a step launch; the side stream waits on it

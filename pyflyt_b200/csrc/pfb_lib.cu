@@ -194,7 +194,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, float 
 }
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#ifdef PFB_TIMELINE
+// experiment build (tools/exp_timeline.py): every warp of the step launch stamps %globaltimer at four points into the buffer
+// that normally receives the noise dump: [warp][4] uint64 = entry, inputs landed, integration done, exit
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define PFB_TL(slot) do { if (noise_dump && threadIdx.x == 0) reinterpret_cast<unsigned long long*>(noise_dump)[(size_t)blockIdx.x * 4 + (slot)] = gtimer(); } while (0)
+#else
+#define PFB_TL(slot) do { } while (0)
+#endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // env.reset() integrated inline (quadx_base_env.py:149-212): Aviary steps [from, to) of the warm-up that follows the start
 // pose + set_mode.  The state is rounded to what a record holds (hi + lo words) before step kWarmSplit in EVERY path, so a
@@ -237,17 +250,26 @@ template <int MODE>
 __device__ __forceinline__ void hover_build(const QuadXParams& p, const HoverParams& h, const RngParams& rng, int b, int builders,
                                             const int32_t* __restrict__ b0_count, const int32_t* __restrict__ b0_list,
                                             const int32_t* __restrict__ b1_count, const int32_t* __restrict__ b1_list,
+                                            uint32_t* __restrict__ b0_elist, const uint32_t* __restrict__ b1_elist,
                                             const float* __restrict__ start_pos, const float* __restrict__ start_orn,
-                                            float* __restrict__ spare, uint32_t* __restrict__ episode, int64_t N) {
+                                            float* __restrict__ spare, uint32_t* __restrict__ episode, int64_t N, float* noise_dump = nullptr) {
   const int phase = b >= builders ? 1 : 0;
   const int slot = b - phase * builders;
   const int32_t* __restrict__ list = phase ? b1_list : b0_list;
+  // The builders' chain of DEPENDENT cold loads (count -> list entry -> episode number -> record) is what they wait for while the
+  // step CTAs' tile burst saturates DRAM: the first list entry (and, in phase 1, the episode number phase 0 left next to it) is
+  // loaded speculatively together with the count — the lists are N entries long, so any index below N is readable
+  int t = slot * kBlock + (int)threadIdx.x;
+  const int64_t t_spec = t < N ? t : N - 1;
+  int32_t i_spec = list[t_spec];
+  uint32_t e_spec = phase ? b1_elist[t_spec] : 0u;
   const int t_end = phase ? *b1_count : *b0_count;
   const int split = h.warmup_steps < kWarmSplit ? h.warmup_steps : kWarmSplit;
 #pragma unroll 1
-  for (int t = slot * kBlock + threadIdx.x; t < t_end; t += builders * kBlock) {
-    const int64_t i = list[t];
-    const uint32_t e = episode[i] + 1u;  // the spare being built; the one being consumed (episode[i]) lives in the other buffer
+  for (; t < t_end; t += builders * kBlock) {
+    const int64_t i = i_spec;
+    // the spare being built; the one being consumed (episode[i]) lives in the other buffer
+    const uint32_t e = phase ? e_spec : episode[i] + 1u;
     float* rec = spare + ((int64_t)(e & 1u) * N + i) * SP_ROWS;
     QuadXRegs s;
     float px = 0.f, py = 0.f, pz = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
@@ -255,13 +277,19 @@ __device__ __forceinline__ void hover_build(const QuadXParams& p, const HoverPar
       px = start_pos[3 * i + 0]; py = start_pos[3 * i + 1]; pz = start_pos[3 * i + 2];
       ox = start_orn[3 * i + 0]; oy = start_orn[3 * i + 1]; oz = start_orn[3 * i + 2];
       s = hover_fresh<MODE>(px, py, pz, ox, oy, oz);
+      b0_elist[t] = e;  // read by phase 1 of the next launch (same list, same position)
     } else {
       int dummy;
       quadx_load_tile<7, 4>(rec, s, dummy);
       const F4 sp = ld_f4(rec + SP_SETPOINT);
       s.sp[0] = sp.x; s.sp[1] = sp.y; s.sp[2] = sp.z; s.sp[3] = sp.w;
     }
+#ifdef PFB_TIMELINE
+    if (s.flags == 0xffffffffu) return;  // consume the loaded state before the stamp
+#endif
+    PFB_TL(1);
     hover_warmup_inline<MODE, false>(p, s, phase ? split : 0, phase ? h.warmup_steps : split, rng, nullptr, N, i, e);
+    PFB_TL(2);
     quadx_store_tile<7, 4>(rec, s, 0);
     if (phase == 0) {
       st_f4(rec + SP_POSE, px, py, pz, ox);
@@ -272,6 +300,11 @@ __device__ __forceinline__ void hover_build(const QuadXParams& p, const HoverPar
       rec[SP_FLAGS] = f_from_bits(s.flags);
       rec[SP_VALID] = 1.0f;
       episode[i] = e;
+    }
+    const int tn = t + builders * kBlock;  // more finished envs than builder lanes (a synchronised truncation): next pass
+    if (tn < t_end) {
+      i_spec = list[tn];
+      if (phase) e_spec = b1_elist[tn];
     }
   }
 }
@@ -289,17 +322,24 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
                  uint8_t* __restrict__ trunc, uint8_t* __restrict__ info, const float* __restrict__ start_pos,
                  const float* __restrict__ start_orn, int32_t* __restrict__ cur_count, int32_t* __restrict__ cur_list,
                  int32_t* __restrict__ next_count, const int32_t* __restrict__ b0_count, const int32_t* __restrict__ b0_list,
-                 const int32_t* __restrict__ b1_count, const int32_t* __restrict__ b1_list, float* __restrict__ spare,
-                 uint32_t* __restrict__ episode, int spare_copy, int builders, float* __restrict__ noise_dump, uint32_t step_seq,
-                 int64_t N) {
+                 const int32_t* __restrict__ b1_count, const int32_t* __restrict__ b1_list, uint32_t* __restrict__ b0_elist,
+                 const uint32_t* __restrict__ b1_elist, float* __restrict__ spare, uint32_t* __restrict__ episode, int spare_copy, int builders,
+                 float* __restrict__ noise_dump, uint32_t step_seq, int64_t N) {
   // builder CTAs come FIRST in the grid: their serial warm-up chain is the longest thing in the launch, so they must be
   // dispatched at t = 0, not behind the ~2000 step CTAs
   const int n_build = AUTORESET ? 2 * builders : 0;
+  PFB_TL(0);
   if (AUTORESET && (int)blockIdx.x < n_build) {  // builder CTA (CTA-uniform role)
-    hover_build<MODE>(p, h, rng, (int)blockIdx.x, builders, b0_count, b0_list, b1_count, b1_list, start_pos, start_orn, spare, episode, N);
+    hover_build<MODE>(p, h, rng, (int)blockIdx.x, builders, b0_count, b0_list, b1_count, b1_list, b0_elist, b1_elist, start_pos, start_orn, spare,
+                      episode, N, noise_dump);
+    PFB_TL(3);
     return;
   }
   const int tile = (int)blockIdx.x - n_build;
+  if (h.stagger_ns > 0) {  // experiment: de-synchronise the memory phases of the single wave
+    const int late = tile % h.stagger_mod;
+    if (late) __nanosleep((unsigned)(late * h.stagger_ns));
+  }
   __shared__ __align__(128) float smem[kBlock * kObsMax];
   const int O = (h.angle_representation == 0 ? 20 : 21) + (MA ? 3 : 0);
   const int lane = threadIdx.x;
@@ -323,7 +363,9 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
   float past[4] = {0.f, 0.f, 0.f, 0.f};
   auto nz = make_noise<INJECT>(noise, N, active ? i : 0, rng, step_seq, TAG_ENV_STEP, p.noise_loc, p.ratio);
   nz.prefetch4();
+#ifndef PFB_TIMELINE
   if (!INJECT && noise_dump && active) nz.set_dump(noise_dump + i, N);
+#endif
   if (RANDACT) {
     uint64_t g = ((uint64_t)rng.env_offset_hi << 32 | rng.env_offset_lo) + (uint64_t)i;
     U4 r = philox4x32_10(U4{(uint32_t)g, (uint32_t)(g >> 32), step_seq, (uint32_t)TAG_ACTION << 24}, rng.k0, rng.k1);
@@ -340,20 +382,20 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
     float4 a4 = __ldg(reinterpret_cast<const float4*>(actions) + i);
     act[0] = a4.x; act[1] = a4.y; act[2] = a4.z; act[3] = a4.w;
   }
+  // the episode number of this env's spare, for EVERY lane, in the shadow of the tile load: a lane that turns out to be
+  // resetting can then pull its record towards L1 at once (nobody writes episode[i] of a resetting env during this launch)
+  uint32_t e_next = (AUTORESET && spare && active) ? episode[i] : 0u;
   QuadXRegs s;
   int step_count;
   mbar_wait(&mbar, 0, nz.dep(0), nz.dep(1), nz.dep(2), nz.dep(3), nz.dep(4), nz.dep(5), nz.dep(6), nz.dep(7));  // the tile has landed
   quadx_load_tile<MODE, kTileGroupStride>(stile + lane * 4, s, step_count);  // LDS.128, conflict-free (lane-contiguous vectors)
+  PFB_TL(1);
   // an env that finished on the previous call: this call is its reset (NEXT_STEP)
   const bool resetting = AUTORESET && active && (s.flags & (FLAG_TERM | FLAG_TRUNC)) != 0;
-  uint32_t e_next = 0u;
-  if (AUTORESET && resetting && spare) {  // pull both of the env's spare records towards L2 while the other lanes integrate
-    e_next = episode[i];                  // (loaded now, first used at the end of the launch)
-#pragma unroll
-    for (int bsel = 0; bsel < 2; ++bsel) {
-      const float* r = spare + ((int64_t)bsel * N + i) * SP_ROWS;
-      prefetch_l2(r); prefetch_l2(r + 32); prefetch_l2(r + 64); prefetch_l2(r + SP_ROWS - 1);
-    }
+  if (AUTORESET && resetting && spare) {  // pull the env's spare record into L1 while the other lanes integrate: the swap at the
+                                          // end of the launch then costs two L1 round trips instead of two cold ones
+    const float* r = spare + ((int64_t)(e_next & 1u) * N + i) * SP_ROWS;
+    prefetch_l1(r); prefetch_l1(r + 32); prefetch_l1(r + 64); prefetch_l1(r + SP_ROWS - 1);
   }
   int n_aviary = (active && !resetting) ? h.env_step_ratio : 0;
   float rew = -0.1f;
@@ -379,6 +421,7 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
     else hover_term_trunc_reward(h, s, step_count, rew);
   }
   step_count += 1;
+  PFB_TL(2);
   if (AUTORESET && __any_sync(0xffffffffu, resetting)) {
     if (resetting) {
       // env.reset(): begin_reset + end_reset (quadx_base_env.py:149-212) — normally a copy of the env's spare
@@ -446,6 +489,7 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
     }
   }
   if (bulk && lane == 0) bulk_store_wait_read();  // the CTA's shared memory must outlive the engine's reads
+  PFB_TL(3);
 }
 
 // After a user reset of every env: each env gets a complete fresh spare (dense warps, all envs).
@@ -596,6 +640,12 @@ int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, i
     c->hover.dome2 = (float)(dome * dome);
   }
   c->hover.ma = (env && env->env_kind == PFB_ENV_MA_QUADX_HOVER) ? 1 : 0;
+  c->hover.stagger_ns = 0;
+  c->hover.stagger_mod = 1;
+  if (const char* e = getenv("PFB_HOVER_STAGGER")) {
+    int ns = 0, mod = 2;
+    if (sscanf(e, "%d,%d", &ns, &mod) >= 1 && ns >= 0 && ns <= 20000 && mod >= 1 && mod <= 8) { c->hover.stagger_ns = ns; c->hover.stagger_mod = mod; }
+  }
   if (c->hover.ma && env->autoreset) {
     delete c;
     return fail("MAQuadXHover is a per-agent epilogue: arenas are reset by the caller (pfb_env_reset with a mask), autoreset must be 0");
@@ -639,7 +689,7 @@ int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, i
   // in one wave the bus idles while all warps compute and then takes the whole output at once.  Requesting dynamic shared
   // memory the kernel never touches caps the CTAs resident per SM, so the step runs as several waves and the output of a wave
   // crosses the bus while the next one computes.  PFB_MAPPED_DYN_SMEM overrides (bytes, <= 48 KB; 0 = one wave).
-  c->mapped_dyn_smem = 0;
+  c->mapped_dyn_smem = 12 * 1024;  // measured on B200 (tools/exp_mapped_waves.py): 149.5 us / step in one wave, 144.8 us with 12-28 KB
   if (const char* e = getenv("PFB_MAPPED_DYN_SMEM")) {
     const int v = atoi(e);
     if (v >= 0 && v <= 40 * 1024) c->mapped_dyn_smem = v;
@@ -658,6 +708,8 @@ int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, i
     CUDA_OK(cudaMalloc(&c->d_spare, rec * (size_t)n_envs * sizeof(float)));
     CUDA_OK(cudaMemset(c->d_spare, 0, rec * (size_t)n_envs * sizeof(float)));
     if (hover) {
+      CUDA_OK(cudaMalloc(&c->d_elist, 4 * (size_t)n_envs * sizeof(uint32_t)));
+      CUDA_OK(cudaMemset(c->d_elist, 0, 4 * (size_t)n_envs * sizeof(uint32_t)));
       CUDA_OK(cudaMalloc(&c->d_episode, (size_t)n_envs * sizeof(uint32_t)));
       CUDA_OK(cudaMemset(c->d_episode, 0, (size_t)n_envs * sizeof(uint32_t)));
     } else {
@@ -684,6 +736,7 @@ int pfb_destroy(PfbHandle h) {
     }
     cudaFree(h->d_spare);
     if (h->d_episode) cudaFree(h->d_episode);
+    if (h->d_elist) cudaFree(h->d_elist);
   }
   cudaFree(h->d_counters);
   cudaFree(h->d_done_list);
@@ -850,6 +903,8 @@ static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool r
   int32_t* list_cur = h->d_done_list + (k % 4) * h->n;
   int32_t* list_b0 = h->d_done_list + ((k + 3) % 4) * h->n;
   int32_t* list_b1 = h->d_done_list + ((k + 2) % 4) * h->n;
+  uint32_t* elist_b0 = h->d_elist ? h->d_elist + ((k + 3) % 4) * h->n : nullptr;  // episode numbers next to the list entries: written by
+  uint32_t* elist_b1 = h->d_elist ? h->d_elist + ((k + 2) % 4) * h->n : nullptr;  // builder phase 0, read by phase 1 of the next launch
   const uint32_t seq = (uint32_t)k;
   const bool spares = autoreset && h->d_spare != nullptr;
   const int spare_copy = (spares && h->env.inline_reset != 1) ? 1 : 0;
@@ -860,8 +915,8 @@ static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool r
   const size_t dyn_smem = (size_t)h->step_dyn_smem;
   if (prof) CUDA_OK(cudaEventRecord(h->prof_ev[2 * h->prof_n], s));
 #define STEP_ARGS h->qx, h->hover, h->rng, h->buf.state, qx_rows(h), actions, noise, h->buf.obs, h->buf.reward, h->buf.term, h->buf.trunc,    \
-                  h->buf.info, h->buf.start_pos, h->buf.start_orn, cnt_cur, list_cur, cnt_next, cnt_b0, list_b0, cnt_b1, list_b1, h->d_spare,  \
-                  h->d_episode, spare_copy, builders, h->noise_dump, seq, h->n
+                  h->buf.info, h->buf.start_pos, h->buf.start_orn, cnt_cur, list_cur, cnt_next, cnt_b0, list_b0, cnt_b1, list_b1, elist_b0,   \
+                  elist_b1, h->d_spare, h->d_episode, spare_copy, builders, h->noise_dump, seq, h->n
   if (autoreset) {
     if (noise) return fail("injected noise (parity mode) is only supported with autoreset = 0");
     if (randact) {

@@ -64,8 +64,9 @@ def dogfight_spawns(seed, num_arenas, seq, rmin=10.0, rmax=50.0, A=2):
     st = Streams(seed, n)
     li = np.arange(n) % A
     first = np.arange(n) - li
-    a = philox4x32_10(st.env_lo[first], st.env_hi[first], np.uint32(seq), np.uint32(6 << 24), st.k0, st.k1)
-    b = philox4x32_10(st.env_lo, st.env_hi, np.uint32(seq), np.uint32((6 << 24) | 1), st.k0, st.k1)
+    seq = np.broadcast_to(np.asarray(seq, dtype=np.uint32), (n,))  # per agent (arena-uniform): the episode number of an autoreset
+    a = philox4x32_10(st.env_lo[first], st.env_hi[first], seq, np.uint32(6 << 24), st.k0, st.k1)
+    b = philox4x32_10(st.env_lo, st.env_hi, seq, np.uint32((6 << 24) | 1), st.k0, st.k1)
     two_pi = np.float32(6.28318530717958647692)
     rad = (two_pi / np.float32(A)) * li.astype(np.float32) + two_pi * unit_open(a[0])
     radius = np.float32(rmin) + np.float32(rmax - rmin) * unit_open(b[0])
