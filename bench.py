@@ -374,6 +374,27 @@ def run_ours(args, rank, local_rank, world):
     launches0 = sum(e.aviary.launch_count for e in rot)
     block_ms = [rotating_block(K, W + r * K) for r in range(R)]
     launches = (sum(e.aviary.launch_count for e in rot) - launches0) // R
+    # ---- region R (context): the same K env steps of the same batches as FUSED rollouts — pfb_env_rollout(16): 16 env steps per
+    #      launch with the state in registers, actions drawn on device, every step's observations / rewards / flags written, spares
+    #      topped up behind every launch (all inside the event pair); "synthetic random-action rollouts" in BASELINE.json's words
+    FUSED_T = 16
+
+    def fused_block(steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for c in range(steps // FUSED_T):
+            rot[c % M].rollout(FUSED_T)
+        e1.record()
+        barrier()
+        return float(e0.elapsed_time(e1))
+
+    Kf = max(FUSED_T, (K // FUSED_T) * FUSED_T)
+    for c in range(2 * M):  # spares three ahead, past the first fused launches
+        rot[c % M].rollout(FUSED_T)
+    fl0 = sum(e.aviary.launch_count for e in rot)
+    fused_ms = _median([fused_block(Kf) for _ in range(min(R, 3))])
+    fused_launches = (sum(e.aviary.launch_count for e in rot) - fl0) // min(R, 3)
     for e in rot[1:]:
         e.close()
     # ---- region F (context, round-1 / round-2a protocol): ONE batch, L2 flushed by a 256 MiB write before every step, a CUDA-event
@@ -439,12 +460,12 @@ def run_ours(args, rank, local_rank, world):
         env_s.close()
 
     # ---- reduce: max over ranks
-    t = torch.tensor(block_ms + [warm_ms, e2e_s * 1e3, float(sum(kern_ms)), strong_ms, e2e_copy_s * 1e3, e2e_mapped_s * 1e3, flushed_ms], dtype=torch.float64,
+    t = torch.tensor(block_ms + [warm_ms, e2e_s * 1e3, float(sum(kern_ms)), strong_ms, e2e_copy_s * 1e3, e2e_mapped_s * 1e3, flushed_ms, fused_ms], dtype=torch.float64,
                      device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     vals = [float(x) for x in t.tolist()]
-    block_ms, (warm_ms, e2e_ms, kern_total_ms, strong_ms, e2e_copy_ms, e2e_mapped_ms, flushed_ms) = vals[:R], vals[R:]
+    block_ms, (warm_ms, e2e_ms, kern_total_ms, strong_ms, e2e_copy_ms, e2e_mapped_ms, flushed_ms, fused_ms) = vals[:R], vals[R:]
     split = dogfight_split_block(rank, world, dev) if (world > 1 and not args.no_dogfight_split) else None
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -460,6 +481,14 @@ def run_ours(args, rank, local_rank, world):
             "l2": f"inputs larger than the L2: {M} independent batches of {n} envs stepped round-robin, ~23 MB touched per step, {(M - 1) * 23} MB between two "
                   "steps of the same batch vs 126 MB of L2; K back-to-back launches inside ONE event pair (no flush kernel, no per-step events)",
             "batches": M,
+            "rollout_fused": {
+                "env_steps_per_s": world * n * Kf / (fused_ms * 1e-3), "us_per_step": fused_ms * 1e3 / Kf, "steps_per_launch": FUSED_T, "steps": Kf,
+                "launches_per_block": fused_launches, "frac_hbm_roofline": ALGO_BYTES_PER_ENV_STEP * n * Kf / (fused_ms * 1e-3) / 1e9 / peak,
+                "note": "pfb_env_rollout(16) on the same rotating batches: k_hover_rollout keeps the state in registers for 16 env steps (one tile load, one "
+                        "tile store), draws the actions on device, writes every step's observations / rewards / flags, and k_hover_spare_topup rebuilds the "
+                        "spares the launch consumed; pinned to the oracle by tests/test_timed_path_parity.py::test_hover_fused_rollout_matches_oracle and to the "
+                        "one-launch-per-step path by tests/test_gpu_parity.py::test_fused_rollout_equals_stepwise.  `value` stays the one-launch-per-step number",
+            },
             "value_l2_flushed_event_pairs": world * n * K / (flushed_ms * 1e-3), "ms_per_step_l2_flushed_event_pairs": flushed_ms / K,
             "l2_flushed_note": "the protocol of the earlier rounds (one batch, 256 MiB write before every step, one CUDA-event pair per step, pairs summed): "
                                "each pair carries ~3 us of launch / completion latency that back-to-back launches overlap (profiles/r02_rotation_sweep.jsonl)",

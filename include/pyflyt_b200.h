@@ -298,8 +298,11 @@ int pfb_env_reset(PfbHandle h, const uint8_t* mask, const float* noise, void* st
 /* env.step(action) for all envs (quadx_base_env.py:269-301): actions device [N][S] (NULL = the bound
  * setpoint buffer); writes obs / reward / term / trunc / info.                                       */
 int pfb_env_step(PfbHandle h, const float* actions, const float* noise, void* stream);
-/* Benchmark rollout: n_steps env.step() calls in one launch with actions drawn on device
- * (uniform in the env's action box) — "synthetic random-action rollouts" of BASELINE.json.           */
+/* Synthetic rollout: n_steps env.step() calls with actions drawn on device (uniform in the env's action box) — "synthetic
+ * random-action rollouts" of BASELINE.json.  QuadX-Hover with autoreset runs n_steps >= 4 as FUSED launches of up to 16 env
+ * steps (the state stays in registers across the steps; every step's observations, rewards, flags and drawn actions are still
+ * written, so afterwards the bound buffers hold the results of the last step, as after n_steps single calls); every other
+ * case is one launch per step.  Single steps and fused rollouts can be mixed freely on one handle.                            */
 int pfb_env_rollout(PfbHandle h, int n_steps, void* stream);
 
 /* Host-buffer convenience used for the end-to-end measurement: H2D(actions) → pfb_env_step →

@@ -54,6 +54,8 @@ struct PfbContext {
   int sm_count;
   // QuadX-Hover reset pipeline (pfb_lib.cu, "spare post-reset states"): library-owned spares + the side stream that rebuilds them
   float* d_spare;          // spare post-reset states (env-major records), zero-initialised; nullptr = warm-ups run inline
+  int2* d_consumed;        // QuadX-Hover fused rollout: (env, episode to rebuild) for every spare a launch consumed
+  int fused_ready;         // every env has its spares kRolloutAhead ahead and the step pipeline is drained (cleared by single steps / resets)
   uint32_t* d_elist;       // QuadX-Hover: [4][N] episode number being built for each done-list entry (builder phase 0 -> phase 1)
   uint32_t* d_episode;     // QuadX-Hover: [N] episode number of each env's current valid spare (its buffer = episode & 1)
   cudaStream_t side;       // k_hover_spare runs here, concurrently with the following step launches

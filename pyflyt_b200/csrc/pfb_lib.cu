@@ -160,6 +160,8 @@ constexpr int kObsMax = 24;  // floats per observation row (20 / 21, + 3 for MAQ
 enum { SP_POSE = QX_ROWS, SP_VALID = QX_ROWS + 6, SP_FLAGS = QX_ROWS + 7, SP_EPISODE = QX_ROWS + 8,
        SP_SETPOINT = QX_ROWS + 12 /* 4: the flight mode's preset setpoint, carried between the two halves of a warm-up */, SP_ROWS = 80 };
 static_assert(QX_ROWS % 4 == 0 && QX_ROWS + 16 <= SP_ROWS && SP_ROWS % 4 == 0, "spare record layout");
+constexpr int kSpareBufs = 4;  // records per env, buffer = episode & 3: the step pipeline uses two neighbours (one being consumed, one being built);
+constexpr uint32_t kSpareMask = kSpareBufs - 1;  // the fused rollout keeps three spares ahead (k_hover_rollout)
 constexpr int kWarmSplit = 5;  // Aviary steps integrated by the first builder phase; every warm-up requantizes its state there
 
 // cp.async.bulk (TMA, 1-D) shared -> global: one instruction moves a warp's whole observation tile
@@ -270,7 +272,7 @@ __device__ __forceinline__ void hover_build(const QuadXParams& p, const HoverPar
     const int64_t i = i_spec;
     // the spare being built; the one being consumed (episode[i]) lives in the other buffer
     const uint32_t e = phase ? e_spec : episode[i] + 1u;
-    float* rec = spare + ((int64_t)(e & 1u) * N + i) * SP_ROWS;
+    float* rec = spare + ((int64_t)(e & kSpareMask) * N + i) * SP_ROWS;
     QuadXRegs s;
     float px = 0.f, py = 0.f, pz = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
     if (phase == 0) {
@@ -394,7 +396,7 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
   const bool resetting = AUTORESET && active && (s.flags & (FLAG_TERM | FLAG_TRUNC)) != 0;
   if (AUTORESET && resetting && spare) {  // pull the env's spare record into L1 while the other lanes integrate: the swap at the
                                           // end of the launch then costs two L1 round trips instead of two cold ones
-    const float* r = spare + ((int64_t)(e_next & 1u) * N + i) * SP_ROWS;
+    const float* r = spare + ((int64_t)(e_next & kSpareMask) * N + i) * SP_ROWS;
     prefetch_l1(r); prefetch_l1(r + 32); prefetch_l1(r + 64); prefetch_l1(r + SP_ROWS - 1);
   }
   int n_aviary = (active && !resetting) ? h.env_step_ratio : 0;
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
       uint32_t nseq = step_seq | 0x40000000u;
       if (spare) {
         nseq = e_next;  // episode number: keys the warm-up noise
-        const float* srec = spare + ((int64_t)(e_next & 1u) * N + i) * SP_ROWS;
+        const float* srec = spare + ((int64_t)(e_next & kSpareMask) * N + i) * SP_ROWS;
         const F4 m0 = ld_f4(srec + SP_POSE), m1 = ld_f4(srec + SP_POSE + 4), m2 = ld_f4(srec + SP_POSE + 8);
         hit = spare_copy && m1.z != 0.0f && bits_from_f(m2.x) == e_next && m0.x == px && m0.y == py && m0.z == pz && m0.w == ox && m1.x == oy &&
               m1.y == oz;
@@ -492,6 +494,229 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
   PFB_TL(3);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fused rollout ("n_env_steps > 1 = persistent rollout with on-device random actions"): T env steps of every env in
+// ONE launch.  A warp loads its tile once, keeps the state in registers for the T steps and stores it once; each step still
+// draws its action and noise from the same Philox counters as a single-step launch, integrates, and writes the step's
+// observation tile (TMA), reward, flags and the action it drew, so after the launch every output buffer holds the results of
+// the LAST of T env steps, like T calls of pfb_env_step.  The state is rounded to the record format at the end of every step —
+// what the store / load of two launches does — so a fused launch performs the same arithmetic as T single-step launches; the
+// results agree bit for bit except where two compiled copies of the same expression round differently (nvcc contracts
+// multiply-adds per inlined copy: ~4e-5 of the env-steps see a one-ulp fp32 difference in a PID term; DESIGN.md 4,
+// tests/test_gpu_parity.py::test_fused_rollout_equals_stepwise), and the fused path is pinned to the fp64 oracle on its own
+// (tests/test_timed_path_parity.py::test_hover_fused_rollout_matches_oracle).
+// Resets: an env that finished on step t takes, on step t + 1, the spare of its next episode out of kSpareBufs records kept
+// kRolloutAhead ahead (k_hover_spare_ahead before the first fused launch, k_hover_spare_topup behind every one: all reset work
+// stays inside the timed region); a missing spare (more than kRolloutAhead resets of one env inside a launch) is integrated
+// inline by the cold path — the same episode number keys the same noise.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kRolloutAhead = 3;
+constexpr int kRolloutMaxSteps = 16;
+
+// one env, one spare: episode `e` of env i, complete warm-up, into its buffer
+template <int MODE>
+__device__ __forceinline__ void hover_build_full(const QuadXParams& p, const HoverParams& h, const RngParams& rng, const float* __restrict__ start_pos,
+                                                 const float* __restrict__ start_orn, float* __restrict__ spare, int64_t N, int64_t i, uint32_t e) {
+  float* rec = spare + ((int64_t)(e & kSpareMask) * N + i) * SP_ROWS;
+  const float px = start_pos[3 * i + 0], py = start_pos[3 * i + 1], pz = start_pos[3 * i + 2];
+  const float ox = start_orn[3 * i + 0], oy = start_orn[3 * i + 1], oz = start_orn[3 * i + 2];
+  QuadXRegs s = hover_fresh<MODE>(px, py, pz, ox, oy, oz);
+  hover_warmup_inline<MODE, false>(p, s, 0, h.warmup_steps, rng, nullptr, N, i, e);
+  quadx_store_tile<7, 4>(rec, s, 0);
+  st_f4(rec + SP_POSE, px, py, pz, ox);
+  st_f4(rec + SP_POSE + 4, oy, oz, 1.0f, f_from_bits(s.flags));
+  st_f4(rec + SP_POSE + 8, f_from_bits(e), 0.0f, 0.0f, 0.0f);
+}
+// before the first fused launch (or after single-step launches): every env gets the spares episode[i] + 1 .. + kRolloutAhead - 1
+// it does not have yet (episode[i] itself is valid by the step pipeline's invariant)
+template <int MODE>
+__global__ void __launch_bounds__(kBlock, kHoverBlocks)
+    k_hover_spare_ahead(const __grid_constant__ QuadXParams p, const __grid_constant__ HoverParams h, const __grid_constant__ RngParams rng,
+                        const float* __restrict__ start_pos, const float* __restrict__ start_orn, float* __restrict__ spare,
+                        const uint32_t* __restrict__ episode, int64_t N) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= N) return;
+  const uint32_t e0 = episode[i];
+#pragma unroll 1
+  for (int a = 1; a < kRolloutAhead; ++a) {
+    const uint32_t e = e0 + (uint32_t)a;
+    const float* rec = spare + ((int64_t)(e & kSpareMask) * N + i) * SP_ROWS;
+    const F4 m0 = ld_f4(rec + SP_POSE), m1 = ld_f4(rec + SP_POSE + 4), m2 = ld_f4(rec + SP_POSE + 8);
+    const bool have = m1.z != 0.0f && bits_from_f(m2.x) == e && m0.x == start_pos[3 * i] && m0.y == start_pos[3 * i + 1] && m0.z == start_pos[3 * i + 2] &&
+                      m0.w == start_orn[3 * i] && m1.x == start_orn[3 * i + 1] && m1.y == start_orn[3 * i + 2];
+    if (!have) hover_build_full<MODE>(p, h, rng, start_pos, start_orn, spare, N, i, e);
+  }
+}
+// behind a fused launch: the spares it consumed, listed as (env, episode to build)
+template <int MODE>
+__global__ void __launch_bounds__(kBlock, kHoverBlocks)
+    k_hover_spare_topup(const __grid_constant__ QuadXParams p, const __grid_constant__ HoverParams h, const __grid_constant__ RngParams rng,
+                        const float* __restrict__ start_pos, const float* __restrict__ start_orn, float* __restrict__ spare,
+                        const int32_t* __restrict__ count, const int2* __restrict__ list, int64_t N) {
+  const int n = *count;
+  for (int t = (int)(blockIdx.x * kBlock + threadIdx.x); t < n; t += (int)(gridDim.x * kBlock)) {
+    const int2 en = list[t];
+    hover_build_full<MODE>(p, h, rng, start_pos, start_orn, spare, N, (int64_t)en.x, (uint32_t)en.y);
+  }
+}
+// switching from single-step launches to the fused rollout: the spares whose first half was integrated by the last step launch
+// are finished here (phase 1 of hover_build on the list the next step launch would have used), so that episode[] is current
+template <int MODE>
+__global__ void __launch_bounds__(kBlock, kHoverBlocks)
+    k_hover_drain(const __grid_constant__ QuadXParams p, const __grid_constant__ HoverParams h, const __grid_constant__ RngParams rng,
+                  const int32_t* __restrict__ b1_count, const int32_t* __restrict__ b1_list, const uint32_t* __restrict__ b1_elist,
+                  const float* __restrict__ start_pos, const float* __restrict__ start_orn, float* __restrict__ spare, uint32_t* __restrict__ episode,
+                  int builders, int64_t N) {
+  hover_build<MODE>(p, h, rng, (int)blockIdx.x + builders, builders, b1_count, b1_list, b1_count, b1_list, nullptr, b1_elist, start_pos, start_orn, spare,
+                    episode, N);
+}
+
+// 14 CTAs per SM: the 2048 tiles of a 65 536-env launch (no builder CTAs here) are still one wave, with 144 registers instead of 128
+template <int MODE>
+__global__ void __launch_bounds__(kBlock, 14)
+    k_hover_rollout(const __grid_constant__ QuadXParams p, const __grid_constant__ HoverParams h, const __grid_constant__ RngParams rng,
+                    float* __restrict__ st, int rows, float* __restrict__ actions, float* __restrict__ obs, float* __restrict__ reward,
+                    uint8_t* __restrict__ term, uint8_t* __restrict__ trunc, uint8_t* __restrict__ info, const float* __restrict__ start_pos,
+                    const float* __restrict__ start_orn, const float* __restrict__ spare, uint32_t* __restrict__ episode,
+                    int32_t* __restrict__ consumed_count, int2* __restrict__ consumed_list, int32_t* __restrict__ last_count,
+                    int32_t* __restrict__ last_list, uint32_t step_seq0, int T, int64_t N) {
+  const int tile = (int)blockIdx.x;
+  __shared__ __align__(128) float smem2[2][kBlock * kObsMax];  // the observation tile of step t leaves by TMA while step t + 1 fills the other one
+  constexpr int kInGroups = qx_groups_moved<MODE>();
+  __shared__ __align__(128) float stile[kInGroups * kTileGroupStride];
+  __shared__ __align__(8) uint64_t mbar;
+  const int O = h.angle_representation == 0 ? 20 : 21;
+  const int lane = threadIdx.x;
+  const int64_t tile_first = (int64_t)tile * kBlock;
+  const int64_t i = tile_first + lane;
+  const bool active = i < N;
+  float* rec = st + qx_tile_base(i, rows);
+  if (lane == 0) {
+    mbar_init(&mbar, 1);
+    bulk_load_g2s(stile, st + qx_tile_base(tile_first, rows), (uint32_t)(kInGroups * kTileGroupStride * sizeof(float)), &mbar);
+  }
+  __syncwarp();
+  uint32_t e_local = active ? episode[i] : 0u;  // the next spare this env consumes
+  float sx = 0.f, sy = 0.f, sz = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
+  if (active) {
+    sx = start_pos[3 * i + 0]; sy = start_pos[3 * i + 1]; sz = start_pos[3 * i + 2];
+    ox = start_orn[3 * i + 0]; oy = start_orn[3 * i + 1]; oz = start_orn[3 * i + 2];
+  }
+  QuadXRegs s;
+  int step_count;
+  mbar_wait(&mbar, 0);
+  quadx_load_tile<MODE, kTileGroupStride>(stile + lane * 4, s, step_count);
+  int64_t nrows = N - tile_first;
+  if (nrows > kBlock) nrows = kBlock;
+  const uint32_t obs_bytes = (uint32_t)nrows * (uint32_t)O * 4u;
+  const bool bulk = (obs_bytes & 15u) == 0u;
+  float* obs_dst = obs + tile_first * O;
+  const uint64_t g = ((uint64_t)rng.env_offset_hi << 32 | rng.env_offset_lo) + (uint64_t)i;
+#pragma unroll 1
+  for (int t = 0; t < T; ++t) {
+    const uint32_t step_seq = step_seq0 + (uint32_t)t;
+    // ---- the step's draws: motor noise and the action, same counters as a single-step launch
+    auto nz = make_noise<false>(nullptr, N, active ? i : 0, rng, step_seq, TAG_ENV_STEP, p.noise_loc, p.ratio);
+    nz.prefetch4();
+    float act[4];
+    {
+      U4 r = philox4x32_10(U4{(uint32_t)g, (uint32_t)(g >> 32), step_seq, (uint32_t)TAG_ACTION << 24}, rng.k0, rng.k1);
+      const float pi = 3.14159265358979323846f;
+      if (MODE == -1) {
+        act[0] = 0.8f * u32_to_unit_open(r.x); act[1] = 0.8f * u32_to_unit_open(r.y);
+        act[2] = 0.8f * u32_to_unit_open(r.z); act[3] = 0.8f * u32_to_unit_open(r.w);
+      } else {
+        act[0] = pi * (2.0f * u32_to_unit_open(r.x) - 1.0f); act[1] = pi * (2.0f * u32_to_unit_open(r.y) - 1.0f);
+        act[2] = pi * (2.0f * u32_to_unit_open(r.z) - 1.0f); act[3] = 0.8f * u32_to_unit_open(r.w);
+      }
+      if (active) reinterpret_cast<float4*>(actions)[i] = make_float4(act[0], act[1], act[2], act[3]);
+    }
+    const bool resetting = active && (s.flags & (FLAG_TERM | FLAG_TRUNC)) != 0;
+    // the lanes that reset on this step are known now: their spare record starts its way to L1 and the slot on the top-up list
+    // is taken (one atomic per warp) while the other lanes integrate
+    const unsigned reset_m = __ballot_sync(0xffffffffu, resetting);
+    int reset_base = 0;
+    if (reset_m != 0u) {
+      if (resetting) {
+        const float* r = spare + ((int64_t)(e_local & kSpareMask) * N + i) * SP_ROWS;
+        prefetch_l1(r); prefetch_l1(r + 32); prefetch_l1(r + 64); prefetch_l1(r + SP_ROWS - 1);
+      }
+      if (lane == __ffs(reset_m) - 1) reset_base = atomicAdd(consumed_count, __popc(reset_m));
+    }
+    const int n_aviary = (active && !resetting) ? h.env_step_ratio : 0;
+    float rew = -0.1f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s.sp[k] = act[k];
+#pragma unroll 1
+    for (int k = 0; k < n_aviary; ++k) {
+      if (s.flags & (FLAG_TERM | FLAG_TRUNC)) break;  // quadx_base_env.py:289-290
+      quadx_aviary_step<MODE>(p, s, nz);
+      hover_term_trunc_reward(h, s, step_count, rew);
+    }
+    step_count += 1;
+    if (reset_m != 0u) {
+      if (resetting) {
+        const float* srec = spare + ((int64_t)(e_local & kSpareMask) * N + i) * SP_ROWS;
+        const F4 m0 = ld_f4(srec + SP_POSE), m1 = ld_f4(srec + SP_POSE + 4), m2 = ld_f4(srec + SP_POSE + 8);
+        const bool hit = m1.z != 0.0f && bits_from_f(m2.x) == e_local && m0.x == sx && m0.y == sy && m0.z == sz && m0.w == ox && m1.x == oy && m1.y == oz;
+        if (hit) {
+          int dummy;
+          quadx_load_tile<MODE, 4>(srec, s, dummy);
+          const F4 pw = ld_f4(srec + QX_PWM);
+          s.pwm[0] = pw.x; s.pwm[1] = pw.y; s.pwm[2] = pw.z; s.pwm[3] = pw.w;
+          s.flags = bits_from_f(m1.w);
+        } else {
+          s = hover_warmup_cold<MODE>(p, hover_fresh<MODE>(sx, sy, sz, ox, oy, oz), h.warmup_steps, rng, N, i, e_local);
+          quadx_requantize(s);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { s.sp[k] = 0.0f; act[k] = 0.0f; }  // self.action = zeros (quadx_base_env.py:165)
+        step_count = 0;
+        rew = 0.0f;
+      }
+      // the consumed spares go on the top-up list: (env, episode that takes the freed place kRolloutAhead ahead)
+      const int base = __shfl_sync(0xffffffffu, reset_base, __ffs(reset_m) - 1);
+      if (resetting) {
+        consumed_list[base + __popc(reset_m & ((1u << lane) - 1u))] = make_int2((int)i, (int)(e_local + (uint32_t)kRolloutAhead));
+        e_local += 1u;
+      }
+    }
+    // ---- outputs of the step
+    float* smem = smem2[t & 1];
+    if (bulk && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the copy that read THIS buffer two steps ago
+    __syncwarp();
+    hover_observation(h, s, act, smem + lane * O);
+    fence_async_smem();
+    __syncwarp();
+    if (bulk) {
+      if (lane == 0) bulk_store_s2g(obs_dst, smem, obs_bytes);
+    } else {
+      for (int j = lane; j < (int)nrows * O; j += kBlock) obs_dst[j] = smem[j];
+    }
+    if (active) {
+      reward[i] = rew;
+      term[i] = (s.flags & FLAG_TERM) ? 1 : 0;
+      trunc[i] = (s.flags & FLAG_TRUNC) ? 1 : 0;
+      if (info) info[i] = (uint8_t)(((s.flags & FLAG_OOB) ? 1 : 0) | ((s.flags & FLAG_COLLISION) ? 2 : 0));
+    }
+    quadx_requantize(s);  // what storing the state and loading it again in the next launch does to the fp64-carried fields
+  }
+  if (active) {
+    quadx_store_tile<MODE, kTileGroupStride>(rec, s, step_count);
+    episode[i] = e_local;
+  }
+  // hand-over to the single-step pipeline: the envs that finished on the LAST step are the done list its next launch expects
+  const bool done = active && (s.flags & (FLAG_TERM | FLAG_TRUNC)) != 0;
+  const unsigned m = __ballot_sync(0xffffffffu, done);
+  if (m != 0u) {
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(last_count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (done) last_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+  }
+  if (bulk && lane == 0) bulk_store_wait_read();  // the CTA's shared memory must outlive the engine's reads
+}
+
 // After a user reset of every env: each env gets a complete fresh spare (dense warps, all envs).
 template <int MODE>
 __global__ void __launch_bounds__(kBlock, kHoverBlocks)
@@ -501,7 +726,7 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (i >= N) return;
   const uint32_t e = episode[i] + 1u;
-  float* rec = spare + ((int64_t)(e & 1u) * N + i) * SP_ROWS;
+  float* rec = spare + ((int64_t)(e & kSpareMask) * N + i) * SP_ROWS;
   const float px = start_pos[3 * i + 0], py = start_pos[3 * i + 1], pz = start_pos[3 * i + 2];
   const float ox = start_orn[3 * i + 0], oy = start_orn[3 * i + 1], oz = start_orn[3 * i + 2];
   QuadXRegs s = hover_fresh<MODE>(px, py, pz, ox, oy, oz);
@@ -704,10 +929,11 @@ int pfb_create(const PfbModel* model, const PfbEnvConfig* env, int64_t n_envs, i
     // builder CTAs inside the step launches; the other env kinds: one per env, rebuilt on a library-owned side stream)
     const bool hover = env->env_kind == PFB_ENV_QUADX_HOVER;
     const size_t rec = env->env_kind == PFB_ENV_QUADX_WAYPOINTS ? (size_t)qwp_spare_rows()
-                       : (env->env_kind == PFB_ENV_DOGFIGHT ? (size_t)df_spare_rows() : (size_t)SP_ROWS * (hover ? 2 : 1));
+                       : (env->env_kind == PFB_ENV_DOGFIGHT ? (size_t)df_spare_rows() : (size_t)SP_ROWS * (hover ? kSpareBufs : 1));
     CUDA_OK(cudaMalloc(&c->d_spare, rec * (size_t)n_envs * sizeof(float)));
     CUDA_OK(cudaMemset(c->d_spare, 0, rec * (size_t)n_envs * sizeof(float)));
     if (hover) {
+      CUDA_OK(cudaMalloc(&c->d_consumed, (size_t)(kRolloutMaxSteps / 2 + 1) * (size_t)n_envs * sizeof(int2)));  // (env, episode) per reset of a fused launch
       CUDA_OK(cudaMalloc(&c->d_elist, 4 * (size_t)n_envs * sizeof(uint32_t)));
       CUDA_OK(cudaMemset(c->d_elist, 0, 4 * (size_t)n_envs * sizeof(uint32_t)));
       CUDA_OK(cudaMalloc(&c->d_episode, (size_t)n_envs * sizeof(uint32_t)));
@@ -737,6 +963,7 @@ int pfb_destroy(PfbHandle h) {
     cudaFree(h->d_spare);
     if (h->d_episode) cudaFree(h->d_episode);
     if (h->d_elist) cudaFree(h->d_elist);
+    if (h->d_consumed) cudaFree(h->d_consumed);
   }
   cudaFree(h->d_counters);
   cudaFree(h->d_done_list);
@@ -791,6 +1018,7 @@ int pfb_bind(PfbHandle h, const PfbBuffers* b) {
 
 
 int pfb_reset(PfbHandle h, const uint8_t* mask, void* stream) {
+  if (h) h->fused_ready = 0;
   REQUIRE_BOUND(h);
   cudaStream_t s = (cudaStream_t)stream;
   if (is_fw(h)) return fw_reset(h, mask, s);
@@ -862,6 +1090,7 @@ static int require_env(PfbHandle h) {
 int pfb_env_reset(PfbHandle h, const uint8_t* mask, const float* noise, void* stream) {
   REQUIRE_BOUND(h);
   if (require_env(h)) return -1;
+  h->fused_ready = 0;
   cudaStream_t s = (cudaStream_t)stream;
   if (is_df(h)) return df_env_reset(h, mask, noise, s);
   if (is_fw(h)) return fw_env_reset(h, mask, noise, s);
@@ -944,6 +1173,7 @@ static int env_step_impl(PfbHandle h, float* actions, const float* noise, bool r
     h->prof_n += 1;
   }
   h->step_seq += 1;
+  h->fused_ready = 0;  // the step pipeline owns the spares again
   return 0;
 }
 
@@ -980,6 +1210,7 @@ int pfb_reseed(PfbHandle h, uint64_t seed, void* stream) {
   if (h->side) CUDA_OK(cudaStreamSynchronize(h->side));  // no spare rebuild of the old streams may still be in flight
   h->rng.k0 = (uint32_t)seed;
   h->rng.k1 = (uint32_t)(seed >> 32);
+  h->fused_ready = 0;
   h->step_seq = 0;
   h->aviary_seq = 0;
   h->reset_seq = 0;
@@ -1001,9 +1232,55 @@ int pfb_env_step(PfbHandle h, const float* actions, const float* noise, void* st
   return env_step_impl(h, actions ? const_cast<float*>(actions) : h->buf.setpoint, noise, false, (cudaStream_t)stream);
 }
 
+// QuadX-Hover with autoreset: n_steps >= kFusedMinSteps run as fused launches of up to kRolloutMaxSteps env steps (k_hover_rollout)
+static bool hover_fused_ok(PfbHandle h) {
+  return h->model.kind == PFB_KIND_QUADX && h->env.env_kind == PFB_ENV_QUADX_HOVER && h->env.autoreset != 0 && h->env.inline_reset == 0 &&
+         h->d_spare != nullptr && h->d_consumed != nullptr && h->noise_dump == nullptr && !(h->prof_ev && h->prof_n < h->prof_cap);
+}
+constexpr int kFusedMinSteps = 4;
+static int hover_rollout_fused(PfbHandle h, int n_steps, cudaStream_t s) {
+  const int mode = h->hover.flight_mode;
+  const int tiles = grid_for(h->n);
+  if (!h->fused_ready) {
+    // finish what the single-step pipeline left half done, then bring every env's spares kRolloutAhead ahead
+    const uint64_t k = h->step_seq;
+    const int builders = h->sm_count < tiles ? h->sm_count : tiles;
+    if (k >= 2) {
+      PFB_MODE_SWITCH(mode, (k_hover_drain<MODE><<<builders, kBlock, 0, s>>>(h->qx, h->hover, h->rng, h->d_counters + ((k + 2) % 4),
+                                                                            h->d_done_list + ((k + 2) % 4) * h->n, h->d_elist + ((k + 2) % 4) * h->n,
+                                                                            h->buf.start_pos, h->buf.start_orn, h->d_spare, h->d_episode, builders, h->n)));
+      LAUNCH_CHECK(h);
+    }
+    PFB_MODE_SWITCH(mode, (k_hover_spare_ahead<MODE><<<tiles, kBlock, 0, s>>>(h->qx, h->hover, h->rng, h->buf.start_pos, h->buf.start_orn, h->d_spare,
+                                                                              h->d_episode, h->n)));
+    LAUNCH_CHECK(h);
+    h->fused_ready = 1;
+  }
+  int topup_grid = 8 * h->sm_count;
+  if (topup_grid > tiles) topup_grid = tiles;
+  while (n_steps > 0) {
+    const int T = n_steps < kRolloutMaxSteps ? n_steps : kRolloutMaxSteps;
+    const uint64_t k0 = h->step_seq, k_last = k0 + (uint64_t)T - 1;
+    CUDA_OK(cudaMemsetAsync(h->d_counters, 0, 8 * sizeof(int32_t), s));  // [0..3] step pipeline lists, [5] spares consumed by this launch
+    PFB_MODE_SWITCH(mode, (k_hover_rollout<MODE><<<tiles, kBlock, 0, s>>>(
+                              h->qx, h->hover, h->rng, h->buf.state, qx_rows(h), h->buf.setpoint, h->buf.obs, h->buf.reward, h->buf.term, h->buf.trunc,
+                              h->buf.info, h->buf.start_pos, h->buf.start_orn, h->d_spare, h->d_episode, h->d_counters + 5, h->d_consumed,
+                              h->d_counters + (k_last % 4), h->d_done_list + (k_last % 4) * h->n, (uint32_t)k0, T, h->n)));
+    LAUNCH_CHECK(h);
+    PFB_MODE_SWITCH(mode, (k_hover_spare_topup<MODE><<<topup_grid, kBlock, 0, s>>>(h->qx, h->hover, h->rng, h->buf.start_pos, h->buf.start_orn, h->d_spare,
+                                                                                   h->d_counters + 5, h->d_consumed, h->n)));
+    LAUNCH_CHECK(h);
+    h->step_seq += (uint64_t)T;
+    n_steps -= T;
+  }
+  return 0;
+}
+
 int pfb_env_rollout(PfbHandle h, int n_steps, void* stream) {
   REQUIRE_BOUND(h);
   if (require_env(h)) return -1;
+  static const int fused_min = getenv("PFB_FUSED_MIN") ? atoi(getenv("PFB_FUSED_MIN")) : kFusedMinSteps;  // tests / experiments
+  if (n_steps >= fused_min && hover_fused_ok(h)) return hover_rollout_fused(h, n_steps, (cudaStream_t)stream);
   for (int k = 0; k < n_steps; ++k)
     if (env_step_impl(h, h->buf.setpoint, nullptr, true, (cudaStream_t)stream)) return -1;
   return 0;

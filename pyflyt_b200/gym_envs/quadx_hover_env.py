@@ -127,7 +127,8 @@ class QuadXHoverVecEnv:
         return a.obs, a.reward, a.term.bool(), a.trunc.bool(), self._info()
 
     def rollout(self, n_steps: int) -> None:
-        """n_steps env steps with on-device uniform random actions (benchmark shape of BASELINE.json)."""
+        """n_steps env steps with on-device uniform random actions (benchmark shape of BASELINE.json).  With autoreset, 4 or more
+        steps run as fused launches of up to 16 env steps each (``pfb_env_rollout``); the buffers then hold the last step's results."""
         self.aviary.env_rollout(n_steps)
 
     def close(self) -> None:

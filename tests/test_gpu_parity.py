@@ -351,3 +351,45 @@ def test_masked_reset_on_autoreset_handle_is_not_reset_twice(kind):
     assert ca == cb and ca > 1000
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,n", [(0, 65536), (0, 1000), (6, 8192)])
+def test_fused_rollout_equals_stepwise(mode, n):
+    """pfb_env_rollout(n >= 4) runs QuadX-Hover as FUSED launches of up to 16 env steps (k_hover_rollout: state in registers across
+    the steps, spares kept three ahead and topped up behind every launch); fewer steps run one launch per step.  Same Philox
+    counters, same arithmetic: the drawn actions are equal bit for bit, always; the physics agrees bit for bit except where the
+    two compiled copies of an expression contract a multiply-add differently (a one-ulp fp32 difference in a PID term a few
+    times per 1e5 env-steps, which an env then carries until its next reset).  The two ways of stepping are freely mixed on one
+    handle here: the hand-over of the reset pipeline in both directions is part of the test."""
+    import torch
+
+    from pyflyt_b200.gym_envs.quadx_hover_env import QuadXHoverVecEnv
+
+    plan = [16, 16, 5, 1, 1, 23, 1, 40, 4, 2, 64]  # fused chunks (>= 4) and single steps, interleaved
+    a = QuadXHoverVecEnv(num_envs=n, seed=21, flight_mode=mode)
+    b = QuadXHoverVecEnv(num_envs=n, seed=21, flight_mode=mode)
+    a.reset()
+    b.reset()
+    done_total, worst, diverged_max, inexact_max = 0, 0.0, 0, 0.0
+    for chunk in plan:
+        a.rollout(chunk)             # fused when chunk >= 4
+        for _ in range(chunk):
+            b.rollout(1)             # always one launch per step
+            done_total += int((b.aviary.term | b.aviary.trunc).sum())
+        A, B = a.aviary, b.aviary
+        assert torch.equal(A.setpoints, B.setpoints), chunk      # the actions of the last step: pure Philox, no physics
+        same = A.state_row_int(17) == B.state_row_int(17)        # same step counter = same reset history
+        diverged_max = max(diverged_max, int((~same).sum()))     # a termination decided within an ulp of its threshold
+        d = (A.obs.double() - B.obs.double()).abs().amax(dim=1)
+        worst = max(worst, float(d[same].max()))
+        inexact_max = max(inexact_max, float((d[same] > 0).double().mean()))
+        assert torch.equal(A.term[same], B.term[same]) and torch.equal(A.trunc[same], B.trunc[same]), chunk
+        assert float((A.reward.double() - B.reward.double()).abs()[same].max()) < 1e-3, chunk
+    print(f"\n[fused vs stepwise, mode {mode}, {n} envs, {sum(plan)} steps] {done_total} episodes finished; envs with a different reset history: "
+          f"at most {diverged_max}; envs not bit-equal at a checkpoint: at most {inexact_max:.2e} of them; max |obs difference| {worst:.2e}")
+    assert done_total > n // 2       # resets everywhere (mode 0: ~6 per env)
+    assert diverged_max <= max(2, n // 4096)
+    assert inexact_max < 1e-2 and worst < (1e-4 if mode == 0 else 1e-2)  # mode 6: the z-velocity PID limit cycle amplifies an ulp (DESIGN 5)
+    a.close()
+    b.close()

@@ -393,3 +393,59 @@ def test_dogfight_philox_autoreset_matches_oracle():
     assert n_flip <= n // 200      # hit / range decisions at fp32 thresholds (lethal cone 1 rad, 150 m): tests/test_dogfight.py allows 2e-3 per step
     assert worst_obs < 2e-2 and worst_rew < 0.1
     env.close()
+
+
+def test_hover_fused_rollout_matches_oracle():
+    """The FUSED rollout (pfb_env_rollout(n >= 4): k_hover_rollout, 16 env steps per launch with the state in registers, on-device
+    actions, autoreset from spares kept three ahead) pinned to the fp64 oracle on its own: the oracle is driven step by step with
+    the replayed actions (bit-exact Philox replay) and noise, and resets on ITS OWN terminations with the replayed warm-up noise;
+    at the end of every fused chunk the two must show the same step counters, flags, observations and rewards."""
+    import torch
+
+    from pyflyt_b200.gym_envs.quadx_hover_env import QuadXHoverVecEnv
+
+    n, seed, chunks = 16384, 77, [16, 16, 7, 16, 32, 16, 16]
+    env = QuadXHoverVecEnv(num_envs=n, seed=seed)
+    av = env.aviary
+    streams = Streams(seed, n, noise_loc=4.0)
+    model = build_model("quadx", "cf2x")
+    orc = OracleEngine(model, hover_config(0, "quaternion", False, 3.0), n, np.tile([[0.0, 0.0, 1.0]], (n, 1)), np.zeros((n, 3)))
+    env.reset()
+    orc.o.env_reset(noise=streams.user_reset_noise(0).astype(np.float64))
+    episode = np.ones(n, dtype=np.int64)
+    done_prev = np.zeros(n, dtype=bool)
+    steps_o = np.zeros(n, dtype=np.int64)
+    k = 0
+    worst_obs = worst_rew = 0.0
+    n_resets = desync_max = 0
+    for chunk in chunks:
+        env.rollout(chunk)
+        assert np.array_equal(av.setpoints.cpu().numpy(), streams.actions(k + chunk - 1))  # the last step's actions, written back
+        for _ in range(chunk):
+            act = streams.actions(k).astype(np.float64)
+            oo, ro, teo, tro, io = orc.o.env_step(act, streams.step_noise(k).astype(np.float64))
+            teo, tro = teo.astype(bool), tro.astype(bool)
+            steps_o += 1
+            if done_prev.any():
+                idx = np.nonzero(done_prev)[0]
+                rz = np.zeros((20, n))
+                rz[:, idx] = streams.autoreset_noise(episode[idx], envs=idx)
+                obs_r = orc.o.env_reset(mask=done_prev.astype(np.uint8), noise=rz)
+                oo[done_prev], ro[done_prev], teo[done_prev], tro[done_prev] = obs_r[done_prev], 0.0, False, False
+                episode[idx] += 1
+                steps_o[idx] = 0
+                n_resets += len(idx)
+            done_prev = teo | tro
+            k += 1
+        og, rg = av.obs.double().cpu().numpy(), av.reward.double().cpu().numpy()
+        teg, trg = av.term.cpu().numpy().astype(bool), av.trunc.cpu().numpy().astype(bool)
+        same = (av.state_row_int(17).cpu().numpy() == steps_o) & (teg == teo) & (trg == tro)  # same reset history and outcome
+        desync_max = max(desync_max, int((~same).sum()))
+        worst_obs = max(worst_obs, float(np.abs(og[same] - oo[same]).max()))
+        worst_rew = max(worst_rew, float(np.abs(rg[same] - ro[same]).max()))
+    print(f"\n[fused rollout vs oracle] {n} envs x {k} steps in chunks {chunks}: {n_resets} oracle resets, envs off the oracle's reset schedule: "
+          f"at most {desync_max}; max |obs| {worst_obs:.2e}, max |reward| {worst_rew:.2e}")
+    assert n_resets > n
+    assert desync_max <= n // 2000   # a termination within rounding of its threshold shifts that env's whole schedule
+    assert worst_obs < 1e-4 and worst_rew < 1e-4
+    env.close()
