@@ -466,8 +466,14 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     vals = [float(x) for x in t.tolist()]
     block_ms, (warm_ms, e2e_ms, kern_total_ms, strong_ms, e2e_copy_ms, e2e_mapped_ms, flushed_ms, fused_ms) = vals[:R], vals[R:]
-    split = dogfight_split_block(rank, world, dev) if (world > 1 and not args.no_dogfight_split) else None
-    if rank == 0:
+    import threading
+
+    emitted = threading.Lock()
+
+    def emit(split):
+        """rank 0 prints THE json line exactly once (also reachable from the watchdog of the split-dogfight block)"""
+        if rank != 0 or not emitted.acquire(blocking=False):
+            return
         peak, peak_src = load_peaks()
         total_ms = _median(block_ms)
         value = world * n * K / (total_ms * 1e-3)
@@ -542,6 +548,25 @@ def run_ours(args, rank, local_rank, world):
                 "sample": f"{steps} env-steps x 16384 envs ({dt:.1f} s) of the same workload on oracle/pfb_oracle.c (fp64, OpenMP; thread count tuned by a short probe)",
             }
         print(json.dumps(line), flush=True)
+
+    # ---- configs[4] (context, world > 1): the split dogfight needs every rank alive at four exchanges per env step.  It runs LAST and
+    #      under a watchdog: whatever happens to it (an exception on one rank, a peer that never arrives), the line above is printed
+    split = None
+    if world > 1 and not args.no_dogfight_split:
+        def expired():
+            emit({"error": f"split-dogfight block did not finish within {args.split_timeout:.0f} s; skipped"})
+            os._exit(0)
+
+        dog = threading.Timer(args.split_timeout, expired)
+        dog.daemon = True
+        dog.start()
+        try:
+            split = dogfight_split_block(rank, world, dev)
+        except Exception as e:  # noqa: BLE001 - reported in the line, the hover numbers stand
+            emit({"error": repr(e)[:300]})
+            os._exit(0)
+        dog.cancel()
+    emit(split)
     if world > 1:
         dist.destroy_process_group()
 
@@ -558,6 +583,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--repeats", type=int, default=5, help="blocks of --steps timed steps; the median block is reported")
     ap.add_argument("--no-dogfight-split", action="store_true", help="skip the configs[4] split-dogfight block under torchrun")
+    ap.add_argument("--split-timeout", type=float, default=240.0, help="watchdog of the split-dogfight block (s)")
     ap.add_argument("--batches", type=int, default=12,
                     help="independent 65 536-env batches stepped round-robin in the timed region (their working set exceeds the L2: every "
                          "launch finds its inputs in DRAM); 1 = one batch, L2-warm")

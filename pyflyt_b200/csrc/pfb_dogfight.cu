@@ -657,10 +657,16 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
                       const int* __restrict__ wait_flags, int world, int epoch, int64_t N) {
   if (wait_flags) {  // every rank's physics kernel has raised its flag for this exchange (acquire, system scope)
     if ((int)threadIdx.x < world) {
+      // bounded: a peer that never launches (crashed rank) must not hang this GPU.  After 2 s the wait gives up; the combat
+      // then reads a stale table, which the caller sees as a parity failure, not as a dead box
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
       int v;
       do {
         asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(wait_flags + threadIdx.x) : "memory");
-      } while (v < epoch);
+        if (v >= epoch) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      } while (t1 - t0 < 2000000000ull);
     }
     __syncthreads();
   }
