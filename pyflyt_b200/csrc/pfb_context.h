@@ -76,6 +76,14 @@ struct PfbContext {
 // the single wave has a shorter tail.  448 threads per SM resident (<= 146 regs/thread) for the generic kernels.
 constexpr int kBlock = 32;
 constexpr int kMinBlocks = 448 / kBlock;
+// the step kernels of the aerodynamic-surface vehicles (Fixedwing-Waypoints, Dogfight): the batch sizes they run at leave
+// < 4 warps per SM, so registers are better spent on interleaving the surfaces than on residency.  Measured on B200 at 16 384
+// aircraft (profiles/r02_aero_full_block.jsonl): 14 CTAs / SM (128 registers) 31.0 / 34.9 us per step, 8 CTAs / SM (145 / 176
+// registers) 30.1 / 33.1 us.  PFB_AERO_MIN_BLOCKS: A/B knob
+#ifndef PFB_AERO_MIN_BLOCKS
+#define PFB_AERO_MIN_BLOCKS 8
+#endif
+constexpr int kAeroBlocks = PFB_AERO_MIN_BLOCKS;
 
 static inline int grid_for(int64_t n) { return (int)((n + kBlock - 1) / kBlock); }
 

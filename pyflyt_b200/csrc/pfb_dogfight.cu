@@ -279,7 +279,7 @@ __device__ __forceinline__ void df_reset_agent(const FixedwingParams& p, const D
 }
 
 template <int A, bool INJECT, bool RANDACT, bool AUTORESET>
-__global__ void __launch_bounds__(kBlock, kMinBlocks)
+__global__ void __launch_bounds__(kBlock, kAeroBlocks)
     k_df_step(const __grid_constant__ FixedwingParams p, const __grid_constant__ DogfightParams d, const __grid_constant__ RngParams rng,
               float* __restrict__ st, int32_t* __restrict__ ist, float* __restrict__ actions, const float* __restrict__ noise,
               float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ term, uint8_t* __restrict__ trunc,
@@ -392,9 +392,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
       s.sp[0] = ag.cur[0]; s.sp[1] = ag.cur[1]; s.sp[2] = ag.cur[2]; s.sp[3] = ag.cur[3] * 0.5f + 0.5f;
       step_count = ist[(int64_t)DI_STEP * N + i];
       auto nz = make_noise<INJECT>(noise, N, i, rng, step_seq, TAG_ENV_STEP, p.noise_loc, p.ratio);
+      const bool full = fixedwing_full_model(p);  // launch-uniform
 #pragma unroll 1
       for (int k = 0; k < d.env_step_ratio; ++k) {  // parallel envs do not break out of the loop (:312-314)
-        fixedwing_aviary_step<0>(p, s, nz);
+        if (full) fixedwing_aviary_step<0, true>(p, s, nz);
+        else fixedwing_aviary_step<0>(p, s, nz);
         df_update_states<A>(d, s, ag, li, base, step_count, k == d.env_step_ratio - 1, row, lanes);
       }
       rew_out = ag.acc_reward;
@@ -615,7 +617,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
     // one Aviary step; the noise stream position is (env-step sequence, Aviary step index)
     auto nz = make_noise<INJECT>(noise, N, i, rng, seq, TAG_ENV_STEP, p.noise_loc, 4);  // ratio > 2 path: one call per step
     nz.seek(sub);
-    fixedwing_aviary_step<0>(p, s, nz);
+    if (fixedwing_full_model(p)) fixedwing_aviary_step<0, true>(p, s, nz);
+    else fixedwing_aviary_step<0>(p, s, nz);
   }
   fixedwing_store(st, ist, N, i, s);
   df_store_agent(st, ist, N, i, ag);

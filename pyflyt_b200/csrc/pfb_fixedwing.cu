@@ -51,7 +51,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
 #pragma unroll
   for (int k = 0; k < 6; ++k) s.sp[k] = k < sp_dim ? __ldg(setpoint + (int64_t)sp_dim * i + k) : 0.0f;
   auto nz = make_noise<INJECT>(noise, N, i, rng, seq, TAG_AVIARY, p.noise_loc, p.ratio);
-  for (int k = 0; k < n_steps; ++k) fixedwing_aviary_step<MODE>(p, s, nz);
+  if (fixedwing_full_model(p)) {  // launch-uniform: all surfaces, no wind -> the one-basic-block substep (pfb_fixedwing.cuh)
+    for (int k = 0; k < n_steps; ++k) fixedwing_aviary_step<MODE, true>(p, s, nz);
+  } else {
+    for (int k = 0; k < n_steps; ++k) fixedwing_aviary_step<MODE>(p, s, nz);
+  }
   fixedwing_store(st, ist, N, i, s);
 }
 
@@ -214,7 +218,7 @@ static_assert(FW_ROWS + 9 <= WSP_ROWS, "spare record too small");
 
 // L = lanes per aircraft (1: one thread per env; 4: pfb_fixedwing.cuh "L lanes per aircraft"): a CTA (one warp) owns kBlock / L envs
 template <bool INJECT, bool RANDACT, bool AUTORESET, int L>
-__global__ void __launch_bounds__(kBlock, kMinBlocks)
+__global__ void __launch_bounds__(kBlock, kAeroBlocks)
     k_fwwp_step(const __grid_constant__ FixedwingParams p, const __grid_constant__ WaypointParams w,
                 const __grid_constant__ RngParams rng, float* __restrict__ st, int32_t* __restrict__ ist,
                 float* __restrict__ actions, const float* __restrict__ noise, float* __restrict__ obs, float* __restrict__ reward,
@@ -330,10 +334,12 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
       wp_load_target0(tb, ts, wp);
       rew = -0.1f;
       auto nz = make_noise<INJECT>(noise, N, i, rng, step_seq, TAG_ENV_STEP, p.noise_loc, p.ratio);
+      const bool full = fixedwing_full_model(p);
 #pragma unroll 1
       for (int k = 0; k < w.env_step_ratio; ++k) {
         if (s.flags & (FLAG_TERM | FLAG_TRUNC)) break;
         if (L > 1) fixedwing_aviary_step_lanes<0, L>(p, ssurf, s, nz, sub, gmask);
+        else if (full) fixedwing_aviary_step<0, true>(p, s, nz);
         else fixedwing_aviary_step<0>(p, s, nz);
         float old = wp_update_distance(s, wp);
         wp_term_trunc_reward(w, s, wp, old, step_count, rew, tb, ts);

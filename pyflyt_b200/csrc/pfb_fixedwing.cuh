@@ -296,19 +296,25 @@ PFB_HD void fixedwing_command(const FixedwingRegs& s, float* cmd) {
 }
 
 // one physics substep: update_physics (fixedwing.py:261-264) + stepSimulation + update_state
+// FULL = the caller has checked (launch-uniform) that the model has all kMaxSurfaces surfaces and no wind.  The generic path
+// tests `i < n_surfaces` and `windy` per surface: uniform branches, but branches — every surface becomes its own chain of basic
+// blocks and ptxas schedules inside a block only, so the five ~230-instruction surfaces run one after the other, each at the
+// pace of its own dependency chain (atan2 -> stall selects -> sincos -> coefficients -> force).  With < 1 warp per scheduler
+// at the batch sizes these vehicles run at (16 384 envs) instruction-level parallelism is the only latency hiding there is:
+// FULL removes the tests at compile time, the surfaces land in ONE basic block and their chains interleave.
+template <bool FULL = false>
 PFB_HD void fixedwing_substep(const FixedwingParams& p, FixedwingRegs& s, const float* cmd, float xi) {
   Vec3 F = Vec3{0.f, 0.f, 0.f}, T = Vec3{0.f, 0.f, 0.f};
   const Vec3 w = Vec3{s.wx, s.wy, s.wz};
-  // fully unrolled: the surfaces are independent until their forces are summed, and with < 1 warp per scheduler at the
-  // batch sizes these vehicles run at (16 384 envs) instruction-level parallelism is the only latency hiding there is;
-  // the surface tables also become immediate constant-bank operands instead of indexed loads
-  const bool windy = p.wind.kind != 0;  // uniform: the parameter block is launch-constant
+  // fully unrolled: the surface tables become immediate constant-bank operands instead of indexed loads
+  const bool windy = FULL ? false : p.wind.kind != 0;  // uniform: the parameter block is launch-constant
   WindCtx wc = WindCtx{Vec3{0.f, 0.f, 0.f}, 0.f, 0.f, 0.f, 0.f};
   if (windy) wc = wind_ctx(p.wind, (float)s.pz, (float)s.R.m00, (float)s.R.m01, (float)s.R.m02, (float)s.R.m10, (float)s.R.m11, (float)s.R.m12,
                            (float)s.R.m20, (float)s.R.m21, (float)s.R.m22);
 #pragma unroll
   for (int i = 0; i < kMaxSurfaces; ++i) {
-    if (i < p.n_surfaces) surface_force(p.surf[i], s.act[i], cmd[i], s.vb, w, F, T, windy ? &p.wind : nullptr, &wc);
+    if (FULL) surface_force(p.surf[i], s.act[i], cmd[i], s.vb, w, F, T);
+    else if (i < p.n_surfaces) surface_force(p.surf[i], s.act[i], cmd[i], s.vb, w, F, T, windy ? &p.wind : nullptr, &wc);
   }
   // motor (motors.py:130-155): thrust + reaction torque along +x at motor_r
   {
@@ -396,15 +402,21 @@ __device__ __forceinline__ void fixedwing_gather_act(FixedwingRegs& s, unsigned 
 }
 #endif
 
-template <int MODE, typename NoiseFn>
+template <int MODE, bool FULL = false, typename NoiseFn>
 PFB_HD void fixedwing_aviary_step(const FixedwingParams& p, FixedwingRegs& s, NoiseFn& noise) {
   s.flags &= ~(uint32_t)FLAG_CONTACT_ARRAY;
   noise.begin_step();
   float cmd[6];
   fixedwing_command<MODE>(s, cmd);
 #pragma unroll 1
-  for (int u = 0; u < p.ratio; ++u) fixedwing_substep(p, s, cmd, noise.get(u));
+  for (int u = 0; u < p.ratio; ++u) fixedwing_substep<FULL>(p, s, cmd, noise.get(u));
 }
+// launch-uniform test for the FULL instantiation
+#ifdef PFB_NO_FULL  // A/B knob: always the generic (branch per surface) substep
+PFB_HD bool fixedwing_full_model(const FixedwingParams&) { return false; }
+#else
+PFB_HD bool fixedwing_full_model(const FixedwingParams& p) { return p.n_surfaces == kMaxSurfaces && p.wind.kind == 0; }
+#endif
 
 // fixedwing.py:194-204 + aviary.py:310-311
 PFB_HD void fixedwing_reset(const FixedwingParams& p, FixedwingRegs& s, float sx, float sy, float sz, float roll, float pitch, float yaw) {
