@@ -210,6 +210,20 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// per-thread asynchronous copies global -> shared (LDGSTS): issued and forgotten, complete in the background, waited for with
+// cp_async_wait_all() by the issuing thread, which may then read what it copied
+__device__ __forceinline__ void cp_async16(float* sdst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* sdst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// Staging of spare records (reset by the owning thread): a resetting lane copies its 320-byte record — in the step kernel also the
+// start pose the record is checked against — into the warp's state-tile buffer, which is dead once the tile has been unpacked.
+// The copies fly while the other lanes integrate; the swap at the end of the step then reads shared memory instead of making two
+// or three DEPENDENT trips to L2 / DRAM (valid word -> pose -> state: ~600 cycles each in the ncu source view of round 2).
+constexpr int kStageFloats = SP_ROWS + 8;
 
 // env.reset() integrated inline (quadx_base_env.py:149-212): Aviary steps [from, to) of the warm-up that follows the start
 // pose + set_mode.  The state is rounded to what a record holds (hi + lo words) before step kWarmSplit in EVERY path, so a
@@ -394,10 +408,27 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
   PFB_TL(1);
   // an env that finished on the previous call: this call is its reset (NEXT_STEP)
   const bool resetting = AUTORESET && active && (s.flags & (FLAG_TERM | FLAG_TRUNC)) != 0;
-  if (AUTORESET && resetting && spare) {  // pull the env's spare record into L1 while the other lanes integrate: the swap at the
-                                          // end of the launch then costs two L1 round trips instead of two cold ones
-    const float* r = spare + ((int64_t)(e_next & kSpareMask) * N + i) * SP_ROWS;
-    prefetch_l1(r); prefetch_l1(r + 32); prefetch_l1(r + 64); prefetch_l1(r + SP_ROWS - 1);
+  const float* staged = nullptr;  // this lane's spare record + start pose in shared memory (see kStageFloats)
+  if (AUTORESET && spare) {
+    constexpr int kSlots = kInGroups * kTileGroupStride / kStageFloats;
+    const unsigned reset_m = __ballot_sync(0xffffffffu, resetting);
+    if (reset_m != 0u) {
+      __syncwarp();  // every lane has unpacked its part of the tile: the buffer is free
+      if (resetting) {
+        const float* r = spare + ((int64_t)(e_next & kSpareMask) * N + i) * SP_ROWS;
+        const int rank = __popc(reset_m & ((1u << lane) - 1u));
+        if (rank < kSlots) {
+          float* q = stile + rank * kStageFloats;
+#pragma unroll
+          for (int g = 0; g < SP_ROWS / 4; ++g) cp_async16(q + 4 * g, r + 4 * g);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { cp_async4(q + SP_ROWS + k, start_pos + 3 * i + k); cp_async4(q + SP_ROWS + 3 + k, start_orn + 3 * i + k); }
+          staged = q;
+        } else {  // more resetting lanes than slots (a synchronised truncation): towards L1 at least
+          prefetch_l1(r); prefetch_l1(r + 32); prefetch_l1(r + 64); prefetch_l1(r + SP_ROWS - 1);
+        }
+      }
+    }
   }
   int n_aviary = (active && !resetting) ? h.env_step_ratio : 0;
   float rew = -0.1f;
@@ -427,13 +458,20 @@ __global__ void __launch_bounds__(kBlock, kHoverBlocks)
   if (AUTORESET && __any_sync(0xffffffffu, resetting)) {
     if (resetting) {
       // env.reset(): begin_reset + end_reset (quadx_base_env.py:149-212) — normally a copy of the env's spare
-      const float px = start_pos[3 * i + 0], py = start_pos[3 * i + 1], pz = start_pos[3 * i + 2];
-      const float ox = start_orn[3 * i + 0], oy = start_orn[3 * i + 1], oz = start_orn[3 * i + 2];
+      float px, py, pz, ox, oy, oz;
+      if (staged) {
+        cp_async_wait_all();
+        px = staged[SP_ROWS + 0]; py = staged[SP_ROWS + 1]; pz = staged[SP_ROWS + 2];
+        ox = staged[SP_ROWS + 3]; oy = staged[SP_ROWS + 4]; oz = staged[SP_ROWS + 5];
+      } else {
+        px = start_pos[3 * i + 0]; py = start_pos[3 * i + 1]; pz = start_pos[3 * i + 2];
+        ox = start_orn[3 * i + 0]; oy = start_orn[3 * i + 1]; oz = start_orn[3 * i + 2];
+      }
       bool hit = false;
       uint32_t nseq = step_seq | 0x40000000u;
       if (spare) {
         nseq = e_next;  // episode number: keys the warm-up noise
-        const float* srec = spare + ((int64_t)(e_next & kSpareMask) * N + i) * SP_ROWS;
+        const float* srec = staged ? staged : spare + ((int64_t)(e_next & kSpareMask) * N + i) * SP_ROWS;
         const F4 m0 = ld_f4(srec + SP_POSE), m1 = ld_f4(srec + SP_POSE + 4), m2 = ld_f4(srec + SP_POSE + 8);
         hit = spare_copy && m1.z != 0.0f && bits_from_f(m2.x) == e_next && m0.x == px && m0.y == py && m0.z == pz && m0.w == ox && m1.x == oy &&
               m1.y == oz;
@@ -606,6 +644,7 @@ __global__ void __launch_bounds__(kBlock, 14)
   int step_count;
   mbar_wait(&mbar, 0);
   quadx_load_tile<MODE, kTileGroupStride>(stile + lane * 4, s, step_count);
+  __syncwarp();  // the tile buffer is dead from here on: it stages the spare records of resetting lanes (kStageFloats)
   int64_t nrows = N - tile_first;
   if (nrows > kBlock) nrows = kBlock;
   const uint32_t obs_bytes = (uint32_t)nrows * (uint32_t)O * 4u;
@@ -636,12 +675,25 @@ __global__ void __launch_bounds__(kBlock, 14)
     // is taken (one atomic per warp) while the other lanes integrate
     const unsigned reset_m = __ballot_sync(0xffffffffu, resetting);
     int reset_base = 0;
+    const float* staged = nullptr;  // this lane's spare record in shared memory (the dead state-tile buffer, see kStageFloats)
     if (reset_m != 0u) {
+      constexpr int kSlots = kInGroups * kTileGroupStride / SP_ROWS;
       if (resetting) {
         const float* r = spare + ((int64_t)(e_local & kSpareMask) * N + i) * SP_ROWS;
-        prefetch_l1(r); prefetch_l1(r + 32); prefetch_l1(r + 64); prefetch_l1(r + SP_ROWS - 1);
+        const int rank = __popc(reset_m & ((1u << lane) - 1u));
+        if (rank < kSlots) {
+          float* q = stile + rank * SP_ROWS;
+#pragma unroll
+          for (int g = 0; g < SP_ROWS / 4; ++g) cp_async16(q + 4 * g, r + 4 * g);
+          staged = q;
+        } else {
+          prefetch_l1(r); prefetch_l1(r + 32); prefetch_l1(r + 64); prefetch_l1(r + SP_ROWS - 1);
+        }
       }
-      if (lane == __ffs(reset_m) - 1) reset_base = atomicAdd(consumed_count, __popc(reset_m));
+      // one slot range on the top-up list per warp.  Inline PTX: a plain atomicAdd is rewritten by the compiler into its
+      // warp-aggregated form, whose broadcast shuffle waits for the atomic's return HERE instead of after the integration
+      if (lane == __ffs(reset_m) - 1)
+        asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(reset_base) : "l"(consumed_count), "r"(__popc(reset_m)) : "memory");
     }
     const int n_aviary = (active && !resetting) ? h.env_step_ratio : 0;
     float rew = -0.1f;
@@ -656,7 +708,8 @@ __global__ void __launch_bounds__(kBlock, 14)
     step_count += 1;
     if (reset_m != 0u) {
       if (resetting) {
-        const float* srec = spare + ((int64_t)(e_local & kSpareMask) * N + i) * SP_ROWS;
+        if (staged) cp_async_wait_all();
+        const float* srec = staged ? staged : spare + ((int64_t)(e_local & kSpareMask) * N + i) * SP_ROWS;
         const F4 m0 = ld_f4(srec + SP_POSE), m1 = ld_f4(srec + SP_POSE + 4), m2 = ld_f4(srec + SP_POSE + 8);
         const bool hit = m1.z != 0.0f && bits_from_f(m2.x) == e_local && m0.x == sx && m0.y == sy && m0.z == sz && m0.w == ox && m1.x == oy && m1.y == oz;
         if (hit) {
