@@ -162,7 +162,10 @@ enum { SP_POSE = QX_ROWS, SP_VALID = QX_ROWS + 6, SP_FLAGS = QX_ROWS + 7, SP_EPI
 static_assert(QX_ROWS % 4 == 0 && QX_ROWS + 16 <= SP_ROWS && SP_ROWS % 4 == 0, "spare record layout");
 constexpr int kSpareBufs = 4;  // records per env, buffer = episode & 3: the step pipeline uses two neighbours (one being consumed, one being built);
 constexpr uint32_t kSpareMask = kSpareBufs - 1;  // the fused rollout keeps three spares ahead (k_hover_rollout)
-constexpr int kWarmSplit = 5;  // Aviary steps integrated by the first builder phase; every warm-up requantizes its state there
+#ifndef PFB_WARM_SPLIT
+#define PFB_WARM_SPLIT 5
+#endif
+constexpr int kWarmSplit = PFB_WARM_SPLIT;  // Aviary steps integrated by the first builder phase; every warm-up requantizes its state there
 
 // cp.async.bulk (TMA, 1-D) shared -> global: one instruction moves a warp's whole observation tile
 __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {

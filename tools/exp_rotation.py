@@ -18,7 +18,7 @@ def main():
     g = torch.Generator(device=dev).manual_seed(1)
     lo = torch.tensor([-3.14159265, -3.14159265, -3.14159265, 0.0], device=dev)
     hi = torch.tensor([3.14159265, 3.14159265, 3.14159265, 0.8], device=dev)
-    for M in (1, 2, 4, 6, 8, 12, 16, 24):
+    for M in ([int(x) for x in os.environ["PFB_ROTATION_M"].split(",")] if os.environ.get("PFB_ROTATION_M") else (1, 2, 4, 6, 8, 12, 16, 24)):
         envs = [QuadXHoverVecEnv(num_envs=n, seed=0, device=dev, env_offset=j * n) for j in range(M)]
         acts = [lo + (hi - lo) * torch.rand((4, n, 4), device=dev, generator=g) for _ in range(M)]
         for e in envs:
@@ -36,7 +36,7 @@ def main():
             torch.cuda.synchronize()
             best.append(e0.elapsed_time(e1) * 1e3 / K)
         best.sort()
-        print(json.dumps({"batches": M, "us_per_step_median": round(best[2], 3), "us_per_step_min": round(best[0], 3), "us_per_step_max": round(best[-1], 3),
+        print(json.dumps({"lib": os.environ.get("PYFLYT_B200_LIB", "default")[-40:], "batches": M, "us_per_step_median": round(best[2], 3), "us_per_step_min": round(best[0], 3), "us_per_step_max": round(best[-1], 3),
                           "env_steps_per_s": n / (best[2] * 1e-6)}), flush=True)
         for e in envs:
             e.close()

@@ -36,12 +36,16 @@ for rep in range(12):
     t0 = t[:, 0].min()
     t = (t - t0) / 1e3  # us since the first warp entered
     b, s = t[:296], t[296:]
+    b0, b1 = b[:148], b[148:]  # phase 0 (start the next spare) / phase 1 (finish the one started by the previous launch)
+    b0, b1 = b0[b0[:, 1] > 0], b1[b1[:, 1] > 0]
     b = b[b[:, 1] > 0]  # builder CTAs that had work
     def q(x):
         return [round(float(np.percentile(x, p)), 2) for p in (0, 10, 50, 90, 100)]
     rows.append({"step_entry": q(s[:, 0]), "step_inputs": q(s[:, 1]), "step_loop_done": q(s[:, 2]), "step_exit": q(s[:, 3]),
                  "builders_with_work": int(len(b)), "b_entry": q(b[:, 0]) if len(b) else None, "b_loaded": q(b[:, 1]) if len(b) else None,
                  "b_chain_done": q(b[:, 2]) if len(b) else None, "b_exit": q(b[:, 3]) if len(b) else None,
+                 "phase0": {"n": int(len(b0)), "loaded": q(b0[:, 1]), "chain_done": q(b0[:, 2]), "exit": q(b0[:, 3])} if len(b0) else None,
+                 "phase1": {"n": int(len(b1)), "loaded": q(b1[:, 1]), "chain_done": q(b1[:, 2]), "exit": q(b1[:, 3])} if len(b1) else None,
                  "last_exit": round(float(t[:, 3].max()), 2)})
 for r in rows[2:]:
     print(json.dumps(r))
