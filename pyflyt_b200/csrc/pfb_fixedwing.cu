@@ -217,6 +217,10 @@ enum { WSP_POSE = FW_ROWS, WSP_VALID = FW_ROWS + 6, WSP_FLAGS = FW_ROWS + 7, WSP
 static_assert(FW_ROWS + 9 <= WSP_ROWS, "spare record too small");
 
 // L = lanes per aircraft (1: one thread per env; 4: pfb_fixedwing.cuh "L lanes per aircraft"): a CTA (one warp) owns kBlock / L envs
+#ifndef PFB_FW_ROLLED
+#define PFB_FW_ROLLED 0
+#endif
+constexpr bool kFwRolled = PFB_FW_ROLLED != 0;  // A/B knob: the step loop runs the surfaces through one rolled copy (instruction-cache footprint)
 template <bool INJECT, bool RANDACT, bool AUTORESET, int L>
 __global__ void __launch_bounds__(kBlock, kAeroBlocks)
     k_fwwp_step(const __grid_constant__ FixedwingParams p, const __grid_constant__ WaypointParams w,
@@ -234,7 +238,7 @@ __global__ void __launch_bounds__(kBlock, kAeroBlocks)
   const int sub = L > 1 ? (int)(threadIdx.x % L) : 0;   // lane within the aircraft's group
   const int slot = L > 1 ? (int)(threadIdx.x / L) : (int)threadIdx.x;  // env within the CTA
   const unsigned gmask = L > 1 ? (((1u << L) - 1u) << (threadIdx.x & ~(L - 1))) : 0xffffffffu;
-  if (L > 1) {
+  if (L > 1 || kFwRolled) {
     for (int j = threadIdx.x; j < (int)(sizeof(SurfaceParams) / 4) * kMaxSurfaces; j += kBlock)
       reinterpret_cast<float*>(ssurf)[j] = reinterpret_cast<const float*>(p.surf)[j];
     __syncthreads();
@@ -339,6 +343,7 @@ __global__ void __launch_bounds__(kBlock, kAeroBlocks)
       for (int k = 0; k < w.env_step_ratio; ++k) {
         if (s.flags & (FLAG_TERM | FLAG_TRUNC)) break;
         if (L > 1) fixedwing_aviary_step_lanes<0, L>(p, ssurf, s, nz, sub, gmask);
+        else if (kFwRolled) fixedwing_aviary_step_lanes<0, 1>(p, ssurf, s, nz, 0, 0xffffffffu);  // experiment: ONE rolled copy of the surface code
         else if (full) fixedwing_aviary_step<0, true>(p, s, nz);
         else fixedwing_aviary_step<0>(p, s, nz);
         float old = wp_update_distance(s, wp);
