@@ -74,8 +74,11 @@ struct PfbContext {
 // One warp per CTA.  Measured on B200 (65 536-env Hover step, L2 flushed / warm): 32 threads 22.1 / 20.5 us, 64 threads
 // 22.5 / 22.6 us, 128 threads 24.7 / 24.5 us: a CTA retires as soon as its own warp is done, so the SM back-fills sooner and
 // the single wave has a shorter tail.  448 threads per SM resident (<= 146 regs/thread) for the generic kernels.
-constexpr int kBlock = 32;
-constexpr int kMinBlocks = 448 / kBlock;
+#ifndef PFB_BLOCK  // A/B knob (per translation unit): threads per CTA
+#define PFB_BLOCK 32
+#endif
+constexpr int kBlock = PFB_BLOCK;
+constexpr int kMinBlocks = 448 / kBlock > 0 ? 448 / kBlock : 1;
 // the step kernels of the aerodynamic-surface vehicles (Fixedwing-Waypoints, Dogfight): the batch sizes they run at leave
 // < 4 warps per SM, so registers are better spent on interleaving the surfaces than on residency.  Measured on B200 at 16 384
 // aircraft (profiles/r02_aero_full_block.jsonl): 14 CTAs / SM (128 registers) 31.0 / 34.9 us per step, 8 CTAs / SM (145 / 176
