@@ -146,17 +146,17 @@ constexpr int kObsMax = 24;  // floats per observation row (20 / 21, + 3 for MAQ
 // owns a SPARE, the post-warm-up state of its NEXT episode, with the warm-up noise keyed by (env id, episode number,
 // Aviary step) so that it does not matter when it is computed.
 //  * An env that finished on call k is reset on call k + 1 BY ITS OWN THREAD: the thread skips the physics loop and, at the
-//    end of the launch, swaps the env's spare record in (prefetched into L2 at the top of the launch) — every observation
-//    row of a warp's tile is written by that warp.
+//    end of the launch, swaps the env's spare record in (staged into the warp's dead state-tile buffer by cp.async while the
+//    other lanes integrate, kStageFloats below) — every observation row of a warp's tile is written by that warp.
 //  * The spare it consumed is rebuilt INSIDE the following two step launches by a few BUILDER CTAs appended to the grid:
 //    launch k + 1 (the one that consumes) integrates the first half of the next spare's warm-up, launch k + 2 the second
 //    half — each half is shorter than an env step, so the builders never stretch a launch — and the spare is valid again
-//    before launch k + 3, the earliest the env can be reset again.  Spares are double-buffered by episode parity, so the
-//    builders never write the record a resetting thread is reading.  One launch per env step: no side stream, no events.
+//    before launch k + 3, the earliest the env can be reset again.  A spare lives in buffer (episode & 3), so the builders
+//    never write the record a resetting thread is reading.  One launch per env step: no side stream, no events.
 //  * If the start pose was edited since a spare was built, or with inline_reset = 1, the spare is ignored and the warm-up
 //    runs inline in the owning thread (same episode number, hence the same result).
-// Library-owned: spare[2][N][SP_ROWS] ENV-MAJOR records (the QX_* state rows in record layout, group stride 4, then the
-// words below) and episode[N], the episode number of each env's current valid spare (its buffer is episode & 1).
+// Library-owned: spare[kSpareBufs][N][SP_ROWS] ENV-MAJOR records (the QX_* state rows in record layout, group stride 4, then
+// the words below) and episode[N], the episode number of each env's current valid spare (its buffer is episode & kSpareMask).
 enum { SP_POSE = QX_ROWS, SP_VALID = QX_ROWS + 6, SP_FLAGS = QX_ROWS + 7, SP_EPISODE = QX_ROWS + 8,
        SP_SETPOINT = QX_ROWS + 12 /* 4: the flight mode's preset setpoint, carried between the two halves of a warm-up */, SP_ROWS = 80 };
 static_assert(QX_ROWS % 4 == 0 && QX_ROWS + 16 <= SP_ROWS && SP_ROWS % 4 == 0, "spare record layout");
@@ -211,7 +211,6 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #else
 #define PFB_TL(slot) do { } while (0)
 #endif
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // per-thread asynchronous copies global -> shared (LDGSTS): issued and forgotten, complete in the background, waited for with
 // cp_async_wait_all() by the issuing thread, which may then read what it copied
