@@ -76,6 +76,18 @@ def ncu_flops():
     return out.get("fp32_flops_per_launch"), out.get("fp64_flops_per_launch")
 
 
+def ncu_warp_instructions():
+    """warp instructions of one step launch (smsp__inst_executed.sum of the committed ncu capture), or None"""
+    try:
+        for line in open(_ncu_summary_path()):
+            f = line.split()
+            if len(f) >= 2 and f[0] == "smsp__inst_executed.sum":
+                return float(f[1])
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
 
@@ -540,6 +552,15 @@ def run_ours(args, rank, local_rank, world):
                 "flops_per_launch": f32, "fp64_flops_per_launch": f64, "achieved_tflops": f32 / kern_avg_s / 1e12, "peak_tflops": peak32,
                 "frac": f32 / kern_avg_s / 1e12 / peak32,
                 "source": "FFMA/FMUL/FADD thread-instruction counters of the step launch in the same ncu capture",
+            }
+        winst = ncu_warp_instructions()
+        if winst:
+            # what actually bounds the kernel: the warp schedulers.  148 SMs x 4 schedulers issue at most one warp
+            # instruction per cycle each; frac = the share of those issue slots the launch uses over its measured duration
+            slots = 148 * 4 * 1.965e9 * kern_avg_s
+            line["roofline"]["issue"] = {
+                "warp_instructions_per_launch": winst, "issue_slots_per_launch": slots, "frac": winst / slots,
+                "note": "context: smsp__inst_executed.sum of the same ncu capture / (592 schedulers x 1.965 GHz x the measured launch duration)",
             }
         if world == 1 and not args.no_cpu_baseline:
             rate, cores, steps, dt = cpu_oracle_rate(16384, args.cpu_seconds)
