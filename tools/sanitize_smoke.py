@@ -16,6 +16,15 @@ def drive(env, n):
 
 drive(QuadXHoverVecEnv(num_envs=1000, seed=1, max_duration_seconds=0.2), 30)          # ragged last CTA, many autoresets
 drive(QuadXHoverVecEnv(num_envs=96, seed=1, flight_mode=6, angle_representation="euler"), 10)
+# fused rollout (k_hover_rollout + spare top-up + the hand-over both ways) and 3-step episodes (every lane of a warp resets at once:
+# the lanes beyond the staging slots take the direct path)
+env = QuadXHoverVecEnv(num_envs=1000, seed=2, max_duration_seconds=0.2)
+env.reset()
+for n in (1, 16, 1, 5, 16):
+    env.rollout(n)
+torch.cuda.synchronize()
+env.close()
+drive(QuadXHoverVecEnv(num_envs=200, seed=3, max_duration_seconds=0.05), 12)
 drive(QuadXWaypointsVecEnv(num_envs=500, seed=1, use_yaw_targets=True, max_duration_seconds=0.3), 20)
 drive(FixedwingWaypointsVecEnv(num_envs=300, seed=1, max_duration_seconds=0.3), 20)
 drive(RocketLandingVecEnv(num_envs=300, seed=1, max_duration_seconds=0.3), 20)
