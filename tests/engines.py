@@ -176,7 +176,8 @@ class HostSimEngine:
             self._chk(self.L.hs_rk_aviary_step(C.byref(self.model), _p(self.st, C.c_float), _p(self.ist, C.c_int32), _p(self.sp, C.c_float), _p(nz, C.c_float), n_steps, C.c_int64(self.n)))
             return
         if self.fw:
-            self._chk(self.L.hs_fw_aviary_step(C.byref(self.model), self.mode, _p(self.st, C.c_float), _p(self.ist, C.c_int32), _p(self.sp, C.c_float), _p(nz, C.c_float), n_steps, C.c_int64(self.n)))
+            fn = self.L.hs_fw_aviary_step_full if getattr(self, "full_block", False) else self.L.hs_fw_aviary_step
+            self._chk(fn(C.byref(self.model), self.mode, _p(self.st, C.c_float), _p(self.ist, C.c_int32), _p(self.sp, C.c_float), _p(nz, C.c_float), n_steps, C.c_int64(self.n)))
             return
         self._chk(self.L.hs_aviary_step(C.byref(self.model), self.mode, _p(self.st, C.c_float), _p(self.ist, C.c_int32), _p(self.sp, C.c_float), _p(nz, C.c_float), n_steps, C.c_int64(self.n)))
 

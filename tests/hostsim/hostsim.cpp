@@ -254,6 +254,26 @@ HS_API int hs_fw_aviary_step(const PfbModel* m, int mode, float* st, int32_t* is
   return 0;
 }
 
+// the one-basic-block instantiation the step kernels take when the model has all its surfaces and there is no wind
+// (fixedwing_substep<FULL>, pfb_fixedwing.cuh): same arithmetic as the generic path, pinned to it by tests/test_fixedwing.py
+HS_API int hs_fw_aviary_step_full(const PfbModel* m, int mode, float* st, int32_t* ist, const float* setpoint, const float* noise, int n_steps, int64_t N) {
+  FixedwingParams p;
+  WaypointParams w;
+  if (fw_build_params_impl(*m, nullptr, p, w)) return -1;
+  if (!fixedwing_full_model(p)) return fail("hs_fw_aviary_step_full: the model is not complete (surfaces / wind)");
+  for (int64_t i = 0; i < N; ++i) {
+    FixedwingRegs s;
+    fixedwing_load(st, ist, N, i, s);
+    for (int k = 0; k < 6; ++k) s.sp[k] = setpoint[6 * i + k];
+    HostNoise nz{noise + i, N};
+    for (int k = 0; k < n_steps; ++k) {
+      if (mode == 0) fixedwing_aviary_step<0, true>(p, s, nz); else fixedwing_aviary_step<-1, true>(p, s, nz);
+    }
+    fixedwing_store(st, ist, N, i, s);
+  }
+  return 0;
+}
+
 HS_API int hs_fw_observe(const float* st, const int32_t* ist, float* drone_state, float* aux, uint8_t* contact, int64_t N) {
   for (int64_t i = 0; i < N; ++i) {
     FixedwingRegs s;

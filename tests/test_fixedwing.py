@@ -37,6 +37,46 @@ def test_kernel_body_on_host(name):
     assert err["pos"] < 2e-4 and err["euler"] < 1e-4 and err["linvel"] < 1e-3, (name, err)
 
 
+class _FullBlockHostEngine(HostSimEngine):
+    """the kernel body with the one-basic-block surface code (fixedwing_substep<FULL>): what the step kernels run when the model has
+    all five surfaces and there is no wind"""
+
+    name = "hostsim-full"
+    full_block = True
+
+
+@pytest.mark.parametrize("name", [n for n in AVIARY if "wind" not in n])
+def test_full_block_kernel_body_on_host(name):
+    err = replay_vehicle(_FullBlockHostEngine, load_golden(name))
+    assert err["contact_mismatch"] == 0
+    assert err["pos"] < 2e-4 and err["euler"] < 1e-4 and err["linvel"] < 1e-3, (name, err)
+
+
+@pytest.mark.parametrize("vehicle", ["fixedwing", "acrowing"])
+def test_full_block_equals_generic_surface_code_on_host(vehicle):
+    """FULL only removes the launch-uniform per-surface tests at compile time: same arithmetic, and with g++ the two instantiations
+    agree bit for bit (64 aircraft, 240 Aviary steps through stalls and recoveries)."""
+    n, steps = 64, 240
+    rng = np.random.default_rng(11)
+    f = lambda a: a.astype(np.float32).astype(np.float64)  # noqa: E731
+    model = build_model("fixedwing", vehicle)
+    start = f(np.column_stack([rng.uniform(-5, 5, n), rng.uniform(-5, 5, n), rng.uniform(40, 60, n)]))
+    orn = f(rng.uniform(-0.3, 0.3, (n, 3)))
+    noise = f(rng.normal(1.0, 1.0, (steps * 2, n)))
+    eng = [HostSimEngine(model, None, n, start, orn), _FullBlockHostEngine(model, None, n, start, orn)]
+    for e in eng:
+        e.reset()
+        e.set_mode(0)
+    for i in range(0, steps, 30):
+        sp = f(np.column_stack([rng.uniform(-0.8, 0.8, (n, 3)), rng.uniform(0.2, 1.0, n)]))
+        for e in eng:
+            e.set_setpoints(sp)
+            e.aviary_step(noise[2 * i : 2 * i + 60], n_steps=30)
+    a, b = eng[0].state(), eng[1].state()
+    assert np.array_equal(a, b), np.abs(a - b).max()
+    assert np.array_equal(eng[0].aux(), eng[1].aux())
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", AVIARY)
 def test_cuda_matches_reference(name):
